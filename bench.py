@@ -1,0 +1,247 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: geometric-multigrid V-cycles on synthetic Poisson hierarchies.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|...]
+
+A "step" is ONE V-cycle (V_cycle_scheme, multigrid.py:231-268) on the named hierarchy.
+Metric: smoother DOF-updates per second = (mu1 + mu2) * sum_{l > coarsest} n_l / (seconds per V-cycle)
+(BASELINE.md section 4); ms_per_step is the V-cycle time.  One JSON line is printed by rank 0.
+
+  value      device-resident: v, f and the hierarchy already in HBM, CUDA-graph replay, CUDA-event timing
+  e2e        the same cycles through the C-ABI call mgb_vcycle(mem = HOST) on pinned host buffers:
+             H2D of v and f and D2H of v inside the timed region, every step
+  roofline   dominant kernel (finest-level weighted-Jacobi sweep): algorithmic bytes / event-timed duration
+  cpu_baseline  the C/OpenMP port of the reference's V-cycle (oracle/mg_oracle.c) on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# name: (dim, c, coarsest, finest, description)        cells per dim at level l = c * 2**l
+WORKLOADS = {
+    "cfg1": (2, 8, 0, 2, "2D Poisson P1 33x33 nodes, 3-level V-cycle (reference CPU case)"),
+    "cfg2": (2, 32, 0, 6, "2D Poisson P1 2049x2049 (4.2M DOFs), 7-level V(2,2), weighted Jacobi, injection"),
+    "cfg2s": (2, 32, 0, 4, "2D Poisson P1 513x513, 5-level V(2,2) (reduced stand-in for quick runs)"),
+    "cfg3": (3, 8, 0, 4, "3D Poisson P1 129^3 Kuhn mesh (2.1M DOFs), 5-level V(2,2), weighted Jacobi, injection"),
+}
+METRIC = "V-cycle smoother DOF-updates/s"
+UNIT = "DOF-updates/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name, mu=2):
+    from multigrid_dolfinx_b200 import problems as pr
+    dim, c, lc, lf, desc = WORKLOADS[name]
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=lc, finest_level=lf, mu1=mu, mu2=mu, with_dicts=False)
+    return H, desc
+
+
+def dof_updates_per_cycle(H):
+    return (H.mu1 + H.mu2) * sum(H.n(l) for l in H.levels() if l > H.coarsest_level)
+
+
+def cpu_port_time(H, cycles, warm=1):
+    """The C/OpenMP restatement of the reference V-cycle on all host cores: seconds per cycle."""
+    from oracle import c_oracle as co
+    cm = co.from_hierarchy(H)
+    lf = H.finest_level
+    f = H.b_dict[lf][:, 0]
+    v = np.zeros_like(f)
+    v = cm.vcycle(v, f, ncycles=warm)
+    t0 = time.perf_counter()
+    v = cm.vcycle(v, f, ncycles=cycles)
+    return (time.perf_counter() - t0) / cycles
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for the same metric/config.  The reference is pure Python
+    over scipy and cannot run config 2 at all (its coordinate keys fail for h < 1/512), so this
+    arm times the oracle port (oracle/mg_oracle.c, OpenMP over rows, all host cores)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    H, desc = build_workload(args.workload)
+    cores = os.cpu_count()
+    per = cpu_port_time(H, max(args.steps, 1), max(args.warmup, 1))
+    val = dof_updates_per_cycle(H) / per
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} full V-cycles of {args.workload} after {args.warmup} warm-up, OpenMP over rows"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_single(args):
+    import torch
+    from multigrid_dolfinx_b200.engine import MGEngine
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    t_setup = time.perf_counter()
+    H, desc = build_workload(args.workload)
+    lf = H.finest_level
+    eng = MGEngine.from_hierarchy(H, r_mode=args.restriction, smoother=args.smoother, device=0,
+                                  options={"fuse_restrict": args.fuse_restrict})
+    n = H.n(lf)
+    f_host = H.b_dict[lf][:, 0]
+    t_setup = time.perf_counter() - t_setup
+    dofu = dof_updates_per_cycle(H)
+    stream = eng.torch_stream()
+
+    # ---- device-resident timing ----------------------------------------------------------------
+    eng.level_buffer(lf, "f").copy_(torch.from_numpy(f_host))
+    eng.level_buffer(lf, "v").zero_()
+    torch.cuda.synchronize()
+    eng.vcycle_resident(lf, args.warmup)
+    eng.synchronize()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clk:
+        torch.cuda.synchronize()
+        e0.record(stream)
+        eng.vcycle_resident(lf, args.steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if args.steps * 1e-3 < 1.0:          # keep the GPU busy long enough for nvidia-smi to see it under load
+            eng.vcycle_resident(lf, int(min(4000, 1.0 / 5e-4)))
+            torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = eng.launch_count() - l0
+    hist = eng.vcycle_resident(lf, 1, history=True)
+
+    # ---- dominant kernel, event-timed launch by launch (same cycles, graph off) ----------------------
+    eng.profile_begin()
+    eng.vcycle_resident(lf, max(3, min(args.steps, 10)))
+    prof = eng.profile_end()
+    dom = max(prof, key=lambda r: r["total_ms"])
+    peak, peak_src = measured_peak()
+    cyc_ms_prof = sum(r["total_ms"] for r in prof) / max(3, min(args.steps, 10))
+    roofline = {"bound": "hbm", "kernel": f"{dom['kind']}@level{dom['level']}", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dom["gbs"] / peak, "frac_of_8TBs": dom["gbs"] / 8000.0, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms_per_launch"],
+                "share_of_cycle": dom["total_ms"] / sum(r["total_ms"] for r in prof),
+                "vcycle_bytes": eng.vcycle_bytes(lf), "vcycle_gbs": eng.vcycle_bytes(lf) / (ms * 1e-3) / 1e9}
+    kernels = sorted(prof, key=lambda r: -r["total_ms"])[:8]
+
+    # ---- end to end through the C ABI with pinned host buffers -----------------------------------------
+    vp = torch.zeros(n, dtype=torch.float64).pin_memory()
+    fp = torch.from_numpy(f_host.copy()).pin_memory()
+    lib, h = eng._lib, eng._h
+    for _ in range(max(1, args.warmup)):
+        eng._ck(lib.mgb_vcycle(h, lf, vp.data_ptr(), fp.data_ptr(), 0, 1, None))
+    e2e_steps = max(3, min(args.steps, 20))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng._ck(lib.mgb_vcycle(h, lf, vp.data_ptr(), fp.data_ptr(), 0, 1, None))    # returns after v is back on the host
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e = {"value": dofu / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n,
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "api": "mgb_vcycle(mem=MGB_MEM_HOST), pinned host v/f"}
+
+    # ---- CPU baseline on a bounded sample ------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        cyc = 5
+        per = cpu_port_time(H, cyc, 1)
+        cpu = {"value": dofu / per, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "ms_per_cycle": per * 1e3,
+               "sample": f"{cyc} full V-cycles of {args.workload} (same hierarchy), C/OpenMP port of the reference over all cores"}
+
+    line = {"metric": METRIC, "value": dofu / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "restriction": args.restriction, "smoother": args.smoother,
+                       "fine_dofs": n, "levels": lf - H.coarsest_level + 1, "mu1": H.mu1, "mu2": H.mu2, "omega": H.omega,
+                       "l2": "fine-level operators (>= 550 MB) exceed the 126 MB L2; no flush needed", "setup_s": t_setup},
+            "fine_dof_cycles_per_s": n / (ms * 1e-3), "resnorm_after": float(hist[0]),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
+            "kernels": [{"k": f"{r['kind']}@{r['level']}", "ms": round(r["ms_per_launch"], 5), "n": r["launches"], "gbs": round(r["gbs"], 1)} for r in kernels],
+            "profiled_cycle_ms": cyc_ms_prof}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--restriction", default="injection", choices=["injection", "full_weighting", "transpose"])
+    ap.add_argument("--smoother", default="jacobi", choices=["jacobi", "jacobi_a", "gs", "gs_color"])
+    ap.add_argument("--fuse-restrict", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        from multigrid_dolfinx_b200 import dist_bench
+        return dist_bench.run(args)
+    return run_single(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,179 @@
+/* mgb200.h -- C ABI of the B200-native geometric-multigrid V-cycle engine (libmgb200.so).
+ *
+ * This is the drop-in boundary for the hot path of nikhilTkur/Multigrid_dolfinx: the V-cycle in
+ * multigrid.py (V_cycle_scheme, multigrid.py:231-268) and what it calls.  The reference has no FFI
+ * of its own (it is pure Python over scipy); each entry point below names the reference code it
+ * replaces.  Signatures use plain pointers and sizes only (no torch / numpy types).
+ *
+ * Conventions
+ *   - every function returns MGB_OK (0) or a negative MGB_ERR_* code; the message is available
+ *     from mgb_last_error().  No C++ exception crosses this boundary.
+ *   - host arrays passed to the mgb_set_* calls are copied during the call and stay caller-owned.
+ *   - vector arguments carry a memory-kind flag: MGB_MEM_HOST pointers are staged through
+ *     cudaMemcpyAsync inside the call (the call returns after the result is back on the host);
+ *     MGB_MEM_DEVICE pointers are borrowed for the duration of the call.
+ *   - one handle = one device + one stream; a handle is NOT thread-safe, distinct handles are
+ *     independent.  Calls with device pointers only enqueue work on the handle's stream
+ *     (mgb_get_stream) and do not synchronise unless they return host data.
+ *   - levels are keyed by the reference's integer level (coarsest_level .. finest_level,
+ *     multigrid.py:13-14; cells per dimension = c * 2^level, Multigrid_prototype.py:63).
+ *   - all floating point is IEEE fp64; column indices are int32 (PETSc 32-bit build); row pointers
+ *     may be handed over as int32 or int64.
+ *   - there is NO CPU fallback: without a CUDA device mgb_create fails with MGB_ERR_CUDA.
+ */
+#ifndef MGB200_H
+#define MGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGB_VERSION 100
+
+#define MGB_OK 0
+#define MGB_ERR_INVALID (-1)     /* bad argument                                  */
+#define MGB_ERR_CUDA (-2)        /* CUDA runtime / driver error, or no device     */
+#define MGB_ERR_STATE (-3)       /* call out of order (e.g. vcycle before finalize) */
+#define MGB_ERR_NOMEM (-4)
+#define MGB_ERR_SINGULAR (-5)    /* zero diagonal / singular coarsest matrix      */
+#define MGB_ERR_UNSUPPORTED (-6)
+#define MGB_ERR_COMM (-7)        /* NCCL error                                    */
+
+typedef struct mgb_handle mgb_handle;
+
+/* restriction modes.  INJECTION is what the reference V-cycle executes
+ * (Restriction2D_direct, multigrid.py:123-132, called at multigrid.py:251-252); FULL_WEIGHTING is
+ * the reference's unused Restriction2D (= 2^-d P^T, multigrid.py:135-198); TRANSPOSE is R = P^T
+ * (north-star wording); EXPLICIT takes any CSR. */
+enum { MGB_R_INJECTION = 0, MGB_R_FULL_WEIGHTING = 1, MGB_R_TRANSPOSE = 2, MGB_R_EXPLICIT = 3 };
+
+/* smoothers.  JACOBI_RJ is the reference formula with the precomputed iteration matrix
+ * (jacobiRelaxation, multigrid.py:223-228 + getJacobiMatrices, multigrid.py:48-56);
+ * JACOBI_A is the algebraically equal single-matrix form v + w D^-1 (f - A v);
+ * GS_LEVEL is natural-order forward Gauss-Seidel executed by level sets (no reference text);
+ * GS_MULTICOLOR is Gauss-Seidel in greedy-colour order (different sweep order, documented option). */
+enum { MGB_SM_JACOBI_RJ = 0, MGB_SM_JACOBI_A = 1, MGB_SM_GS_LEVEL = 2, MGB_SM_GS_MULTICOLOR = 3 };
+
+enum { MGB_MEM_HOST = 0, MGB_MEM_DEVICE = 1 };
+
+/* artefacts that must be bit-exact (mgb_get_artifact) */
+enum {
+    MGB_ART_RJ_INDPTR = 0,     /* int32[n+1]  R_omega row pointers  (multigrid.py:52-55)          */
+    MGB_ART_RJ_INDICES = 1,    /* int32[nnz]                                                     */
+    MGB_ART_RJ_VALUES = 2,     /* double[nnz] fl(fl(1/a_ii) * a_ij)                              */
+    MGB_ART_DINV = 3,          /* double[n]   fl(1/a_ii)            (multigrid.py:53)             */
+    MGB_ART_LEVEL_OF_ROW = 4,  /* int32[n]    Gauss-Seidel dependency level of each row           */
+    MGB_ART_LEVEL_ORDER = 5,   /* int32[n]    execution order (stable sort by level)              */
+    MGB_ART_LEVEL_OFFSETS = 6, /* int32[nlev+1]                                                   */
+    MGB_ART_COLOUR_OF_ROW = 7, /* int32[n]    first-fit greedy colour                             */
+    MGB_ART_COLOUR_ORDER = 8,  /* int32[n]                                                        */
+    MGB_ART_COLOUR_OFFSETS = 9,/* int32[ncol+1]                                                   */
+    MGB_ART_R_INDPTR = 10,     /* int32[n_c+1] restriction CSR built from P (FULL_WEIGHTING/TRANSPOSE) */
+    MGB_ART_R_INDICES = 11,
+    MGB_ART_R_VALUES = 12,
+    MGB_ART_COARSE_INVERSE = 13 /* double[n_c*n_c] row-major dense inverse of the coarsest matrix  */
+};
+
+/* per-level device buffers (mgb_level_buffer) */
+enum { MGB_BUF_V = 0, MGB_BUF_F = 1, MGB_BUF_R = 2 };
+
+/* kernel kinds reported by the profiler (mgb_profile_get) */
+enum {
+    MGB_K_JACOBI = 0, MGB_K_RESIDUAL = 1, MGB_K_RESTRICT = 2, MGB_K_PROLONG_ADD = 3, MGB_K_COARSE = 4,
+    MGB_K_INIT_GUESS = 5, MGB_K_GS = 6, MGB_K_NORM = 7, MGB_K_SPMV = 8, MGB_K_HALO = 9, MGB_K_COPY = 10,
+    MGB_K_COUNT = 11
+};
+
+typedef struct {
+    int32_t kind;        /* MGB_K_*                                            */
+    int32_t level;
+    int64_t launches;
+    double total_ms;     /* CUDA-event time summed over launches                */
+    double bytes;        /* algorithmic bytes of ONE launch   */
+} mgb_profile_record;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int mgb_version(void);
+/* replaces the module-global hierarchy container set by initialize_problem (multigrid.py:10-45) */
+int mgb_create(mgb_handle** out, int device_id);
+int mgb_destroy(mgb_handle* h);
+/* h == NULL: message of the last failed mgb_create in this thread */
+const char* mgb_last_error(const mgb_handle* h);
+
+/* ---- hierarchy upload -------------------------------------------------------------------- */
+/* A_l exactly as exported from PETSc into scipy (Multigrid_prototype.py:95-99: A_sp_dict[l]).
+ * indptr_bytes is 4 (int32) or 8 (int64).  Explicit zeros are kept. */
+int mgb_set_level(mgb_handle* h, int level, int64_t n, int64_t nnz, const void* indptr, int indptr_bytes,
+                  const int32_t* indices, const double* values);
+/* Transfer pair between coarse_level and coarse_level+1.
+ * P (n_fine x n_coarse) is the matrix of Interpolation2D (multigrid.py:59-120); row entries are summed
+ * in stored order.  r_mode INJECTION needs inj[n_coarse] = fine dof of each coarse dof
+ * (Restriction2D_direct, multigrid.py:128-131); EXPLICIT needs the R CSR (n_coarse x n_fine);
+ * FULL_WEIGHTING / TRANSPOSE build R from P at finalize.  dim_for_fw: 2 or 3 (scale 2^-dim). */
+int mgb_set_transfer(mgb_handle* h, int coarse_level, int64_t n_fine, int64_t n_coarse,
+                     int64_t p_nnz, const void* p_indptr, int p_indptr_bytes, const int32_t* p_indices, const double* p_values,
+                     int r_mode, int dim_for_fw, const int32_t* inj,
+                     int64_t r_nnz, const void* r_indptr, int r_indptr_bytes, const int32_t* r_indices, const double* r_values);
+/* mu1, mu2, omega (multigrid.py:19-21), smoother = MGB_SM_* */
+int mgb_set_params(mgb_handle* h, double omega, int mu1, int mu2, int smoother);
+/* named numeric options, see DESIGN.md:  "rj_order" (0 = as stored in A, 1 = reversed = scipy's
+ * DIA*CSR product order, default 1), "use_graph" (default 1), "kernel_family" (0 auto, 1 tile, 2 sub-warp),
+ * "lanes_per_row" (0 auto), "coarse_refine" (0/1), "fuse_restrict" (0/1) */
+int mgb_set_option(mgb_handle* h, const char* key, double value);
+/* builds R_omega and D^-1 (getJacobiMatrices, multigrid.py:48-56), R from P, the dense inverse of the
+ * coarsest matrix (replaces spsolve, multigrid.py:239), level sets / colours when a GS smoother is
+ * selected, uploads everything and allocates the per-level vectors. */
+int mgb_finalize(mgb_handle* h);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+/* ncycles x V_cycle_scheme(A_jacobi_sp_dict[top_level], v, f) (multigrid.py:231-268), v updated in place.
+ * resnorm_hist (HOST pointer, nullable): ||f - A v||_2 after each cycle (the quantity multigrid.py:291 forms). */
+int mgb_vcycle(mgb_handle* h, int top_level, double* v, const double* f, int mem, int ncycles, double* resnorm_hist);
+/* one cycle with the reference's test=True outputs (multigrid.py:262-266): f2h = restricted residual,
+ * v2h = coarse-level result, err_h = interpolated correction (all of top_level / top_level-1 size). */
+int mgb_vcycle_debug(mgb_handle* h, int top_level, double* v, const double* f, int mem,
+                     double* f2h, double* v2h, double* err_h);
+/* same as mgb_vcycle but v and f already live in the engine's own level buffers (mgb_level_buffer):
+ * no copy of any kind inside the call; resnorm_hist (host, nullable) forces a sync at the end. */
+int mgb_vcycle_resident(mgb_handle* h, int top_level, int ncycles, double* resnorm_hist);
+
+/* ---- per-operator entry points (parity tests, profiling) -------------------------------------- */
+int mgb_spmv(mgb_handle* h, int level, const double* x, double* y, int mem);                       /* A.dot(x), multigrid.py:244 */
+int mgb_residual(mgb_handle* h, int level, const double* v, const double* f, double* r, int mem); /* f - A v, multigrid.py:244  */
+int mgb_smooth(mgb_handle* h, int level, double* v, const double* f, int nsweeps, int mem);       /* jacobiRelaxation, multigrid.py:223-228 (or GS) */
+int mgb_restrict(mgb_handle* h, int fine_level, const double* r_fine, double* f_coarse, int mem); /* multigrid.py:251-252 */
+int mgb_prolong_add(mgb_handle* h, int fine_level, const double* e_coarse, double* v_fine, int mem); /* multigrid.py:258-260 */
+int mgb_coarse_solve(mgb_handle* h, const double* f, double* u, int mem);                          /* multigrid.py:238-241 */
+int mgb_norm2(mgb_handle* h, int64_t n, const double* x, int mem, double* out_host);
+
+/* ---- introspection ----------------------------------------------------------------------- */
+int mgb_get_artifact(mgb_handle* h, int level, int kind, void* out, int64_t capacity_bytes, int64_t* size_bytes);
+int mgb_level_buffer(mgb_handle* h, int level, int which, void** device_ptr, int64_t* n);
+int mgb_get_stream(mgb_handle* h, void** cuda_stream);
+int mgb_synchronize(mgb_handle* h);
+int mgb_launch_count(mgb_handle* h, int64_t* kernels_launched);
+/* event-timed, non-graph execution of everything between begin and end; records are per (kind, level) */
+int mgb_profile_begin(mgb_handle* h);
+int mgb_profile_end(mgb_handle* h);
+int mgb_profile_get(mgb_handle* h, mgb_profile_record* out, int capacity, int* count);
+/* algorithmic bytes of one V-cycle at top_level with the current parameters */
+int mgb_vcycle_bytes(mgb_handle* h, int top_level, double* bytes);
+/* human-readable description of the kernel variant chosen for each (level, operator) */
+int mgb_describe(mgb_handle* h, char* out, int64_t capacity);
+
+/* ---- host-side setup routines (no device needed; what mgb_finalize runs internally) ------------ */
+/* R_omega / D^-1 from A (multigrid.py:48-56).  Call with rj_indices == NULL to query rj_nnz only. */
+int mgb_host_build_rj(int64_t n, const int64_t* indptr, const int32_t* indices, const double* values, int reversed,
+                      int64_t* rj_nnz, int32_t* rj_indptr, int32_t* rj_indices, double* rj_values, double* dinv);
+int mgb_host_level_sets(int64_t n, const int64_t* indptr, const int32_t* indices, const double* values,
+                        int32_t* level_of_row, int32_t* order, int64_t* nlevels, int32_t* offsets, int64_t offsets_capacity);
+int mgb_host_colouring(int64_t n, const int64_t* indptr, const int32_t* indices, const double* values,
+                       int32_t* colour_of_row, int32_t* order, int64_t* ncolours, int32_t* offsets, int64_t offsets_capacity);
+int mgb_host_dense_inverse(int64_t n, const int64_t* indptr, const int32_t* indices, const double* values, double* inv_row_major);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGB200_H */

@@ -1,0 +1,1017 @@
+// The device-resident level hierarchy and the V-cycle (drop-in for V_cycle_scheme, multigrid.py:231-268)
+// behind the C ABI of include/mgb200.h.  One handle = one device + one stream; the whole cycle is a
+// fixed sequence of launches, captured once per top level into a CUDA graph and replayed.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mgb200.h"
+#include "mgb_internal.h"
+#include "mgb_kernels.cuh"
+
+using namespace mgb;
+
+namespace {
+
+constexpr int THREADS = 256;
+thread_local std::string g_create_error;
+
+struct DevCsr {
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    int32_t* rowptr = nullptr;
+    int32_t* cols = nullptr;
+    double* vals = nullptr;
+    int32_t* tiles = nullptr;
+    int ntiles = 0;
+    int iter = 2;       // tile kernel: groups of 4 entries per thread
+    int family = 1;     // 1 tile, 2 sub-warp
+    int lpr = 4;        // sub-warp lanes per row
+    int max_row = 0;
+    std::vector<int32_t> break_tile;   // tile index at each row breakpoint (colour boundaries)
+    bool present() const { return rowptr != nullptr; }
+};
+
+struct Level {
+    int level = 0;
+    int64_t n = 0;
+    HostCsr A_host;                  // released after finalize
+    HostCsr P_host, R_host;          // transfer from level-1 to this level (this level = fine side)
+    std::vector<int32_t> inj_host;
+    int r_mode = MGB_R_INJECTION;
+    int dim_fw = 2;
+    bool has_transfer = false;       // transfer pair (level-1, level) was set
+    int64_t n_coarse = 0;
+
+    DevCsr A, RJ, P, R, G;           // G: Gauss-Seidel off-diagonal operator, rows in execution order
+    double* dinv = nullptr;
+    int32_t* inj = nullptr;
+    double *v = nullptr, *vtmp = nullptr, *f = nullptr, *r = nullptr, *g = nullptr;
+    // Gauss-Seidel artefacts (host copies are what mgb_get_artifact returns)
+    std::vector<int32_t> lev_of_row, lev_order, lev_off, col_of_row, col_order, col_off;
+    int32_t* gs_order = nullptr;     // device: execution order actually used by G
+    int32_t* gs_off = nullptr;       // device: level offsets (GS_LEVEL)
+    double* gs_diag = nullptr;       // device: a_ii in execution order
+    int gs_groups = 0;               // number of levels / colours
+    int gs_max_width = 0;
+};
+
+struct ProfEvent { int kind, level; double bytes; cudaEvent_t e0, e1; };
+
+}  // namespace
+
+struct mgb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::map<int, Level> levels;
+    bool finalized = false;
+    double omega = 2.0 / 3.0;
+    int mu1 = 2, mu2 = 2, smoother = MGB_SM_JACOBI_RJ;
+    // options
+    int rj_reversed = 1, use_graph = 1, opt_family = 0, opt_lpr = 0, opt_iter = 0, coarse_refine = 0, fuse_restrict = 0;
+    int coarsest = 0, finest = 0;
+    double* coarse_inv = nullptr;
+    std::vector<double> coarse_inv_host;
+    double *d_partial = nullptr, *d_hist = nullptr;
+    int hist_cap = 0;
+    int norm_blocks = 0;
+    std::map<int, cudaGraphExec_t> graphs;
+    std::map<int, int64_t> graph_kernels;
+    bool prof = false;
+    std::vector<ProfEvent> prof_events;
+    std::map<std::pair<int, int>, mgb_profile_record> prof_records;
+    int64_t launches = 0;
+    int sm_count = 148;
+    int gs_coop_blocks_per_sm = 0;
+};
+
+namespace {
+
+int fail(mgb_handle* h, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail(h, MGB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(call)                 \
+    do {                          \
+        int rc_ = (call);         \
+        if (rc_ != MGB_OK) return rc_; \
+    } while (0)
+
+template <class T>
+int dev_alloc(mgb_handle* h, T** p, size_t count)
+{
+    *p = nullptr;
+    CU(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    return MGB_OK;
+}
+
+template <class T>
+int dev_upload(mgb_handle* h, T** p, const T* src, size_t count, size_t pad = 0)
+{
+    TRY(dev_alloc(h, p, count + pad));
+    if (pad) CU(cudaMemsetAsync(*p + count, 0, pad * sizeof(T), h->stream));
+    if (count) CU(cudaMemcpyAsync(*p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return MGB_OK;
+}
+
+void free_csr(DevCsr& D)
+{
+    cudaFree(D.rowptr); cudaFree(D.cols); cudaFree(D.vals); cudaFree(D.tiles);
+    D = DevCsr();
+}
+
+int tile_cap(int iter) { return 4 * THREADS * iter; }
+
+// Upload a host CSR and choose the kernel family / tile shape for it.
+int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int32_t>& breaks = {})
+{
+    const int64_t n = M.nrows, nnz = M.nnz();
+    if (n >= (int64_t)2147483000 || nnz >= (int64_t)2147483000)
+        return fail(h, MGB_ERR_UNSUPPORTED, "operator with %lld rows / %lld entries exceeds the int32 row-pointer range of one device shard",
+                    (long long)n, (long long)nnz);
+    D.nrows = n; D.ncols = M.ncols; D.nnz = nnz;
+    std::vector<int32_t> rp((size_t)n + 1);
+    int mx = 0;
+    for (int64_t i = 0; i <= n; ++i) rp[i] = (int32_t)M.ip[i];
+    for (int64_t i = 0; i < n; ++i) mx = std::max<int>(mx, rp[i + 1] - rp[i]);
+    D.max_row = mx;
+    TRY(dev_upload(h, &D.rowptr, rp.data(), rp.size()));
+    TRY(dev_upload(h, &D.cols, M.ix.data(), (size_t)nnz, 8));
+    TRY(dev_upload(h, &D.vals, M.ax.data(), (size_t)nnz, 8));
+    // family
+    int family = h->opt_family;
+    if (family == 0) family = 1;
+    int iter = h->opt_iter ? h->opt_iter : 2;
+    if (family == 1) {
+        if (!h->opt_iter && nnz / tile_cap(2) < 2 * h->sm_count) iter = 1;   // small level: more, smaller tiles
+        std::vector<int32_t> tiles;
+        bool ok = make_tiles(M.ip, tile_cap(iter) - 4, 4 * THREADS, breaks, tiles, &D.break_tile);
+        if (!ok && !h->opt_iter) { iter = 4; ok = make_tiles(M.ip, tile_cap(iter) - 4, 4 * THREADS, breaks, tiles, &D.break_tile); }
+        if (ok) {
+            D.ntiles = (int)tiles.size() - 1;
+            TRY(dev_upload(h, &D.tiles, tiles.data(), tiles.size()));
+        } else {
+            family = 2;                                  // a row longer than a tile: warp per row
+        }
+    }
+    D.family = family; D.iter = iter;
+    if (family == 2) {
+        int lpr = h->opt_lpr;
+        if (!lpr) {
+            const double avg = n ? (double)nnz / (double)n : 0.0;
+            lpr = 1;
+            while (lpr < 32 && lpr < avg) lpr *= 2;
+            if (mx > 4 * tile_cap(4)) lpr = 32;
+        }
+        D.lpr = lpr;
+        // breakpoints for the sub-warp family are plain row indices
+        D.break_tile.assign(breaks.begin(), breaks.end());
+    }
+    return MGB_OK;
+}
+
+// ---- launch bookkeeping -------------------------------------------------------------------------------
+template <class F>
+int launch(mgb_handle* h, int kind, int level, double bytes, F&& fn)
+{
+    ProfEvent pe{kind, level, bytes, nullptr, nullptr};
+    if (h->prof) {
+        CU(cudaEventCreate(&pe.e0)); CU(cudaEventCreate(&pe.e1));
+        CU(cudaEventRecord(pe.e0, h->stream));
+    }
+    fn();
+    CU(cudaGetLastError());
+    if (h->prof) {
+        CU(cudaEventRecord(pe.e1, h->stream));
+        h->prof_events.push_back(pe);
+    }
+    h->launches++;
+    return MGB_OK;
+}
+
+template <class Epi, bool NCX>
+void launch_tile(mgb_handle* h, const DevCsr& D, int t0, int t1, const double* x, const Epi& epi)
+{
+    const int nt = t1 - t0;
+    if (nt <= 0) return;
+    switch (D.iter) {
+        case 1: k_tile<1, THREADS, NCX, Epi><<<nt, THREADS, 0, h->stream>>>(D.rowptr, D.cols, D.vals, D.tiles, t0, x, epi); break;
+        case 2: k_tile<2, THREADS, NCX, Epi><<<nt, THREADS, 0, h->stream>>>(D.rowptr, D.cols, D.vals, D.tiles, t0, x, epi); break;
+        default: k_tile<4, THREADS, NCX, Epi><<<nt, THREADS, 0, h->stream>>>(D.rowptr, D.cols, D.vals, D.tiles, t0, x, epi); break;
+    }
+}
+
+template <class Epi, bool NCX>
+void launch_subwarp(mgb_handle* h, const DevCsr& D, int r0, int r1, const double* x, const Epi& epi)
+{
+    const int64_t rows = r1 - r0;
+    if (rows <= 0) return;
+    const int64_t threads = rows * D.lpr;
+    const int grid = (int)((threads + 255) / 256);
+    switch (D.lpr) {
+        case 1: k_subwarp<1, NCX, Epi><<<grid, 256, 0, h->stream>>>(D.rowptr, D.cols, D.vals, r0, r1, x, epi); break;
+        case 2: k_subwarp<2, NCX, Epi><<<grid, 256, 0, h->stream>>>(D.rowptr, D.cols, D.vals, r0, r1, x, epi); break;
+        case 4: k_subwarp<4, NCX, Epi><<<grid, 256, 0, h->stream>>>(D.rowptr, D.cols, D.vals, r0, r1, x, epi); break;
+        case 8: k_subwarp<8, NCX, Epi><<<grid, 256, 0, h->stream>>>(D.rowptr, D.cols, D.vals, r0, r1, x, epi); break;
+        case 16: k_subwarp<16, NCX, Epi><<<grid, 256, 0, h->stream>>>(D.rowptr, D.cols, D.vals, r0, r1, x, epi); break;
+        default: k_subwarp<32, NCX, Epi><<<grid, 256, 0, h->stream>>>(D.rowptr, D.cols, D.vals, r0, r1, x, epi); break;
+    }
+}
+
+// all rows of D (group < 0) or the rows of one breakpoint group (colour)
+template <class Epi, bool NCX = true>
+int row_sums(mgb_handle* h, int kind, int level, double bytes, const DevCsr& D, const double* x, const Epi& epi, int group = -1)
+{
+    if (D.nrows == 0) return MGB_OK;
+    return launch(h, kind, level, bytes, [&] {
+        if (D.family == 1) {
+            int t0 = 0, t1 = D.ntiles;
+            if (group >= 0) { t0 = D.break_tile[group]; t1 = D.break_tile[group + 1]; }
+            launch_tile<Epi, NCX>(h, D, t0, t1, x, epi);
+        } else {
+            int r0 = 0, r1 = (int)D.nrows;
+            if (group >= 0) { r0 = D.break_tile[group]; r1 = D.break_tile[group + 1]; }
+            launch_subwarp<Epi, NCX>(h, D, r0, r1, x, epi);
+        }
+    });
+}
+
+// ---- algorithmic byte counts (SURVEY 8d / DESIGN.md) ---------------------------------------------------
+double bytes_rowsum(const DevCsr& D, double vec_terms) { return 12.0 * (double)D.nnz + 4.0 * (double)D.nrows + 8.0 * vec_terms; }
+
+Level* find_level(mgb_handle* h, int level)
+{
+    auto it = h->levels.find(level);
+    return it == h->levels.end() ? nullptr : &it->second;
+}
+
+// ---- smoothers ---------------------------------------------------------------------------------------
+int gs_sweep(mgb_handle* h, Level& L, double* v, const double* f)
+{
+    const DevCsr& G = L.G;
+    const double nb = 12.0 * (double)G.nnz + 8.0 * (double)L.n /*rowptr+order*/ + 8.0 * 3.0 * (double)L.n;
+    if (h->smoother == MGB_SM_GS_LEVEL) {
+        return launch(h, MGB_K_GS, L.level, nb, [&] {
+            int blocks = std::max(1, std::min(h->gs_coop_blocks_per_sm * h->sm_count, (L.gs_max_width + 255) / 256));
+            const int32_t* rp = G.rowptr; const int32_t* cl = G.cols; const double* vl = G.vals;
+            const int32_t* ord = L.gs_order; const double* dg = L.gs_diag; const int32_t* off = L.gs_off;
+            int nlev = L.gs_groups;
+            void* args[] = {(void*)&rp, (void*)&cl, (void*)&vl, (void*)&ord, (void*)&dg, (void*)&f, (void*)&v, (void*)&off, (void*)&nlev};
+            cudaLaunchCooperativeKernel((void*)k_gs_levels, dim3(blocks), dim3(256), args, 0, h->stream);
+        });
+    }
+    // multicolour: one launch per colour, in place (rows of one colour never read each other)
+    for (int c = 0; c < L.gs_groups; ++c) {
+        const double share = L.n ? (double)(L.col_off[c + 1] - L.col_off[c]) / (double)L.n : 0.0;
+        EpiGaussSeidel epi{L.gs_order, L.gs_diag, f, v};
+        TRY((row_sums<EpiGaussSeidel, false>(h, MGB_K_GS, L.level, nb * share, G, v, epi, c)));
+    }
+    return MGB_OK;
+}
+
+// nsweeps relaxation sweeps on level L.  v: current iterate, o: scratch of the same size (Jacobi
+// ping-pong); on return v points at the result.  g_valid: L.g already holds w*(dinv*f) for this f.
+int smooth(mgb_handle* h, Level& L, double*& v, double*& o, const double* f, int nsweeps, bool& g_valid)
+{
+    const double n = (double)L.n;
+    for (int s = 0; s < nsweeps; ++s) {
+        if (h->smoother == MGB_SM_JACOBI_RJ) {
+            if (!g_valid) {
+                EpiJacobiRJFirst epi{v, L.dinv, f, L.g, o, 1 - h->omega, h->omega};
+                TRY(row_sums(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.RJ, 5 * n), L.RJ, v, epi));
+                g_valid = true;
+            } else {
+                EpiJacobiRJ epi{v, L.g, o, 1 - h->omega, h->omega};
+                TRY(row_sums(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.RJ, 3 * n), L.RJ, v, epi));
+            }
+            std::swap(v, o);
+        } else if (h->smoother == MGB_SM_JACOBI_A) {
+            EpiJacobiA epi{v, L.dinv, f, o, h->omega};
+            TRY(row_sums(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.A, 4 * n), L.A, v, epi));
+            std::swap(v, o);
+        } else {
+            TRY(gs_sweep(h, L, v, f));
+        }
+    }
+    return MGB_OK;
+}
+
+int residual(mgb_handle* h, Level& L, const double* v, const double* f, double* r)
+{
+    EpiResidual epi{f, r};
+    return row_sums(h, MGB_K_RESIDUAL, L.level, bytes_rowsum(L.A, 3.0 * (double)L.n), L.A, v, epi);
+}
+
+// restriction from fine level L to its coarse neighbour: f_c = R r  (multigrid.py:251-252)
+int restrict_to(mgb_handle* h, Level& L, const double* r_fine, double* f_coarse)
+{
+    const int64_t nc = L.n_coarse;
+    if (L.r_mode == MGB_R_INJECTION) {
+        return launch(h, MGB_K_RESTRICT, L.level, 20.0 * (double)nc, [&] {
+            if (nc > 0) k_gather<<<(int)((nc + 255) / 256), 256, 0, h->stream>>>((int)nc, L.inj, r_fine, f_coarse);
+        });
+    }
+    EpiStore epi{f_coarse};
+    return row_sums(h, MGB_K_RESTRICT, L.level, bytes_rowsum(L.R, (double)L.n + (double)nc), L.R, r_fine, epi);
+}
+
+// fused residual + injection: f_c[i] = f[g_i] - (A v)[g_i]   (multigrid.py:244 + :128-131)
+int residual_injected(mgb_handle* h, Level& L, const double* v, const double* f, double* f_coarse)
+{
+    const int64_t nc = L.n_coarse;
+    const double avg = L.A.nrows ? (double)L.A.nnz / (double)L.A.nrows : 0.0;
+    return launch(h, MGB_K_RESIDUAL, L.level, (12.0 * avg + 4.0 + 8.0 + 4.0 + 8.0 + 8.0) * (double)nc + 8.0 * (double)L.n, [&] {
+        if (nc <= 0) return;
+        if (avg <= 8.0) k_residual_injected<8><<<(int)((nc * 8 + 255) / 256), 256, 0, h->stream>>>((int)nc, L.inj, L.A.rowptr, L.A.cols, L.A.vals, f, v, f_coarse);
+        else k_residual_injected<16><<<(int)((nc * 16 + 255) / 256), 256, 0, h->stream>>>((int)nc, L.inj, L.A.rowptr, L.A.cols, L.A.vals, f, v, f_coarse);
+    });
+}
+
+int prolong_add(mgb_handle* h, Level& L, const double* e_coarse, double* v_fine, double* err)
+{
+    EpiProlongAdd epi{v_fine, err};
+    return row_sums(h, MGB_K_PROLONG_ADD, L.level, bytes_rowsum(L.P, (double)L.n_coarse + 2.0 * (double)L.n), L.P, e_coarse, epi);
+}
+
+int coarse_apply(mgb_handle* h, Level& C, const double* f, double* u)
+{
+    const int n = (int)C.n;
+    const double nb = 8.0 * (double)n * (double)n + 16.0 * (double)n;
+    TRY(launch(h, MGB_K_COARSE, C.level, nb, [&] {
+        k_dense_gemv<<<(n * 32 + 255) / 256, 256, 0, h->stream>>>(n, h->coarse_inv, f, nullptr, u);
+    }));
+    if (h->coarse_refine) {          // u += Ainv (f - A u): one step of iterative refinement
+        TRY(residual(h, C, u, f, C.r));
+        TRY(launch(h, MGB_K_COARSE, C.level, nb, [&] {
+            k_dense_gemv<<<(n * 32 + 255) / 256, 256, 0, h->stream>>>(n, h->coarse_inv, C.r, u, C.vtmp);
+        }));
+        CU(cudaMemcpyAsync(u, C.vtmp, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return MGB_OK;
+}
+
+int norm2_device(mgb_handle* h, int64_t n, const double* x, double* out_dev, int level)
+{
+    return launch(h, MGB_K_NORM, level, 8.0 * (double)n, [&] {
+        k_sumsq_partial<<<h->norm_blocks, 256, 0, h->stream>>>(n, x, h->d_partial);
+        k_sumsq_final<<<1, 1024, 0, h->stream>>>(h->norm_blocks, h->d_partial, out_dev);
+    });
+}
+
+// ---- one V-cycle, enqueued on the stream (multigrid.py:231-268 unrolled into a down and an up sweep) ----
+// v and f of the top level live in levels[top].v / .f.  dbg: copy the test=True outputs into L.r (err_h);
+// f2h / v2h are left in the coarse level's f / v buffers.
+int enqueue_cycle(mgb_handle* h, int top, bool debug, double** v2h_ptr)
+{
+    if (top == h->coarsest) {          // multigrid.py:238-241
+        Level& C = h->levels[top];
+        TRY(coarse_apply(h, C, C.f, C.vtmp));
+        CU(cudaMemcpyAsync(C.v, C.vtmp, sizeof(double) * (size_t)C.n, cudaMemcpyDeviceToDevice, h->stream));
+        return MGB_OK;
+    }
+    std::map<int, double*> cur, oth;
+    std::map<int, bool> gv;
+    const bool jacobi = h->smoother == MGB_SM_JACOBI_RJ || h->smoother == MGB_SM_JACOBI_A;
+    for (int l = top; l > h->coarsest; --l) {
+        Level& L = h->levels[l];
+        Level& C = h->levels[l - 1];
+        double* v = L.v; double* o = L.vtmp;
+        bool g_valid = false;
+        int sweeps = h->mu1;
+        if (l != top) {                                 // zero initial guess (multigrid.py:253)
+            if (jacobi && h->mu1 > 0) {
+                TRY(launch(h, MGB_K_INIT_GUESS, l, 32.0 * (double)L.n, [&] {
+                    k_init_guess<<<(int)((L.n + 255) / 256), 256, 0, h->stream>>>((int)L.n, L.dinv, L.f, h->omega, L.g, v);
+                }));
+                g_valid = (h->smoother == MGB_SM_JACOBI_RJ);
+                sweeps = h->mu1 - 1;
+            } else {
+                CU(cudaMemsetAsync(v, 0, sizeof(double) * (size_t)L.n, h->stream));
+            }
+        }
+        TRY(smooth(h, L, v, o, L.f, sweeps, g_valid));                    // multigrid.py:243
+        if (L.r_mode == MGB_R_INJECTION && h->fuse_restrict && !debug) {
+            TRY(residual_injected(h, L, v, L.f, C.f));                     // multigrid.py:244 + :251
+        } else {
+            TRY(residual(h, L, v, L.f, L.r));                              // multigrid.py:244
+            TRY(restrict_to(h, L, L.r, C.f));                              // multigrid.py:251-252
+        }
+        cur[l] = v; oth[l] = o; gv[l] = g_valid;
+    }
+    Level& C0 = h->levels[h->coarsest];
+    TRY(coarse_apply(h, C0, C0.f, C0.v));                                  // multigrid.py:238-241
+    cur[h->coarsest] = C0.v;
+    for (int l = h->coarsest + 1; l <= top; ++l) {
+        Level& L = h->levels[l];
+        double* v = cur[l]; double* o = oth[l];
+        bool g_valid = gv[l];
+        double* err = (debug && l == top) ? L.r : nullptr;
+        TRY(prolong_add(h, L, cur[l - 1], v, err));                        // multigrid.py:258-260
+        TRY(smooth(h, L, v, o, L.f, h->mu2, g_valid));                     // multigrid.py:261
+        cur[l] = v;
+    }
+    Level& T = h->levels[top];
+    if (cur[top] != T.v)
+        CU(cudaMemcpyAsync(T.v, cur[top], sizeof(double) * (size_t)T.n, cudaMemcpyDeviceToDevice, h->stream));
+    if (v2h_ptr) *v2h_ptr = cur[top - 1];
+    return MGB_OK;
+}
+
+void drop_graphs(mgb_handle* h)
+{
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
+    h->graph_kernels.clear();
+}
+
+int run_cycle(mgb_handle* h, int top)
+{
+    const bool graphable = h->use_graph && !h->prof && h->smoother != MGB_SM_GS_LEVEL;
+    if (!graphable) return enqueue_cycle(h, top, false, nullptr);
+    auto it = h->graphs.find(top);
+    if (it == h->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        const int64_t before = h->launches;
+        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_cycle(h, top, false, nullptr);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        const int64_t captured = h->launches - before;
+        h->launches = before;
+        if (rc != MGB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return fail(h, MGB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(h, MGB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        h->graphs[top] = exec;
+        h->graph_kernels[top] = captured;
+        it = h->graphs.find(top);
+    }
+    CU(cudaGraphLaunch(it->second, h->stream));
+    h->launches += h->graph_kernels[top];
+    return MGB_OK;
+}
+
+int ensure_hist(mgb_handle* h, int n)
+{
+    if (n <= h->hist_cap) return MGB_OK;
+    cudaFree(h->d_hist);
+    TRY(dev_alloc(h, &h->d_hist, (size_t)n));
+    h->hist_cap = n;
+    return MGB_OK;
+}
+
+int copy_in(mgb_handle* h, double* dst, const double* src, int64_t n, int mem)
+{
+    if (dst == src || n == 0) return MGB_OK;
+    CU(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, mem == MGB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+    return MGB_OK;
+}
+int copy_out(mgb_handle* h, double* dst, const double* src, int64_t n, int mem)
+{
+    if (dst == src || n == 0) return MGB_OK;
+    CU(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, mem == MGB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+    return MGB_OK;
+}
+
+int check_ready(mgb_handle* h, int level, Level** L)
+{
+    if (!h) return MGB_ERR_INVALID;
+    if (!h->finalized) return fail(h, MGB_ERR_STATE, "mgb_finalize has not been called");
+    *L = find_level(h, level);
+    if (!*L) return fail(h, MGB_ERR_INVALID, "unknown level %d", level);
+    CU(cudaSetDevice(h->device));
+    return MGB_OK;
+}
+
+int cycles_on_buffers(mgb_handle* h, int top, int ncycles, double* resnorm_hist)
+{
+    Level& T = h->levels[top];
+    if (resnorm_hist) TRY(ensure_hist(h, ncycles));
+    for (int c = 0; c < ncycles; ++c) {
+        TRY(run_cycle(h, top));
+        if (resnorm_hist) {                    // the residual the reference's driver forms after each cycle (multigrid.py:291)
+            TRY(residual(h, T, T.v, T.f, T.r));
+            TRY(norm2_device(h, T.n, T.r, h->d_hist + c, top));
+        }
+    }
+    if (resnorm_hist) {
+        CU(cudaMemcpyAsync(resnorm_hist, h->d_hist, sizeof(double) * (size_t)ncycles, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return MGB_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int mgb_version(void) { return MGB_VERSION; }
+
+const char* mgb_last_error(const mgb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mgb_create(mgb_handle** out, int device_id)
+{
+    mgb_handle* h = nullptr;
+    if (!out) return fail(h, MGB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(h, MGB_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= count) return fail(h, MGB_ERR_INVALID, "device %d out of range (0..%d)", device_id, count - 1);
+    e = cudaSetDevice(device_id);
+    if (e != cudaSuccess) return fail(h, MGB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    mgb_handle* H = new mgb_handle();
+    H->device = device_id;
+    e = cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete H; return fail(h, MGB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device_id);
+    H->sm_count = prop.multiProcessorCount;
+    H->norm_blocks = 4 * H->sm_count;
+    cudaMalloc((void**)&H->d_partial, sizeof(double) * (size_t)H->norm_blocks);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&H->gs_coop_blocks_per_sm, k_gs_levels, 256, 0);
+    *out = H;
+    return MGB_OK;
+}
+
+int mgb_destroy(mgb_handle* h)
+{
+    if (!h) return MGB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    drop_graphs(h);
+    for (auto& kv : h->levels) {
+        Level& L = kv.second;
+        free_csr(L.A); free_csr(L.RJ); free_csr(L.P); free_csr(L.R); free_csr(L.G);
+        cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.v); cudaFree(L.vtmp); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
+        cudaFree(L.gs_order); cudaFree(L.gs_off); cudaFree(L.gs_diag);
+    }
+    cudaFree(h->coarse_inv); cudaFree(h->d_partial); cudaFree(h->d_hist);
+    for (auto& pe : h->prof_events) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return MGB_OK;
+}
+
+int mgb_set_level(mgb_handle* h, int level, int64_t n, int64_t nnz, const void* indptr, int indptr_bytes,
+                  const int32_t* indices, const double* values)
+{
+    if (!h) return MGB_ERR_INVALID;
+    if (h->finalized) return fail(h, MGB_ERR_STATE, "hierarchy already finalized");
+    Level& L = h->levels[level];
+    L.level = level; L.n = n;
+    std::string e = import_csr(L.A_host, n, n, nnz, indptr, indptr_bytes, indices, values);
+    if (!e.empty()) { h->levels.erase(level); return fail(h, MGB_ERR_INVALID, "level %d: %s", level, e.c_str()); }
+    return MGB_OK;
+}
+
+int mgb_set_transfer(mgb_handle* h, int coarse_level, int64_t n_fine, int64_t n_coarse,
+                     int64_t p_nnz, const void* p_indptr, int p_indptr_bytes, const int32_t* p_indices, const double* p_values,
+                     int r_mode, int dim_for_fw, const int32_t* inj,
+                     int64_t r_nnz, const void* r_indptr, int r_indptr_bytes, const int32_t* r_indices, const double* r_values)
+{
+    if (!h) return MGB_ERR_INVALID;
+    if (h->finalized) return fail(h, MGB_ERR_STATE, "hierarchy already finalized");
+    Level* F = find_level(h, coarse_level + 1);
+    Level* C = find_level(h, coarse_level);
+    if (!F || !C) return fail(h, MGB_ERR_STATE, "set levels %d and %d before their transfer", coarse_level, coarse_level + 1);
+    if (F->n != n_fine || C->n != n_coarse) return fail(h, MGB_ERR_INVALID, "transfer sizes (%lld, %lld) do not match the levels (%lld, %lld)",
+                                                        (long long)n_fine, (long long)n_coarse, (long long)F->n, (long long)C->n);
+    if (r_mode < MGB_R_INJECTION || r_mode > MGB_R_EXPLICIT) return fail(h, MGB_ERR_INVALID, "bad r_mode %d", r_mode);
+    std::string e = import_csr(F->P_host, n_fine, n_coarse, p_nnz, p_indptr, p_indptr_bytes, p_indices, p_values);
+    if (!e.empty()) return fail(h, MGB_ERR_INVALID, "P: %s", e.c_str());
+    F->r_mode = r_mode; F->dim_fw = dim_for_fw; F->n_coarse = n_coarse;
+    if (r_mode == MGB_R_INJECTION) {
+        if (!inj) return fail(h, MGB_ERR_INVALID, "injection list is null");
+        F->inj_host.assign(inj, inj + n_coarse);
+        for (int64_t i = 0; i < n_coarse; ++i)
+            if (inj[i] < 0 || inj[i] >= n_fine) return fail(h, MGB_ERR_INVALID, "injection index out of range at %lld", (long long)i);
+    } else if (r_mode == MGB_R_EXPLICIT) {
+        e = import_csr(F->R_host, n_coarse, n_fine, r_nnz, r_indptr, r_indptr_bytes, r_indices, r_values);
+        if (!e.empty()) return fail(h, MGB_ERR_INVALID, "R: %s", e.c_str());
+    } else if (dim_for_fw != 2 && dim_for_fw != 3 && r_mode == MGB_R_FULL_WEIGHTING) {
+        return fail(h, MGB_ERR_INVALID, "dim_for_fw must be 2 or 3");
+    }
+    F->has_transfer = true;
+    return MGB_OK;
+}
+
+int mgb_set_params(mgb_handle* h, double omega, int mu1, int mu2, int smoother)
+{
+    if (!h) return MGB_ERR_INVALID;
+    if (mu1 < 0 || mu2 < 0) return fail(h, MGB_ERR_INVALID, "negative sweep count");
+    if (smoother < MGB_SM_JACOBI_RJ || smoother > MGB_SM_GS_MULTICOLOR) return fail(h, MGB_ERR_INVALID, "bad smoother %d", smoother);
+    if (h->finalized && smoother != h->smoother) {
+        const bool was_gs = h->smoother >= MGB_SM_GS_LEVEL, is_gs = smoother >= MGB_SM_GS_LEVEL;
+        if (is_gs || was_gs) return fail(h, MGB_ERR_STATE, "Gauss-Seidel operators are built at finalize: choose the smoother before mgb_finalize");
+    }
+    h->omega = omega; h->mu1 = mu1; h->mu2 = mu2; h->smoother = smoother;
+    drop_graphs(h);
+    return MGB_OK;
+}
+
+int mgb_set_option(mgb_handle* h, const char* key, double value)
+{
+    if (!h || !key) return MGB_ERR_INVALID;
+    const std::string k(key);
+    const int iv = (int)value;
+    const bool pre = !h->finalized;
+    if (k == "use_graph") { h->use_graph = iv; drop_graphs(h); }
+    else if (k == "coarse_refine") { h->coarse_refine = iv; drop_graphs(h); }
+    else if (k == "fuse_restrict") { h->fuse_restrict = iv; drop_graphs(h); }
+    else if (k == "rj_order" && pre) h->rj_reversed = iv;
+    else if (k == "kernel_family" && pre) h->opt_family = iv;
+    else if (k == "lanes_per_row" && pre) h->opt_lpr = iv;
+    else if (k == "tile_iter" && pre) h->opt_iter = iv;
+    else return fail(h, pre ? MGB_ERR_INVALID : MGB_ERR_STATE, "option '%s' unknown or not settable %s finalize", key, pre ? "before" : "after");
+    return MGB_OK;
+}
+
+int mgb_finalize(mgb_handle* h)
+{
+    if (!h) return MGB_ERR_INVALID;
+    if (h->finalized) return fail(h, MGB_ERR_STATE, "already finalized");
+    if (h->levels.empty()) return fail(h, MGB_ERR_STATE, "no levels set");
+    CU(cudaSetDevice(h->device));
+    h->coarsest = h->levels.begin()->first;
+    h->finest = h->levels.rbegin()->first;
+    for (int l = h->coarsest; l <= h->finest; ++l) {
+        Level* L = find_level(h, l);
+        if (!L) return fail(h, MGB_ERR_STATE, "level %d missing (levels must be contiguous)", l);
+        if (l > h->coarsest && !L->has_transfer) return fail(h, MGB_ERR_STATE, "transfer between levels %d and %d missing", l - 1, l);
+    }
+    if (h->opt_iter && h->opt_iter != 1 && h->opt_iter != 2 && h->opt_iter != 4) return fail(h, MGB_ERR_INVALID, "tile_iter must be 1, 2 or 4");
+    if (h->opt_lpr && (h->opt_lpr & (h->opt_lpr - 1) || h->opt_lpr > 32)) return fail(h, MGB_ERR_INVALID, "lanes_per_row must be a power of two <= 32");
+    for (auto& kv : h->levels) {
+        Level& L = kv.second;
+        const size_t n = (size_t)L.n;
+        TRY(upload_csr(h, L.A_host, L.A));
+        {
+            HostCsr RJ; std::vector<double> dinv;
+            if (!build_rj(L.A_host, h->rj_reversed != 0, RJ, dinv))            // multigrid.py:48-56
+                return fail(h, MGB_ERR_SINGULAR, "level %d: zero or missing diagonal entry", kv.first);
+            TRY(upload_csr(h, RJ, L.RJ));
+            TRY(dev_upload(h, &L.dinv, dinv.data(), n));
+        }
+        if (h->smoother >= MGB_SM_GS_LEVEL && kv.first > h->coarsest) {
+            HostCsr G0, G; std::vector<double> diag, dperm(n);
+            if (!split_offdiag(L.A_host, G0, diag)) return fail(h, MGB_ERR_SINGULAR, "level %d: zero or missing diagonal entry", kv.first);
+            level_sets(L.A_host, L.lev_of_row, L.lev_order, L.lev_off);
+            greedy_colouring(L.A_host, L.col_of_row, L.col_order, L.col_off);
+            const bool lvl = h->smoother == MGB_SM_GS_LEVEL;
+            const std::vector<int32_t>& order = lvl ? L.lev_order : L.col_order;
+            const std::vector<int32_t>& off = lvl ? L.lev_off : L.col_off;
+            permute_rows(G0, order, G);
+            for (size_t p = 0; p < n; ++p) dperm[p] = diag[order[p]];
+            L.gs_groups = (int)off.size() - 1;
+            for (int g = 0; g < L.gs_groups; ++g) L.gs_max_width = std::max(L.gs_max_width, off[g + 1] - off[g]);
+            if (lvl) {
+                const int sf = h->opt_family; h->opt_family = 2;      // rows are read directly by k_gs_levels
+                int rc = upload_csr(h, G, L.G); h->opt_family = sf; TRY(rc);
+            } else {
+                TRY(upload_csr(h, G, L.G, off));
+            }
+            TRY(dev_upload(h, &L.gs_order, order.data(), n));
+            TRY(dev_upload(h, &L.gs_off, off.data(), off.size()));
+            TRY(dev_upload(h, &L.gs_diag, dperm.data(), n));
+        }
+        if (L.has_transfer) {
+            TRY(upload_csr(h, L.P_host, L.P));
+            if (L.r_mode == MGB_R_INJECTION) {
+                TRY(dev_upload(h, &L.inj, L.inj_host.data(), L.inj_host.size()));
+            } else {
+                if (L.r_mode == MGB_R_FULL_WEIGHTING) transpose_scaled(L.P_host, std::ldexp(1.0, -L.dim_fw), L.R_host);
+                else if (L.r_mode == MGB_R_TRANSPOSE) transpose_scaled(L.P_host, 1.0, L.R_host);
+                TRY(upload_csr(h, L.R_host, L.R));
+            }
+        }
+        TRY(dev_alloc(h, &L.v, n)); TRY(dev_alloc(h, &L.vtmp, n)); TRY(dev_alloc(h, &L.f, n));
+        TRY(dev_alloc(h, &L.r, n)); TRY(dev_alloc(h, &L.g, n));
+        CU(cudaMemsetAsync(L.v, 0, n * sizeof(double), h->stream));
+        CU(cudaMemsetAsync(L.f, 0, n * sizeof(double), h->stream));
+    }
+    {   // dense inverse of the coarsest matrix: replaces spsolve (multigrid.py:239)
+        Level& C = h->levels[h->coarsest];
+        if (C.n > 8192) return fail(h, MGB_ERR_UNSUPPORTED, "coarsest level has %lld rows; the dense coarse solver is limited to 8192 (add levels)", (long long)C.n);
+        if (!dense_inverse(C.A_host, h->coarse_inv_host)) return fail(h, MGB_ERR_SINGULAR, "coarsest matrix is singular");
+        TRY(dev_upload(h, &h->coarse_inv, h->coarse_inv_host.data(), h->coarse_inv_host.size()));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    for (auto& kv : h->levels) {      // host copies are no longer needed (artefacts are read back from the device)
+        Level& L = kv.second;
+        L.A_host = HostCsr(); L.P_host = HostCsr(); L.R_host = HostCsr();
+        std::vector<int32_t>().swap(L.inj_host);
+    }
+    h->finalized = true;
+    return MGB_OK;
+}
+
+int mgb_vcycle(mgb_handle* h, int top_level, double* v, const double* f, int mem, int ncycles, double* resnorm_hist)
+{
+    Level* T;
+    TRY(check_ready(h, top_level, &T));
+    if (!v || !f || ncycles < 0) return fail(h, MGB_ERR_INVALID, "null vector or negative cycle count");
+    TRY(copy_in(h, T->f, f, T->n, mem));
+    TRY(copy_in(h, T->v, v, T->n, mem));
+    TRY(cycles_on_buffers(h, top_level, ncycles, resnorm_hist));
+    TRY(copy_out(h, v, T->v, T->n, mem));
+    if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream));
+    return MGB_OK;
+}
+
+int mgb_vcycle_resident(mgb_handle* h, int top_level, int ncycles, double* resnorm_hist)
+{
+    Level* T;
+    TRY(check_ready(h, top_level, &T));
+    if (ncycles < 0) return fail(h, MGB_ERR_INVALID, "negative cycle count");
+    return cycles_on_buffers(h, top_level, ncycles, resnorm_hist);
+}
+
+int mgb_vcycle_debug(mgb_handle* h, int top_level, double* v, const double* f, int mem, double* f2h, double* v2h, double* err_h)
+{
+    Level* T;
+    TRY(check_ready(h, top_level, &T));
+    if (top_level == h->coarsest) return fail(h, MGB_ERR_INVALID, "the debug outputs need a level above the coarsest");
+    if (!v || !f) return fail(h, MGB_ERR_INVALID, "null vector");
+    Level& C = h->levels[top_level - 1];
+    TRY(copy_in(h, T->f, f, T->n, mem));
+    TRY(copy_in(h, T->v, v, T->n, mem));
+    double* v2 = nullptr;
+    // f2h must be saved before the coarse recursion overwrites nothing -- C.f is only written by the restriction
+    TRY(enqueue_cycle(h, top_level, true, &v2));
+    TRY(copy_out(h, v, T->v, T->n, mem));
+    if (f2h) TRY(copy_out(h, f2h, C.f, C.n, mem));
+    if (v2h) TRY(copy_out(h, v2h, v2, C.n, mem));
+    if (err_h) TRY(copy_out(h, err_h, T->r, T->n, mem));
+    if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream));
+    return MGB_OK;
+}
+
+int mgb_spmv(mgb_handle* h, int level, const double* x, double* y, int mem)
+{
+    Level* L;
+    TRY(check_ready(h, level, &L));
+    const double* xd = x; double* yd = y;
+    if (mem == MGB_MEM_HOST) { TRY(copy_in(h, L->v, x, L->n, mem)); xd = L->v; yd = L->r; }
+    EpiStore epi{yd};
+    TRY(row_sums(h, MGB_K_SPMV, level, bytes_rowsum(L->A, 2.0 * (double)L->n), L->A, xd, epi));
+    if (mem == MGB_MEM_HOST) { TRY(copy_out(h, y, yd, L->n, mem)); CU(cudaStreamSynchronize(h->stream)); }
+    return MGB_OK;
+}
+
+int mgb_residual(mgb_handle* h, int level, const double* v, const double* f, double* r, int mem)
+{
+    Level* L;
+    TRY(check_ready(h, level, &L));
+    const double *vd = v, *fd = f; double* rd = r;
+    if (mem == MGB_MEM_HOST) { TRY(copy_in(h, L->v, v, L->n, mem)); TRY(copy_in(h, L->f, f, L->n, mem)); vd = L->v; fd = L->f; rd = L->r; }
+    TRY(residual(h, *L, vd, fd, rd));
+    if (mem == MGB_MEM_HOST) { TRY(copy_out(h, r, rd, L->n, mem)); CU(cudaStreamSynchronize(h->stream)); }
+    return MGB_OK;
+}
+
+int mgb_smooth(mgb_handle* h, int level, double* v, const double* f, int nsweeps, int mem)
+{
+    Level* L;
+    TRY(check_ready(h, level, &L));
+    if (level == h->coarsest && h->smoother >= MGB_SM_GS_LEVEL) return fail(h, MGB_ERR_STATE, "no Gauss-Seidel operator on the coarsest level");
+    double* vd = v; const double* fd = f;
+    if (mem == MGB_MEM_HOST) { TRY(copy_in(h, L->v, v, L->n, mem)); TRY(copy_in(h, L->f, f, L->n, mem)); vd = L->v; fd = L->f; }
+    double* cur = vd; double* oth = L->vtmp;
+    bool g_valid = false;
+    TRY(smooth(h, *L, cur, oth, fd, nsweeps, g_valid));
+    if (cur != vd) CU(cudaMemcpyAsync(vd, cur, sizeof(double) * (size_t)L->n, cudaMemcpyDeviceToDevice, h->stream));
+    if (mem == MGB_MEM_HOST) { TRY(copy_out(h, v, vd, L->n, mem)); CU(cudaStreamSynchronize(h->stream)); }
+    return MGB_OK;
+}
+
+int mgb_restrict(mgb_handle* h, int fine_level, const double* r_fine, double* f_coarse, int mem)
+{
+    Level* L;
+    TRY(check_ready(h, fine_level, &L));
+    if (!L->has_transfer) return fail(h, MGB_ERR_INVALID, "level %d has no coarser neighbour", fine_level);
+    Level& C = h->levels[fine_level - 1];
+    const double* rd = r_fine; double* fd = f_coarse;
+    if (mem == MGB_MEM_HOST) { TRY(copy_in(h, L->r, r_fine, L->n, mem)); rd = L->r; fd = C.f; }
+    TRY(restrict_to(h, *L, rd, fd));
+    if (mem == MGB_MEM_HOST) { TRY(copy_out(h, f_coarse, fd, C.n, mem)); CU(cudaStreamSynchronize(h->stream)); }
+    return MGB_OK;
+}
+
+int mgb_prolong_add(mgb_handle* h, int fine_level, const double* e_coarse, double* v_fine, int mem)
+{
+    Level* L;
+    TRY(check_ready(h, fine_level, &L));
+    if (!L->has_transfer) return fail(h, MGB_ERR_INVALID, "level %d has no coarser neighbour", fine_level);
+    Level& C = h->levels[fine_level - 1];
+    const double* ed = e_coarse; double* vd = v_fine;
+    if (mem == MGB_MEM_HOST) { TRY(copy_in(h, C.v, e_coarse, C.n, mem)); TRY(copy_in(h, L->v, v_fine, L->n, mem)); ed = C.v; vd = L->v; }
+    TRY(prolong_add(h, *L, ed, vd, nullptr));
+    if (mem == MGB_MEM_HOST) { TRY(copy_out(h, v_fine, vd, L->n, mem)); CU(cudaStreamSynchronize(h->stream)); }
+    return MGB_OK;
+}
+
+int mgb_coarse_solve(mgb_handle* h, const double* f, double* u, int mem)
+{
+    Level* C;
+    if (!h) return MGB_ERR_INVALID;
+    TRY(check_ready(h, h->coarsest, &C));
+    const double* fd = f; double* ud = u;
+    if (mem == MGB_MEM_HOST) { TRY(copy_in(h, C->f, f, C->n, mem)); fd = C->f; ud = C->v; }
+    TRY(coarse_apply(h, *C, fd, ud));
+    if (mem == MGB_MEM_HOST) { TRY(copy_out(h, u, ud, C->n, mem)); CU(cudaStreamSynchronize(h->stream)); }
+    return MGB_OK;
+}
+
+int mgb_norm2(mgb_handle* h, int64_t n, const double* x, int mem, double* out_host)
+{
+    if (!h || !x || !out_host || n < 0) return MGB_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    const double* xd = x;
+    double* tmp = nullptr;
+    if (mem == MGB_MEM_HOST) { TRY(dev_alloc(h, &tmp, (size_t)n)); TRY(copy_in(h, tmp, x, n, mem)); xd = tmp; }
+    TRY(ensure_hist(h, 1));
+    TRY(norm2_device(h, n, xd, h->d_hist, -1));
+    CU(cudaMemcpyAsync(out_host, h->d_hist, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(tmp);
+    return MGB_OK;
+}
+
+int mgb_get_artifact(mgb_handle* h, int level, int kind, void* out, int64_t capacity_bytes, int64_t* size_bytes)
+{
+    Level* L;
+    TRY(check_ready(h, level, &L));
+    const void* src = nullptr; bool on_device = true; int64_t bytes = 0;
+    auto host_vec = [&](const std::vector<int32_t>& v) { src = v.data(); bytes = (int64_t)v.size() * 4; on_device = false; };
+    switch (kind) {
+        case MGB_ART_RJ_INDPTR: src = L->RJ.rowptr; bytes = (L->RJ.nrows + 1) * 4; break;
+        case MGB_ART_RJ_INDICES: src = L->RJ.cols; bytes = L->RJ.nnz * 4; break;
+        case MGB_ART_RJ_VALUES: src = L->RJ.vals; bytes = L->RJ.nnz * 8; break;
+        case MGB_ART_DINV: src = L->dinv; bytes = L->n * 8; break;
+        case MGB_ART_LEVEL_OF_ROW: host_vec(L->lev_of_row); break;
+        case MGB_ART_LEVEL_ORDER: host_vec(L->lev_order); break;
+        case MGB_ART_LEVEL_OFFSETS: host_vec(L->lev_off); break;
+        case MGB_ART_COLOUR_OF_ROW: host_vec(L->col_of_row); break;
+        case MGB_ART_COLOUR_ORDER: host_vec(L->col_order); break;
+        case MGB_ART_COLOUR_OFFSETS: host_vec(L->col_off); break;
+        case MGB_ART_R_INDPTR: src = L->R.rowptr; bytes = L->R.present() ? (L->R.nrows + 1) * 4 : 0; break;
+        case MGB_ART_R_INDICES: src = L->R.cols; bytes = L->R.nnz * 4; break;
+        case MGB_ART_R_VALUES: src = L->R.vals; bytes = L->R.nnz * 8; break;
+        case MGB_ART_COARSE_INVERSE:
+            src = h->coarse_inv_host.data(); bytes = (int64_t)h->coarse_inv_host.size() * 8; on_device = false; break;
+        default: return fail(h, MGB_ERR_INVALID, "unknown artefact kind %d", kind);
+    }
+    if (size_bytes) *size_bytes = bytes;
+    if (!out) return MGB_OK;
+    if (capacity_bytes < bytes) return fail(h, MGB_ERR_INVALID, "artefact needs %lld bytes, buffer has %lld", (long long)bytes, (long long)capacity_bytes);
+    if (bytes == 0) return MGB_OK;
+    if (on_device) {
+        CU(cudaMemcpyAsync(out, src, (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    } else {
+        std::memcpy(out, src, (size_t)bytes);
+    }
+    return MGB_OK;
+}
+
+int mgb_level_buffer(mgb_handle* h, int level, int which, void** device_ptr, int64_t* n)
+{
+    Level* L;
+    TRY(check_ready(h, level, &L));
+    if (!device_ptr) return MGB_ERR_INVALID;
+    switch (which) {
+        case MGB_BUF_V: *device_ptr = L->v; break;
+        case MGB_BUF_F: *device_ptr = L->f; break;
+        case MGB_BUF_R: *device_ptr = L->r; break;
+        default: return fail(h, MGB_ERR_INVALID, "unknown buffer %d", which);
+    }
+    if (n) *n = L->n;
+    return MGB_OK;
+}
+
+int mgb_get_stream(mgb_handle* h, void** cuda_stream)
+{
+    if (!h || !cuda_stream) return MGB_ERR_INVALID;
+    *cuda_stream = (void*)h->stream;
+    return MGB_OK;
+}
+
+int mgb_synchronize(mgb_handle* h)
+{
+    if (!h) return MGB_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return MGB_OK;
+}
+
+int mgb_launch_count(mgb_handle* h, int64_t* kernels_launched)
+{
+    if (!h || !kernels_launched) return MGB_ERR_INVALID;
+    *kernels_launched = h->launches;
+    return MGB_OK;
+}
+
+int mgb_profile_begin(mgb_handle* h)
+{
+    if (!h) return MGB_ERR_INVALID;
+    CU(cudaStreamSynchronize(h->stream));
+    h->prof = true;
+    h->prof_records.clear();
+    return MGB_OK;
+}
+
+int mgb_profile_end(mgb_handle* h)
+{
+    if (!h) return MGB_ERR_INVALID;
+    CU(cudaStreamSynchronize(h->stream));
+    for (auto& pe : h->prof_events) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, pe.e0, pe.e1);
+        mgb_profile_record& r = h->prof_records[{pe.kind, pe.level}];
+        r.kind = pe.kind; r.level = pe.level; r.launches++; r.total_ms += ms; r.bytes = pe.bytes;
+        cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1);
+    }
+    h->prof_events.clear();
+    h->prof = false;
+    return MGB_OK;
+}
+
+int mgb_profile_get(mgb_handle* h, mgb_profile_record* out, int capacity, int* count)
+{
+    if (!h || !count) return MGB_ERR_INVALID;
+    *count = (int)h->prof_records.size();
+    if (!out) return MGB_OK;
+    int i = 0;
+    for (auto& kv : h->prof_records) { if (i >= capacity) break; out[i++] = kv.second; }
+    return MGB_OK;
+}
+
+int mgb_vcycle_bytes(mgb_handle* h, int top_level, double* bytes)
+{
+    Level* T;
+    TRY(check_ready(h, top_level, &T));
+    if (!bytes) return MGB_ERR_INVALID;
+    double b = 0.0;
+    for (int l = h->coarsest + 1; l <= top_level; ++l) {
+        Level& L = h->levels[l];
+        const double n = (double)L.n, nc = (double)L.n_coarse;
+        const int sweeps = h->mu1 + h->mu2;
+        if (h->smoother == MGB_SM_JACOBI_RJ) b += sweeps * bytes_rowsum(L.RJ, 3 * n);
+        else if (h->smoother == MGB_SM_JACOBI_A) b += sweeps * bytes_rowsum(L.A, 4 * n);
+        else b += sweeps * (12.0 * (double)L.G.nnz + 8.0 * n + 24.0 * n);
+        b += bytes_rowsum(L.A, 3 * n);
+        b += L.r_mode == MGB_R_INJECTION ? 20.0 * nc : bytes_rowsum(L.R, n + nc);
+        b += bytes_rowsum(L.P, nc + 2 * n);
+    }
+    const double n0 = (double)h->levels[h->coarsest].n;
+    b += 8.0 * n0 * n0 + 16.0 * n0;
+    *bytes = b;
+    return MGB_OK;
+}
+
+int mgb_describe(mgb_handle* h, char* out, int64_t capacity)
+{
+    if (!h || !out || capacity <= 0) return MGB_ERR_INVALID;
+    std::string s;
+    char buf[256];
+    auto one = [&](const char* name, const DevCsr& D) {
+        if (!D.present()) return;
+        if (D.family == 1) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d tile(cap=%d) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, tile_cap(D.iter), D.ntiles);
+        else snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d subwarp(lanes=%d)\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.lpr);
+        s += buf;
+    };
+    for (auto& kv : h->levels) {
+        snprintf(buf, sizeof buf, "level %d n=%lld\n", kv.first, (long long)kv.second.n);
+        s += buf;
+        one("A", kv.second.A); one("RJ", kv.second.RJ); one("P", kv.second.P); one("R", kv.second.R); one("G", kv.second.G);
+    }
+    snprintf(out, (size_t)capacity, "%s", s.c_str());
+    return MGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,389 @@
+"""Python face of the C ABI: one ``MGEngine`` = one ``mgb_handle`` (one device, one stream).
+
+Everything numerical happens in libmgb200.so; this class only marshals pointers.  Vectors may be
+numpy arrays (host memory: staged by the library inside the call) or torch CUDA float64 tensors
+(device memory: borrowed, no copy through the host)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _as_csr_arrays(M):
+    indptr = np.ascontiguousarray(M.indptr)
+    if indptr.dtype not in (np.int32, np.int64):
+        indptr = indptr.astype(np.int64)
+    indices = np.ascontiguousarray(M.indices, dtype=np.int32)
+    data = np.ascontiguousarray(M.data, dtype=np.float64)
+    return indptr, indices, data
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class MGEngine:
+    """Device-resident level hierarchy + V-cycle.  Mirrors the protocol of the reference
+    (getJacobiMatrices -> initialize_problem -> V_cycle_scheme, Multigrid_prototype.py:135-143)."""
+
+    def __init__(self, device=0):
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        rc = self._lib.mgb_create(C.byref(self._h), int(device))
+        if rc != L.OK:
+            msg = self._lib.mgb_last_error(None).decode()
+            self._h = None
+            raise L.MGBError(rc, msg)
+        self.device = int(device)
+        self.n = {}
+        self.finalized = False
+        self._ext_stream = None
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != L.OK:
+            raise L.MGBError(rc, self._lib.mgb_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mgb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stream_ptr(self):
+        p = C.c_void_p()
+        self._ck(self._lib.mgb_get_stream(self._h, C.byref(p)))
+        return p.value
+
+    def torch_stream(self):
+        """The engine's stream as a torch.cuda.ExternalStream (for events / ordering)."""
+        import torch
+        if self._ext_stream is None:
+            self._ext_stream = torch.cuda.ExternalStream(self.stream_ptr(), device=self.device)
+        return self._ext_stream
+
+    def synchronize(self):
+        self._ck(self._lib.mgb_synchronize(self._h))
+
+    # -- hierarchy upload ---------------------------------------------------------------------------
+    def set_level(self, level, A):
+        """A_sp_dict[level][0] as exported from PETSc (Multigrid_prototype.py:95-99)."""
+        ip, ix, ax = _as_csr_arrays(A)
+        n = A.shape[0]
+        self._ck(self._lib.mgb_set_level(self._h, int(level), n, len(ax), ip.ctypes.data, ip.dtype.itemsize,
+                                         ix.ctypes.data, ax.ctypes.data))
+        self.n[int(level)] = n
+
+    def set_transfer(self, coarse_level, P, r_mode="injection", inj=None, R=None, dim=2):
+        pip, pix, pax = _as_csr_arrays(P)
+        mode = L.R_MODES[r_mode] if isinstance(r_mode, str) else int(r_mode)
+        injp = None
+        if inj is not None:
+            inj = np.ascontiguousarray(inj, dtype=np.int32)
+            injp = inj.ctypes.data
+        rargs = (0, None, 8, None, None)
+        if R is not None:
+            rip, rix, rax = _as_csr_arrays(R)
+            rargs = (len(rax), rip.ctypes.data, rip.dtype.itemsize, rix.ctypes.data, rax.ctypes.data)
+        self._ck(self._lib.mgb_set_transfer(self._h, int(coarse_level), P.shape[0], P.shape[1], len(pax), pip.ctypes.data,
+                                            pip.dtype.itemsize, pix.ctypes.data, pax.ctypes.data, mode, int(dim), injp, *rargs))
+
+    def set_params(self, omega=2.0 / 3.0, mu1=2, mu2=2, smoother="jacobi"):
+        sm = L.SMOOTHERS[smoother] if isinstance(smoother, str) else int(smoother)
+        self._ck(self._lib.mgb_set_params(self._h, float(omega), int(mu1), int(mu2), sm))
+
+    def set_option(self, key, value):
+        self._ck(self._lib.mgb_set_option(self._h, key.encode(), float(value)))
+
+    def finalize(self):
+        self._ck(self._lib.mgb_finalize(self._h))
+        self.finalized = True
+
+    @classmethod
+    def from_hierarchy(cls, H, r_mode="injection", smoother="jacobi", device=0, options=None, levels=None):
+        """Upload a ``problems.Hierarchy`` (or any object with A_sp_dict / P / inj / mu1 / mu2 / omega)."""
+        eng = cls(device)
+        lv = list(H.levels()) if levels is None else list(levels)
+        for k, v in (options or {}).items():
+            eng.set_option(k, v)
+        for l in lv:
+            eng.set_level(l, H.A_sp_dict[l][0])
+        for l in lv[:-1]:
+            eng.set_transfer(l, H.P[l], r_mode=r_mode, inj=H.inj[l] if r_mode == "injection" else None, dim=H.dim)
+        eng.set_params(H.omega, H.mu1, H.mu2, smoother)
+        eng.finalize()
+        return eng
+
+    # -- vector marshalling -------------------------------------------------------------------------
+    def _in(self, x, n, name):
+        """-> (pointer, mem kind, keepalive object)."""
+        if _is_torch(x):
+            import torch
+            if not x.is_cuda or x.dtype != torch.float64 or x.device.index != self.device:
+                raise ValueError(f"{name}: torch tensors must be float64 on cuda:{self.device}")
+            t = x.contiguous().view(-1)
+            if t.numel() != n:
+                raise ValueError(f"{name}: expected {n} entries, got {t.numel()}")
+            return t.data_ptr(), L.MEM_DEVICE, t
+        a = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        if a.size != n:
+            raise ValueError(f"{name}: expected {n} entries, got {a.size}")
+        return a.ctypes.data, L.MEM_HOST, a
+
+    def _out_like(self, x, n):
+        if _is_torch(x):
+            import torch
+            t = torch.empty(n, dtype=torch.float64, device=x.device)
+            return t.data_ptr(), t
+        a = np.empty(n, dtype=np.float64)
+        return a.ctypes.data, a
+
+    def _fence_in(self, *xs):
+        """Make the engine stream wait for torch's current stream when device tensors are passed."""
+        if any(_is_torch(x) for x in xs if x is not None):
+            import torch
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self.torch_stream().wait_event(ev)
+            return True
+        return False
+
+    def _fence_out(self, used):
+        if used:
+            import torch
+            ev = torch.cuda.Event()
+            ev.record(self.torch_stream())
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    @staticmethod
+    def _shape_like(res, x):
+        if _is_torch(x):
+            return res.view(x.shape) if x.dim() > 1 else res
+        x = np.asarray(x)
+        return res.reshape(x.shape) if x.ndim > 1 else res
+
+    # -- the hot path --------------------------------------------------------------------------------
+    def vcycle(self, level, v, f, ncycles=1, history=False):
+        """ncycles x V_cycle_scheme (multigrid.py:231-268).  Inputs are not modified; returns the new
+        iterate shaped like ``v`` (and the per-cycle residual norms if ``history``)."""
+        n = self.n[level]
+        fence = self._fence_in(v, f)
+        if _is_torch(v):
+            vv = v.detach().clone().contiguous().view(-1)
+            vp, mem, keep = vv.data_ptr(), L.MEM_DEVICE, vv
+        else:
+            vv = np.array(v, dtype=np.float64).reshape(-1).copy()
+            vp, mem, keep = vv.ctypes.data, L.MEM_HOST, vv
+        fp, memf, keepf = self._in(f, n, "f")
+        if mem != memf:
+            raise ValueError("v and f must both be numpy arrays or both be CUDA tensors")
+        if vv.size != n if not _is_torch(v) else vv.numel() != n:
+            raise ValueError(f"v: expected {n} entries")
+        hist = np.zeros(ncycles) if history else None
+        self._ck(self._lib.mgb_vcycle(self._h, int(level), vp, fp, mem, int(ncycles), hist.ctypes.data if history else None))
+        self._fence_out(fence)
+        out = self._shape_like(vv, v)
+        return (out, hist) if history else out
+
+    def vcycle_debug(self, level, v, f):
+        """One cycle + the reference's test=True tuple (multigrid.py:262-266): (v, f_2h, v_2h, err_h)."""
+        n, nc = self.n[level], self.n[level - 1]
+        vv = np.array(v, dtype=np.float64).reshape(-1).copy()
+        ff = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
+        f2, v2, e = np.empty(nc), np.empty(nc), np.empty(n)
+        self._ck(self._lib.mgb_vcycle_debug(self._h, int(level), vv.ctypes.data, ff.ctypes.data, L.MEM_HOST,
+                                            f2.ctypes.data, v2.ctypes.data, e.ctypes.data))
+        col = (lambda a: a.reshape(-1, 1)) if np.asarray(v).ndim > 1 else (lambda a: a)
+        return col(vv), col(f2), col(v2), col(e)
+
+    def vcycle_resident(self, level, ncycles=1, history=False):
+        """Cycles on the engine's own level buffers (see ``level_buffer``): no copies at all."""
+        hist = np.zeros(ncycles) if history else None
+        self._ck(self._lib.mgb_vcycle_resident(self._h, int(level), int(ncycles), hist.ctypes.data if history else None))
+        return hist
+
+    def level_buffer(self, level, which="v"):
+        """Engine-owned device vector as a torch tensor view (no copy)."""
+        import torch
+        p, n = C.c_void_p(), C.c_int64()
+        self._ck(self._lib.mgb_level_buffer(self._h, int(level), {"v": L.BUF_V, "f": L.BUF_F, "r": L.BUF_R}[which], C.byref(p), C.byref(n)))
+        iface = {"shape": (n.value,), "typestr": "<f8", "data": (p.value, False), "version": 2}
+        holder = type("MgbBuf", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=f"cuda:{self.device}")
+
+    # -- per-operator entry points ---------------------------------------------------------------------
+    def _binary(self, fn, level, n_in, n_out, x, name):
+        fence = self._fence_in(x)
+        xp, mem, keep = self._in(x, n_in, name)
+        yp, y = self._out_like(x, n_out)
+        self._ck(fn(self._h, int(level), xp, yp, mem))
+        self._fence_out(fence)
+        return y
+
+    def spmv(self, level, x):
+        return self._shape_like(self._binary(self._lib.mgb_spmv, level, self.n[level], self.n[level], x, "x"), x)
+
+    def residual(self, level, v, f):
+        n = self.n[level]
+        fence = self._fence_in(v, f)
+        vp, mem, k1 = self._in(v, n, "v")
+        fp, mem2, k2 = self._in(f, n, "f")
+        rp, r = self._out_like(v, n)
+        self._ck(self._lib.mgb_residual(self._h, int(level), vp, fp, rp, mem))
+        self._fence_out(fence)
+        return self._shape_like(r, v)
+
+    def smooth(self, level, v, f, nsweeps):
+        """jacobiRelaxation (multigrid.py:223-228) or the selected Gauss-Seidel; inputs not modified."""
+        n = self.n[level]
+        fence = self._fence_in(v, f)
+        if _is_torch(v):
+            vv = v.detach().clone().contiguous().view(-1); vp, mem = vv.data_ptr(), L.MEM_DEVICE
+        else:
+            vv = np.array(v, dtype=np.float64).reshape(-1).copy(); vp, mem = vv.ctypes.data, L.MEM_HOST
+        fp, memf, keep = self._in(f, n, "f")
+        self._ck(self._lib.mgb_smooth(self._h, int(level), vp, fp, int(nsweeps), mem))
+        self._fence_out(fence)
+        return self._shape_like(vv, v)
+
+    def restrict(self, fine_level, r):
+        y = self._binary(self._lib.mgb_restrict, fine_level, self.n[fine_level], self.n[fine_level - 1], r, "r")
+        return y.reshape(-1, 1) if (not _is_torch(r) and np.asarray(r).ndim > 1) else (y.view(-1, 1) if _is_torch(r) and r.dim() > 1 else y)
+
+    def prolong_add(self, fine_level, e, v):
+        n, nc = self.n[fine_level], self.n[fine_level - 1]
+        fence = self._fence_in(e, v)
+        if _is_torch(v):
+            vv = v.detach().clone().contiguous().view(-1); vp, mem = vv.data_ptr(), L.MEM_DEVICE
+        else:
+            vv = np.array(v, dtype=np.float64).reshape(-1).copy(); vp, mem = vv.ctypes.data, L.MEM_HOST
+        ep, meme, keep = self._in(e, nc, "e")
+        self._ck(self._lib.mgb_prolong_add(self._h, int(fine_level), ep, vp, mem))
+        self._fence_out(fence)
+        return self._shape_like(vv, v)
+
+    def coarse_solve(self, f):
+        lc = min(self.n)
+        n = self.n[lc]
+        fence = self._fence_in(f)
+        fp, mem, keep = self._in(f, n, "f")
+        up, u = self._out_like(f, n)
+        self._ck(self._lib.mgb_coarse_solve(self._h, fp, up, mem))
+        self._fence_out(fence)
+        return self._shape_like(u, f)
+
+    def norm2(self, x):
+        fence = self._fence_in(x)
+        n = x.numel() if _is_torch(x) else np.asarray(x).size
+        xp, mem, keep = self._in(x, n, "x")
+        out = C.c_double()
+        self._ck(self._lib.mgb_norm2(self._h, n, xp, mem, C.byref(out)))
+        return out.value
+
+    # -- introspection ---------------------------------------------------------------------------------
+    def artifact(self, level, kind):
+        size = C.c_int64()
+        self._ck(self._lib.mgb_get_artifact(self._h, int(level), int(kind), None, 0, C.byref(size)))
+        is_f64 = kind in (L.ART_RJ_VALUES, L.ART_DINV, L.ART_R_VALUES, L.ART_COARSE_INVERSE)
+        out = np.empty(size.value // (8 if is_f64 else 4), dtype=np.float64 if is_f64 else np.int32)
+        if size.value:
+            self._ck(self._lib.mgb_get_artifact(self._h, int(level), int(kind), out.ctypes.data, size.value, None))
+        return out
+
+    def rj_matrix(self, level):
+        """R_omega of ``level`` as scipy CSR + D^-1 (what getJacobiMatrices returns, multigrid.py:56)."""
+        import scipy.sparse as sp
+        ip = self.artifact(level, L.ART_RJ_INDPTR); ix = self.artifact(level, L.ART_RJ_INDICES)
+        ax = self.artifact(level, L.ART_RJ_VALUES); d = self.artifact(level, L.ART_DINV)
+        n = self.n[level]
+        return sp.csr_matrix((ax, ix, ip), shape=(n, n)), d
+
+    def launch_count(self):
+        c = C.c_int64()
+        self._ck(self._lib.mgb_launch_count(self._h, C.byref(c)))
+        return c.value
+
+    def vcycle_bytes(self, level):
+        b = C.c_double()
+        self._ck(self._lib.mgb_vcycle_bytes(self._h, int(level), C.byref(b)))
+        return b.value
+
+    def describe(self):
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self._lib.mgb_describe(self._h, buf, len(buf)))
+        return buf.value.decode()
+
+    def profile_begin(self):
+        self._ck(self._lib.mgb_profile_begin(self._h))
+
+    def profile_end(self):
+        """-> list of dicts {kind, level, launches, total_ms, bytes, gbs}."""
+        self._ck(self._lib.mgb_profile_end(self._h))
+        cnt = C.c_int()
+        self._ck(self._lib.mgb_profile_get(self._h, None, 0, C.byref(cnt)))
+        arr = (L.ProfileRecord * max(cnt.value, 1))()
+        self._ck(self._lib.mgb_profile_get(self._h, arr, cnt.value, C.byref(cnt)))
+        out = []
+        for i in range(cnt.value):
+            r = arr[i]
+            ms = r.total_ms / max(r.launches, 1)
+            out.append({"kind": L.KERNEL_KINDS[r.kind], "level": r.level, "launches": r.launches, "total_ms": r.total_ms,
+                        "ms_per_launch": ms, "bytes": r.bytes, "gbs": (r.bytes / (ms * 1e-3) / 1e9) if ms > 0 else 0.0})
+        return out
+
+
+# ---- host-side setup routines (usable without a GPU) -------------------------------------------------
+
+def host_build_rj(A, reversed_order=True):
+    lib = L.load()
+    ip = np.ascontiguousarray(A.indptr, dtype=np.int64); ix = np.ascontiguousarray(A.indices, dtype=np.int32)
+    ax = np.ascontiguousarray(A.data, dtype=np.float64)
+    n = A.shape[0]
+    nnz = C.c_int64()
+    lib.mgb_host_build_rj(n, ip.ctypes.data, ix.ctypes.data, ax.ctypes.data, int(reversed_order), C.byref(nnz), None, None, None, None)
+    rip = np.empty(n + 1, dtype=np.int32); rix = np.empty(nnz.value, dtype=np.int32)
+    rax = np.empty(nnz.value); dinv = np.empty(n)
+    rc = lib.mgb_host_build_rj(n, ip.ctypes.data, ix.ctypes.data, ax.ctypes.data, int(reversed_order), C.byref(nnz),
+                               rip.ctypes.data, rix.ctypes.data, rax.ctypes.data, dinv.ctypes.data)
+    if rc != L.OK:
+        raise L.MGBError(rc, "zero or missing diagonal")
+    return rip, rix, rax, dinv
+
+
+def _host_groups(fn, A):
+    ip = np.ascontiguousarray(A.indptr, dtype=np.int64); ix = np.ascontiguousarray(A.indices, dtype=np.int32)
+    ax = np.ascontiguousarray(A.data, dtype=np.float64)
+    n = A.shape[0]
+    key = np.empty(n, dtype=np.int32); order = np.empty(n, dtype=np.int32); off = np.empty(n + 2, dtype=np.int32)
+    cnt = C.c_int64()
+    rc = fn(n, ip.ctypes.data, ix.ctypes.data, ax.ctypes.data, key.ctypes.data, order.ctypes.data, C.byref(cnt), off.ctypes.data, n + 2)
+    if rc != L.OK:
+        raise L.MGBError(rc, "host artefact routine failed")
+    return key, order, off[:cnt.value + 1].copy()
+
+
+def host_level_sets(A):
+    return _host_groups(L.load().mgb_host_level_sets, A)
+
+
+def host_colouring(A):
+    return _host_groups(L.load().mgb_host_colouring, A)
+
+
+def host_dense_inverse(A):
+    ip = np.ascontiguousarray(A.indptr, dtype=np.int64); ix = np.ascontiguousarray(A.indices, dtype=np.int32)
+    ax = np.ascontiguousarray(A.data, dtype=np.float64)
+    n = A.shape[0]
+    inv = np.empty((n, n))
+    rc = L.load().mgb_host_dense_inverse(n, ip.ctypes.data, ix.ctypes.data, ax.ctypes.data, inv.ctypes.data)
+    if rc != L.OK:
+        raise L.MGBError(rc, "singular matrix")
+    return inv

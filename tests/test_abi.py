@@ -1,0 +1,84 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/mgb200.h declares, fails
+loudly without a device, and its host-side setup routines reproduce the oracle's artefacts bit for bit."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_SMALL, ROOT, have_gpu, load_golden
+from multigrid_dolfinx_b200 import _lib, engine as en, problems as pr
+from oracle import c_oracle as co
+from oracle import restated as rs
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "mgb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mgb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    lib = C.CDLL(lib_built)
+    names = header_symbols()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/mgb200.h but not exported"
+    assert sorted(_lib.SYMBOLS) == names, "python binding table and header drifted apart"
+    assert _lib.load().mgb_version() == 100
+
+
+def test_no_cpu_fallback(lib_built):
+    if have_gpu():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.MGBError) as ei:
+        en.MGEngine(0)
+    assert ei.value.code == _lib.ERR_CUDA and "no CPU fallback" in str(ei.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "multigrid_dolfinx_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("the oracle", "").replace("oracle's", "").replace("oracle does", ""), f"{f} mentions oracle"
+
+
+@pytest.mark.parametrize("name", GOLDEN_SMALL)
+def test_host_rj_equals_reference_getJacobiMatrices(lib_built, name):
+    """mgb_host_build_rj (what mgb_finalize runs) vs the arrays getJacobiMatrices produced in the reference run."""
+    d, kw, K = load_golden(name)
+    H = pr.build_hierarchy(dim=2, with_dicts=False, with_rhs=False, **kw)
+    A = H.A_sp_dict[H.finest_level][0]
+    rip, rix, rax, dinv = en.host_build_rj(A, reversed_order=True)
+    assert np.array_equal(rip, d["rj_indptr"]) and np.array_equal(rix, d["rj_indices"])
+    assert np.array_equal(rax, d["rj_data"]) and np.array_equal(dinv, d["rj_dinv"])
+    ip, ix, ax, di = rs.rj_pattern_from_values(A)       # as-stored order option
+    rip2, rix2, rax2, _ = en.host_build_rj(A, reversed_order=False)
+    assert np.array_equal(rip2, ip) and np.array_equal(rix2, ix) and np.array_equal(rax2, ax)
+
+
+@pytest.mark.parametrize("dim,m,seed", [(2, 24, None), (2, 24, 8), (3, 6, None), (3, 6, 2)])
+def test_host_gs_artefacts_equal_oracle(lib_built, dim, m, seed):
+    A = pr.stencil_p1(m, dim, pr.make_permutation((m + 1) ** dim, seed))
+    for a, b in zip(en.host_level_sets(A), co.level_sets(A)):
+        assert np.array_equal(a, b)
+    for a, b in zip(en.host_colouring(A), co.greedy_colouring(A)):
+        assert np.array_equal(a, b)
+
+
+def test_host_dense_inverse(lib_built):
+    A = pr.stencil_p1(16, 2, pr.make_permutation(17 ** 2, 3))
+    inv = en.host_dense_inverse(A)
+    assert np.abs(inv @ A.toarray() - np.eye(A.shape[0])).max() < 1e-13
+    import scipy.sparse as sp
+    with pytest.raises(_lib.MGBError):
+        en.host_dense_inverse(sp.csr_matrix(np.array([[1.0, 2.0], [2.0, 4.0]])))
+
+
+def test_singular_diagonal_is_reported(lib_built):
+    import scipy.sparse as sp
+    with pytest.raises(_lib.MGBError):
+        en.host_build_rj(sp.csr_matrix(np.array([[0.0, 1.0], [1.0, 2.0]])))

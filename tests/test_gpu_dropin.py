@@ -1,0 +1,72 @@
+"""The drop-in module speaks the reference's protocol (Multigrid_prototype.py:135-143)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from multigrid_dolfinx_b200 import problems as pr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_prototype_protocol_from_coordinate_dicts():
+    """getJacobiMatrices -> initialize_problem -> FullMultiGrid_test / V_cycle_scheme with ONLY the reference's
+    16 attributes (transfers are derived from the coordinate dicts like the reference does)."""
+    from multigrid_dolfinx_b200 import multigrid as mg
+    d, kw, K = load_golden("proto_perm_mu50")
+    H = pr.build_hierarchy(dim=2, with_dicts=True, **kw)
+
+    class Var_initializer:          # Multigrid_prototype.py:15-32
+        pass
+    obj = Var_initializer()
+    for a in ("mesh_dof_list_dict", "element_size", "coarsest_level_elements_per_dim", "coarsest_level", "finest_level",
+              "A_sp_dict", "b_dict", "mu0", "mu1", "mu2", "omega", "residual_per_V_cycle_finest",
+              "error_per_V_cycle_finest", "u_exact_fine", "V_fine_dolfx"):
+        setattr(obj, a, getattr(H, a))
+    obj.A_jacobi_sp_dict = {k: mg.getJacobiMatrices(v) for k, v in H.A_sp_dict.items()}      # proto:135-136
+    mg.initialize_problem(obj)                                                               # proto:138-140
+    lf = H.finest_level
+    v = np.zeros((H.n(lf), 1))
+    for k in range(K):
+        v = mg.V_cycle_scheme(obj.A_jacobi_sp_dict[lf], v, H.b_dict[lf])
+        assert v.shape == (H.n(lf), 1)
+        assert np.abs(v[:, 0] - d["vcycle_v"][k]).max() <= 1e-10 * np.abs(d["vcycle_v"][k]).max()
+    out = mg.V_cycle_scheme(obj.A_jacobi_sp_dict[lf], np.zeros((H.n(lf), 1)), H.b_dict[lf], True)
+    assert len(out) == 4 and out[1].shape == (H.n(lf - 1), 1)
+    # lazy Jacobi tuple materialises the reference's matrices
+    assert np.array_equal(obj.A_jacobi_sp_dict[lf][0].data, d["rj_data"])
+    # FMG test driver (the one the prototype runs, proto:141-143)
+    u, f2h, v2h, errh = mg.FullMultiGrid_test(obj.A_jacobi_sp_dict[lf], H.b_dict[lf], True)
+    assert u.shape == (H.n(lf), 1) and errh.shape == (H.n(lf), 1)
+    with pytest.raises(ValueError):
+        mg.FullMultiGrid_test(obj.A_jacobi_sp_dict[lf], H.b_dict[lf], False)      # reference quirk, multigrid.py:331-333
+    # transfer functions with the reference's signatures (test/test_restriction_interpolation.py:119-122)
+    md = H.mesh_dof_list_dict
+    e = d["in_e"].reshape(-1, 1); x = d["in_x"].reshape(-1, 1)
+    assert np.array_equal(mg.Interpolation2D(e, md[lf - 1], md[lf], H.element_size[lf - 1], H.element_size[lf], H.n(lf))[:, 0], d["interp"])
+    assert np.array_equal(mg.Restriction2D_direct(x, md[lf - 1], md[lf], H.n(lf - 1))[:, 0], d["inj"])
+    fw = mg.Restriction2D(x, md[lf - 1], md[lf], H.element_size[lf - 1], H.element_size[lf], H.n(lf - 1))[:, 0]
+    assert np.abs(fw - d["fw"]).max() <= 4e-16 * np.abs(d["fw"]).max()
+    assert np.array_equal(mg.jacobiRelaxation(obj.A_jacobi_sp_dict[lf], x, d["in_g"].reshape(-1, 1), 5)[:, 0], d["jac_5"])
+
+
+def test_fmg_driver_converges():
+    from multigrid_dolfinx_b200 import multigrid as mg
+    H = pr.build_hierarchy(dim=2, c=8, coarsest_level=0, finest_level=3, mu1=2, mu2=2, with_dicts=False)
+    mg.restriction = "transpose"
+    try:
+        H.A_jacobi_sp_dict = {k: mg.getJacobiMatrices(v) for k, v in H.A_sp_dict.items()}
+        mg.initialize_problem(H)
+        import os, tempfile
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as td:
+            os.chdir(td)
+            try:
+                u = mg.FullMultiGrid(H.A_jacobi_sp_dict[3], H.b_dict[3])
+                assert os.path.exists("iter_count_for_diff_num_elems_4_levels.csv")
+            finally:
+                os.chdir(cwd)
+    finally:
+        mg.restriction = "injection"
+    A = H.A_sp_dict[3][0]
+    assert np.linalg.norm(H.b_dict[3] - A.dot(u)) <= 1e-10
+    assert H.residual_per_V_cycle_finest[-1] <= 1e-11

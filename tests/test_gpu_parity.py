@@ -1,0 +1,285 @@
+"""GPU parity tests (call through the C ABI).  Bars (BASELINE.json north_star):
+  * sparsity patterns / level orderings / colourings: bit-exact
+  * per-cycle fp64 residual norms: 1e-12 relative; final solutions: 1e-10
+The tile kernels sum every row in stored order without FMA, so every operator except the coarsest
+solve is in fact required to be BIT-EXACT against the golden vectors the reference produced."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, GOLDEN_SMALL, ROOT, load_golden
+from multigrid_dolfinx_b200 import _lib as L
+from multigrid_dolfinx_b200 import problems as pr
+from multigrid_dolfinx_b200.engine import MGEngine
+from oracle import c_oracle as co
+from oracle import restated as rs
+
+pytestmark = pytest.mark.gpu
+
+RTOL_RESNORM = 1e-12
+RTOL_SOLUTION = 1e-10
+
+
+def _report(name, **kw):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.jsonl"), "a") as f:
+        f.write(json.dumps({"test": name, **{k: (float(v) if np.isscalar(v) else v) for k, v in kw.items()}}) + "\n")
+
+
+def relmax(a, b):
+    return float(np.abs(np.asarray(a).ravel() - np.asarray(b).ravel()).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+
+@pytest.mark.parametrize("name", GOLDEN_SMALL)
+def test_operators_bit_exact_vs_reference_golden(name):
+    d, kw, K = load_golden(name)
+    H = pr.build_hierarchy(dim=2, with_dicts=False, **kw)
+    lf = H.finest_level
+    eng = MGEngine.from_hierarchy(H)
+    # artefacts: R_omega pattern + values, D^-1  (getJacobiMatrices, multigrid.py:48-56)
+    assert np.array_equal(eng.artifact(lf, L.ART_RJ_INDPTR), d["rj_indptr"])
+    assert np.array_equal(eng.artifact(lf, L.ART_RJ_INDICES), d["rj_indices"])
+    assert np.array_equal(eng.artifact(lf, L.ART_RJ_VALUES), d["rj_data"])
+    assert np.array_equal(eng.artifact(lf, L.ART_DINV), d["rj_dinv"])
+    x, g, e = d["in_x"], d["in_g"], d["in_e"]
+    assert np.array_equal(eng.smooth(lf, x, g, 1), d["jac_1"])            # jacobiRelaxation, multigrid.py:223-228
+    assert np.array_equal(eng.smooth(lf, x, g, 5), d["jac_5"])
+    assert np.array_equal(eng.prolong_add(lf, e, np.zeros_like(x)), d["interp"])   # Interpolation2D, multigrid.py:59-120
+    assert np.array_equal(eng.restrict(lf, x), d["inj"])                  # Restriction2D_direct, multigrid.py:123-132
+    A = H.A_sp_dict[lf][0]
+    assert np.array_equal(eng.spmv(lf, x), A.dot(x))                      # multigrid.py:244
+    assert np.array_equal(eng.residual(lf, x, g), g - A.dot(x))
+    eng.close()
+    eng = MGEngine.from_hierarchy(H, r_mode="full_weighting")
+    fw = eng.restrict(lf, x)                                              # Restriction2D, multigrid.py:135-198
+    assert np.abs(fw - d["fw"]).max() <= 4e-16 * np.abs(d["fw"]).max()
+    eng.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_vcycle_matches_reference_golden(name):
+    """V_cycle_scheme (multigrid.py:231-268): K consecutive cycles from v0 = 0."""
+    d, kw, K = load_golden(name)
+    H = pr.build_hierarchy(dim=2, with_dicts=False, **kw)
+    lf = H.finest_level
+    eng = MGEngine.from_hierarchy(H)
+    f = H.b_dict[lf]
+    v = np.zeros_like(f)
+    A = H.A_sp_dict[lf][0]
+    worst_r = worst_v = 0.0
+    for k in range(K):
+        v = eng.vcycle(lf, v, f)
+        rn = np.linalg.norm(f - A.dot(v))
+        worst_r = max(worst_r, abs(rn - d["vcycle_resnorm"][k]) / d["vcycle_resnorm"][k])
+        if d["vcycle_v"].shape[0] == K:
+            worst_v = max(worst_v, relmax(v, d["vcycle_v"][k]))
+    worst_v = max(worst_v, relmax(v, d["vcycle_v"][-1]))
+    # same thing in one call with the device-side norm history
+    v2, hist = eng.vcycle(lf, np.zeros_like(f), f, ncycles=K, history=True)
+    worst_h = float(np.abs(hist - d["vcycle_resnorm"]).max() / d["vcycle_resnorm"].max())
+    _report("vcycle_golden", case=name, resnorm_rel=worst_r, solution_rel=worst_v, hist_rel=worst_h)
+    assert worst_r <= RTOL_RESNORM and worst_h <= RTOL_RESNORM
+    assert worst_v <= RTOL_SOLUTION
+    assert np.array_equal(v2, v)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["cfg1_perm_mu2", "proto_perm_mu50"])
+def test_debug_tuple_matches_reference(name):
+    """test=True 4-tuple (multigrid.py:262-266) of the K-th cycle."""
+    d, kw, K = load_golden(name)
+    H = pr.build_hierarchy(dim=2, with_dicts=False, **kw)
+    lf = H.finest_level
+    eng = MGEngine.from_hierarchy(H)
+    f = H.b_dict[lf]
+    v = np.zeros_like(f)
+    for k in range(K - 1):
+        v = eng.vcycle(lf, v, f)
+    v, f2h, v2h, errh = eng.vcycle_debug(lf, v, f)
+    assert relmax(v, d["vcycle_v"][-1]) <= RTOL_SOLUTION
+    assert relmax(f2h, d["dbg_f2h"]) <= 1e-10 and relmax(v2h, d["dbg_v2h"]) <= 1e-10 and relmax(errh, d["dbg_errh"]) <= 1e-10
+    eng.close()
+
+
+@pytest.mark.parametrize("dim,c,lc,lf,seed", [(2, 8, 0, 5, None), (2, 8, 0, 4, 3), (3, 2, 0, 4, None), (3, 2, 0, 3, 5)])
+@pytest.mark.parametrize("r_mode", ["injection", "transpose", "full_weighting"])
+def test_vcycle_vs_oracle_larger(dim, c, lc, lf, seed, r_mode):
+    """Sizes the reference cannot run (3-D, > 513^2): C oracle on the same seeded inputs."""
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=lc, finest_level=lf, perm_seed=seed, with_dicts=False)
+    eng = MGEngine.from_hierarchy(H, r_mode=r_mode)
+    cm = co.from_hierarchy(H, r_mode=r_mode)
+    f = H.b_dict[lf][:, 0]
+    vo, ho = cm.vcycle(np.zeros_like(f), f, ncycles=5, history=True)
+    vg, hg = eng.vcycle(lf, np.zeros_like(f), f, ncycles=5, history=True)
+    r = float(np.abs(hg - ho).max() / ho.max()); s = relmax(vg, vo)
+    _report("vcycle_oracle", dim=dim, n=H.n(lf), seed=seed, r_mode=r_mode, resnorm_rel=r, solution_rel=s)
+    assert r <= RTOL_RESNORM and s <= RTOL_SOLUTION
+    eng.close()
+
+
+@pytest.mark.parametrize("family,lanes", [(2, 0), (2, 4), (2, 32)])
+def test_subwarp_family_within_tolerance(family, lanes):
+    H = pr.build_hierarchy(dim=3, c=2, coarsest_level=0, finest_level=3, perm_seed=2, with_dicts=False)
+    eng = MGEngine.from_hierarchy(H, options={"kernel_family": family, "lanes_per_row": lanes})
+    cm = co.from_hierarchy(H)
+    f = H.b_dict[3][:, 0]
+    vo, ho = cm.vcycle(np.zeros_like(f), f, ncycles=4, history=True)
+    vg, hg = eng.vcycle(3, np.zeros_like(f), f, ncycles=4, history=True)
+    assert np.abs(hg - ho).max() / ho.max() <= RTOL_RESNORM and relmax(vg, vo) <= RTOL_SOLUTION
+    assert "subwarp" in eng.describe()
+    eng.close()
+
+
+@pytest.mark.parametrize("opts", [{"tile_iter": 1}, {"tile_iter": 4}, {"use_graph": 0}, {"fuse_restrict": 1}, {"rj_order": 0}])
+def test_kernel_options_do_not_change_results(opts):
+    H = pr.build_hierarchy(dim=2, c=8, coarsest_level=0, finest_level=4, perm_seed=1, with_dicts=False)
+    f = H.b_dict[4][:, 0]
+    base = MGEngine.from_hierarchy(H)
+    v0 = base.vcycle(4, np.zeros_like(f), f, ncycles=3)
+    eng = MGEngine.from_hierarchy(H, options=opts)
+    v1 = eng.vcycle(4, np.zeros_like(f), f, ncycles=3)
+    if "rj_order" in opts:
+        assert relmax(v1, v0) <= 1e-13          # different summation order inside R_omega rows
+    else:
+        assert np.array_equal(v1, v0)           # bit-identical
+    base.close(); eng.close()
+
+
+def test_jacobi_a_form_and_coarse_refine():
+    H = pr.build_hierarchy(dim=2, c=8, coarsest_level=0, finest_level=3, perm_seed=4, with_dicts=False)
+    f = H.b_dict[3][:, 0]
+    cm = co.from_hierarchy(H, smoother="jacobi_a")
+    vo, ho = cm.vcycle(np.zeros_like(f), f, ncycles=4, history=True)
+    eng = MGEngine.from_hierarchy(H, smoother="jacobi_a", options={"coarse_refine": 1})
+    vg, hg = eng.vcycle(3, np.zeros_like(f), f, ncycles=4, history=True)
+    assert np.abs(hg - ho).max() / ho.max() <= RTOL_RESNORM and relmax(vg, vo) <= RTOL_SOLUTION
+    eng.close()
+
+
+@pytest.mark.parametrize("dim,c,lf,seed", [(2, 8, 3, None), (2, 8, 3, 6), (3, 2, 3, None), (3, 2, 2, 7)])
+def test_gauss_seidel_level_scheduled_bit_exact(dim, c, lf, seed):
+    """Level-scheduled GS must reproduce the sequential natural-order sweep; artefacts bit-exact."""
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=seed, with_dicts=False)
+    A = H.A_sp_dict[lf][0]
+    eng = MGEngine.from_hierarchy(H, smoother="gs")
+    lev, order, off = co.level_sets(A)
+    assert np.array_equal(eng.artifact(lf, L.ART_LEVEL_OF_ROW), lev)
+    assert np.array_equal(eng.artifact(lf, L.ART_LEVEL_ORDER), order)
+    assert np.array_equal(eng.artifact(lf, L.ART_LEVEL_OFFSETS), off)
+    rng = np.random.default_rng(0)
+    x, f = rng.standard_normal(H.n(lf)), rng.standard_normal(H.n(lf))
+    xo = x.copy()
+    for _ in range(3):
+        xo = co.gs_forward(A, xo, f)
+    assert np.array_equal(eng.smooth(lf, x, f, 3), xo)
+    cm = co.from_hierarchy(H, smoother="gs")
+    b = H.b_dict[lf][:, 0]
+    vo, ho = cm.vcycle(np.zeros_like(b), b, ncycles=3, history=True)
+    vg, hg = eng.vcycle(lf, np.zeros_like(b), b, ncycles=3, history=True)
+    assert np.abs(hg - ho).max() / ho.max() <= RTOL_RESNORM and relmax(vg, vo) <= RTOL_SOLUTION
+    eng.close()
+
+
+@pytest.mark.parametrize("dim,c,lf,seed", [(2, 8, 3, None), (2, 8, 3, 6), (3, 2, 3, None), (3, 2, 2, 7)])
+def test_gauss_seidel_multicolour(dim, c, lf, seed):
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=seed, with_dicts=False)
+    A = H.A_sp_dict[lf][0]
+    eng = MGEngine.from_hierarchy(H, smoother="gs_color")
+    col, order, off = co.greedy_colouring(A)
+    assert np.array_equal(eng.artifact(lf, L.ART_COLOUR_OF_ROW), col)
+    assert np.array_equal(eng.artifact(lf, L.ART_COLOUR_ORDER), order)
+    assert np.array_equal(eng.artifact(lf, L.ART_COLOUR_OFFSETS), off)
+    rng = np.random.default_rng(0)
+    x, f = rng.standard_normal(H.n(lf)), rng.standard_normal(H.n(lf))
+    xo = x.copy()
+    for _ in range(2):
+        xo = co.gs_forward(A, xo, f, order)
+    assert np.array_equal(eng.smooth(lf, x, f, 2), xo)
+    cm = co.from_hierarchy(H, smoother="gs_color")
+    b = H.b_dict[lf][:, 0]
+    vo, ho = cm.vcycle(np.zeros_like(b), b, ncycles=3, history=True)
+    vg, hg = eng.vcycle(lf, np.zeros_like(b), b, ncycles=3, history=True)
+    assert np.abs(hg - ho).max() / ho.max() <= RTOL_RESNORM and relmax(vg, vo) <= RTOL_SOLUTION
+    eng.close()
+
+
+def test_edge_cases():
+    """nw = 0 returns v (multigrid.py:223-228); mu1 = 0 / mu2 = 0 / odd sweep totals; top level = any level
+    (FullMultiGrid calls the cycle with every level as top, multigrid.py:305-306); coarsest as top = direct solve."""
+    H = pr.build_hierarchy(dim=2, c=4, coarsest_level=0, finest_level=3, perm_seed=9, with_dicts=False)
+    for mu1, mu2 in [(0, 0), (0, 3), (3, 0), (1, 2), (2, 1)]:
+        H.mu1, H.mu2 = mu1, mu2
+        eng = MGEngine.from_hierarchy(H)
+        mg = rs.from_hierarchy(H)
+        for top in (3, 2, 1):
+            f = H.b_dict[top]
+            vo = mg.vcycle(top, np.zeros_like(f), f)
+            vo = mg.vcycle(top, vo, f)
+            vg = eng.vcycle(top, np.zeros_like(f), f, ncycles=2)
+            assert relmax(vg, vo) <= RTOL_SOLUTION, (mu1, mu2, top)
+        x = np.arange(H.n(3), dtype=np.float64)
+        assert np.array_equal(eng.smooth(3, x, x, 0), x)
+        f0 = H.b_dict[0]
+        assert relmax(eng.vcycle(0, np.zeros_like(f0), f0), mg.vcycle(0, np.zeros_like(f0), f0)) <= 1e-12
+        eng.close()
+
+
+def test_device_pointer_path_and_resident_mode():
+    import torch
+    H = pr.build_hierarchy(dim=2, c=8, coarsest_level=0, finest_level=4, with_dicts=False)
+    eng = MGEngine.from_hierarchy(H)
+    f = H.b_dict[4][:, 0]
+    v_host = eng.vcycle(4, np.zeros_like(f), f, ncycles=3)
+    ft = torch.tensor(f, device="cuda:0"); vt = torch.zeros_like(ft)
+    out = eng.vcycle(4, vt, ft, ncycles=3)
+    assert np.array_equal(out.cpu().numpy(), v_host) and float(vt.abs().max()) == 0.0      # inputs untouched
+    eng.level_buffer(4, "f").copy_(ft); eng.level_buffer(4, "v").zero_()
+    torch.cuda.synchronize()
+    hist = eng.vcycle_resident(4, 3, history=True)
+    assert np.array_equal(eng.level_buffer(4, "v").cpu().numpy(), v_host)
+    A = H.A_sp_dict[4][0]
+    assert abs(hist[-1] - np.linalg.norm(f - A.dot(v_host))) <= 1e-12 * hist[0]
+    assert eng.launch_count() > 0
+    eng.close()
+
+
+def test_errors_are_reported_not_swallowed():
+    H = pr.build_hierarchy(dim=2, c=4, coarsest_level=0, finest_level=1, with_dicts=False)
+    eng = MGEngine(0)
+    eng.set_level(0, H.A_sp_dict[0][0]); eng.set_level(1, H.A_sp_dict[1][0])
+    with pytest.raises(L.MGBError):
+        eng.finalize()                                    # transfer missing
+    with pytest.raises(L.MGBError):
+        eng.set_transfer(0, H.P[0], inj=None)             # injection list missing
+    with pytest.raises(L.MGBError):
+        eng._ck(eng._lib.mgb_vcycle(eng._h, 1, None, None, 0, 1, None))   # not finalized
+    eng.close()
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 (2049^2, 7 levels, V(2,2)): size-independent properties.
+    linearity in f (exact for a power-of-two scale), determinism, graph == eager, residual reduction."""
+    H = pr.build_hierarchy(dim=2, c=32, coarsest_level=0, finest_level=6, with_dicts=False)
+    assert H.n(6) == 2049 ** 2 and H.A_sp_dict[6][0].nnz == 29372417
+    eng = MGEngine.from_hierarchy(H)
+    f = H.b_dict[6][:, 0]
+    v1, h1 = eng.vcycle(6, np.zeros_like(f), f, ncycles=3, history=True)
+    v2, h2 = eng.vcycle(6, np.zeros_like(f), 4.0 * f, ncycles=3, history=True)
+    assert np.array_equal(4.0 * v1, v2) and np.array_equal(4.0 * h1, h2)
+    v3 = eng.vcycle(6, np.zeros_like(f), f, ncycles=3)
+    assert np.array_equal(v1, v3)
+    eng.set_option("use_graph", 0)
+    v4 = eng.vcycle(6, np.zeros_like(f), f, ncycles=3)
+    assert np.array_equal(v1, v4)
+    assert h1[2] < h1[1] < h1[0]
+    A = H.A_sp_dict[6][0]
+    assert abs(np.linalg.norm(f - A.dot(v1)) - h1[2]) <= 1e-12 * h1[2]
+    # the C oracle on the same input (a few seconds)
+    cm = co.from_hierarchy(H)
+    vo, ho = cm.vcycle(np.zeros_like(f), f, ncycles=3, history=True)
+    r = float(np.abs(h1 - ho).max() / ho.max()); s = relmax(v1, vo)
+    _report("config2_full", resnorm_rel=r, solution_rel=s, hist=[float(x) for x in h1])
+    assert r <= RTOL_RESNORM and s <= RTOL_SOLUTION
+    eng.close()
