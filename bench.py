@@ -165,11 +165,11 @@ def run_single(args):
         eng.vcycle_resident(lf, args.steps)
         e1.record(stream)
         torch.cuda.synchronize()
+        launches = eng.launch_count() - l0
         if args.steps * 1e-3 < 1.0:          # keep the GPU busy long enough for nvidia-smi to see it under load
             eng.vcycle_resident(lf, int(min(4000, 1.0 / 5e-4)))
             torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    launches = eng.launch_count() - l0
     hist = eng.vcycle_resident(lf, 1, history=True)
 
     # ---- dominant kernel, event-timed launch by launch (same cycles, graph off) ----------------------

@@ -139,7 +139,7 @@ void free_csr(DevCsr& D)
     D = DevCsr();
 }
 
-int tile_cap(int iter) { return 4 * THREADS * iter; }
+int tile_cap(int iter) { return TILE_ENT * THREADS * iter; }
 
 // Upload a host CSR and choose the kernel family / tile shape for it.
 int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int32_t>& breaks = {})
@@ -155,17 +155,16 @@ int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int
     for (int64_t i = 0; i < n; ++i) mx = std::max<int>(mx, rp[i + 1] - rp[i]);
     D.max_row = mx;
     TRY(dev_upload(h, &D.rowptr, rp.data(), rp.size()));
-    TRY(dev_upload(h, &D.cols, M.ix.data(), (size_t)nnz, 8));
-    TRY(dev_upload(h, &D.vals, M.ax.data(), (size_t)nnz, 8));
+    TRY(dev_upload(h, &D.cols, M.ix.data(), (size_t)nnz, 16));   // padding: the last 8-wide group may read past nnz
+    TRY(dev_upload(h, &D.vals, M.ax.data(), (size_t)nnz, 16));
     // family
     int family = h->opt_family;
     if (family == 0) family = 1;
-    int iter = h->opt_iter ? h->opt_iter : 2;
+    int iter = h->opt_iter ? h->opt_iter : 1;
     if (family == 1) {
-        if (!h->opt_iter && nnz / tile_cap(2) < 2 * h->sm_count) iter = 1;   // small level: more, smaller tiles
         std::vector<int32_t> tiles;
-        bool ok = make_tiles(M.ip, tile_cap(iter) - 4, 4 * THREADS, breaks, tiles, &D.break_tile);
-        if (!ok && !h->opt_iter) { iter = 4; ok = make_tiles(M.ip, tile_cap(iter) - 4, 4 * THREADS, breaks, tiles, &D.break_tile); }
+        bool ok = make_tiles(M.ip, tile_cap(iter), 4 * THREADS, breaks, tiles, &D.break_tile);
+        if (!ok && !h->opt_iter) { iter = 2; ok = make_tiles(M.ip, tile_cap(iter), 4 * THREADS, breaks, tiles, &D.break_tile); }
         if (ok) {
             D.ntiles = (int)tiles.size() - 1;
             TRY(dev_upload(h, &D.tiles, tiles.data(), tiles.size()));
@@ -180,7 +179,7 @@ int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int
             const double avg = n ? (double)nnz / (double)n : 0.0;
             lpr = 1;
             while (lpr < 32 && lpr < avg) lpr *= 2;
-            if (mx > 4 * tile_cap(4)) lpr = 32;
+            if (mx > tile_cap(2)) lpr = 32;
         }
         D.lpr = lpr;
         // breakpoints for the sub-warp family are plain row indices
@@ -215,8 +214,7 @@ void launch_tile(mgb_handle* h, const DevCsr& D, int t0, int t1, const double* x
     if (nt <= 0) return;
     switch (D.iter) {
         case 1: k_tile<1, THREADS, NCX, Epi><<<nt, THREADS, 0, h->stream>>>(D.rowptr, D.cols, D.vals, D.tiles, t0, x, epi); break;
-        case 2: k_tile<2, THREADS, NCX, Epi><<<nt, THREADS, 0, h->stream>>>(D.rowptr, D.cols, D.vals, D.tiles, t0, x, epi); break;
-        default: k_tile<4, THREADS, NCX, Epi><<<nt, THREADS, 0, h->stream>>>(D.rowptr, D.cols, D.vals, D.tiles, t0, x, epi); break;
+        default: k_tile<2, THREADS, NCX, Epi><<<nt, THREADS, 0, h->stream>>>(D.rowptr, D.cols, D.vals, D.tiles, t0, x, epi); break;
     }
 }
 
@@ -664,7 +662,7 @@ int mgb_finalize(mgb_handle* h)
         if (!L) return fail(h, MGB_ERR_STATE, "level %d missing (levels must be contiguous)", l);
         if (l > h->coarsest && !L->has_transfer) return fail(h, MGB_ERR_STATE, "transfer between levels %d and %d missing", l - 1, l);
     }
-    if (h->opt_iter && h->opt_iter != 1 && h->opt_iter != 2 && h->opt_iter != 4) return fail(h, MGB_ERR_INVALID, "tile_iter must be 1, 2 or 4");
+    if (h->opt_iter && h->opt_iter != 1 && h->opt_iter != 2) return fail(h, MGB_ERR_INVALID, "tile_iter must be 1 or 2");
     if (h->opt_lpr && (h->opt_lpr & (h->opt_lpr - 1) || h->opt_lpr > 32)) return fail(h, MGB_ERR_INVALID, "lanes_per_row must be a power of two <= 32");
     for (auto& kv : h->levels) {
         Level& L = kv.second;

@@ -46,7 +46,7 @@ void permute_rows(const HostCsr& M, const std::vector<int32_t>& order, HostCsr& 
 bool dense_inverse(const HostCsr& A, std::vector<double>& inv);
 
 // Row tiles for the tile kernel: tile t covers rows [tiles[t], tiles[t+1]); every tile satisfies
-//   rowptr[tiles[t+1]] - (rowptr[tiles[t]] & ~3) <= cap   and   rows <= row_cap,
+//   rowptr[tiles[t+1]] - (rowptr[tiles[t]] & ~7) <= cap   and   rows <= row_cap,
 // and no tile straddles a breakpoint (breaks = sorted row indices, may be empty).
 // Returns false if a single row exceeds cap.
 bool make_tiles(const std::vector<int64_t>& ip, int64_t cap, int64_t row_cap, const std::vector<int32_t>& breaks,

@@ -13,87 +13,109 @@
 namespace mgb {
 namespace cg = cooperative_groups;
 
-// ---- streaming loads: matrix arrays are read exactly once per launch -> keep them out of L1 --------
-__device__ __forceinline__ int4 ld_stream_i4(const int32_t* p)
+// ---- streaming loads: matrix arrays are read exactly once per launch.  sm_100 has 256-bit global loads;
+// .L1::no_allocate keeps the stream out of L1 and .L2::evict_first keeps it from flushing x out of L2
+// (SASS: LDG.E.NA.EFL2.256.CONSTANT) ------------------------------------------------------------------
+struct I8 { int v[8]; };
+struct D4 { double v[4]; };
+__device__ __forceinline__ I8 ld_stream_i8(const int32_t* p)
 {
-    int4 r;
-    asm("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    I8 r;
+    asm("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
     return r;
 }
-__device__ __forceinline__ double2 ld_stream_d2(const double* p)
+__device__ __forceinline__ D4 ld_stream_d4(const double* p)
 {
-    double2 r;
-    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    D4 r;
+    asm("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
+        : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
     return r;
 }
 
 // ---- epilogues --------------------------------------------------------------------------------------
+// An epilogue turns the row sum s of row i into the output.  load(i) fetches the per-row operands and is
+// issued BEFORE the row sum is available (so their DRAM latency overlaps the matrix stream);
+// store(i, s, pre) finishes the row.
 // y = A x                                                   (multigrid.py:244, A.dot(v))
 struct EpiStore {
     double* y;
-    __device__ __forceinline__ void operator()(int r, double s) const { y[r] = s; }
+    struct Pre {};
+    __device__ __forceinline__ Pre load(int) const { return Pre{}; }
+    __device__ __forceinline__ void store(int i, double s, const Pre&) const { y[i] = s; }
 };
 // r = f - A v                                               (multigrid.py:244)
 struct EpiResidual {
     const double* f; double* r;
-    __device__ __forceinline__ void operator()(int i, double s) const { r[i] = __dsub_rn(f[i], s); }
+    struct Pre { double f; };
+    __device__ __forceinline__ Pre load(int i) const { return Pre{f[i]}; }
+    __device__ __forceinline__ void store(int i, double s, const Pre& p) const { r[i] = __dsub_rn(p.f, s); }
 };
 // weighted Jacobi, reference form (multigrid.py:226): out = ((1-w)*v + g) - w*s, g = w*(dinv*f)
 struct EpiJacobiRJ {
     const double* v; const double* g; double* out; double om1, om;
-    __device__ __forceinline__ void operator()(int i, double s) const
+    struct Pre { double v, g; };
+    __device__ __forceinline__ Pre load(int i) const { return Pre{v[i], g[i]}; }
+    __device__ __forceinline__ void store(int i, double s, const Pre& p) const
     {
-        out[i] = __dsub_rn(__dadd_rn(__dmul_rn(om1, v[i]), g[i]), __dmul_rn(om, s));
+        out[i] = __dsub_rn(__dadd_rn(__dmul_rn(om1, p.v), p.g), __dmul_rn(om, s));
     }
 };
 // same, first sweep of a relaxation call: also produces g (multigrid.py:226 recomputes w*(Dinv f) per sweep;
 // the product is identical every time, so it is formed once and kept)
 struct EpiJacobiRJFirst {
     const double* v; const double* dinv; const double* f; double* g; double* out; double om1, om;
-    __device__ __forceinline__ void operator()(int i, double s) const
+    struct Pre { double v, g; };
+    __device__ __forceinline__ Pre load(int i) const { return Pre{v[i], __dmul_rn(om, __dmul_rn(dinv[i], f[i]))}; }
+    __device__ __forceinline__ void store(int i, double s, const Pre& p) const
     {
-        const double gi = __dmul_rn(om, __dmul_rn(dinv[i], f[i]));
-        g[i] = gi;
-        out[i] = __dsub_rn(__dadd_rn(__dmul_rn(om1, v[i]), gi), __dmul_rn(om, s));
+        g[i] = p.g;
+        out[i] = __dsub_rn(__dadd_rn(__dmul_rn(om1, p.v), p.g), __dmul_rn(om, s));
     }
 };
 // single-matrix Jacobi: out = v + w*(dinv*(f - s)), s = (A v)_i
 struct EpiJacobiA {
     const double* v; const double* dinv; const double* f; double* out; double om;
-    __device__ __forceinline__ void operator()(int i, double s) const
+    struct Pre { double v, dinv, f; };
+    __device__ __forceinline__ Pre load(int i) const { return Pre{v[i], dinv[i], f[i]}; }
+    __device__ __forceinline__ void store(int i, double s, const Pre& p) const
     {
-        out[i] = __dadd_rn(v[i], __dmul_rn(om, __dmul_rn(dinv[i], __dsub_rn(f[i], s))));
+        out[i] = __dadd_rn(p.v, __dmul_rn(om, __dmul_rn(p.dinv, __dsub_rn(p.f, s))));
     }
 };
 // v = v + P e   (multigrid.py:258-260); err (nullable) receives P e (the test=True output, multigrid.py:265)
 struct EpiProlongAdd {
     double* v; double* err;
-    __device__ __forceinline__ void operator()(int i, double s) const
+    struct Pre { double v; };
+    __device__ __forceinline__ Pre load(int i) const { return Pre{v[i]}; }
+    __device__ __forceinline__ void store(int i, double s, const Pre& p) const
     {
         if (err) err[i] = s;
-        v[i] = __dadd_rn(v[i], s);
+        v[i] = __dadd_rn(p.v, s);
     }
 };
 // Gauss-Seidel row update on a row-permuted off-diagonal operator: v[order[p]] = (f - s) / d
 struct EpiGaussSeidel {
     const int32_t* order; const double* diag; const double* f; double* v;
-    __device__ __forceinline__ void operator()(int p, double s) const
-    {
-        const int i = order[p];
-        v[i] = __ddiv_rn(__dsub_rn(f[i], s), diag[p]);
-    }
+    struct Pre { int i; double f, d; };
+    __device__ __forceinline__ Pre load(int p) const { const int i = order[p]; return Pre{i, f[i], diag[p]}; }
+    __device__ __forceinline__ void store(int, double s, const Pre& p) const { v[p.i] = __ddiv_rn(__dsub_rn(p.f, s), p.d); }
 };
 
 // ---- tile family ------------------------------------------------------------------------------------
-// One CTA per row tile.  Phase 1 streams the tile's (cols, vals) with 16-byte loads (coalesced, ITER
-// independent groups of 4 entries per thread in flight), gathers x through L2/L1 and parks the products
-// in shared memory.  Phase 2 is thread-per-row: each row is summed sequentially in stored order.
-// Shared index i is padded to i + (i >> 4) so that the stride-4 / stride-8 row starts of phase 2 fall
-// into distinct 8-byte banks.
+// One CTA per row tile.  Phase 1 streams the tile's (cols, vals) with 256-bit loads (coalesced; ITER
+// independent groups of 8 entries = 96 bytes per thread in flight), gathers x through L1/L2 and parks the
+// products in shared memory.  Phase 2 is thread-per-row: each row is summed sequentially in stored order.
+// The per-row epilogue operands and row pointers of the first RPT rows of every thread are fetched
+// together with the matrix stream.  Shared index i is padded to i + (i >> 4) so that the stride-4 /
+// stride-8 row starts of phase 2 fall into distinct 8-byte banks.
+constexpr int TILE_ENT = 8;     // entries per thread per iteration
+constexpr int TILE_RPT = 2;     // rows per thread with prefetched epilogue operands
+
 template <int ITER, int THREADS>
 struct TileCfg {
-    static constexpr int CAP = 4 * THREADS * ITER;          // entries staged per tile
-    static constexpr int SMEM_DOUBLES = CAP + CAP / 16 + 4;
+    static constexpr int CAP = TILE_ENT * THREADS * ITER;          // entries staged per tile
+    static constexpr int SMEM_DOUBLES = CAP + CAP / 16 + 8;
 };
 
 __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
@@ -117,37 +139,60 @@ k_tile(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, con
     const int t = tile_base + blockIdx.x;
     const int row0 = tile_rows[t], row1 = tile_rows[t + 1];
     const int nz0 = rowptr[row0], nz1 = rowptr[row1];
-    const int nz0a = nz0 & ~3;
+    const int nz0a = nz0 & ~(TILE_ENT - 1);
 
-    int4 c[ITER];
-    double2 va[ITER], vb[ITER];
+    I8 c[ITER];
+    D4 va[ITER], vb[ITER];
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {
-        const int k = nz0a + 4 * (threadIdx.x + it * THREADS);
+        const int k = nz0a + TILE_ENT * (threadIdx.x + it * THREADS);
         if (k < nz1) {
-            c[it] = ld_stream_i4(cols + k);
-            va[it] = ld_stream_d2(vals + k);
-            vb[it] = ld_stream_d2(vals + k + 2);
+            c[it] = ld_stream_i8(cols + k);
+            va[it] = ld_stream_d4(vals + k);
+            vb[it] = ld_stream_d4(vals + k + 4);
+        }
+    }
+    // epilogue operands of this thread's rows: independent of the stream above, issued right behind it
+    int ra[TILE_RPT], rb[TILE_RPT];
+    typename Epi::Pre pre[TILE_RPT];
+#pragma unroll
+    for (int j = 0; j < TILE_RPT; ++j) {
+        const int r = row0 + threadIdx.x + j * THREADS;
+        if (r < row1) {
+            ra[j] = rowptr[r]; rb[j] = rowptr[r + 1];
+            pre[j] = epi.load(r);
         }
     }
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {
-        const int k = nz0a + 4 * (threadIdx.x + it * THREADS);
+        const int k = nz0a + TILE_ENT * (threadIdx.x + it * THREADS);
         if (k < nz1) {
-            const double x0 = ld_x<NCX>(x, c[it].x), x1 = ld_x<NCX>(x, c[it].y), x2 = ld_x<NCX>(x, c[it].z), x3 = ld_x<NCX>(x, c[it].w);
-            const int b = pad16(k - nz0a);                 // k - nz0a is a multiple of 4: the 4 entries share one pad offset
-            prod[b + 0] = __dmul_rn(va[it].x, x0);
-            prod[b + 1] = __dmul_rn(va[it].y, x1);
-            prod[b + 2] = __dmul_rn(vb[it].x, x2);
-            prod[b + 3] = __dmul_rn(vb[it].y, x3);
+            double xv[TILE_ENT];
+#pragma unroll
+            for (int e = 0; e < TILE_ENT; ++e) xv[e] = ld_x<NCX>(x, c[it].v[e]);
+            const int b = pad16(k - nz0a);          // k - nz0a is a multiple of 8: the 8 entries share one pad offset
+#pragma unroll
+            for (int e = 0; e < 4; ++e) prod[b + e] = __dmul_rn(va[it].v[e], xv[e]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) prod[b + 4 + e] = __dmul_rn(vb[it].v[e], xv[4 + e]);
         }
     }
     __syncthreads();
-    for (int r = row0 + threadIdx.x; r < row1; r += THREADS) {
+#pragma unroll
+    for (int j = 0; j < TILE_RPT; ++j) {
+        const int r = row0 + threadIdx.x + j * THREADS;
+        if (r < row1) {
+            double s = 0.0;
+            for (int k = ra[j] - nz0a; k < rb[j] - nz0a; ++k) s = __dadd_rn(s, prod[pad16(k)]);
+            epi.store(r, s, pre[j]);
+        }
+    }
+    for (int r = row0 + threadIdx.x + TILE_RPT * THREADS; r < row1; r += THREADS) {     // tiles of many short rows
         const int a = rowptr[r] - nz0a, b = rowptr[r + 1] - nz0a;
+        const typename Epi::Pre p = epi.load(r);
         double s = 0.0;
         for (int k = a; k < b; ++k) s = __dadd_rn(s, prod[pad16(k)]);
-        epi(r, s);
+        epi.store(r, s, p);
     }
 }
 
@@ -164,11 +209,13 @@ k_subwarp(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, 
     const bool active = row < row_end;
     if (!active) row = row_end - 1;
     const int a = rowptr[row], b = rowptr[row + 1];
+    typename Epi::Pre pre;
+    if (active && lane == 0) pre = epi.load(row);
     double s = 0.0;
     for (int k = a + lane; k < b; k += LPR) s = __dadd_rn(s, __dmul_rn(vals[k], ld_x<NCX>(x, cols[k])));
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
-    if (active && lane == 0) epi(row, s);
+    if (active && lane == 0) epi.store(row, s, pre);
 }
 
 // ---- small kernels ----------------------------------------------------------------------------------

@@ -238,7 +238,7 @@ bool make_tiles(const std::vector<int64_t>& ip, int64_t cap, int64_t row_cap, co
     while (bi < breaks.size() && breaks[bi] <= 0) { if (break_tile_index) break_tile_index->push_back(0); ++bi; }
     while (r < n) {
         const int64_t next_break = bi < breaks.size() ? breaks[bi] : n;
-        const int64_t base = ip[r] & ~(int64_t)3;
+        const int64_t base = ip[r] & ~(int64_t)7;
         int64_t e = r;
         while (e < n && e < next_break && (e - r) < row_cap && (ip[e + 1] - base) <= cap) ++e;
         if (e == r) return false;            // a single row does not fit

@@ -114,9 +114,9 @@ void orc_gs_forward(i64 n, const i64 *ip, const i32 *ix, const double *ax, const
 
 double orc_norm2(i64 n, const double *x)
 {
-    double s = 0.0;
-    for (i64 i = 0; i < n; ++i) s += x[i] * x[i];
-    return sqrt(s);
+    long double s = 0.0L;      /* extended accumulator: the norm itself must not be the noisy part of a 1e-12 comparison */
+    for (i64 i = 0; i < n; ++i) s += (long double)x[i] * (long double)x[i];
+    return (double)sqrtl(s);
 }
 
 /* ---------------------------------------------------------------- artefacts */
