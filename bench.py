@@ -144,7 +144,7 @@ def run_single(args):
     H, desc = build_workload(args.workload)
     lf = H.finest_level
     eng = MGEngine.from_hierarchy(H, r_mode=args.restriction, smoother=args.smoother, device=0,
-                                  options={"fuse_restrict": args.fuse_restrict})
+                                  options={"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg})
     n = H.n(lf)
     f_host = H.b_dict[lf][:, 0]
     t_setup = time.perf_counter() - t_setup
@@ -231,7 +231,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--restriction", default="injection", choices=["injection", "full_weighting", "transpose"])
     ap.add_argument("--smoother", default="jacobi", choices=["jacobi", "jacobi_a", "gs", "gs_color"])
-    ap.add_argument("--fuse-restrict", type=int, default=0)
+    ap.add_argument("--fuse-restrict", type=int, default=1)
+    ap.add_argument("--stream-cfg", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -30,6 +30,9 @@ struct DevCsr {
     double* vals = nullptr;
     int32_t* tiles = nullptr;
     int ntiles = 0;
+    int4* sdesc = nullptr;   // stream kernel: per-tile {row0, nrows, nz0a, nent}
+    int sntiles = 0;
+    std::vector<int4> sdesc_host;
     int iter = 2;       // tile kernel: groups of 4 entries per thread
     int family = 1;     // 1 tile, 2 sub-warp
     int lpr = 4;        // sub-warp lanes per row
@@ -52,6 +55,10 @@ struct Level {
     DevCsr A, RJ, P, R, G;           // G: Gauss-Seidel off-diagonal operator, rows in execution order
     double* dinv = nullptr;
     int32_t* inj = nullptr;
+    int32_t* cmap = nullptr;         // fine dof -> coarse dof or -1 (fused residual + injection)
+    int4* inj_desc = nullptr;        // the stream tiles of A that contain at least one injected row
+    int inj_ntiles = 0;
+    double inj_fraction = 1.0;       // share of A's entries in those tiles
     double *v = nullptr, *vtmp = nullptr, *f = nullptr, *r = nullptr, *g = nullptr;
     // Gauss-Seidel artefacts (host copies are what mgb_get_artifact returns)
     std::vector<int32_t> lev_of_row, lev_order, lev_off, col_of_row, col_order, col_off;
@@ -75,7 +82,9 @@ struct mgb_handle {
     double omega = 2.0 / 3.0;
     int mu1 = 2, mu2 = 2, smoother = MGB_SM_JACOBI_RJ;
     // options
-    int rj_reversed = 1, use_graph = 1, opt_family = 0, opt_lpr = 0, opt_iter = 0, coarse_refine = 0, fuse_restrict = 0;
+    int rj_reversed = 1, use_graph = 1, opt_family = 0, opt_lpr = 0, opt_iter = 0, coarse_refine = 0, fuse_restrict = 1;
+    int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
+    bool allow_stream = true;      // false while borrowed user pointers are in play (no padding / alignment guarantee)
     int coarsest = 0, finest = 0;
     double* coarse_inv = nullptr;
     std::vector<double> coarse_inv_host;
@@ -135,11 +144,25 @@ int dev_upload(mgb_handle* h, T** p, const T* src, size_t count, size_t pad = 0)
 
 void free_csr(DevCsr& D)
 {
-    cudaFree(D.rowptr); cudaFree(D.cols); cudaFree(D.vals); cudaFree(D.tiles);
+    cudaFree(D.rowptr); cudaFree(D.cols); cudaFree(D.vals); cudaFree(D.tiles); cudaFree(D.sdesc);
     D = DevCsr();
 }
 
 int tile_cap(int iter) { return TILE_ENT * THREADS * iter; }
+
+// TMA stream kernel configurations (option "stream_cfg"): consumer threads, entries per thread, stages
+struct StreamChoice { int threads, ept, stages; };
+StreamChoice stream_choice(int cfg)
+{
+    switch (cfg) {
+        case 1: return {256, 8, 2};      // 2048-entry tiles, 2 CTAs/SM
+        case 2: return {512, 4, 2};      // 2048-entry tiles, 2 CTAs/SM, twice the consumer threads
+        case 3: return {256, 4, 2};      // 1024-entry tiles, 5 CTAs/SM
+        case 4: return {256, 4, 3};      // 1024-entry tiles, 3 CTAs/SM
+        case 5: return {128, 8, 2};      // 1024-entry tiles, 5 CTAs/SM
+        default: return {256, 8, 3};     // 2048-entry tiles, 1 CTA/SM, deep ring
+    }
+}
 
 // Upload a host CSR and choose the kernel family / tile shape for it.
 int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int32_t>& breaks = {})
@@ -154,7 +177,7 @@ int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int
     for (int64_t i = 0; i <= n; ++i) rp[i] = (int32_t)M.ip[i];
     for (int64_t i = 0; i < n; ++i) mx = std::max<int>(mx, rp[i + 1] - rp[i]);
     D.max_row = mx;
-    TRY(dev_upload(h, &D.rowptr, rp.data(), rp.size()));
+    TRY(dev_upload(h, &D.rowptr, rp.data(), rp.size(), 8));
     TRY(dev_upload(h, &D.cols, M.ix.data(), (size_t)nnz, 16));   // padding: the last 8-wide group may read past nnz
     TRY(dev_upload(h, &D.vals, M.ax.data(), (size_t)nnz, 16));
     // family
@@ -173,6 +196,22 @@ int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int
         }
     }
     D.family = family; D.iter = iter;
+    if (family == 1 && h->stream_cfg > 0 && breaks.empty()) {     // descriptors for the TMA stream kernel
+        const StreamChoice sc = stream_choice(h->stream_cfg);
+        const int cap = sc.threads * sc.ept;
+        std::vector<int32_t> st;
+        if (make_tiles(M.ip, cap, cap / 4, {}, st, nullptr, 4)) {
+            std::vector<int4> desc(st.size() - 1);
+            for (size_t t = 0; t + 1 < st.size(); ++t) {
+                const int64_t r0 = st[t], r1 = st[t + 1];
+                const int64_t z0 = M.ip[r0] & ~(int64_t)7, z1 = M.ip[r1];
+                desc[t] = make_int4((int)r0, (int)(r1 - r0), (int)z0, (int)((z1 - z0 + 7) & ~(int64_t)7));
+            }
+            D.sntiles = (int)desc.size();
+            if (D.sntiles > 0) TRY(dev_upload(h, &D.sdesc, desc.data(), desc.size()));
+            D.sdesc_host.swap(desc);
+        }
+    }
     if (family == 2) {
         int lpr = h->opt_lpr;
         if (!lpr) {
@@ -218,6 +257,38 @@ void launch_tile(mgb_handle* h, const DevCsr& D, int t0, int t1, const double* x
     }
 }
 
+template <int T, int E, int S, class Epi>
+void launch_stream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi)
+{
+    auto kern = k_stream<T, E, S, true, Epi>;
+    constexpr int smem = StreamCfg<T, E, Epi::NOPS, EpiNI<Epi>::value>::smem_bytes(S);
+    static int occ = -1;                 // per instantiation (one device per process)
+    if (occ < 0) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T + 32, smem);
+        if (occ < 1) occ = 1;
+    }
+    const int grid = std::min(ntiles, h->sm_count * occ);
+    kern<<<grid, T + 32, smem, h->stream>>>(D.rowptr, D.cols, D.vals, desc, ntiles, x, epi);
+}
+
+template <class Epi>
+void launch_stream(mgb_handle* h, const DevCsr& D, const double* x, const Epi& epi, const int4* desc = nullptr, int ntiles = 0)
+{
+    if (!desc) { desc = D.sdesc; ntiles = D.sntiles; }
+    if (ntiles <= 0) return;
+    if constexpr (Epi::CONTIG) {
+        switch (h->stream_cfg) {
+            case 1: launch_stream_cfg<256, 8, 2, Epi>(h, D, desc, ntiles, x, epi); break;
+            case 2: launch_stream_cfg<512, 4, 2, Epi>(h, D, desc, ntiles, x, epi); break;
+            case 3: launch_stream_cfg<256, 4, 2, Epi>(h, D, desc, ntiles, x, epi); break;
+            case 4: launch_stream_cfg<256, 4, 3, Epi>(h, D, desc, ntiles, x, epi); break;
+            case 5: launch_stream_cfg<128, 8, 2, Epi>(h, D, desc, ntiles, x, epi); break;
+            default: launch_stream_cfg<256, 8, 3, Epi>(h, D, desc, ntiles, x, epi); break;
+        }
+    }
+}
+
 template <class Epi, bool NCX>
 void launch_subwarp(mgb_handle* h, const DevCsr& D, int r0, int r1, const double* x, const Epi& epi)
 {
@@ -241,7 +312,9 @@ int row_sums(mgb_handle* h, int kind, int level, double bytes, const DevCsr& D, 
 {
     if (D.nrows == 0) return MGB_OK;
     return launch(h, kind, level, bytes, [&] {
-        if (D.family == 1) {
+        if (Epi::CONTIG && NCX && D.family == 1 && group < 0 && D.sdesc && h->stream_cfg > 0 && h->allow_stream) {
+            launch_stream<Epi>(h, D, x, epi);
+        } else if (D.family == 1) {
             int t0 = 0, t1 = D.ntiles;
             if (group >= 0) { t0 = D.break_tile[group]; t1 = D.break_tile[group + 1]; }
             launch_tile<Epi, NCX>(h, D, t0, t1, x, epi);
@@ -337,6 +410,14 @@ int residual_injected(mgb_handle* h, Level& L, const double* v, const double* f,
 {
     const int64_t nc = L.n_coarse;
     const double avg = L.A.nrows ? (double)L.A.nnz / (double)L.A.nrows : 0.0;
+    if (L.inj_desc && L.inj_fraction < 0.8 && h->stream_cfg > 0 && h->allow_stream) {
+        // stream only the tiles of A that hold injected rows; every row of such a tile is summed, injected ones are stored
+        const double nb = L.inj_fraction * (12.0 * (double)L.A.nnz + (4.0 + 8.0 + 4.0) * (double)L.n) + 8.0 * (double)L.n + 8.0 * (double)nc;
+        return launch(h, MGB_K_RESIDUAL, L.level, nb, [&] {
+            EpiResidualInject epi{f, L.cmap, f_coarse};
+            launch_stream<EpiResidualInject>(h, L.A, v, epi, L.inj_desc, L.inj_ntiles);
+        });
+    }
     return launch(h, MGB_K_RESIDUAL, L.level, (12.0 * avg + 4.0 + 8.0 + 4.0 + 8.0 + 8.0) * (double)nc + 8.0 * (double)L.n, [&] {
         if (nc <= 0) return;
         if (avg <= 8.0) k_residual_injected<8><<<(int)((nc * 8 + 255) / 256), 256, 0, h->stream>>>((int)nc, L.inj, L.A.rowptr, L.A.cols, L.A.vals, f, v, f_coarse);
@@ -449,7 +530,7 @@ int run_cycle(mgb_handle* h, int top)
     if (it == h->graphs.end()) {
         cudaGraph_t graph = nullptr;
         const int64_t before = h->launches;
-        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
         int rc = enqueue_cycle(h, top, false, nullptr);
         cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
         const int64_t captured = h->launches - before;
@@ -490,6 +571,13 @@ int copy_out(mgb_handle* h, double* dst, const double* src, int64_t n, int mem)
     CU(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, mem == MGB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
     return MGB_OK;
 }
+
+// per-operator calls on borrowed device pointers: no padding / alignment guarantee -> no bulk-copy kernel
+struct BorrowGuard {
+    mgb_handle* h; bool saved;
+    BorrowGuard(mgb_handle* h_, int mem) : h(h_), saved(h_->allow_stream) { if (mem == MGB_MEM_DEVICE) h->allow_stream = false; }
+    ~BorrowGuard() { h->allow_stream = saved; }
+};
 
 int check_ready(mgb_handle* h, int level, Level** L)
 {
@@ -565,7 +653,7 @@ int mgb_destroy(mgb_handle* h)
     for (auto& kv : h->levels) {
         Level& L = kv.second;
         free_csr(L.A); free_csr(L.RJ); free_csr(L.P); free_csr(L.R); free_csr(L.G);
-        cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.v); cudaFree(L.vtmp); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
+        cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.cmap); cudaFree(L.inj_desc); cudaFree(L.v); cudaFree(L.vtmp); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
         cudaFree(L.gs_order); cudaFree(L.gs_off); cudaFree(L.gs_diag);
     }
     cudaFree(h->coarse_inv); cudaFree(h->d_partial); cudaFree(h->d_hist);
@@ -645,6 +733,7 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "kernel_family" && pre) h->opt_family = iv;
     else if (k == "lanes_per_row" && pre) h->opt_lpr = iv;
     else if (k == "tile_iter" && pre) h->opt_iter = iv;
+    else if (k == "stream_cfg" && pre) h->stream_cfg = iv;
     else return fail(h, pre ? MGB_ERR_INVALID : MGB_ERR_STATE, "option '%s' unknown or not settable %s finalize", key, pre ? "before" : "after");
     return MGB_OK;
 }
@@ -673,7 +762,7 @@ int mgb_finalize(mgb_handle* h)
             if (!build_rj(L.A_host, h->rj_reversed != 0, RJ, dinv))            // multigrid.py:48-56
                 return fail(h, MGB_ERR_SINGULAR, "level %d: zero or missing diagonal entry", kv.first);
             TRY(upload_csr(h, RJ, L.RJ));
-            TRY(dev_upload(h, &L.dinv, dinv.data(), n));
+            TRY(dev_upload(h, &L.dinv, dinv.data(), n, 16));
         }
         if (h->smoother >= MGB_SM_GS_LEVEL && kv.first > h->coarsest) {
             HostCsr G0, G; std::vector<double> diag, dperm(n);
@@ -701,16 +790,31 @@ int mgb_finalize(mgb_handle* h)
             TRY(upload_csr(h, L.P_host, L.P));
             if (L.r_mode == MGB_R_INJECTION) {
                 TRY(dev_upload(h, &L.inj, L.inj_host.data(), L.inj_host.size()));
+                if (!L.A.sdesc_host.empty()) {
+                    std::vector<int32_t> cmap(n + 16, -1);
+                    for (size_t c = 0; c < L.inj_host.size(); ++c) cmap[(size_t)L.inj_host[c]] = (int32_t)c;
+                    std::vector<int4> keep;
+                    int64_t ent = 0;
+                    for (const int4& d : L.A.sdesc_host) {
+                        bool any = false;
+                        for (int r = d.x; r < d.x + d.y && !any; ++r) any = cmap[(size_t)r] >= 0;
+                        if (any) { keep.push_back(d); ent += d.w; }
+                    }
+                    TRY(dev_upload(h, &L.cmap, cmap.data(), cmap.size()));
+                    if (!keep.empty()) TRY(dev_upload(h, &L.inj_desc, keep.data(), keep.size()));
+                    L.inj_ntiles = (int)keep.size();
+                    L.inj_fraction = L.A.nnz ? (double)ent / (double)L.A.nnz : 1.0;
+                }
             } else {
                 if (L.r_mode == MGB_R_FULL_WEIGHTING) transpose_scaled(L.P_host, std::ldexp(1.0, -L.dim_fw), L.R_host);
                 else if (L.r_mode == MGB_R_TRANSPOSE) transpose_scaled(L.P_host, 1.0, L.R_host);
                 TRY(upload_csr(h, L.R_host, L.R));
             }
         }
-        TRY(dev_alloc(h, &L.v, n)); TRY(dev_alloc(h, &L.vtmp, n)); TRY(dev_alloc(h, &L.f, n));
-        TRY(dev_alloc(h, &L.r, n)); TRY(dev_alloc(h, &L.g, n));
-        CU(cudaMemsetAsync(L.v, 0, n * sizeof(double), h->stream));
-        CU(cudaMemsetAsync(L.f, 0, n * sizeof(double), h->stream));
+        const size_t np = n + 16;         // tail padding: bulk copies of operand slices round up to 16 bytes
+        TRY(dev_alloc(h, &L.v, np)); TRY(dev_alloc(h, &L.vtmp, np)); TRY(dev_alloc(h, &L.f, np));
+        TRY(dev_alloc(h, &L.r, np)); TRY(dev_alloc(h, &L.g, np));
+        for (double* p : {L.v, L.vtmp, L.f, L.r, L.g}) CU(cudaMemsetAsync(p, 0, np * sizeof(double), h->stream));
     }
     {   // dense inverse of the coarsest matrix: replaces spsolve (multigrid.py:239)
         Level& C = h->levels[h->coarsest];
@@ -725,6 +829,12 @@ int mgb_finalize(mgb_handle* h)
         std::vector<int32_t>().swap(L.inj_host);
     }
     h->finalized = true;
+    {   // one eager cycle on zero data: sets kernel attributes outside any graph capture and faults early if a kernel is broken
+        const int64_t before = h->launches;
+        TRY(enqueue_cycle(h, h->finest, false, nullptr));
+        CU(cudaStreamSynchronize(h->stream));
+        h->launches = before;
+    }
     return MGB_OK;
 }
 
@@ -773,6 +883,7 @@ int mgb_spmv(mgb_handle* h, int level, const double* x, double* y, int mem)
 {
     Level* L;
     TRY(check_ready(h, level, &L));
+    BorrowGuard guard(h, mem);
     const double* xd = x; double* yd = y;
     if (mem == MGB_MEM_HOST) { TRY(copy_in(h, L->v, x, L->n, mem)); xd = L->v; yd = L->r; }
     EpiStore epi{yd};
@@ -785,6 +896,7 @@ int mgb_residual(mgb_handle* h, int level, const double* v, const double* f, dou
 {
     Level* L;
     TRY(check_ready(h, level, &L));
+    BorrowGuard guard(h, mem);
     const double *vd = v, *fd = f; double* rd = r;
     if (mem == MGB_MEM_HOST) { TRY(copy_in(h, L->v, v, L->n, mem)); TRY(copy_in(h, L->f, f, L->n, mem)); vd = L->v; fd = L->f; rd = L->r; }
     TRY(residual(h, *L, vd, fd, rd));
@@ -796,6 +908,7 @@ int mgb_smooth(mgb_handle* h, int level, double* v, const double* f, int nsweeps
 {
     Level* L;
     TRY(check_ready(h, level, &L));
+    BorrowGuard guard(h, mem);
     if (level == h->coarsest && h->smoother >= MGB_SM_GS_LEVEL) return fail(h, MGB_ERR_STATE, "no Gauss-Seidel operator on the coarsest level");
     double* vd = v; const double* fd = f;
     if (mem == MGB_MEM_HOST) { TRY(copy_in(h, L->v, v, L->n, mem)); TRY(copy_in(h, L->f, f, L->n, mem)); vd = L->v; fd = L->f; }
@@ -811,6 +924,7 @@ int mgb_restrict(mgb_handle* h, int fine_level, const double* r_fine, double* f_
 {
     Level* L;
     TRY(check_ready(h, fine_level, &L));
+    BorrowGuard guard(h, mem);
     if (!L->has_transfer) return fail(h, MGB_ERR_INVALID, "level %d has no coarser neighbour", fine_level);
     Level& C = h->levels[fine_level - 1];
     const double* rd = r_fine; double* fd = f_coarse;
@@ -824,6 +938,7 @@ int mgb_prolong_add(mgb_handle* h, int fine_level, const double* e_coarse, doubl
 {
     Level* L;
     TRY(check_ready(h, fine_level, &L));
+    BorrowGuard guard(h, mem);
     if (!L->has_transfer) return fail(h, MGB_ERR_INVALID, "level %d has no coarser neighbour", fine_level);
     Level& C = h->levels[fine_level - 1];
     const double* ed = e_coarse; double* vd = v_fine;
@@ -838,6 +953,7 @@ int mgb_coarse_solve(mgb_handle* h, const double* f, double* u, int mem)
     Level* C;
     if (!h) return MGB_ERR_INVALID;
     TRY(check_ready(h, h->coarsest, &C));
+    BorrowGuard guard(h, mem);
     const double* fd = f; double* ud = u;
     if (mem == MGB_MEM_HOST) { TRY(copy_in(h, C->f, f, C->n, mem)); fd = C->f; ud = C->v; }
     TRY(coarse_apply(h, *C, fd, ud));

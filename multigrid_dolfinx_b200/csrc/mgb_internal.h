@@ -48,8 +48,9 @@ bool dense_inverse(const HostCsr& A, std::vector<double>& inv);
 // Row tiles for the tile kernel: tile t covers rows [tiles[t], tiles[t+1]); every tile satisfies
 //   rowptr[tiles[t+1]] - (rowptr[tiles[t]] & ~7) <= cap   and   rows <= row_cap,
 // and no tile straddles a breakpoint (breaks = sorted row indices, may be empty).
+// row_align > 1 (only without breakpoints): every tile start is a multiple of row_align.
 // Returns false if a single row exceeds cap.
 bool make_tiles(const std::vector<int64_t>& ip, int64_t cap, int64_t row_cap, const std::vector<int32_t>& breaks,
-                std::vector<int32_t>& tiles, std::vector<int32_t>* break_tile_index);
+                std::vector<int32_t>& tiles, std::vector<int32_t>* break_tile_index, int64_t row_align = 1);
 
 }  // namespace mgb

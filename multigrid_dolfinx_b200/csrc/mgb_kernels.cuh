@@ -34,73 +34,113 @@ __device__ __forceinline__ D4 ld_stream_d4(const double* p)
 }
 
 // ---- epilogues --------------------------------------------------------------------------------------
-// An epilogue turns the row sum s of row i into the output.  load(i) fetches the per-row operands and is
-// issued BEFORE the row sum is available (so their DRAM latency overlaps the matrix stream);
-// store(i, s, pre) finishes the row.
+// An epilogue turns the row sum s of row i into the output.  CONTIG epilogues read NOPS per-row operands
+// from contiguous f64 arrays (operand(j)[i]); the kernels fetch them BEFORE the row sum is available (the
+// tile kernel into registers, the stream kernel with the same bulk copies as the matrix), so their DRAM
+// latency overlaps the matrix stream.  store(i, s, o) finishes the row.
 // y = A x                                                   (multigrid.py:244, A.dot(v))
 struct EpiStore {
+    static constexpr int NOPS = 0; static constexpr bool CONTIG = true;
     double* y;
-    struct Pre {};
-    __device__ __forceinline__ Pre load(int) const { return Pre{}; }
-    __device__ __forceinline__ void store(int i, double s, const Pre&) const { y[i] = s; }
+    __device__ __forceinline__ const double* operand(int) const { return nullptr; }
+    __device__ __forceinline__ void store(int i, double s, const double*) const { y[i] = s; }
 };
 // r = f - A v                                               (multigrid.py:244)
 struct EpiResidual {
+    static constexpr int NOPS = 1; static constexpr bool CONTIG = true;
     const double* f; double* r;
-    struct Pre { double f; };
-    __device__ __forceinline__ Pre load(int i) const { return Pre{f[i]}; }
-    __device__ __forceinline__ void store(int i, double s, const Pre& p) const { r[i] = __dsub_rn(p.f, s); }
+    __device__ __forceinline__ const double* operand(int) const { return f; }
+    __device__ __forceinline__ void store(int i, double s, const double* o) const { r[i] = __dsub_rn(o[0], s); }
 };
 // weighted Jacobi, reference form (multigrid.py:226): out = ((1-w)*v + g) - w*s, g = w*(dinv*f)
 struct EpiJacobiRJ {
+    static constexpr int NOPS = 2; static constexpr bool CONTIG = true;
     const double* v; const double* g; double* out; double om1, om;
-    struct Pre { double v, g; };
-    __device__ __forceinline__ Pre load(int i) const { return Pre{v[i], g[i]}; }
-    __device__ __forceinline__ void store(int i, double s, const Pre& p) const
+    __device__ __forceinline__ const double* operand(int j) const { return j == 0 ? v : g; }
+    __device__ __forceinline__ void store(int i, double s, const double* o) const
     {
-        out[i] = __dsub_rn(__dadd_rn(__dmul_rn(om1, p.v), p.g), __dmul_rn(om, s));
+        out[i] = __dsub_rn(__dadd_rn(__dmul_rn(om1, o[0]), o[1]), __dmul_rn(om, s));
     }
 };
 // same, first sweep of a relaxation call: also produces g (multigrid.py:226 recomputes w*(Dinv f) per sweep;
 // the product is identical every time, so it is formed once and kept)
 struct EpiJacobiRJFirst {
+    static constexpr int NOPS = 3; static constexpr bool CONTIG = true;
     const double* v; const double* dinv; const double* f; double* g; double* out; double om1, om;
-    struct Pre { double v, g; };
-    __device__ __forceinline__ Pre load(int i) const { return Pre{v[i], __dmul_rn(om, __dmul_rn(dinv[i], f[i]))}; }
-    __device__ __forceinline__ void store(int i, double s, const Pre& p) const
+    __device__ __forceinline__ const double* operand(int j) const { return j == 0 ? v : (j == 1 ? dinv : f); }
+    __device__ __forceinline__ void store(int i, double s, const double* o) const
     {
-        g[i] = p.g;
-        out[i] = __dsub_rn(__dadd_rn(__dmul_rn(om1, p.v), p.g), __dmul_rn(om, s));
+        const double gi = __dmul_rn(om, __dmul_rn(o[1], o[2]));
+        g[i] = gi;
+        out[i] = __dsub_rn(__dadd_rn(__dmul_rn(om1, o[0]), gi), __dmul_rn(om, s));
     }
 };
 // single-matrix Jacobi: out = v + w*(dinv*(f - s)), s = (A v)_i
 struct EpiJacobiA {
+    static constexpr int NOPS = 3; static constexpr bool CONTIG = true;
     const double* v; const double* dinv; const double* f; double* out; double om;
-    struct Pre { double v, dinv, f; };
-    __device__ __forceinline__ Pre load(int i) const { return Pre{v[i], dinv[i], f[i]}; }
-    __device__ __forceinline__ void store(int i, double s, const Pre& p) const
+    __device__ __forceinline__ const double* operand(int j) const { return j == 0 ? v : (j == 1 ? dinv : f); }
+    __device__ __forceinline__ void store(int i, double s, const double* o) const
     {
-        out[i] = __dadd_rn(p.v, __dmul_rn(om, __dmul_rn(p.dinv, __dsub_rn(p.f, s))));
+        out[i] = __dadd_rn(o[0], __dmul_rn(om, __dmul_rn(o[1], __dsub_rn(o[2], s))));
     }
 };
 // v = v + P e   (multigrid.py:258-260); err (nullable) receives P e (the test=True output, multigrid.py:265)
 struct EpiProlongAdd {
+    static constexpr int NOPS = 1; static constexpr bool CONTIG = true;
     double* v; double* err;
-    struct Pre { double v; };
-    __device__ __forceinline__ Pre load(int i) const { return Pre{v[i]}; }
-    __device__ __forceinline__ void store(int i, double s, const Pre& p) const
+    __device__ __forceinline__ const double* operand(int) const { return v; }
+    __device__ __forceinline__ void store(int i, double s, const double* o) const
     {
         if (err) err[i] = s;
-        v[i] = __dadd_rn(p.v, s);
+        v[i] = __dadd_rn(o[0], s);
     }
 };
 // Gauss-Seidel row update on a row-permuted off-diagonal operator: v[order[p]] = (f - s) / d
 struct EpiGaussSeidel {
+    static constexpr int NOPS = 0; static constexpr bool CONTIG = false;
     const int32_t* order; const double* diag; const double* f; double* v;
     struct Pre { int i; double f, d; };
     __device__ __forceinline__ Pre load(int p) const { const int i = order[p]; return Pre{i, f[i], diag[p]}; }
     __device__ __forceinline__ void store(int, double s, const Pre& p) const { v[p.i] = __ddiv_rn(__dsub_rn(p.f, s), p.d); }
 };
+
+// fused residual + injection: out[cmap[i]] = f[i] - s for the fine rows that have a coarse image
+// (multigrid.py:244 followed by Restriction2D_direct, multigrid.py:128-131); cmap[i] = coarse dof or -1
+struct EpiResidualInject {
+    static constexpr int NOPS = 1; static constexpr bool CONTIG = true; static constexpr int NIOPS = 1;
+    const double* f; const int32_t* cmap; double* out;
+    __device__ __forceinline__ const double* operand(int) const { return f; }
+    __device__ __forceinline__ const int32_t* ioperand() const { return cmap; }
+    __device__ __forceinline__ void store_i(int, double s, const double* o, int c) const { if (c >= 0) out[c] = __dsub_rn(o[0], s); }
+};
+
+template <class Epi, class = void> struct EpiNI { static constexpr int value = 0; };
+template <class Epi> struct EpiNI<Epi, decltype((void)Epi::NIOPS)> { static constexpr int value = Epi::NIOPS; };
+
+template <class Epi>
+struct EpiOperands { double o[Epi::NOPS > 0 ? Epi::NOPS : 1]; int io; };
+
+template <class Epi>
+__device__ __forceinline__ auto epi_load(const Epi& e, int r)
+{
+    if constexpr (Epi::CONTIG) {
+        EpiOperands<Epi> p;
+#pragma unroll
+        for (int j = 0; j < Epi::NOPS; ++j) p.o[j] = e.operand(j)[r];
+        if constexpr (EpiNI<Epi>::value > 0) p.io = e.ioperand()[r];
+        return p;
+    } else {
+        return e.load(r);
+    }
+}
+template <class Epi, class P>
+__device__ __forceinline__ void epi_store(const Epi& e, int r, double s, const P& p)
+{
+    if constexpr (!Epi::CONTIG) e.store(r, s, p);
+    else if constexpr (EpiNI<Epi>::value > 0) e.store_i(r, s, p.o, p.io);
+    else e.store(r, s, p.o);
+}
 
 // ---- tile family ------------------------------------------------------------------------------------
 // One CTA per row tile.  Phase 1 streams the tile's (cols, vals) with 256-bit loads (coalesced; ITER
@@ -154,13 +194,13 @@ k_tile(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, con
     }
     // epilogue operands of this thread's rows: independent of the stream above, issued right behind it
     int ra[TILE_RPT], rb[TILE_RPT];
-    typename Epi::Pre pre[TILE_RPT];
+    decltype(epi_load(epi, 0)) pre[TILE_RPT];
 #pragma unroll
     for (int j = 0; j < TILE_RPT; ++j) {
         const int r = row0 + threadIdx.x + j * THREADS;
         if (r < row1) {
             ra[j] = rowptr[r]; rb[j] = rowptr[r + 1];
-            pre[j] = epi.load(r);
+            pre[j] = epi_load(epi, r);
         }
     }
 #pragma unroll
@@ -184,15 +224,180 @@ k_tile(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, con
         if (r < row1) {
             double s = 0.0;
             for (int k = ra[j] - nz0a; k < rb[j] - nz0a; ++k) s = __dadd_rn(s, prod[pad16(k)]);
-            epi.store(r, s, pre[j]);
+            epi_store(epi, r, s, pre[j]);
         }
     }
     for (int r = row0 + threadIdx.x + TILE_RPT * THREADS; r < row1; r += THREADS) {     // tiles of many short rows
         const int a = rowptr[r] - nz0a, b = rowptr[r + 1] - nz0a;
-        const typename Epi::Pre p = epi.load(r);
+        const auto p = epi_load(epi, r);
         double s = 0.0;
         for (int k = a; k < b; ++k) s = __dadd_rn(s, prod[pad16(k)]);
-        epi.store(r, s, p);
+        epi_store(epi, r, s, p);
+    }
+}
+
+// ---- stream family: TMA bulk-copy pipeline ------------------------------------------------------------
+// Persistent CTAs (grid = SMs x CTAs/SM).  One producer lane walks this CTA's tiles and, per tile, issues
+// 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) of the tile's cols / vals /
+// row-pointer slice and of the epilogue's operand slices into a ring of STAGES shared-memory stages, up to
+// STAGES tiles ahead of the consumers; matrix bytes carry an L2 evict-first policy.  THREADS consumer
+// threads wait on the stage's "full" mbarrier, gather x, write products to a padded product buffer
+// (phase A), sum each row sequentially in stored order and run the epilogue (phase B), then hand the stage
+// back through its "empty" mbarrier.  Bytes in flight per SM = (STAGES-1) x stage size, independent of
+// what the consumers are doing -- that is what the register-staged tile kernel cannot do.
+// Requirements (checked on the host): tile starts are multiples of 4 rows, tiles hold <= EPT*THREADS entries
+// and a quarter as many rows, operand arrays are 16-byte aligned and padded by >= 2 doubles.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(b);
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000LL) __trap();      // ~2 s: a lost copy must fault, never hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+template <int THREADS, int EPT, int NOPS, int NIOPS = 0>
+struct StreamCfg {
+    static constexpr int CAP = EPT * THREADS;            // entries per tile
+    static constexpr int ROWCAP = CAP / 4;               // rows per tile
+    static constexpr int HDR_BYTES = 128;
+    static constexpr int COLS_BYTES = CAP * 4;
+    static constexpr int VALS_BYTES = CAP * 8;
+    static constexpr int RP_BYTES = ((ROWCAP + 4) * 4 + 127) / 128 * 128;
+    static constexpr int OP_BYTES = ROWCAP * 8;
+    static constexpr int IOP_BYTES = ROWCAP * 4;
+    static constexpr int STAGE_BYTES = HDR_BYTES + COLS_BYTES + VALS_BYTES + RP_BYTES + NOPS * OP_BYTES + NIOPS * IOP_BYTES;
+    static constexpr int PROD_BYTES = ((CAP + CAP / 16 + 8) * 8 + 127) / 128 * 128;
+    static constexpr int BAR_BYTES = 128;
+    static constexpr int smem_bytes(int stages) { return BAR_BYTES + PROD_BYTES + stages * STAGE_BYTES; }
+};
+
+template <int THREADS, int EPT, int STAGES, bool NCX, class Epi>
+__global__ void __launch_bounds__(THREADS + 32)
+k_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, const double* __restrict__ vals,
+         const int4* __restrict__ desc, int ntiles, const double* x, Epi epi)
+{
+    static_assert(Epi::CONTIG, "stream kernel needs contiguous epilogue operands");
+    static_assert(STAGES <= 8, "barrier block holds 8 stages");
+    constexpr int NIOPS = EpiNI<Epi>::value;
+    using Cfg = StreamCfg<THREADS, EPT, Epi::NOPS, NIOPS>;
+    static_assert(EPT % 2 == 0, "entries are handled in pairs");
+    constexpr int NJ = EPT / 2;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + 8;
+    double* prod = reinterpret_cast<double*>(smem + Cfg::BAR_BYTES);
+    unsigned char* stage0 = smem + Cfg::BAR_BYTES + Cfg::PROD_BYTES;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (tid >= THREADS) {                                   // ---- producer warp (one lane works)
+        if (tid == THREADS) {
+            uint64_t pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            for (int i = 0; i < my_tiles; ++i) {
+                const int s = i % STAGES;
+                if (i >= STAGES) mbar_wait(empty + s, (uint32_t)((i / STAGES - 1) & 1));
+                const int4 d = __ldg(desc + blockIdx.x + (size_t)i * gridDim.x);     // {row0, nrows, nz0a, nent}
+                unsigned char* st = stage0 + (size_t)s * Cfg::STAGE_BYTES;
+                *reinterpret_cast<int4*>(st) = d;                                    // published by the arrive below (release)
+                const uint32_t b_cols = (uint32_t)d.w * 4u, b_vals = (uint32_t)d.w * 8u;
+                const uint32_t b_rp = (uint32_t)((d.y + 1 + 3) & ~3) * 4u, b_op = (uint32_t)((d.y + 1) & ~1) * 8u;
+                const uint32_t b_iop = (uint32_t)((d.y + 3) & ~3) * 4u;
+                mbar_expect_tx(full + s, b_cols + b_vals + b_rp + (uint32_t)Epi::NOPS * b_op + (uint32_t)NIOPS * b_iop);
+                unsigned char* p = st + Cfg::HDR_BYTES;
+                bulk_g2s_hint(p, cols + d.z, b_cols, full + s, pol);  p += Cfg::COLS_BYTES;
+                bulk_g2s_hint(p, vals + d.z, b_vals, full + s, pol);  p += Cfg::VALS_BYTES;
+                bulk_g2s(p, rowptr + d.x, b_rp, full + s);            p += Cfg::RP_BYTES;
+#pragma unroll
+                for (int j = 0; j < Epi::NOPS; ++j) { bulk_g2s(p, epi.operand(j) + d.x, b_op, full + s); p += Cfg::OP_BYTES; }
+                if constexpr (NIOPS > 0) bulk_g2s(p, epi.ioperand() + d.x, b_iop, full + s);
+            }
+        }
+        return;
+    }
+
+    for (int i = 0; i < my_tiles; ++i) {                     // ---- consumers
+        const int s = i % STAGES;
+        mbar_wait(full + s, (uint32_t)((i / STAGES) & 1));
+        const unsigned char* st = stage0 + (size_t)s * Cfg::STAGE_BYTES;
+        const int4 d = *reinterpret_cast<const int4*>(st);
+        const int32_t* scols = reinterpret_cast<const int32_t*>(st + Cfg::HDR_BYTES);
+        const double* svals = reinterpret_cast<const double*>(st + Cfg::HDR_BYTES + Cfg::COLS_BYTES);
+        const int32_t* srp = reinterpret_cast<const int32_t*>(st + Cfg::HDR_BYTES + Cfg::COLS_BYTES + Cfg::VALS_BYTES);
+        const double* sops = reinterpret_cast<const double*>(st + Cfg::HDR_BYTES + Cfg::COLS_BYTES + Cfg::VALS_BYTES + Cfg::RP_BYTES);
+        // phase A: entries (2*tid, 2*tid+1) + j*2*THREADS: 16-byte / 8-byte shared loads contiguous across the warp
+        int2 c[NJ];
+        double2 v[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int e = j * 2 * THREADS + 2 * tid;
+            if (e < d.w) {
+                c[j] = *reinterpret_cast<const int2*>(scols + e);
+                v[j] = *reinterpret_cast<const double2*>(svals + e);
+            }
+        }
+        double xa[NJ], xb[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int e = j * 2 * THREADS + 2 * tid;
+            if (e < d.w) { xa[j] = ld_x<NCX>(x, c[j].x); xb[j] = ld_x<NCX>(x, c[j].y); }
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int e = j * 2 * THREADS + 2 * tid;
+            if (e < d.w) {
+                const int b = pad16(e);
+                prod[b] = __dmul_rn(v[j].x, xa[j]);
+                prod[b + 1] = __dmul_rn(v[j].y, xb[j]);
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+        // phase B: thread per row, sequential sum in stored order
+        for (int r = tid; r < d.y; r += THREADS) {
+            const int a = srp[r] - d.z, b = srp[r + 1] - d.z;
+            double sum = 0.0;
+            for (int k = a; k < b; ++k) sum = __dadd_rn(sum, prod[pad16(k)]);
+            double o[Epi::NOPS > 0 ? Epi::NOPS : 1];
+#pragma unroll
+            for (int j = 0; j < Epi::NOPS; ++j) o[j] = sops[j * Cfg::ROWCAP + r];
+            if constexpr (NIOPS > 0) epi.store_i(d.x + r, sum, o, reinterpret_cast<const int32_t*>(sops + Epi::NOPS * Cfg::ROWCAP)[r]);
+            else epi.store(d.x + r, sum, o);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+        if (tid == 0) mbar_arrive(empty + s);
     }
 }
 
@@ -209,13 +414,13 @@ k_subwarp(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, 
     const bool active = row < row_end;
     if (!active) row = row_end - 1;
     const int a = rowptr[row], b = rowptr[row + 1];
-    typename Epi::Pre pre;
-    if (active && lane == 0) pre = epi.load(row);
+    decltype(epi_load(epi, 0)) pre;
+    if (active && lane == 0) pre = epi_load(epi, row);
     double s = 0.0;
     for (int k = a + lane; k < b; k += LPR) s = __dadd_rn(s, __dmul_rn(vals[k], ld_x<NCX>(x, cols[k])));
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
-    if (active && lane == 0) epi.store(row, s, pre);
+    if (active && lane == 0) epi_store(epi, row, s, pre);
 }
 
 // ---- small kernels ----------------------------------------------------------------------------------

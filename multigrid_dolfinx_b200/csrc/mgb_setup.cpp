@@ -228,7 +228,7 @@ bool dense_inverse(const HostCsr& A, std::vector<double>& inv)
 }
 
 bool make_tiles(const std::vector<int64_t>& ip, int64_t cap, int64_t row_cap, const std::vector<int32_t>& breaks,
-                std::vector<int32_t>& tiles, std::vector<int32_t>* break_tile_index)
+                std::vector<int32_t>& tiles, std::vector<int32_t>* break_tile_index, int64_t row_align)
 {
     const int64_t n = (int64_t)ip.size() - 1;
     tiles.clear();
@@ -242,6 +242,11 @@ bool make_tiles(const std::vector<int64_t>& ip, int64_t cap, int64_t row_cap, co
         int64_t e = r;
         while (e < n && e < next_break && (e - r) < row_cap && (ip[e + 1] - base) <= cap) ++e;
         if (e == r) return false;            // a single row does not fit
+        if (row_align > 1 && e < n && e < next_break) {      // keep every tile start a multiple of row_align
+            const int64_t ea = e - (e % row_align);
+            if (ea <= r) return false;
+            e = ea;
+        }
         tiles.push_back((int32_t)r);
         r = e;
         while (bi < breaks.size() && breaks[bi] <= r) {

@@ -132,19 +132,22 @@ def test_subwarp_family_within_tolerance(family, lanes):
     eng.close()
 
 
-@pytest.mark.parametrize("opts", [{"tile_iter": 1}, {"tile_iter": 2}, {"use_graph": 0}, {"fuse_restrict": 1}, {"rj_order": 0}])
+@pytest.mark.parametrize("opts", [{"tile_iter": 1}, {"tile_iter": 2}, {"use_graph": 0}, {"fuse_restrict": 1}, {"rj_order": 0},
+                                  {"stream_cfg": 1}, {"stream_cfg": 2}, {"stream_cfg": 3}, {"stream_cfg": 4}, {"stream_cfg": 5}, {"stream_cfg": 6},
+                                  {"stream_cfg": 1, "fuse_restrict": 0}])
 def test_kernel_options_do_not_change_results(opts):
-    H = pr.build_hierarchy(dim=2, c=8, coarsest_level=0, finest_level=4, perm_seed=1, with_dicts=False)
-    f = H.b_dict[4][:, 0]
-    base = MGEngine.from_hierarchy(H)
-    v0 = base.vcycle(4, np.zeros_like(f), f, ncycles=3)
-    eng = MGEngine.from_hierarchy(H, options=opts)
-    v1 = eng.vcycle(4, np.zeros_like(f), f, ncycles=3)
-    if "rj_order" in opts:
-        assert relmax(v1, v0) <= 1e-13          # different summation order inside R_omega rows
-    else:
-        assert np.array_equal(v1, v0)           # bit-identical
-    base.close(); eng.close()
+    for dim, c, lf, seed, r_mode in [(2, 8, 4, 1, "injection"), (3, 2, 3, None, "transpose"), (2, 5, 3, None, "full_weighting")]:
+        H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=seed, with_dicts=False)
+        f = H.b_dict[lf][:, 0]
+        base = MGEngine.from_hierarchy(H, r_mode=r_mode, options={"stream_cfg": 0, "fuse_restrict": 0})
+        v0 = base.vcycle(lf, np.zeros_like(f), f, ncycles=3)
+        eng = MGEngine.from_hierarchy(H, r_mode=r_mode, options=opts)
+        v1 = eng.vcycle(lf, np.zeros_like(f), f, ncycles=3)
+        if "rj_order" in opts:
+            assert relmax(v1, v0) <= 1e-13          # different summation order inside R_omega rows
+        else:
+            assert np.array_equal(v1, v0)           # bit-identical
+        base.close(); eng.close()
 
 
 def test_jacobi_a_form_and_coarse_refine():

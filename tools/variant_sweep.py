@@ -15,12 +15,18 @@ import bench  # noqa: E402
 from multigrid_dolfinx_b200.engine import MGEngine  # noqa: E402
 
 VARIANTS = [
-    ("tile_iter1", {"tile_iter": 1}),
-    ("tile_iter2", {"tile_iter": 2}),
+    ("tile_iter1", {"tile_iter": 1, "stream_cfg": 0, "fuse_restrict": 0}),
+    ("stream1_nofuse", {"stream_cfg": 1, "fuse_restrict": 0}),
+    ("tile_iter2", {"tile_iter": 2, "stream_cfg": 0}),
     ("subwarp4", {"kernel_family": 2, "lanes_per_row": 4}),
     ("subwarp8", {"kernel_family": 2, "lanes_per_row": 8}),
-    ("subwarp_auto", {"kernel_family": 2}),
-    ("tile_iter1_fused_restrict", {"tile_iter": 1, "fuse_restrict": 1}),
+    ("stream1_256x8x2", {"stream_cfg": 1}),
+    ("stream2_512x4x2", {"stream_cfg": 2}),
+    ("stream3_256x4x2", {"stream_cfg": 3}),
+    ("stream4_256x4x3", {"stream_cfg": 4}),
+    ("stream5_128x8x2", {"stream_cfg": 5}),
+    ("stream6_256x8x3", {"stream_cfg": 6}),
+    ("tile_iter1_fused_restrict", {"tile_iter": 1, "stream_cfg": 0, "fuse_restrict": 1}),
 ]
 
 
@@ -32,6 +38,7 @@ def main():
     ap.add_argument("--cycles", type=int, default=10)
     ap.add_argument("--smoother", default="jacobi")
     ap.add_argument("--restriction", default="injection")
+    ap.add_argument("--only", default="")
     args = ap.parse_args()
     H, desc = bench.build_workload(args.workload)
     lf = H.finest_level
@@ -39,6 +46,8 @@ def main():
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "a") as out:
         for name, opts in VARIANTS:
+            if args.only and not any(name.startswith(o) for o in args.only.split(",")):
+                continue
             eng = MGEngine.from_hierarchy(H, r_mode=args.restriction, smoother=args.smoother, options=opts)
             eng.level_buffer(lf, "f").copy_(torch.from_numpy(f)); eng.level_buffer(lf, "v").zero_()
             torch.cuda.synchronize()
