@@ -34,6 +34,7 @@ WORKLOADS = {
     "cfg2": (2, 32, 0, 6, "2D Poisson P1 2049x2049 (4.2M DOFs), 7-level V(2,2), weighted Jacobi, injection"),
     "cfg2s": (2, 32, 0, 4, "2D Poisson P1 513x513, 5-level V(2,2) (reduced stand-in for quick runs)"),
     "cfg3": (3, 8, 0, 4, "3D Poisson P1 129^3 Kuhn mesh (2.1M DOFs), 5-level V(2,2), weighted Jacobi, injection"),
+    "cfg5h": (3, 8, 0, 5, "3D Poisson P1 257^3 Kuhn mesh (17M DOFs), 6-level V(2,2), weighted Jacobi, injection"),
 }
 METRIC = "V-cycle smoother DOF-updates/s"
 UNIT = "DOF-updates/s"
@@ -228,7 +229,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="auto")
+    ap.add_argument("--gather-threshold", type=int, default=300000)
+    ap.add_argument("--use-graph", type=int, default=1)
     ap.add_argument("--restriction", default="injection", choices=["injection", "full_weighting", "transpose"])
     ap.add_argument("--smoother", default="jacobi", choices=["jacobi", "jacobi_a", "gs", "gs_color"])
     ap.add_argument("--fuse-restrict", type=int, default=1)
@@ -236,9 +239,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    multi = args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1
+    if args.workload == "auto":
+        args.workload = "cfg5h" if multi else "cfg2"
     if args.impl == "reference":
         return run_reference(args)
-    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    if multi:
         from multigrid_dolfinx_b200 import dist_bench
         return dist_bench.run(args)
     return run_single(args)

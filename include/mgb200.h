@@ -116,6 +116,26 @@ int mgb_set_transfer(mgb_handle* h, int coarse_level, int64_t n_fine, int64_t n_
                      int64_t p_nnz, const void* p_indptr, int p_indptr_bytes, const int32_t* p_indices, const double* p_values,
                      int r_mode, int dim_for_fw, const int32_t* inj,
                      int64_t r_nnz, const void* r_indptr, int r_indptr_bytes, const int32_t* r_indices, const double* r_values);
+/* ---- row-sharded hierarchies: one process (and one handle) per GPU ------------------------------------ */
+/* The reference is single-rank; these calls have no counterpart there.  Rank 0 creates an NCCL
+ * unique id (>= 128 bytes), the host side broadcasts it (torch.distributed, MPI, ...), every rank calls
+ * mgb_dist_init before uploading levels. */
+int mgb_dist_unique_id(void* out, int capacity);
+int mgb_dist_init(mgb_handle* h, int rank, int world, const void* unique_id, int id_bytes);
+/* This rank's row block of A_l: n_owned rows, columns renumbered [owned 0..n_owned) | ghost n_owned..n_owned+n_ghost).
+ * Vectors of that level hold n_owned + n_ghost entries on this rank.  Row entry order is untouched, so results
+ * are bit-identical to the single-GPU engine. */
+int mgb_set_level_local(mgb_handle* h, int level, int64_t n_owned, int64_t n_ghost, int64_t nnz, const void* indptr, int indptr_bytes,
+                        const int32_t* indices, const double* values);
+/* Halo plan of a sharded level: for every neighbour rank the owned local indices to send (concatenated) and the
+ * number of ghost entries received from it (ghost slots are ordered neighbour after neighbour). */
+int mgb_set_halo(mgb_handle* h, int level, int npeers, const int32_t* peer_ranks, const int32_t* send_counts,
+                 const int32_t* send_indices, const int32_t* recv_counts);
+/* Declares `level` (and everything coarser) to live on rank 0 only.  offsets[world+1]: the slice of that level's
+ * right-hand side each rank produces when restricting from level+1.  On rank 0 the level must already be set in
+ * full (mgb_set_level); on other ranks it must not be set at all. */
+int mgb_set_gather_level(mgb_handle* h, int level, int64_t n_global, const int64_t* offsets);
+
 /* mu1, mu2, omega (multigrid.py:19-21), smoother = MGB_SM_* */
 int mgb_set_params(mgb_handle* h, double omega, int mu1, int mu2, int smoother);
 /* named numeric options, see DESIGN.md:  "rj_order" (0 = as stored in A, 1 = reversed = scipy's

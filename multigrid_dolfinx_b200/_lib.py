@@ -42,6 +42,11 @@ SYMBOLS = {
     "mgb_last_error": (C.c_char_p, [_vp]),
     "mgb_set_level": (_i, [_vp, _i, _i64, _i64, _vp, _i, _vp, _vp]),
     "mgb_set_transfer": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i, _vp, _vp, _i, _i, _vp, _i64, _vp, _i, _vp, _vp]),
+    "mgb_dist_unique_id": (_i, [_vp, _i]),
+    "mgb_dist_init": (_i, [_vp, _i, _i, _vp, _i]),
+    "mgb_set_level_local": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i, _vp, _vp]),
+    "mgb_set_halo": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "mgb_set_gather_level": (_i, [_vp, _i, _i64, _vp]),
     "mgb_set_params": (_i, [_vp, _d, _i, _i, _i]),
     "mgb_set_option": (_i, [_vp, C.c_char_p, _d]),
     "mgb_finalize": (_i, [_vp]),

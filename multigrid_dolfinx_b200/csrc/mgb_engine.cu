@@ -2,8 +2,11 @@
 // behind the C ABI of include/mgb200.h.  One handle = one device + one stream; the whole cycle is a
 // fixed sequence of launches, captured once per top level into a CUDA graph and replayed.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -50,7 +53,17 @@ struct Level {
     int r_mode = MGB_R_INJECTION;
     int dim_fw = 2;
     bool has_transfer = false;       // transfer pair (level-1, level) was set
-    int64_t n_coarse = 0;
+    int64_t n_coarse = 0;            // coarse rows this rank produces when restricting from this level
+    // ---- row-sharded (multi-GPU) state: this rank owns n rows; vectors hold n + n_ghost entries, ghosts last
+    int64_t n_ghost = 0;
+    bool stub = false;               // gathered level on a non-root rank: full-size vectors, no operators
+    bool gathered = false;           // first level that lives on rank 0 only; every rank owns a slice of its RHS
+    int64_t my_off = 0, my_cnt = 0;  // this rank's slice of the gathered level
+    std::vector<int64_t> gather_off; // world + 1 offsets of all slices
+    std::vector<int> peers, send_cnt, recv_cnt;
+    int32_t* send_idx = nullptr;     // device: owned local indices to pack, peer after peer
+    double* send_buf = nullptr;
+    int64_t send_total = 0;
 
     DevCsr A, RJ, P, R, G;           // G: Gauss-Seidel off-diagonal operator, rows in execution order
     double* dinv = nullptr;
@@ -97,6 +110,11 @@ struct mgb_handle {
     std::vector<ProfEvent> prof_events;
     std::map<std::pair<int, int>, mgb_profile_record> prof_records;
     int64_t launches = 0;
+    // ---- multi-GPU: one process per GPU, NCCL communicator created from a broadcast unique id
+    bool dist = false;
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    int gather_level = INT_MIN;      // level that is gathered to rank 0 (INT_MIN: none)
     int sm_count = 148;
     int gs_coop_blocks_per_sm = 0;
 };
@@ -335,6 +353,103 @@ Level* find_level(mgb_handle* h, int level)
     return it == h->levels.end() ? nullptr : &it->second;
 }
 
+// ---- NCCL, loaded at run time (libnccl.so.2 of the process, i.e. the one torch already loaded) ---------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+const char* load_nccl()
+{
+    if (g_nccl.lib) return nullptr;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return "libnccl.so.2 not found";
+#define NCCL_SYM(name) *(void**)(&g_nccl.name) = dlsym(lib, "nccl" #name); if (!g_nccl.name) return "symbol nccl" #name " missing";
+    NCCL_SYM(GetUniqueId) NCCL_SYM(CommInitRank) NCCL_SYM(CommDestroy) NCCL_SYM(Send) NCCL_SYM(Recv) NCCL_SYM(Broadcast)
+    NCCL_SYM(AllReduce) NCCL_SYM(GroupStart) NCCL_SYM(GroupEnd) NCCL_SYM(GetErrorString)
+#undef NCCL_SYM
+    g_nccl.lib = lib;
+    return nullptr;
+}
+
+#define NC(call)                                                                                       \
+    do {                                                                                               \
+        ncclResult_t r_ = (call);                                                                      \
+        if (r_ != ncclSuccess) return fail(h, MGB_ERR_COMM, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+__global__ void k_pack(int n, const int32_t* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) buf[i] = v[idx[i]];
+}
+__global__ void k_sqrt_inplace(double* x) { *x = sqrt(*x); }
+
+// Halo exchange of one level vector: pack the owned entries the neighbours need, one grouped
+// ncclSend/ncclRecv per neighbour; the ghost section of `vec` (behind the n owned entries) is the receive buffer.
+int exchange(mgb_handle* h, Level& L, double* vec)
+{
+    if (!h->dist || L.peers.empty()) return MGB_OK;
+    int rc = MGB_OK;
+    TRY(launch(h, MGB_K_HALO, L.level, 16.0 * (double)L.send_total, [&] {
+        if (L.send_total > 0) k_pack<<<(int)((L.send_total + 255) / 256), 256, 0, h->stream>>>((int)L.send_total, L.send_idx, vec, L.send_buf);
+        ncclResult_t r = g_nccl.GroupStart();
+        int64_t so = 0, ro = 0;
+        for (size_t p = 0; p < L.peers.size() && r == ncclSuccess; ++p) {
+            if (L.send_cnt[p] > 0) r = g_nccl.Send(L.send_buf + so, (size_t)L.send_cnt[p], ncclDouble, L.peers[p], h->comm, h->stream);
+            if (r == ncclSuccess && L.recv_cnt[p] > 0) r = g_nccl.Recv(vec + L.n + ro, (size_t)L.recv_cnt[p], ncclDouble, L.peers[p], h->comm, h->stream);
+            so += L.send_cnt[p]; ro += L.recv_cnt[p];
+        }
+        ncclResult_t e = g_nccl.GroupEnd();
+        if (r == ncclSuccess) r = e;
+        if (r != ncclSuccess) rc = fail(h, MGB_ERR_COMM, "halo exchange on level %d: %s", L.level, g_nccl.GetErrorString(r));
+    }));
+    return rc;
+}
+
+// slices of the gathered level's right-hand side -> rank 0
+int gather_to_root(mgb_handle* h, Level& C, double* f)
+{
+    int rc = MGB_OK;
+    TRY(launch(h, MGB_K_HALO, C.level, 8.0 * (double)C.n, [&] {
+        ncclResult_t r = g_nccl.GroupStart();
+        if (h->rank == 0) {
+            for (int q = 1; q < h->world && r == ncclSuccess; ++q) {
+                const int64_t cnt = C.gather_off[q + 1] - C.gather_off[q];
+                if (cnt > 0) r = g_nccl.Recv(f + C.gather_off[q], (size_t)cnt, ncclDouble, q, h->comm, h->stream);
+            }
+        } else if (C.my_cnt > 0) {
+            r = g_nccl.Send(f + C.my_off, (size_t)C.my_cnt, ncclDouble, 0, h->comm, h->stream);
+        }
+        ncclResult_t e = g_nccl.GroupEnd();
+        if (r == ncclSuccess) r = e;
+        if (r != ncclSuccess) rc = fail(h, MGB_ERR_COMM, "gather to rank 0: %s", g_nccl.GetErrorString(r));
+    }));
+    return rc;
+}
+
+// coarse-grid correction of the gathered level: rank 0 -> everybody
+int bcast_from_root(mgb_handle* h, Level& C, const double* src, double* dst)
+{
+    int rc = MGB_OK;
+    TRY(launch(h, MGB_K_HALO, C.level, 8.0 * (double)C.n, [&] {
+        ncclResult_t r = g_nccl.Broadcast(src, dst, (size_t)C.n, ncclDouble, 0, h->comm, h->stream);
+        if (r != ncclSuccess) rc = fail(h, MGB_ERR_COMM, "broadcast from rank 0: %s", g_nccl.GetErrorString(r));
+    }));
+    return rc;
+}
+
 // ---- smoothers ---------------------------------------------------------------------------------------
 int gs_sweep(mgb_handle* h, Level& L, double* v, const double* f)
 {
@@ -365,6 +480,7 @@ int smooth(mgb_handle* h, Level& L, double*& v, double*& o, const double* f, int
 {
     const double n = (double)L.n;
     for (int s = 0; s < nsweeps; ++s) {
+        TRY(exchange(h, L, v));                    // ghost entries of the current iterate
         if (h->smoother == MGB_SM_JACOBI_RJ) {
             if (!g_valid) {
                 EpiJacobiRJFirst epi{v, L.dinv, f, L.g, o, 1 - h->omega, h->omega};
@@ -388,6 +504,7 @@ int smooth(mgb_handle* h, Level& L, double*& v, double*& o, const double* f, int
 
 int residual(mgb_handle* h, Level& L, const double* v, const double* f, double* r)
 {
+    TRY(exchange(h, L, const_cast<double*>(v)));
     EpiResidual epi{f, r};
     return row_sums(h, MGB_K_RESIDUAL, L.level, bytes_rowsum(L.A, 3.0 * (double)L.n), L.A, v, epi);
 }
@@ -401,6 +518,7 @@ int restrict_to(mgb_handle* h, Level& L, const double* r_fine, double* f_coarse)
             if (nc > 0) k_gather<<<(int)((nc + 255) / 256), 256, 0, h->stream>>>((int)nc, L.inj, r_fine, f_coarse);
         });
     }
+    TRY(exchange(h, L, const_cast<double*>(r_fine)));
     EpiStore epi{f_coarse};
     return row_sums(h, MGB_K_RESTRICT, L.level, bytes_rowsum(L.R, (double)L.n + (double)nc), L.R, r_fine, epi);
 }
@@ -410,6 +528,7 @@ int residual_injected(mgb_handle* h, Level& L, const double* v, const double* f,
 {
     const int64_t nc = L.n_coarse;
     const double avg = L.A.nrows ? (double)L.A.nnz / (double)L.A.nrows : 0.0;
+    TRY(exchange(h, L, const_cast<double*>(v)));
     if (L.inj_desc && L.inj_fraction < 0.8 && h->stream_cfg > 0 && h->allow_stream) {
         // stream only the tiles of A that hold injected rows; every row of such a tile is summed, injected ones are stored
         const double nb = L.inj_fraction * (12.0 * (double)L.A.nnz + (4.0 + 8.0 + 4.0) * (double)L.n) + 8.0 * (double)L.n + 8.0 * (double)nc;
@@ -427,6 +546,8 @@ int residual_injected(mgb_handle* h, Level& L, const double* v, const double* f,
 
 int prolong_add(mgb_handle* h, Level& L, const double* e_coarse, double* v_fine, double* err)
 {
+    Level* C = find_level(h, L.level - 1);
+    if (C && !C->gathered && !C->stub) TRY(exchange(h, *C, const_cast<double*>(e_coarse)));   // gathered level: everybody has all of e
     EpiProlongAdd epi{v_fine, err};
     return row_sums(h, MGB_K_PROLONG_ADD, L.level, bytes_rowsum(L.P, (double)L.n_coarse + 2.0 * (double)L.n), L.P, e_coarse, epi);
 }
@@ -450,10 +571,17 @@ int coarse_apply(mgb_handle* h, Level& C, const double* f, double* u)
 
 int norm2_device(mgb_handle* h, int64_t n, const double* x, double* out_dev, int level)
 {
-    return launch(h, MGB_K_NORM, level, 8.0 * (double)n, [&] {
+    int rc = MGB_OK;
+    TRY(launch(h, MGB_K_NORM, level, 8.0 * (double)n, [&] {
         k_sumsq_partial<<<h->norm_blocks, 256, 0, h->stream>>>(n, x, h->d_partial);
-        k_sumsq_final<<<1, 1024, 0, h->stream>>>(h->norm_blocks, h->d_partial, out_dev);
-    });
+        k_sumsq_final<<<1, 1024, 0, h->stream>>>(h->norm_blocks, h->d_partial, out_dev, h->dist ? 0 : 1);
+        if (h->dist) {          // sum of squares over all row blocks, then the root
+            ncclResult_t r = g_nccl.AllReduce(out_dev, out_dev, 1, ncclDouble, ncclSum, h->comm, h->stream);
+            if (r != ncclSuccess) rc = fail(h, MGB_ERR_COMM, "allreduce: %s", g_nccl.GetErrorString(r));
+            k_sqrt_inplace<<<1, 1, 0, h->stream>>>(out_dev);
+        }
+    }));
+    return rc;
 }
 
 // ---- one V-cycle, enqueued on the stream (multigrid.py:231-268 unrolled into a down and an up sweep) ----
@@ -463,14 +591,18 @@ int enqueue_cycle(mgb_handle* h, int top, bool debug, double** v2h_ptr)
 {
     if (top == h->coarsest) {          // multigrid.py:238-241
         Level& C = h->levels[top];
+        if (C.stub) return fail(h, MGB_ERR_UNSUPPORTED, "level %d lives on rank 0 only", top);
         TRY(coarse_apply(h, C, C.f, C.vtmp));
         CU(cudaMemcpyAsync(C.v, C.vtmp, sizeof(double) * (size_t)C.n, cudaMemcpyDeviceToDevice, h->stream));
         return MGB_OK;
     }
+    if (h->dist && top <= h->gather_level) return fail(h, MGB_ERR_UNSUPPORTED, "in a row-sharded hierarchy the top level must be a sharded level");
     std::map<int, double*> cur, oth;
     std::map<int, bool> gv;
     const bool jacobi = h->smoother == MGB_SM_JACOBI_RJ || h->smoother == MGB_SM_JACOBI_A;
-    for (int l = top; l > h->coarsest; --l) {
+    // ranks other than 0 stop at the gathered level: everything below it runs on rank 0 only
+    const int bottom = h->coarsest;            // (on those ranks the gathered level IS the coarsest level they hold)
+    for (int l = top; l > bottom; --l) {
         Level& L = h->levels[l];
         Level& C = h->levels[l - 1];
         double* v = L.v; double* o = L.vtmp;
@@ -488,22 +620,31 @@ int enqueue_cycle(mgb_handle* h, int top, bool debug, double** v2h_ptr)
             }
         }
         TRY(smooth(h, L, v, o, L.f, sweeps, g_valid));                    // multigrid.py:243
+        double* fc = C.f + (C.gathered || C.stub ? C.my_off : 0);         // gathered level: this rank fills its slice
         if (L.r_mode == MGB_R_INJECTION && h->fuse_restrict && !debug) {
-            TRY(residual_injected(h, L, v, L.f, C.f));                     // multigrid.py:244 + :251
+            TRY(residual_injected(h, L, v, L.f, fc));                      // multigrid.py:244 + :251
         } else {
             TRY(residual(h, L, v, L.f, L.r));                              // multigrid.py:244
-            TRY(restrict_to(h, L, L.r, C.f));                              // multigrid.py:251-252
+            TRY(restrict_to(h, L, L.r, fc));                               // multigrid.py:251-252
         }
+        if (h->dist && l - 1 == h->gather_level) TRY(gather_to_root(h, C, C.f));
         cur[l] = v; oth[l] = o; gv[l] = g_valid;
     }
     Level& C0 = h->levels[h->coarsest];
-    TRY(coarse_apply(h, C0, C0.f, C0.v));                                  // multigrid.py:238-241
-    cur[h->coarsest] = C0.v;
-    for (int l = h->coarsest + 1; l <= top; ++l) {
+    if (!C0.stub) {
+        TRY(coarse_apply(h, C0, C0.f, C0.v));                              // multigrid.py:238-241
+        cur[h->coarsest] = C0.v;
+    }
+    for (int l = bottom + 1; l <= top; ++l) {
         Level& L = h->levels[l];
         double* v = cur[l]; double* o = oth[l];
         bool g_valid = gv[l];
         double* err = (debug && l == top) ? L.r : nullptr;
+        if (h->dist && l - 1 == h->gather_level) {                         // coarse-grid correction computed on rank 0
+            Level& C = h->levels[l - 1];
+            TRY(bcast_from_root(h, C, h->rank == 0 ? cur[l - 1] : C.v, C.v));
+            cur[l - 1] = C.v;
+        }
         TRY(prolong_add(h, L, cur[l - 1], v, err));                        // multigrid.py:258-260
         TRY(smooth(h, L, v, o, L.f, h->mu2, g_valid));                     // multigrid.py:261
         cur[l] = v;
@@ -653,10 +794,11 @@ int mgb_destroy(mgb_handle* h)
     for (auto& kv : h->levels) {
         Level& L = kv.second;
         free_csr(L.A); free_csr(L.RJ); free_csr(L.P); free_csr(L.R); free_csr(L.G);
-        cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.cmap); cudaFree(L.inj_desc); cudaFree(L.v); cudaFree(L.vtmp); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
+        cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.cmap); cudaFree(L.inj_desc); cudaFree(L.send_idx); cudaFree(L.send_buf); cudaFree(L.v); cudaFree(L.vtmp); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
         cudaFree(L.gs_order); cudaFree(L.gs_off); cudaFree(L.gs_diag);
     }
     cudaFree(h->coarse_inv); cudaFree(h->d_partial); cudaFree(h->d_hist);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (auto& pe : h->prof_events) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
     cudaStreamDestroy(h->stream);
     delete h;
@@ -675,6 +817,94 @@ int mgb_set_level(mgb_handle* h, int level, int64_t n, int64_t nnz, const void* 
     return MGB_OK;
 }
 
+int mgb_dist_unique_id(void* out, int capacity)
+{
+    mgb_handle* h = nullptr;
+    if (!out || capacity < (int)sizeof(ncclUniqueId)) return fail(h, MGB_ERR_INVALID, "unique id buffer needs %d bytes", (int)sizeof(ncclUniqueId));
+    if (const char* e = load_nccl()) return fail(h, MGB_ERR_COMM, "%s", e);
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(h, MGB_ERR_COMM, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+    std::memcpy(out, &id, sizeof id);
+    return MGB_OK;
+}
+
+int mgb_dist_init(mgb_handle* h, int rank, int world, const void* unique_id, int id_bytes)
+{
+    if (!h) return MGB_ERR_INVALID;
+    if (h->finalized || h->dist) return fail(h, MGB_ERR_STATE, "mgb_dist_init must be called once, before the hierarchy is finalized");
+    if (world < 1 || rank < 0 || rank >= world || !unique_id || id_bytes < (int)sizeof(ncclUniqueId)) return fail(h, MGB_ERR_INVALID, "bad rank/world/id");
+    if (const char* e = load_nccl()) return fail(h, MGB_ERR_COMM, "%s", e);
+    CU(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof id);
+    NC(g_nccl.CommInitRank(&h->comm, world, id, rank));
+    h->dist = true; h->rank = rank; h->world = world;
+    return MGB_OK;
+}
+
+int mgb_set_level_local(mgb_handle* h, int level, int64_t n_owned, int64_t n_ghost, int64_t nnz, const void* indptr, int indptr_bytes,
+                        const int32_t* indices, const double* values)
+{
+    if (!h) return MGB_ERR_INVALID;
+    if (h->finalized) return fail(h, MGB_ERR_STATE, "hierarchy already finalized");
+    if (n_ghost < 0) return fail(h, MGB_ERR_INVALID, "negative ghost count");
+    Level& L = h->levels[level];
+    L.level = level; L.n = n_owned; L.n_ghost = n_ghost;
+    std::string e = import_csr(L.A_host, n_owned, n_owned + n_ghost, nnz, indptr, indptr_bytes, indices, values);
+    if (!e.empty()) { h->levels.erase(level); return fail(h, MGB_ERR_INVALID, "level %d: %s", level, e.c_str()); }
+    return MGB_OK;
+}
+
+int mgb_set_halo(mgb_handle* h, int level, int npeers, const int32_t* peer_ranks, const int32_t* send_counts,
+                 const int32_t* send_indices, const int32_t* recv_counts)
+{
+    if (!h) return MGB_ERR_INVALID;
+    if (h->finalized) return fail(h, MGB_ERR_STATE, "hierarchy already finalized");
+    if (!h->dist) return fail(h, MGB_ERR_STATE, "mgb_dist_init first");
+    Level* L = find_level(h, level);
+    if (!L) return fail(h, MGB_ERR_STATE, "set level %d before its halo plan", level);
+    if (npeers < 0 || (npeers > 0 && (!peer_ranks || !send_counts || !recv_counts))) return fail(h, MGB_ERR_INVALID, "bad halo plan");
+    CU(cudaSetDevice(h->device));
+    L->peers.assign(peer_ranks, peer_ranks + npeers);
+    L->send_cnt.assign(send_counts, send_counts + npeers);
+    L->recv_cnt.assign(recv_counts, recv_counts + npeers);
+    int64_t st = 0, rt = 0;
+    for (int p = 0; p < npeers; ++p) {
+        if (peer_ranks[p] < 0 || peer_ranks[p] >= h->world || peer_ranks[p] == h->rank) return fail(h, MGB_ERR_INVALID, "bad peer rank %d", peer_ranks[p]);
+        st += send_counts[p]; rt += recv_counts[p];
+    }
+    if (rt != L->n_ghost) return fail(h, MGB_ERR_INVALID, "level %d: receive counts (%lld) do not add up to the ghost count (%lld)", level, (long long)rt, (long long)L->n_ghost);
+    for (int64_t k = 0; k < st; ++k)
+        if (send_indices[k] < 0 || send_indices[k] >= L->n) return fail(h, MGB_ERR_INVALID, "send index out of the owned range");
+    L->send_total = st;
+    cudaFree(L->send_idx); cudaFree(L->send_buf);
+    TRY(dev_upload(h, &L->send_idx, send_indices, (size_t)st));
+    TRY(dev_alloc(h, &L->send_buf, (size_t)st));
+    return MGB_OK;
+}
+
+int mgb_set_gather_level(mgb_handle* h, int level, int64_t n_global, const int64_t* offsets)
+{
+    if (!h) return MGB_ERR_INVALID;
+    if (h->finalized) return fail(h, MGB_ERR_STATE, "hierarchy already finalized");
+    if (!h->dist) return fail(h, MGB_ERR_STATE, "mgb_dist_init first");
+    if (!offsets || offsets[0] != 0 || offsets[h->world] != n_global) return fail(h, MGB_ERR_INVALID, "bad gather offsets");
+    Level* L = find_level(h, level);
+    if (h->rank == 0) {
+        if (!L || L->n != n_global || L->n_ghost != 0) return fail(h, MGB_ERR_STATE, "rank 0 must hold level %d completely before it is declared gathered", level);
+    } else {
+        if (L) return fail(h, MGB_ERR_STATE, "level %d must not be set on ranks other than 0", level);
+        L = &h->levels[level];
+        L->level = level; L->n = n_global; L->stub = true;
+    }
+    L->gathered = true;
+    L->gather_off.assign(offsets, offsets + h->world + 1);
+    L->my_off = offsets[h->rank]; L->my_cnt = offsets[h->rank + 1] - offsets[h->rank];
+    h->gather_level = level;
+    return MGB_OK;
+}
+
 int mgb_set_transfer(mgb_handle* h, int coarse_level, int64_t n_fine, int64_t n_coarse,
                      int64_t p_nnz, const void* p_indptr, int p_indptr_bytes, const int32_t* p_indices, const double* p_values,
                      int r_mode, int dim_for_fw, const int32_t* inj,
@@ -685,19 +915,23 @@ int mgb_set_transfer(mgb_handle* h, int coarse_level, int64_t n_fine, int64_t n_
     Level* F = find_level(h, coarse_level + 1);
     Level* C = find_level(h, coarse_level);
     if (!F || !C) return fail(h, MGB_ERR_STATE, "set levels %d and %d before their transfer", coarse_level, coarse_level + 1);
-    if (F->n != n_fine || C->n != n_coarse) return fail(h, MGB_ERR_INVALID, "transfer sizes (%lld, %lld) do not match the levels (%lld, %lld)",
-                                                        (long long)n_fine, (long long)n_coarse, (long long)F->n, (long long)C->n);
+    // sharded hierarchies: n_fine = owned fine rows; n_coarse = coarse rows this rank produces (its slice of a gathered
+    // level); P has one column per owned-or-ghost coarse entry, R / inj address owned-or-ghost fine entries
+    const int64_t nc_rows = (C->gathered || C->stub) ? C->my_cnt : C->n;
+    if (F->n != n_fine || nc_rows != n_coarse) return fail(h, MGB_ERR_INVALID, "transfer sizes (%lld, %lld) do not match the levels (%lld, %lld)",
+                                                           (long long)n_fine, (long long)n_coarse, (long long)F->n, (long long)nc_rows);
+    const int64_t p_cols = C->n + C->n_ghost, r_cols = F->n + F->n_ghost;
     if (r_mode < MGB_R_INJECTION || r_mode > MGB_R_EXPLICIT) return fail(h, MGB_ERR_INVALID, "bad r_mode %d", r_mode);
-    std::string e = import_csr(F->P_host, n_fine, n_coarse, p_nnz, p_indptr, p_indptr_bytes, p_indices, p_values);
+    std::string e = import_csr(F->P_host, n_fine, p_cols, p_nnz, p_indptr, p_indptr_bytes, p_indices, p_values);
     if (!e.empty()) return fail(h, MGB_ERR_INVALID, "P: %s", e.c_str());
     F->r_mode = r_mode; F->dim_fw = dim_for_fw; F->n_coarse = n_coarse;
     if (r_mode == MGB_R_INJECTION) {
         if (!inj) return fail(h, MGB_ERR_INVALID, "injection list is null");
         F->inj_host.assign(inj, inj + n_coarse);
         for (int64_t i = 0; i < n_coarse; ++i)
-            if (inj[i] < 0 || inj[i] >= n_fine) return fail(h, MGB_ERR_INVALID, "injection index out of range at %lld", (long long)i);
+            if (inj[i] < 0 || inj[i] >= n_fine) return fail(h, MGB_ERR_INVALID, "injection index out of range (or not owned by this rank) at %lld", (long long)i);
     } else if (r_mode == MGB_R_EXPLICIT) {
-        e = import_csr(F->R_host, n_coarse, n_fine, r_nnz, r_indptr, r_indptr_bytes, r_indices, r_values);
+        e = import_csr(F->R_host, n_coarse, r_cols, r_nnz, r_indptr, r_indptr_bytes, r_indices, r_values);
         if (!e.empty()) return fail(h, MGB_ERR_INVALID, "R: %s", e.c_str());
     } else if (dim_for_fw != 2 && dim_for_fw != 3 && r_mode == MGB_R_FULL_WEIGHTING) {
         return fail(h, MGB_ERR_INVALID, "dim_for_fw must be 2 or 3");
@@ -753,9 +987,19 @@ int mgb_finalize(mgb_handle* h)
     }
     if (h->opt_iter && h->opt_iter != 1 && h->opt_iter != 2) return fail(h, MGB_ERR_INVALID, "tile_iter must be 1 or 2");
     if (h->opt_lpr && (h->opt_lpr & (h->opt_lpr - 1) || h->opt_lpr > 32)) return fail(h, MGB_ERR_INVALID, "lanes_per_row must be a power of two <= 32");
+    if (h->dist && h->smoother >= MGB_SM_GS_LEVEL)
+        return fail(h, MGB_ERR_UNSUPPORTED, "Gauss-Seidel smoothers are single-GPU only in this version (see DESIGN.md, multi-GPU)");
     for (auto& kv : h->levels) {
         Level& L = kv.second;
         const size_t n = (size_t)L.n;
+        if (L.stub) {                       // gathered level on a rank other than 0: vectors only
+            const size_t np = n + 16;
+            TRY(dev_alloc(h, &L.v, np)); TRY(dev_alloc(h, &L.f, np));
+            for (double* p : {L.v, L.f}) CU(cudaMemsetAsync(p, 0, np * sizeof(double), h->stream));
+            continue;
+        }
+        if (h->dist && L.has_transfer && (L.r_mode == MGB_R_FULL_WEIGHTING || L.r_mode == MGB_R_TRANSPOSE))
+            return fail(h, MGB_ERR_UNSUPPORTED, "row-sharded levels need the restriction rows explicitly (MGB_R_EXPLICIT) or injection");
         TRY(upload_csr(h, L.A_host, L.A));
         {
             HostCsr RJ; std::vector<double> dinv;
@@ -811,12 +1055,12 @@ int mgb_finalize(mgb_handle* h)
                 TRY(upload_csr(h, L.R_host, L.R));
             }
         }
-        const size_t np = n + 16;         // tail padding: bulk copies of operand slices round up to 16 bytes
+        const size_t np = n + (size_t)L.n_ghost + 16;   // [owned | ghost | tail padding for 16-byte bulk copies]
         TRY(dev_alloc(h, &L.v, np)); TRY(dev_alloc(h, &L.vtmp, np)); TRY(dev_alloc(h, &L.f, np));
         TRY(dev_alloc(h, &L.r, np)); TRY(dev_alloc(h, &L.g, np));
         for (double* p : {L.v, L.vtmp, L.f, L.r, L.g}) CU(cudaMemsetAsync(p, 0, np * sizeof(double), h->stream));
     }
-    {   // dense inverse of the coarsest matrix: replaces spsolve (multigrid.py:239)
+    if (!h->levels[h->coarsest].stub) {   // dense inverse of the coarsest matrix: replaces spsolve (multigrid.py:239)
         Level& C = h->levels[h->coarsest];
         if (C.n > 8192) return fail(h, MGB_ERR_UNSUPPORTED, "coarsest level has %lld rows; the dense coarse solver is limited to 8192 (add levels)", (long long)C.n);
         if (!dense_inverse(C.A_host, h->coarse_inv_host)) return fail(h, MGB_ERR_SINGULAR, "coarsest matrix is singular");

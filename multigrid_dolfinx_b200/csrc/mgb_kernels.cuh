@@ -513,7 +513,7 @@ k_sumsq_partial(int64_t n, const double* __restrict__ x, double* __restrict__ pa
         partial[blockIdx.x] = t;
     }
 }
-__global__ void k_sumsq_final(int nb, const double* __restrict__ partial, double* __restrict__ out)
+__global__ void k_sumsq_final(int nb, const double* __restrict__ partial, double* __restrict__ out, int take_root)
 {
     __shared__ double sh[32];
     double s = 0.0;
@@ -525,7 +525,7 @@ __global__ void k_sumsq_final(int nb, const double* __restrict__ partial, double
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
-        *out = sqrt(t);
+        *out = take_root ? sqrt(t) : t;
     }
 }
 

@@ -82,7 +82,36 @@ class MGEngine:
                                          ix.ctypes.data, ax.ctypes.data))
         self.n[int(level)] = n
 
-    def set_transfer(self, coarse_level, P, r_mode="injection", inj=None, R=None, dim=2):
+    # -- row-sharded hierarchies (one engine per rank; see dist.py) -----------------------------------------
+    def dist_unique_id(self):
+        buf = C.create_string_buffer(256)
+        rc = self._lib.mgb_dist_unique_id(buf, 256)
+        if rc != L.OK:
+            raise L.MGBError(rc, self._lib.mgb_last_error(None).decode())
+        return bytes(buf.raw)
+
+    def dist_init(self, rank, world, unique_id):
+        self._ck(self._lib.mgb_dist_init(self._h, int(rank), int(world), unique_id, len(unique_id)))
+
+    def set_level_local(self, level, A_local, n_owned, n_ghost):
+        ip, ix, ax = _as_csr_arrays(A_local)
+        self._ck(self._lib.mgb_set_level_local(self._h, int(level), int(n_owned), int(n_ghost), len(ax), ip.ctypes.data,
+                                               ip.dtype.itemsize, ix.ctypes.data, ax.ctypes.data))
+        self.n[int(level)] = int(n_owned)
+
+    def set_halo(self, level, peers, send_idx, recv_cnt):
+        peers_a = np.ascontiguousarray(peers, dtype=np.int32)
+        sc = np.ascontiguousarray([len(x) for x in send_idx], dtype=np.int32)
+        si = np.ascontiguousarray(np.concatenate(send_idx) if len(send_idx) else np.zeros(0), dtype=np.int32)
+        rc = np.ascontiguousarray(recv_cnt, dtype=np.int32)
+        self._ck(self._lib.mgb_set_halo(self._h, int(level), len(peers_a), peers_a.ctypes.data, sc.ctypes.data, si.ctypes.data, rc.ctypes.data))
+
+    def set_gather_level(self, level, n_global, offsets):
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._ck(self._lib.mgb_set_gather_level(self._h, int(level), int(n_global), off.ctypes.data))
+        self.n.setdefault(int(level), int(n_global))
+
+    def set_transfer(self, coarse_level, P, r_mode="injection", inj=None, R=None, dim=2, n_fine=None, n_coarse_rows=None):
         pip, pix, pax = _as_csr_arrays(P)
         mode = L.R_MODES[r_mode] if isinstance(r_mode, str) else int(r_mode)
         injp = None
@@ -93,7 +122,9 @@ class MGEngine:
         if R is not None:
             rip, rix, rax = _as_csr_arrays(R)
             rargs = (len(rax), rip.ctypes.data, rip.dtype.itemsize, rix.ctypes.data, rax.ctypes.data)
-        self._ck(self._lib.mgb_set_transfer(self._h, int(coarse_level), P.shape[0], P.shape[1], len(pax), pip.ctypes.data,
+        nf = P.shape[0] if n_fine is None else int(n_fine)
+        ncr = P.shape[1] if n_coarse_rows is None else int(n_coarse_rows)
+        self._ck(self._lib.mgb_set_transfer(self._h, int(coarse_level), nf, ncr, len(pax), pip.ctypes.data,
                                             pip.dtype.itemsize, pix.ctypes.data, pax.ctypes.data, mode, int(dim), injp, *rargs))
 
     def set_params(self, omega=2.0 / 3.0, mu1=2, mu2=2, smoother="jacobi"):
@@ -185,7 +216,7 @@ class MGEngine:
         fp, memf, keepf = self._in(f, n, "f")
         if mem != memf:
             raise ValueError("v and f must both be numpy arrays or both be CUDA tensors")
-        if vv.size != n if not _is_torch(v) else vv.numel() != n:
+        if (vv.numel() if _is_torch(v) else vv.size) != n:
             raise ValueError(f"v: expected {n} entries")
         hist = np.zeros(ncycles) if history else None
         self._ck(self._lib.mgb_vcycle(self._h, int(level), vp, fp, mem, int(ncycles), hist.ctypes.data if history else None))

@@ -277,16 +277,27 @@ def rhs_p1(m, dim, perm=None):
 # grid transfers in matrix form
 # --------------------------------------------------------------------------------------------
 
-def prolongation(Nc, dim, perm_c=None, perm_f=None):
+def prolongation(Nc, dim, perm_c=None, perm_f=None, rows=None):
     """P (n_f x n_c): tensor-product linear interpolation, the matrix of ``Interpolation2D``
     (multigrid.py:59-120; 3-D is its tensor-product extension).
 
     Row entries are stored in the reference's summation order -- (i-,j-), (i+,j-), (i-,j+), (i+,j+),
     x fastest (multigrid.py:109-118) -- NOT sorted by column, so that a sequential row sum
-    reproduces the reference's result bit for bit (weights are powers of two)."""
+    reproduces the reference's result bit for bit (weights are powers of two).
+
+    ``rows`` (lexicographic numbering only): (start, stop) -> only those rows of P (shape (stop-start, n_c))."""
     Nf = 2 * Nc - 1
-    nf, nc = Nf ** dim, Nc ** dim
-    mi = node_multi_index(Nf, dim)
+    nc = Nc ** dim
+    if rows is None:
+        nf = Nf ** dim
+        mi = node_multi_index(Nf, dim)
+    else:
+        assert perm_c is None and perm_f is None
+        nf = rows[1] - rows[0]
+        t = np.arange(rows[0], rows[1], dtype=np.int64)
+        mi = []
+        for _ in range(dim):
+            mi.append(t % Nf); t = t // Nf
     ncomb = 2 ** dim
     cols = np.zeros((nf, ncomb), dtype=np.int64)
     wts = np.ones((nf, ncomb), dtype=np.float64)
