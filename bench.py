@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--gather-threshold", type=int, default=300000)
     ap.add_argument("--use-graph", type=int, default=1)
+    ap.add_argument("--device-gen", type=int, default=1, help="generate the sharded levels on the device (structured workloads)")
     ap.add_argument("--restriction", default="injection", choices=["injection", "full_weighting", "transpose"])
     ap.add_argument("--smoother", default="jacobi", choices=["jacobi", "jacobi_a", "gs", "gs_color"])
     ap.add_argument("--fuse-restrict", type=int, default=1)
@@ -244,7 +245,7 @@ def main():
         args.workload = "cfg5h" if multi else "cfg2"
     if args.impl == "reference":
         return run_reference(args)
-    if multi:
+    if multi or args.workload == "cfg5":          # 513^3 never exists on the host: same code path as the sharded arm, world = 1
         from multigrid_dolfinx_b200 import dist_bench
         return dist_bench.run(args)
     return run_single(args)

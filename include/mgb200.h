@@ -73,7 +73,14 @@ enum {
     MGB_ART_R_INDPTR = 10,     /* int32[n_c+1] restriction CSR built from P (FULL_WEIGHTING/TRANSPOSE) */
     MGB_ART_R_INDICES = 11,
     MGB_ART_R_VALUES = 12,
-    MGB_ART_COARSE_INVERSE = 13 /* double[n_c*n_c] row-major dense inverse of the coarsest matrix  */
+    MGB_ART_COARSE_INVERSE = 13,/* double[n_c*n_c] row-major dense inverse of the coarsest matrix  */
+    MGB_ART_A_INDPTR = 14,     /* the level matrix as held on the device (checks the device-side generator) */
+    MGB_ART_A_INDICES = 15,
+    MGB_ART_A_VALUES = 16,
+    MGB_ART_P_INDPTR = 17,     /* interpolation rows of this level (fine side)                     */
+    MGB_ART_P_INDICES = 18,
+    MGB_ART_P_VALUES = 19,
+    MGB_ART_INJECTION = 20     /* int32[n_c] injection list of this level (fine side)              */
 };
 
 /* per-level device buffers (mgb_level_buffer) */
@@ -135,6 +142,17 @@ int mgb_set_halo(mgb_handle* h, int level, int npeers, const int32_t* peer_ranks
  * right-hand side each rank produces when restricting from level+1.  On rank 0 the level must already be set in
  * full (mgb_set_level); on other ranks it must not be set at all. */
 int mgb_set_gather_level(mgb_handle* h, int level, int64_t n_global, const int64_t* offsets);
+
+/* ---- device-side input generation (stand-in for the host assembly of Multigrid_prototype.py:62-118) ------ */
+/* Generates rows [row_begin, row_end) of the synthetic P1 Poisson matrix (unit square / cube, lexicographic DOFs,
+ * dolfinx-shaped pattern with stored zeros, Dirichlet rows) straight into device CSR -- bit-identical to
+ * multigrid_dolfinx_b200.problems.stencil_p1.  Columns are numbered [owned | ghost_lo..row_begin | row_end..ghost_hi).
+ * R_omega / D^-1 (multigrid.py:48-56) are then also built on the device at mgb_finalize. */
+int mgb_synth_poisson_level(mgb_handle* h, int level, int dim, int cells_per_dim, int64_t row_begin, int64_t row_end,
+                            int64_t ghost_lo, int64_t ghost_hi);
+/* Interpolation rows (matrix of Interpolation2D, multigrid.py:59-120; tensor product in 3-D) of the generated level
+ * coarse_level+1 and the injection list (multigrid.py:128-131) of the coarse rows [inj_coarse_begin, inj_coarse_end). */
+int mgb_synth_poisson_transfer(mgb_handle* h, int coarse_level, int64_t inj_coarse_begin, int64_t inj_coarse_end);
 
 /* mu1, mu2, omega (multigrid.py:19-21), smoother = MGB_SM_* */
 int mgb_set_params(mgb_handle* h, double omega, int mu1, int mu2, int smoother);

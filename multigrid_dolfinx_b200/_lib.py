@@ -19,7 +19,8 @@ SM_JACOBI_RJ, SM_JACOBI_A, SM_GS_LEVEL, SM_GS_MULTICOLOR = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 (ART_RJ_INDPTR, ART_RJ_INDICES, ART_RJ_VALUES, ART_DINV, ART_LEVEL_OF_ROW, ART_LEVEL_ORDER, ART_LEVEL_OFFSETS,
  ART_COLOUR_OF_ROW, ART_COLOUR_ORDER, ART_COLOUR_OFFSETS, ART_R_INDPTR, ART_R_INDICES, ART_R_VALUES,
- ART_COARSE_INVERSE) = range(14)
+ ART_COARSE_INVERSE, ART_A_INDPTR, ART_A_INDICES, ART_A_VALUES, ART_P_INDPTR, ART_P_INDICES, ART_P_VALUES,
+ ART_INJECTION) = range(21)
 BUF_V, BUF_F, BUF_R = 0, 1, 2
 KERNEL_KINDS = ["jacobi", "residual", "restrict", "prolong_add", "coarse", "init_guess", "gs", "norm", "spmv", "halo", "copy"]
 
@@ -47,6 +48,8 @@ SYMBOLS = {
     "mgb_set_level_local": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i, _vp, _vp]),
     "mgb_set_halo": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "mgb_set_gather_level": (_i, [_vp, _i, _i64, _vp]),
+    "mgb_synth_poisson_level": (_i, [_vp, _i, _i, _i, _i64, _i64, _i64, _i64]),
+    "mgb_synth_poisson_transfer": (_i, [_vp, _i, _i64, _i64]),
     "mgb_set_params": (_i, [_vp, _d, _i, _i, _i]),
     "mgb_set_option": (_i, [_vp, C.c_char_p, _d]),
     "mgb_finalize": (_i, [_vp]),

@@ -2,6 +2,7 @@
 // behind the C ABI of include/mgb200.h.  One handle = one device + one stream; the whole cycle is a
 // fixed sequence of launches, captured once per top level into a CUDA graph and replayed.
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -57,6 +58,9 @@ struct Level {
     // ---- row-sharded (multi-GPU) state: this rank owns n rows; vectors hold n + n_ghost entries, ghosts last
     int64_t n_ghost = 0;
     bool stub = false;               // gathered level on a non-root rank: full-size vectors, no operators
+    bool device_born = false;        // operators were generated on the device (mgb_synth_*): no host copy exists
+    int syn_dim = 0, syn_m = 0;      // geometry of a generated level
+    int64_t row_begin = 0, row_end = 0, ghost_lo = 0, ghost_hi = 0;   // global row range owned / ghost ranges around it
     bool gathered = false;           // first level that lives on rank 0 only; every rank owns a slice of its RHS
     int64_t my_off = 0, my_cnt = 0;  // this rank's slice of the gathered level
     std::vector<int64_t> gather_off; // world + 1 offsets of all slices
@@ -183,29 +187,21 @@ StreamChoice stream_choice(int cfg)
 }
 
 // Upload a host CSR and choose the kernel family / tile shape for it.
-int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int32_t>& breaks = {})
+// Kernel family, row tiles and stream descriptors of an operator whose arrays are already on the device.
+// Needs only the row pointers on the host (ip).
+int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const std::vector<int32_t>& breaks = {})
 {
-    const int64_t n = M.nrows, nnz = M.nnz();
-    if (n >= (int64_t)2147483000 || nnz >= (int64_t)2147483000)
-        return fail(h, MGB_ERR_UNSUPPORTED, "operator with %lld rows / %lld entries exceeds the int32 row-pointer range of one device shard",
-                    (long long)n, (long long)nnz);
-    D.nrows = n; D.ncols = M.ncols; D.nnz = nnz;
-    std::vector<int32_t> rp((size_t)n + 1);
+    const int64_t n = D.nrows, nnz = D.nnz;
     int mx = 0;
-    for (int64_t i = 0; i <= n; ++i) rp[i] = (int32_t)M.ip[i];
-    for (int64_t i = 0; i < n; ++i) mx = std::max<int>(mx, rp[i + 1] - rp[i]);
+    for (int64_t i = 0; i < n; ++i) mx = std::max<int>(mx, (int)(ip[i + 1] - ip[i]));
     D.max_row = mx;
-    TRY(dev_upload(h, &D.rowptr, rp.data(), rp.size(), 8));
-    TRY(dev_upload(h, &D.cols, M.ix.data(), (size_t)nnz, 16));   // padding: the last 8-wide group may read past nnz
-    TRY(dev_upload(h, &D.vals, M.ax.data(), (size_t)nnz, 16));
-    // family
     int family = h->opt_family;
     if (family == 0) family = 1;
     int iter = h->opt_iter ? h->opt_iter : 1;
     if (family == 1) {
         std::vector<int32_t> tiles;
-        bool ok = make_tiles(M.ip, tile_cap(iter), 4 * THREADS, breaks, tiles, &D.break_tile);
-        if (!ok && !h->opt_iter) { iter = 2; ok = make_tiles(M.ip, tile_cap(iter), 4 * THREADS, breaks, tiles, &D.break_tile); }
+        bool ok = make_tiles(ip, tile_cap(iter), 4 * THREADS, breaks, tiles, &D.break_tile);
+        if (!ok && !h->opt_iter) { iter = 2; ok = make_tiles(ip, tile_cap(iter), 4 * THREADS, breaks, tiles, &D.break_tile); }
         if (ok) {
             D.ntiles = (int)tiles.size() - 1;
             TRY(dev_upload(h, &D.tiles, tiles.data(), tiles.size()));
@@ -218,11 +214,11 @@ int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int
         const StreamChoice sc = stream_choice(h->stream_cfg);
         const int cap = sc.threads * sc.ept;
         std::vector<int32_t> st;
-        if (make_tiles(M.ip, cap, cap / 4, {}, st, nullptr, 4)) {
+        if (make_tiles(ip, cap, cap / 4, {}, st, nullptr, 4)) {
             std::vector<int4> desc(st.size() - 1);
             for (size_t t = 0; t + 1 < st.size(); ++t) {
                 const int64_t r0 = st[t], r1 = st[t + 1];
-                const int64_t z0 = M.ip[r0] & ~(int64_t)7, z1 = M.ip[r1];
+                const int64_t z0 = ip[r0] & ~(int64_t)7, z1 = ip[r1];
                 desc[t] = make_int4((int)r0, (int)(r1 - r0), (int)z0, (int)((z1 - z0 + 7) & ~(int64_t)7));
             }
             D.sntiles = (int)desc.size();
@@ -244,6 +240,34 @@ int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int
     }
     return MGB_OK;
 }
+
+// Upload a host CSR and choose the kernel family / tile shape for it.
+int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int32_t>& breaks = {})
+{
+    const int64_t n = M.nrows, nnz = M.nnz();
+    if (n >= (int64_t)2147483000 || nnz >= (int64_t)2147483000)
+        return fail(h, MGB_ERR_UNSUPPORTED, "operator with %lld rows / %lld entries exceeds the int32 row-pointer range of one device shard",
+                    (long long)n, (long long)nnz);
+    D.nrows = n; D.ncols = M.ncols; D.nnz = nnz;
+    std::vector<int32_t> rp((size_t)n + 1);
+    for (int64_t i = 0; i <= n; ++i) rp[i] = (int32_t)M.ip[i];
+    TRY(dev_upload(h, &D.rowptr, rp.data(), rp.size(), 8));
+    TRY(dev_upload(h, &D.cols, M.ix.data(), (size_t)nnz, 16));   // padding: the last 8-wide group may read past nnz
+    TRY(dev_upload(h, &D.vals, M.ax.data(), (size_t)nnz, 16));
+    return finish_csr(h, D, M.ip, breaks);
+}
+
+// Row pointers of a device-resident operator back on the host (int64), for finish_csr.
+int fetch_rowptr(mgb_handle* h, const DevCsr& D, std::vector<int64_t>& ip)
+{
+    std::vector<int32_t> rp((size_t)D.nrows + 1);
+    CU(cudaMemcpyAsync(rp.data(), D.rowptr, rp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    ip.assign(rp.begin(), rp.end());
+    return MGB_OK;
+}
+
+#include "mgb_synth.cuh"
 
 // ---- launch bookkeeping -------------------------------------------------------------------------------
 template <class F>
@@ -817,6 +841,75 @@ int mgb_set_level(mgb_handle* h, int level, int64_t n, int64_t nnz, const void* 
     return MGB_OK;
 }
 
+int mgb_synth_poisson_level(mgb_handle* h, int level, int dim, int cells_per_dim, int64_t row_begin, int64_t row_end,
+                            int64_t ghost_lo, int64_t ghost_hi)
+{
+    if (!h) return MGB_ERR_INVALID;
+    if (h->finalized) return fail(h, MGB_ERR_STATE, "hierarchy already finalized");
+    if ((dim != 2 && dim != 3) || cells_per_dim < 2) return fail(h, MGB_ERR_INVALID, "dim must be 2 or 3, cells per dim >= 2");
+    const SynthGeom g = make_geom(dim, cells_per_dim);
+    if (row_begin < 0 || row_end > g.n || row_begin > row_end || ghost_lo < 0 || ghost_lo > row_begin || ghost_hi < row_end || ghost_hi > g.n)
+        return fail(h, MGB_ERR_INVALID, "bad row / ghost ranges");
+    const int64_t band = g.lin[g.noff - 1];
+    if ((row_begin - ghost_lo < band && ghost_lo > 0) || (ghost_hi - row_end < band && ghost_hi < g.n))
+        return fail(h, MGB_ERR_INVALID, "ghost ranges must cover the matrix bandwidth (%lld rows) or reach the ends", (long long)band);
+    CU(cudaSetDevice(h->device));
+    Level& L = h->levels[level];
+    if (L.A.present()) return fail(h, MGB_ERR_STATE, "level %d already set", level);
+    const int64_t n = row_end - row_begin;
+    if (n >= 2147483000LL) return fail(h, MGB_ERR_UNSUPPORTED, "more than 2^31 rows in one shard");
+    L.level = level; L.n = n; L.n_ghost = (row_begin - ghost_lo) + (ghost_hi - row_end);
+    L.device_born = true; L.syn_dim = dim; L.syn_m = cells_per_dim;
+    L.row_begin = row_begin; L.row_end = row_end; L.ghost_lo = ghost_lo; L.ghost_hi = ghost_hi;
+    const int nr = (int)n;
+    TRY(dev_alloc(h, &L.A.rowptr, (size_t)n + 1 + 8));
+    CU(cudaMemsetAsync(L.A.rowptr, 0, ((size_t)n + 1 + 8) * sizeof(int32_t), h->stream));
+    if (nr > 0) k_synth_a_count<<<(nr + 255) / 256, 256, 0, h->stream>>>(g, row_begin, nr, L.A.rowptr);
+    TRY(scan_counts(h, L.A.rowptr, n + 1));
+    TRY(alloc_csr_from_counts(h, L.A, n, n + L.n_ghost));
+    const ColMap cm{row_begin, row_end, ghost_lo};
+    if (nr > 0) k_synth_a_fill<<<(nr + 255) / 256, 256, 0, h->stream>>>(g, row_begin, nr, L.A.rowptr, L.A.cols, L.A.vals, cm);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    return MGB_OK;
+}
+
+int mgb_synth_poisson_transfer(mgb_handle* h, int coarse_level, int64_t inj_coarse_begin, int64_t inj_coarse_end)
+{
+    if (!h) return MGB_ERR_INVALID;
+    if (h->finalized) return fail(h, MGB_ERR_STATE, "hierarchy already finalized");
+    Level* F = find_level(h, coarse_level + 1);
+    Level* C = find_level(h, coarse_level);
+    if (!F || !C || !F->device_born) return fail(h, MGB_ERR_STATE, "generate level %d (mgb_synth_poisson_level) and set level %d first", coarse_level + 1, coarse_level);
+    if (F->syn_m % 2) return fail(h, MGB_ERR_INVALID, "fine level has an odd number of cells per dimension");
+    CU(cudaSetDevice(h->device));
+    const int dim = F->syn_dim, Nf = F->syn_m + 1, Nc = F->syn_m / 2 + 1;
+    int64_t nc_glob = 1; for (int d = 0; d < dim; ++d) nc_glob *= Nc;
+    ColMap cm{0, nc_glob, 0};                       // coarse level held in full (single GPU, or gathered on rank 0)
+    int64_t expect_rows = (C->gathered || C->stub) ? C->my_cnt : C->n;
+    if (C->device_born) cm = ColMap{C->row_begin, C->row_end, C->ghost_lo};
+    else if (C->n != nc_glob) return fail(h, MGB_ERR_INVALID, "coarse level %d has %lld rows, the nested grid has %lld", coarse_level, (long long)C->n, (long long)nc_glob);
+    const int64_t ncr = inj_coarse_end - inj_coarse_begin;
+    if (ncr != expect_rows) return fail(h, MGB_ERR_INVALID, "this rank must produce %lld coarse rows, got %lld", (long long)expect_rows, (long long)ncr);
+    const int nr = (int)F->n;
+    TRY(dev_alloc(h, &F->P.rowptr, (size_t)F->n + 1 + 8));
+    CU(cudaMemsetAsync(F->P.rowptr, 0, ((size_t)F->n + 1 + 8) * sizeof(int32_t), h->stream));
+    if (nr > 0) k_synth_p_count<<<(nr + 255) / 256, 256, 0, h->stream>>>(dim, Nf, F->row_begin, nr, F->P.rowptr);
+    TRY(scan_counts(h, F->P.rowptr, F->n + 1));
+    TRY(alloc_csr_from_counts(h, F->P, F->n, C->n + C->n_ghost));
+    if (nr > 0) k_synth_p_fill<<<(nr + 255) / 256, 256, 0, h->stream>>>(dim, Nf, Nc, F->row_begin, nr, F->P.rowptr, F->P.cols, F->P.vals, cm);
+    TRY(dev_alloc(h, &F->inj, (size_t)ncr + 16));
+    if (ncr > 0) k_synth_inj<<<(int)((ncr + 255) / 256), 256, 0, h->stream>>>(dim, Nf, Nc, inj_coarse_begin, (int)ncr, F->row_begin, F->inj);
+    CU(cudaGetLastError());
+    F->inj_host.resize((size_t)ncr);
+    CU(cudaMemcpyAsync(F->inj_host.data(), F->inj, sizeof(int32_t) * (size_t)ncr, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < ncr; ++i)
+        if (F->inj_host[i] < 0 || F->inj_host[i] >= F->n) return fail(h, MGB_ERR_INVALID, "row blocks are not aligned with the injection map");
+    F->r_mode = MGB_R_INJECTION; F->n_coarse = ncr; F->has_transfer = true;
+    return MGB_OK;
+}
+
 int mgb_dist_unique_id(void* out, int capacity)
 {
     mgb_handle* h = nullptr;
@@ -1000,8 +1093,14 @@ int mgb_finalize(mgb_handle* h)
         }
         if (h->dist && L.has_transfer && (L.r_mode == MGB_R_FULL_WEIGHTING || L.r_mode == MGB_R_TRANSPOSE))
             return fail(h, MGB_ERR_UNSUPPORTED, "row-sharded levels need the restriction rows explicitly (MGB_R_EXPLICIT) or injection");
-        TRY(upload_csr(h, L.A_host, L.A));
-        {
+        if (L.device_born) {
+            if (h->smoother >= MGB_SM_GS_LEVEL) return fail(h, MGB_ERR_UNSUPPORTED, "Gauss-Seidel needs the host copy of the level matrix; generated levels have none");
+            std::vector<int64_t> ip;
+            TRY(fetch_rowptr(h, L.A, ip));
+            TRY(finish_csr(h, L.A, ip));
+            TRY(build_rj_device(h, L));                                        // multigrid.py:48-56 on the device
+        } else {
+            TRY(upload_csr(h, L.A_host, L.A));
             HostCsr RJ; std::vector<double> dinv;
             if (!build_rj(L.A_host, h->rj_reversed != 0, RJ, dinv))            // multigrid.py:48-56
                 return fail(h, MGB_ERR_SINGULAR, "level %d: zero or missing diagonal entry", kv.first);
@@ -1031,9 +1130,15 @@ int mgb_finalize(mgb_handle* h)
             TRY(dev_upload(h, &L.gs_diag, dperm.data(), n));
         }
         if (L.has_transfer) {
-            TRY(upload_csr(h, L.P_host, L.P));
+            if (L.device_born) {
+                std::vector<int64_t> ip;
+                TRY(fetch_rowptr(h, L.P, ip));
+                TRY(finish_csr(h, L.P, ip));
+            } else {
+                TRY(upload_csr(h, L.P_host, L.P));
+            }
             if (L.r_mode == MGB_R_INJECTION) {
-                TRY(dev_upload(h, &L.inj, L.inj_host.data(), L.inj_host.size()));
+                if (!L.device_born) TRY(dev_upload(h, &L.inj, L.inj_host.data(), L.inj_host.size()));
                 if (!L.A.sdesc_host.empty()) {
                     std::vector<int32_t> cmap(n + 16, -1);
                     for (size_t c = 0; c < L.inj_host.size(); ++c) cmap[(size_t)L.inj_host[c]] = (int32_t)c;
@@ -1240,6 +1345,13 @@ int mgb_get_artifact(mgb_handle* h, int level, int kind, void* out, int64_t capa
         case MGB_ART_R_INDPTR: src = L->R.rowptr; bytes = L->R.present() ? (L->R.nrows + 1) * 4 : 0; break;
         case MGB_ART_R_INDICES: src = L->R.cols; bytes = L->R.nnz * 4; break;
         case MGB_ART_R_VALUES: src = L->R.vals; bytes = L->R.nnz * 8; break;
+        case MGB_ART_A_INDPTR: src = L->A.rowptr; bytes = L->A.present() ? (L->A.nrows + 1) * 4 : 0; break;
+        case MGB_ART_A_INDICES: src = L->A.cols; bytes = L->A.nnz * 4; break;
+        case MGB_ART_A_VALUES: src = L->A.vals; bytes = L->A.nnz * 8; break;
+        case MGB_ART_P_INDPTR: src = L->P.rowptr; bytes = L->P.present() ? (L->P.nrows + 1) * 4 : 0; break;
+        case MGB_ART_P_INDICES: src = L->P.cols; bytes = L->P.nnz * 4; break;
+        case MGB_ART_P_VALUES: src = L->P.vals; bytes = L->P.nnz * 8; break;
+        case MGB_ART_INJECTION: src = L->inj; bytes = L->inj ? L->n_coarse * 4 : 0; break;
         case MGB_ART_COARSE_INVERSE:
             src = h->coarse_inv_host.data(); bytes = (int64_t)h->coarse_inv_host.size() * 8; on_device = false; break;
         default: return fail(h, MGB_ERR_INVALID, "unknown artefact kind %d", kind);

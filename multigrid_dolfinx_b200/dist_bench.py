@@ -29,20 +29,34 @@ def run(args):
     local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
     torch.cuda.set_device(local_rank)
-    td.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    multi = world > 1
+    if multi:
+        td.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if multi:
+            td.barrier()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if multi:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
     name = args.workload if args.workload in DIST_WORKLOADS else "cfg5h"
     dim, c, lc, lf, desc = DIST_WORKLOADS[name]
     t0 = time.perf_counter()
     src = ds.StructuredSource(dim, c, lc, lf)
     mg = ds.DistMG(src, device=local_rank, r_mode=args.restriction, smoother=args.smoother, gather_threshold=args.gather_threshold,
-                   options={"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg, "use_graph": args.use_graph})
+                   options={"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg, "use_graph": args.use_graph},
+                   device_gen=bool(args.device_gen) and args.restriction == "injection")
     setup_s = time.perf_counter() - t0
     eng = mg.eng
     stream = eng.torch_stream()
     dofu = mg.dof_updates_per_cycle()
     mg.load_rhs()
     mg.cycles(args.warmup)
-    eng.synchronize(); td.barrier(); torch.cuda.synchronize()
+    eng.synchronize(); barrier(); torch.cuda.synchronize()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with B.ClockSampler(local_rank) as clk:
@@ -51,12 +65,10 @@ def run(args):
         e1.record(stream)
         torch.cuda.synchronize()
         launches = eng.launch_count() - l0
-        td.barrier()
+        barrier()
         if args.steps * 2e-3 < 1.0:
             mg.cycles(200); torch.cuda.synchronize()
-    ms_local = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
-    td.all_reduce(ms_local, op=td.ReduceOp.MAX)
-    ms = float(ms_local.item())
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     hist = mg.cycles(1, history=True)
 
     # dominant kernel on rank 0, event-timed (all ranks run the same cycles: the halo exchanges are collective)
@@ -65,19 +77,17 @@ def run(args):
     # end to end through the C ABI with pinned host buffers (each rank stages its own row block)
     n_loc = mg.n_local
     vp = torch.zeros(n_loc, dtype=torch.float64).pin_memory()
-    fp = torch.from_numpy(np.ascontiguousarray(mg.local["levels"][lf].rhs)).pin_memory()
+    fp = torch.from_numpy(np.ascontiguousarray(mg.local_rhs())).pin_memory()
     lib, h = eng._lib, eng._h
     for _ in range(2):
         eng._ck(lib.mgb_vcycle(h, lf, vp.data_ptr(), fp.data_ptr(), 0, 1, None))
     e2e_steps = max(3, min(args.steps, 10))
-    td.barrier(); torch.cuda.synchronize()
+    barrier(); torch.cuda.synchronize()
     t1 = time.perf_counter()
     for _ in range(e2e_steps):
         eng._ck(lib.mgb_vcycle(h, lf, vp.data_ptr(), fp.data_ptr(), 0, 1, None))
-    td.barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - t1) / e2e_steps], device="cuda")
-    td.all_reduce(e2e_s, op=td.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t1) / e2e_steps)
     if rank == 0:
         peak, peak_src = B.measured_peak()
         comp = [r for r in prof if r["kind"] not in ("halo",)]
@@ -88,7 +98,8 @@ def run(args):
         line = {"metric": B.METRIC, "value": dofu / (ms * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{name}: {desc}", "restriction": args.restriction, "smoother": args.smoother, "fine_dofs": n_glob,
-                           "levels": lf - lc + 1, "mu1": src.mu1, "mu2": src.mu2, "parallelism": f"row-sharded x{world}, levels <= {mg.gather_level} on rank 0",
+                           "levels": lf - lc + 1, "mu1": src.mu1, "mu2": src.mu2, "generated_on_device": bool(mg.device_gen),
+                           "parallelism": f"row-sharded x{world}, levels <= {mg.gather_level} on rank 0" if multi else "single GPU",
                            "l2": "per-rank fine-level operators exceed the 126 MB L2" if n_glob / world > 2e6 else "fine level partly L2-resident", "setup_s": setup_s},
                 "fine_dof_cycles_per_s": n_glob / (ms * 1e-3), "resnorm_after": float(hist[0]),
                 "roofline": {"bound": "hbm", "kernel": f"{dom['kind']}@level{dom['level']} (rank 0 shard)", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
@@ -102,6 +113,7 @@ def run(args):
                 "kernels": [{"k": f"{r['kind']}@{r['level']}", "ms": round(r["ms_per_launch"], 5), "n": r["launches"], "gbs": round(r["gbs"], 1)}
                             for r in sorted(prof, key=lambda r: -r["total_ms"])[:10]]}
         print(json.dumps(line), flush=True)
-    td.barrier()
+    barrier()
     mg.close()
-    td.destroy_process_group()
+    if multi:
+        td.destroy_process_group()

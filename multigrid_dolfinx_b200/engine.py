@@ -111,6 +111,16 @@ class MGEngine:
         self._ck(self._lib.mgb_set_gather_level(self._h, int(level), int(n_global), off.ctypes.data))
         self.n.setdefault(int(level), int(n_global))
 
+    # -- device-side generation of the synthetic structured hierarchy (problems.stencil_p1 / prolongation / injection) --
+    def synth_level(self, level, dim, cells_per_dim, row_begin, row_end, ghost_lo=None, ghost_hi=None):
+        glo = row_begin if ghost_lo is None else ghost_lo
+        ghi = row_end if ghost_hi is None else ghost_hi
+        self._ck(self._lib.mgb_synth_poisson_level(self._h, int(level), int(dim), int(cells_per_dim), int(row_begin), int(row_end), int(glo), int(ghi)))
+        self.n[int(level)] = int(row_end - row_begin)
+
+    def synth_transfer(self, coarse_level, inj_coarse_begin, inj_coarse_end):
+        self._ck(self._lib.mgb_synth_poisson_transfer(self._h, int(coarse_level), int(inj_coarse_begin), int(inj_coarse_end)))
+
     def set_transfer(self, coarse_level, P, r_mode="injection", inj=None, R=None, dim=2, n_fine=None, n_coarse_rows=None):
         pip, pix, pax = _as_csr_arrays(P)
         mode = L.R_MODES[r_mode] if isinstance(r_mode, str) else int(r_mode)
@@ -323,7 +333,7 @@ class MGEngine:
     def artifact(self, level, kind):
         size = C.c_int64()
         self._ck(self._lib.mgb_get_artifact(self._h, int(level), int(kind), None, 0, C.byref(size)))
-        is_f64 = kind in (L.ART_RJ_VALUES, L.ART_DINV, L.ART_R_VALUES, L.ART_COARSE_INVERSE)
+        is_f64 = kind in (L.ART_RJ_VALUES, L.ART_DINV, L.ART_R_VALUES, L.ART_COARSE_INVERSE, L.ART_A_VALUES, L.ART_P_VALUES)
         out = np.empty(size.value // (8 if is_f64 else 4), dtype=np.float64 if is_f64 else np.int32)
         if size.value:
             self._ck(self._lib.mgb_get_artifact(self._h, int(level), int(kind), out.ctypes.data, size.value, None))

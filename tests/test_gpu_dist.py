@@ -31,12 +31,12 @@ def _worker(rank, world, port, case, q):
     td.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         dim, c, lf, seed, r_mode, glevel, opts = case
-        if seed == "structured":
+        if seed in ("structured", "generated"):
             src = ds.StructuredSource(dim, c, 0, lf)
         else:
             H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=seed, with_dicts=False)
             src = ds.HierarchySource(H)
-        mg = ds.DistMG(src, device=rank, r_mode=r_mode, gather_level=glevel, options=opts)
+        mg = ds.DistMG(src, device=rank, r_mode=r_mode, gather_level=glevel, options=opts, device_gen=seed == "generated")
         mg.load_rhs()
         hist = mg.cycles(4, history=True)
         v = mg.gather_solution()
@@ -56,6 +56,8 @@ CASES = [
     (3, 2, 3, None, "transpose", 0, {}),
     (2, 8, 3, 7, "injection", 1, {}),                 # random numbering: ghosts everywhere, explicit injection rows
     (3, 4, 3, "structured", "injection", 1, {"stream_cfg": 0}),
+    (3, 4, 4, "generated", "injection", 1, {}),       # sharded levels generated on the device, range ghosts
+    (2, 16, 4, "generated", "injection", 0, {}),
 ]
 
 
@@ -66,7 +68,7 @@ def test_sharded_equals_single_gpu(case):
     from multigrid_dolfinx_b200 import dist as ds
     from multigrid_dolfinx_b200 import problems as pr
     from multigrid_dolfinx_b200.engine import MGEngine
-    world = min(_ngpu(), 4) if case[3] == "structured" else 2
+    world = min(_ngpu(), 4) if case[3] in ("structured", "generated") else 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -81,8 +83,8 @@ def test_sharded_equals_single_gpu(case):
     v = [r[1] for r in res if r[0] == 0][0]
     hist = [r[2] for r in res if r[0] == 0][0]
     dim, c, lf, seed, r_mode, glevel, opts = case
-    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=None if seed == "structured" else seed, with_dicts=False)
-    if seed == "structured":
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=None if seed in ("structured", "generated") else seed, with_dicts=False)
+    if seed in ("structured", "generated"):
         f = ds.StructuredSource(dim, c, 0, lf).rhs_rows(lf, 0, H.n(lf))
     else:
         f = H.b_dict[lf][:, 0]

@@ -286,3 +286,32 @@ def test_full_size_properties_config2():
     _report("config2_full", resnorm_rel=r, solution_rel=s, hist=[float(x) for x in h1])
     assert r <= RTOL_RESNORM and s <= RTOL_SOLUTION
     eng.close()
+
+
+@pytest.mark.parametrize("dim,c,lf,glevel", [(2, 8, 4, 1), (3, 2, 4, 0), (3, 4, 3, 2)])
+def test_device_side_generation_matches_host_assembler(dim, c, lf, glevel):
+    """mgb_synth_poisson_* (device-born CSR + device-built R_omega) vs problems.py + the host setup path:
+    matrices, transfers, injection lists and R_omega bit-identical, hence identical V-cycles."""
+    from multigrid_dolfinx_b200 import dist as ds
+    src = ds.StructuredSource(dim, c, 0, lf)
+    mg = ds.DistMG(src, device=0, gather_level=glevel, device_gen=True)          # world = 1, no process group
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, with_dicts=False)
+    ref = MGEngine.from_hierarchy(H)
+    for l in range(glevel + 1, lf + 1):
+        A = H.A_sp_dict[l][0]
+        assert np.array_equal(mg.eng.artifact(l, L.ART_A_INDPTR), A.indptr)
+        assert np.array_equal(mg.eng.artifact(l, L.ART_A_INDICES), A.indices)
+        assert np.array_equal(mg.eng.artifact(l, L.ART_A_VALUES), A.data)
+        P = H.P[l - 1]
+        assert np.array_equal(mg.eng.artifact(l, L.ART_P_INDPTR), P.indptr)
+        assert np.array_equal(mg.eng.artifact(l, L.ART_P_INDICES), P.indices)
+        assert np.array_equal(mg.eng.artifact(l, L.ART_P_VALUES), P.data)
+        assert np.array_equal(mg.eng.artifact(l, L.ART_INJECTION), H.inj[l - 1])
+        for kind in (L.ART_RJ_INDPTR, L.ART_RJ_INDICES, L.ART_RJ_VALUES, L.ART_DINV):
+            assert np.array_equal(mg.eng.artifact(l, kind), ref.artifact(l, kind))
+    f = src.rhs_rows(lf, 0, src.n(lf))
+    mg.load_rhs()
+    h1 = mg.cycles(3, history=True)
+    v0, h0 = ref.vcycle(lf, np.zeros_like(f), f, ncycles=3, history=True)
+    assert np.array_equal(mg.local_solution(), v0) and np.array_equal(h1, h0)
+    mg.close(); ref.close()
