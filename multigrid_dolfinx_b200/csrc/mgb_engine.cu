@@ -37,6 +37,12 @@ struct DevCsr {
     int4* sdesc = nullptr;   // stream kernel: per-tile {row0, nrows, nz0a, nent}
     int sntiles = 0;
     std::vector<int4> sdesc_host;
+    // row-sharded operators: stream tiles split into [boundary-low | interior | boundary-high]; interior rows reference
+    // no ghost column, so they can run while the halo exchange is in flight
+    bool split = false;
+    int t_int0 = 0, t_int1 = 0;      // interior tiles = sdesc[t_int0 .. t_int1)
+    int4* sdesc_bnd = nullptr;       // boundary tiles, low block then high block
+    int n_bnd = 0;
     int iter = 2;       // tile kernel: groups of 4 entries per thread
     int family = 1;     // 1 tile, 2 sub-warp
     int lpr = 4;        // sub-warp lanes per row
@@ -75,6 +81,7 @@ struct Level {
     int32_t* cmap = nullptr;         // fine dof -> coarse dof or -1 (fused residual + injection)
     int4* inj_desc = nullptr;        // the stream tiles of A that contain at least one injected row
     int inj_ntiles = 0;
+    int inj_n_int = 0, inj_n_bnd = 0;   // sharded: the list is stored [interior tiles | boundary tiles]
     double inj_fraction = 1.0;       // share of A's entries in those tiles
     double *v = nullptr, *vtmp = nullptr, *f = nullptr, *r = nullptr, *g = nullptr;
     // Gauss-Seidel artefacts (host copies are what mgb_get_artifact returns)
@@ -118,6 +125,9 @@ struct mgb_handle {
     bool dist = false;
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
+    cudaStream_t comm_stream = nullptr;      // halo exchanges run here while interior rows run on `stream`
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int overlap = 1;                         // option "overlap_halo"
     int gather_level = INT_MIN;      // level that is gathered to rank 0 (INT_MIN: none)
     int sm_count = 148;
     int gs_coop_blocks_per_sm = 0;
@@ -166,7 +176,7 @@ int dev_upload(mgb_handle* h, T** p, const T* src, size_t count, size_t pad = 0)
 
 void free_csr(DevCsr& D)
 {
-    cudaFree(D.rowptr); cudaFree(D.cols); cudaFree(D.vals); cudaFree(D.tiles); cudaFree(D.sdesc);
+    cudaFree(D.rowptr); cudaFree(D.cols); cudaFree(D.vals); cudaFree(D.tiles); cudaFree(D.sdesc); cudaFree(D.sdesc_bnd);
     D = DevCsr();
 }
 
@@ -189,7 +199,8 @@ StreamChoice stream_choice(int cfg)
 // Upload a host CSR and choose the kernel family / tile shape for it.
 // Kernel family, row tiles and stream descriptors of an operator whose arrays are already on the device.
 // Needs only the row pointers on the host (ip).
-int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const std::vector<int32_t>& breaks = {})
+int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const std::vector<int32_t>& breaks = {},
+               const int64_t* interior = nullptr)
 {
     const int64_t n = D.nrows, nnz = D.nnz;
     int mx = 0;
@@ -213,8 +224,12 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
     if (family == 1 && h->stream_cfg > 0 && breaks.empty()) {     // descriptors for the TMA stream kernel
         const StreamChoice sc = stream_choice(h->stream_cfg);
         const int cap = sc.threads * sc.ept;
-        std::vector<int32_t> st;
-        if (make_tiles(ip, cap, cap / 4, {}, st, nullptr, 4)) {
+        std::vector<int32_t> st, sbreaks, sbt;
+        if (interior) {                          // interior row range [b0, b1), shrunk to multiples of 4 rows
+            const int64_t b0 = (interior[0] + 3) & ~(int64_t)3, b1 = interior[1] == n ? n : (interior[1] & ~(int64_t)3);
+            if (b1 > b0) sbreaks = {(int32_t)b0, (int32_t)b1};
+        }
+        if (make_tiles(ip, cap, cap / 4, sbreaks, st, &sbt, 4)) {
             std::vector<int4> desc(st.size() - 1);
             for (size_t t = 0; t + 1 < st.size(); ++t) {
                 const int64_t r0 = st[t], r1 = st[t + 1];
@@ -223,6 +238,15 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
             }
             D.sntiles = (int)desc.size();
             if (D.sntiles > 0) TRY(dev_upload(h, &D.sdesc, desc.data(), desc.size()));
+            if (interior) {
+                D.split = true;
+                D.t_int0 = sbreaks.empty() ? 0 : sbt[0];
+                D.t_int1 = sbreaks.empty() ? 0 : sbt[1];
+                std::vector<int4> bnd(desc.begin(), desc.begin() + D.t_int0);
+                bnd.insert(bnd.end(), desc.begin() + D.t_int1, desc.end());
+                D.n_bnd = (int)bnd.size();
+                if (D.n_bnd > 0) TRY(dev_upload(h, &D.sdesc_bnd, bnd.data(), bnd.size()));
+            }
             D.sdesc_host.swap(desc);
         }
     }
@@ -241,8 +265,43 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
     return MGB_OK;
 }
 
-// Upload a host CSR and choose the kernel family / tile shape for it.
-int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int32_t>& breaks = {})
+__global__ void k_row_refs_ghost(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, int n_owned_cols,
+                                 unsigned char* __restrict__ flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned char f = 0;
+    for (int k = rp[i]; k < rp[i + 1]; ++k) f |= (cols[k] >= n_owned_cols);
+    flag[i] = f;
+}
+
+// Longest run of rows that reference no ghost column (columns >= n_owned_cols).  out[0..1] = [b0, b1).
+int interior_rows(mgb_handle* h, const DevCsr& D, int64_t n_owned_cols, int64_t* out)
+{
+    const int n = (int)D.nrows;
+    out[0] = out[1] = 0;
+    if (n == 0) return MGB_OK;
+    unsigned char* d = nullptr;
+    TRY(dev_alloc(h, &d, (size_t)n));
+    k_row_refs_ghost<<<(n + 255) / 256, 256, 0, h->stream>>>(n, D.rowptr, D.cols, (int)n_owned_cols, d);
+    std::vector<unsigned char> f((size_t)n);
+    CU(cudaMemcpyAsync(f.data(), d, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    int64_t best0 = 0, best1 = 0, run0 = 0;
+    for (int64_t i = 0; i <= n; ++i) {
+        if (i == n || f[(size_t)i]) {
+            if (i - run0 > best1 - best0) { best0 = run0; best1 = i; }
+            run0 = i + 1;
+        }
+    }
+    out[0] = best0; out[1] = best1;
+    return MGB_OK;
+}
+
+// Upload a host CSR and choose the kernel family / tile shape for it.  x_owned >= 0: the operator reads a sharded
+// vector with x_owned owned entries followed by ghosts -> also split its tiles into interior / boundary.
+int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int32_t>& breaks = {}, int64_t x_owned = -1)
 {
     const int64_t n = M.nrows, nnz = M.nnz();
     if (n >= (int64_t)2147483000 || nnz >= (int64_t)2147483000)
@@ -254,7 +313,9 @@ int upload_csr(mgb_handle* h, const HostCsr& M, DevCsr& D, const std::vector<int
     TRY(dev_upload(h, &D.rowptr, rp.data(), rp.size(), 8));
     TRY(dev_upload(h, &D.cols, M.ix.data(), (size_t)nnz, 16));   // padding: the last 8-wide group may read past nnz
     TRY(dev_upload(h, &D.vals, M.ax.data(), (size_t)nnz, 16));
-    return finish_csr(h, D, M.ip, breaks);
+    int64_t in[2];
+    if (x_owned >= 0) TRY(interior_rows(h, D, x_owned, in));
+    return finish_csr(h, D, M.ip, breaks, x_owned >= 0 ? in : nullptr);
 }
 
 // Row pointers of a device-resident operator back on the host (int64), for finish_csr.
@@ -422,23 +483,58 @@ __global__ void k_sqrt_inplace(double* x) { *x = sqrt(*x); }
 
 // Halo exchange of one level vector: pack the owned entries the neighbours need, one grouped
 // ncclSend/ncclRecv per neighbour; the ghost section of `vec` (behind the n owned entries) is the receive buffer.
+int exchange_on(mgb_handle* h, Level& L, double* vec, cudaStream_t st)
+{
+    if (L.send_total > 0) k_pack<<<(int)((L.send_total + 255) / 256), 256, 0, st>>>((int)L.send_total, L.send_idx, vec, L.send_buf);
+    ncclResult_t r = g_nccl.GroupStart();
+    int64_t so = 0, ro = 0;
+    for (size_t p = 0; p < L.peers.size() && r == ncclSuccess; ++p) {
+        if (L.send_cnt[p] > 0) r = g_nccl.Send(L.send_buf + so, (size_t)L.send_cnt[p], ncclDouble, L.peers[p], h->comm, st);
+        if (r == ncclSuccess && L.recv_cnt[p] > 0) r = g_nccl.Recv(vec + L.n + ro, (size_t)L.recv_cnt[p], ncclDouble, L.peers[p], h->comm, st);
+        so += L.send_cnt[p]; ro += L.recv_cnt[p];
+    }
+    ncclResult_t e = g_nccl.GroupEnd();
+    if (r == ncclSuccess) r = e;
+    if (r != ncclSuccess) return fail(h, MGB_ERR_COMM, "halo exchange on level %d: %s", L.level, g_nccl.GetErrorString(r));
+    return MGB_OK;
+}
+
 int exchange(mgb_handle* h, Level& L, double* vec)
 {
     if (!h->dist || L.peers.empty()) return MGB_OK;
     int rc = MGB_OK;
-    TRY(launch(h, MGB_K_HALO, L.level, 16.0 * (double)L.send_total, [&] {
-        if (L.send_total > 0) k_pack<<<(int)((L.send_total + 255) / 256), 256, 0, h->stream>>>((int)L.send_total, L.send_idx, vec, L.send_buf);
-        ncclResult_t r = g_nccl.GroupStart();
-        int64_t so = 0, ro = 0;
-        for (size_t p = 0; p < L.peers.size() && r == ncclSuccess; ++p) {
-            if (L.send_cnt[p] > 0) r = g_nccl.Send(L.send_buf + so, (size_t)L.send_cnt[p], ncclDouble, L.peers[p], h->comm, h->stream);
-            if (r == ncclSuccess && L.recv_cnt[p] > 0) r = g_nccl.Recv(vec + L.n + ro, (size_t)L.recv_cnt[p], ncclDouble, L.peers[p], h->comm, h->stream);
-            so += L.send_cnt[p]; ro += L.recv_cnt[p];
+    TRY(launch(h, MGB_K_HALO, L.level, 16.0 * (double)L.send_total, [&] { rc = exchange_on(h, L, vec, h->stream); }));
+    return rc;
+}
+
+// Row sums of a sharded operator whose input vector x lives on level XL: exchange XL's ghosts, overlapped with the
+// interior tiles when the operator has an interior / boundary split.
+template <class Epi>
+int row_sums_halo(mgb_handle* h, int kind, int level, double bytes, const DevCsr& D, Level& XL, double* x, const Epi& epi,
+                  const int4* sub_desc = nullptr, int sub_int = 0, int sub_bnd = 0)
+{
+    const bool need = h->dist && !XL.peers.empty();
+    const bool can_overlap = need && h->overlap && !h->prof && D.split && D.sdesc && h->stream_cfg > 0 && h->allow_stream && D.family == 1;
+    if (!can_overlap) {
+        if (need) TRY(exchange(h, XL, x));
+        if (sub_desc) {
+            return launch(h, kind, level, bytes, [&] { launch_stream<Epi>(h, D, x, epi, sub_desc, sub_int + sub_bnd); });
         }
-        ncclResult_t e = g_nccl.GroupEnd();
-        if (r == ncclSuccess) r = e;
-        if (r != ncclSuccess) rc = fail(h, MGB_ERR_COMM, "halo exchange on level %d: %s", L.level, g_nccl.GetErrorString(r));
+        return row_sums(h, kind, level, bytes, D, x, epi);
+    }
+    int rc = MGB_OK;
+    TRY(launch(h, kind, level, bytes, [&] {
+        cudaEventRecord(h->ev_fork, h->stream);
+        cudaStreamWaitEvent(h->comm_stream, h->ev_fork, 0);
+        rc = exchange_on(h, XL, x, h->comm_stream);
+        cudaEventRecord(h->ev_join, h->comm_stream);
+        if (sub_desc) launch_stream<Epi>(h, D, x, epi, sub_desc, sub_int);
+        else launch_stream<Epi>(h, D, x, epi, D.sdesc + D.t_int0, D.t_int1 - D.t_int0);
+        cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+        if (sub_desc) launch_stream<Epi>(h, D, x, epi, sub_desc + sub_int, sub_bnd);
+        else launch_stream<Epi>(h, D, x, epi, D.sdesc_bnd, D.n_bnd);
     }));
+    h->launches += 2;
     return rc;
 }
 
@@ -504,20 +600,19 @@ int smooth(mgb_handle* h, Level& L, double*& v, double*& o, const double* f, int
 {
     const double n = (double)L.n;
     for (int s = 0; s < nsweeps; ++s) {
-        TRY(exchange(h, L, v));                    // ghost entries of the current iterate
-        if (h->smoother == MGB_SM_JACOBI_RJ) {
+        if (h->smoother == MGB_SM_JACOBI_RJ) {     // (the ghost entries of the iterate are exchanged inside row_sums_halo)
             if (!g_valid) {
                 EpiJacobiRJFirst epi{v, L.dinv, f, L.g, o, 1 - h->omega, h->omega};
-                TRY(row_sums(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.RJ, 5 * n), L.RJ, v, epi));
+                TRY(row_sums_halo(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.RJ, 5 * n), L.RJ, L, v, epi));
                 g_valid = true;
             } else {
                 EpiJacobiRJ epi{v, L.g, o, 1 - h->omega, h->omega};
-                TRY(row_sums(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.RJ, 3 * n), L.RJ, v, epi));
+                TRY(row_sums_halo(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.RJ, 3 * n), L.RJ, L, v, epi));
             }
             std::swap(v, o);
         } else if (h->smoother == MGB_SM_JACOBI_A) {
             EpiJacobiA epi{v, L.dinv, f, o, h->omega};
-            TRY(row_sums(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.A, 4 * n), L.A, v, epi));
+            TRY(row_sums_halo(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.A, 4 * n), L.A, L, v, epi));
             std::swap(v, o);
         } else {
             TRY(gs_sweep(h, L, v, f));
@@ -528,9 +623,8 @@ int smooth(mgb_handle* h, Level& L, double*& v, double*& o, const double* f, int
 
 int residual(mgb_handle* h, Level& L, const double* v, const double* f, double* r)
 {
-    TRY(exchange(h, L, const_cast<double*>(v)));
     EpiResidual epi{f, r};
-    return row_sums(h, MGB_K_RESIDUAL, L.level, bytes_rowsum(L.A, 3.0 * (double)L.n), L.A, v, epi);
+    return row_sums_halo(h, MGB_K_RESIDUAL, L.level, bytes_rowsum(L.A, 3.0 * (double)L.n), L.A, L, const_cast<double*>(v), epi);
 }
 
 // restriction from fine level L to its coarse neighbour: f_c = R r  (multigrid.py:251-252)
@@ -542,9 +636,8 @@ int restrict_to(mgb_handle* h, Level& L, const double* r_fine, double* f_coarse)
             if (nc > 0) k_gather<<<(int)((nc + 255) / 256), 256, 0, h->stream>>>((int)nc, L.inj, r_fine, f_coarse);
         });
     }
-    TRY(exchange(h, L, const_cast<double*>(r_fine)));
     EpiStore epi{f_coarse};
-    return row_sums(h, MGB_K_RESTRICT, L.level, bytes_rowsum(L.R, (double)L.n + (double)nc), L.R, r_fine, epi);
+    return row_sums_halo(h, MGB_K_RESTRICT, L.level, bytes_rowsum(L.R, (double)L.n + (double)nc), L.R, L, const_cast<double*>(r_fine), epi);
 }
 
 // fused residual + injection: f_c[i] = f[g_i] - (A v)[g_i]   (multigrid.py:244 + :128-131)
@@ -552,15 +645,13 @@ int residual_injected(mgb_handle* h, Level& L, const double* v, const double* f,
 {
     const int64_t nc = L.n_coarse;
     const double avg = L.A.nrows ? (double)L.A.nnz / (double)L.A.nrows : 0.0;
-    TRY(exchange(h, L, const_cast<double*>(v)));
     if (L.inj_desc && L.inj_fraction < 0.8 && h->stream_cfg > 0 && h->allow_stream) {
         // stream only the tiles of A that hold injected rows; every row of such a tile is summed, injected ones are stored
         const double nb = L.inj_fraction * (12.0 * (double)L.A.nnz + (4.0 + 8.0 + 4.0) * (double)L.n) + 8.0 * (double)L.n + 8.0 * (double)nc;
-        return launch(h, MGB_K_RESIDUAL, L.level, nb, [&] {
-            EpiResidualInject epi{f, L.cmap, f_coarse};
-            launch_stream<EpiResidualInject>(h, L.A, v, epi, L.inj_desc, L.inj_ntiles);
-        });
+        EpiResidualInject epi{f, L.cmap, f_coarse};
+        return row_sums_halo(h, MGB_K_RESIDUAL, L.level, nb, L.A, L, const_cast<double*>(v), epi, L.inj_desc, L.inj_n_int, L.inj_n_bnd);
     }
+    TRY(exchange(h, L, const_cast<double*>(v)));
     return launch(h, MGB_K_RESIDUAL, L.level, (12.0 * avg + 4.0 + 8.0 + 4.0 + 8.0 + 8.0) * (double)nc + 8.0 * (double)L.n, [&] {
         if (nc <= 0) return;
         if (avg <= 8.0) k_residual_injected<8><<<(int)((nc * 8 + 255) / 256), 256, 0, h->stream>>>((int)nc, L.inj, L.A.rowptr, L.A.cols, L.A.vals, f, v, f_coarse);
@@ -571,9 +662,11 @@ int residual_injected(mgb_handle* h, Level& L, const double* v, const double* f,
 int prolong_add(mgb_handle* h, Level& L, const double* e_coarse, double* v_fine, double* err)
 {
     Level* C = find_level(h, L.level - 1);
-    if (C && !C->gathered && !C->stub) TRY(exchange(h, *C, const_cast<double*>(e_coarse)));   // gathered level: everybody has all of e
     EpiProlongAdd epi{v_fine, err};
-    return row_sums(h, MGB_K_PROLONG_ADD, L.level, bytes_rowsum(L.P, (double)L.n_coarse + 2.0 * (double)L.n), L.P, e_coarse, epi);
+    const double nb = bytes_rowsum(L.P, (double)L.n_coarse + 2.0 * (double)L.n);
+    if (C && !C->gathered && !C->stub)          // (gathered level: everybody already has all of e)
+        return row_sums_halo(h, MGB_K_PROLONG_ADD, L.level, nb, L.P, *C, const_cast<double*>(e_coarse), epi);
+    return row_sums(h, MGB_K_PROLONG_ADD, L.level, nb, L.P, e_coarse, epi);
 }
 
 int coarse_apply(mgb_handle* h, Level& C, const double* f, double* u)
@@ -823,6 +916,7 @@ int mgb_destroy(mgb_handle* h)
     }
     cudaFree(h->coarse_inv); cudaFree(h->d_partial); cudaFree(h->d_hist);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     for (auto& pe : h->prof_events) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
     cudaStreamDestroy(h->stream);
     delete h;
@@ -932,6 +1026,9 @@ int mgb_dist_init(mgb_handle* h, int rank, int world, const void* unique_id, int
     ncclUniqueId id;
     std::memcpy(&id, unique_id, sizeof id);
     NC(g_nccl.CommInitRank(&h->comm, world, id, rank));
+    CU(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     h->dist = true; h->rank = rank; h->world = world;
     return MGB_OK;
 }
@@ -1061,6 +1158,7 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "lanes_per_row" && pre) h->opt_lpr = iv;
     else if (k == "tile_iter" && pre) h->opt_iter = iv;
     else if (k == "stream_cfg" && pre) h->stream_cfg = iv;
+    else if (k == "overlap_halo") { h->overlap = iv; drop_graphs(h); }
     else return fail(h, pre ? MGB_ERR_INVALID : MGB_ERR_STATE, "option '%s' unknown or not settable %s finalize", key, pre ? "before" : "after");
     return MGB_OK;
 }
@@ -1093,18 +1191,21 @@ int mgb_finalize(mgb_handle* h)
         }
         if (h->dist && L.has_transfer && (L.r_mode == MGB_R_FULL_WEIGHTING || L.r_mode == MGB_R_TRANSPOSE))
             return fail(h, MGB_ERR_UNSUPPORTED, "row-sharded levels need the restriction rows explicitly (MGB_R_EXPLICIT) or injection");
+        const int64_t xo_self = (h->dist && L.n_ghost > 0) ? L.n : -1;       // operators reading this level's vectors
         if (L.device_born) {
             if (h->smoother >= MGB_SM_GS_LEVEL) return fail(h, MGB_ERR_UNSUPPORTED, "Gauss-Seidel needs the host copy of the level matrix; generated levels have none");
             std::vector<int64_t> ip;
+            int64_t in[2];
             TRY(fetch_rowptr(h, L.A, ip));
-            TRY(finish_csr(h, L.A, ip));
+            if (xo_self >= 0) TRY(interior_rows(h, L.A, xo_self, in));
+            TRY(finish_csr(h, L.A, ip, {}, xo_self >= 0 ? in : nullptr));
             TRY(build_rj_device(h, L));                                        // multigrid.py:48-56 on the device
         } else {
-            TRY(upload_csr(h, L.A_host, L.A));
+            TRY(upload_csr(h, L.A_host, L.A, {}, xo_self));
             HostCsr RJ; std::vector<double> dinv;
             if (!build_rj(L.A_host, h->rj_reversed != 0, RJ, dinv))            // multigrid.py:48-56
                 return fail(h, MGB_ERR_SINGULAR, "level %d: zero or missing diagonal entry", kv.first);
-            TRY(upload_csr(h, RJ, L.RJ));
+            TRY(upload_csr(h, RJ, L.RJ, {}, xo_self));
             TRY(dev_upload(h, &L.dinv, dinv.data(), n, 16));
         }
         if (h->smoother >= MGB_SM_GS_LEVEL && kv.first > h->coarsest) {
@@ -1130,25 +1231,35 @@ int mgb_finalize(mgb_handle* h)
             TRY(dev_upload(h, &L.gs_diag, dperm.data(), n));
         }
         if (L.has_transfer) {
+            Level& Cl = h->levels[kv.first - 1];
+            const int64_t xo_coarse = (h->dist && Cl.n_ghost > 0) ? Cl.n : -1;     // P reads the coarse level's vectors
             if (L.device_born) {
                 std::vector<int64_t> ip;
+                int64_t in[2];
                 TRY(fetch_rowptr(h, L.P, ip));
-                TRY(finish_csr(h, L.P, ip));
+                if (xo_coarse >= 0) TRY(interior_rows(h, L.P, xo_coarse, in));
+                TRY(finish_csr(h, L.P, ip, {}, xo_coarse >= 0 ? in : nullptr));
             } else {
-                TRY(upload_csr(h, L.P_host, L.P));
+                TRY(upload_csr(h, L.P_host, L.P, {}, xo_coarse));
             }
             if (L.r_mode == MGB_R_INJECTION) {
                 if (!L.device_born) TRY(dev_upload(h, &L.inj, L.inj_host.data(), L.inj_host.size()));
                 if (!L.A.sdesc_host.empty()) {
                     std::vector<int32_t> cmap(n + 16, -1);
                     for (size_t c = 0; c < L.inj_host.size(); ++c) cmap[(size_t)L.inj_host[c]] = (int32_t)c;
-                    std::vector<int4> keep;
+                    std::vector<int4> keep, keep_bnd;          // [interior tiles | boundary tiles]
                     int64_t ent = 0;
-                    for (const int4& d : L.A.sdesc_host) {
+                    for (size_t t = 0; t < L.A.sdesc_host.size(); ++t) {
+                        const int4& d = L.A.sdesc_host[t];
                         bool any = false;
                         for (int r = d.x; r < d.x + d.y && !any; ++r) any = cmap[(size_t)r] >= 0;
-                        if (any) { keep.push_back(d); ent += d.w; }
+                        if (!any) continue;
+                        ent += d.w;
+                        const bool interior = !L.A.split || ((int)t >= L.A.t_int0 && (int)t < L.A.t_int1);
+                        (interior ? keep : keep_bnd).push_back(d);
                     }
+                    L.inj_n_int = (int)keep.size(); L.inj_n_bnd = (int)keep_bnd.size();
+                    keep.insert(keep.end(), keep_bnd.begin(), keep_bnd.end());
                     TRY(dev_upload(h, &L.cmap, cmap.data(), cmap.size()));
                     if (!keep.empty()) TRY(dev_upload(h, &L.inj_desc, keep.data(), keep.size()));
                     L.inj_ntiles = (int)keep.size();
@@ -1157,7 +1268,7 @@ int mgb_finalize(mgb_handle* h)
             } else {
                 if (L.r_mode == MGB_R_FULL_WEIGHTING) transpose_scaled(L.P_host, std::ldexp(1.0, -L.dim_fw), L.R_host);
                 else if (L.r_mode == MGB_R_TRANSPOSE) transpose_scaled(L.P_host, 1.0, L.R_host);
-                TRY(upload_csr(h, L.R_host, L.R));
+                TRY(upload_csr(h, L.R_host, L.R, {}, xo_self));
             }
         }
         const size_t np = n + (size_t)L.n_ghost + 16;   // [owned | ghost | tail padding for 16-byte bulk copies]

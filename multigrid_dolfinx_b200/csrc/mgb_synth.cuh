@@ -238,7 +238,10 @@ int build_rj_device(mgb_handle* h, Level& L)
     cudaFree(bad);
     if (hb) return fail(h, MGB_ERR_SINGULAR, "level %d: zero or missing diagonal entry", L.level);
     std::vector<int64_t> ip;
+    int64_t in[2];
+    const bool sharded = h->dist && L.n_ghost > 0;
     TRY(fetch_rowptr(h, L.RJ, ip));
-    return finish_csr(h, L.RJ, ip);
+    if (sharded) TRY(interior_rows(h, L.RJ, L.n, in));
+    return finish_csr(h, L.RJ, ip, {}, sharded ? in : nullptr);
 }
 

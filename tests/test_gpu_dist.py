@@ -54,6 +54,8 @@ CASES = [
     (2, 8, 4, None, "injection", 1, {}),
     (3, 2, 4, None, "injection", 1, {"use_graph": 0}),
     (3, 2, 3, None, "transpose", 0, {}),
+    (3, 2, 4, None, "injection", 1, {"overlap_halo": 0}),
+    (3, 2, 4, None, "full_weighting", 2, {"fuse_restrict": 0}),
     (2, 8, 3, 7, "injection", 1, {}),                 # random numbering: ghosts everywhere, explicit injection rows
     (3, 4, 3, "structured", "injection", 1, {"stream_cfg": 0}),
     (3, 4, 4, "generated", "injection", 1, {}),       # sharded levels generated on the device, range ghosts
