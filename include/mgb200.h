@@ -164,6 +164,9 @@ int mgb_set_option(mgb_handle* h, const char* key, double value);
  * coarsest matrix (replaces spsolve, multigrid.py:239), level sets / colours when a GS smoother is
  * selected, uploads everything and allocates the per-level vectors. */
 int mgb_finalize(mgb_handle* h);
+/* the argument / state checks of mgb_finalize alone: no device work, no communication.  Row-sharded callers run it on
+ * every rank and agree on the outcome before the (collective) mgb_finalize. */
+int mgb_precheck(mgb_handle* h);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 /* ncycles x V_cycle_scheme(A_jacobi_sp_dict[top_level], v, f) (multigrid.py:231-268), v updated in place.

@@ -53,6 +53,7 @@ SYMBOLS = {
     "mgb_set_params": (_i, [_vp, _d, _i, _i, _i]),
     "mgb_set_option": (_i, [_vp, C.c_char_p, _d]),
     "mgb_finalize": (_i, [_vp]),
+    "mgb_precheck": (_i, [_vp]),
     "mgb_vcycle": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
     "mgb_vcycle_debug": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "mgb_vcycle_resident": (_i, [_vp, _i, _i, _vp]),

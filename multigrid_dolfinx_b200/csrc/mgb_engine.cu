@@ -361,7 +361,7 @@ void launch_tile(mgb_handle* h, const DevCsr& D, int t0, int t1, const double* x
 }
 
 template <int T, int E, int S, class Epi>
-void launch_stream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi)
+void launch_stream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
 {
     auto kern = k_stream<T, E, S, true, Epi>;
     constexpr int smem = StreamCfg<T, E, Epi::NOPS, EpiNI<Epi>::value>::smem_bytes(S);
@@ -371,23 +371,28 @@ void launch_stream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nti
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T + 32, smem);
         if (occ < 1) occ = 1;
     }
-    const int grid = std::min(ntiles, h->sm_count * occ);
-    kern<<<grid, T + 32, smem, h->stream>>>(D.rowptr, D.cols, D.vals, desc, ntiles, x, epi);
+    int grid = std::min(ntiles, h->sm_count * occ), tpc = 0;
+    if (chunked) {                       // CTAs that retire: about 8 waves of them (see k_stream)
+        tpc = std::max(1, std::min(64, ntiles / (h->sm_count * occ * 8)));
+        grid = (ntiles + tpc - 1) / tpc;
+    }
+    kern<<<grid, T + 32, smem, h->stream>>>(D.rowptr, D.cols, D.vals, desc, ntiles, tpc, x, epi);
 }
 
 template <class Epi>
-void launch_stream(mgb_handle* h, const DevCsr& D, const double* x, const Epi& epi, const int4* desc = nullptr, int ntiles = 0)
+void launch_stream(mgb_handle* h, const DevCsr& D, const double* x, const Epi& epi, const int4* desc = nullptr, int ntiles = 0,
+                   bool chunked = false)
 {
     if (!desc) { desc = D.sdesc; ntiles = D.sntiles; }
     if (ntiles <= 0) return;
     if constexpr (Epi::CONTIG) {
         switch (h->stream_cfg) {
-            case 1: launch_stream_cfg<256, 8, 2, Epi>(h, D, desc, ntiles, x, epi); break;
-            case 2: launch_stream_cfg<512, 4, 2, Epi>(h, D, desc, ntiles, x, epi); break;
-            case 3: launch_stream_cfg<256, 4, 2, Epi>(h, D, desc, ntiles, x, epi); break;
-            case 4: launch_stream_cfg<256, 4, 3, Epi>(h, D, desc, ntiles, x, epi); break;
-            case 5: launch_stream_cfg<128, 8, 2, Epi>(h, D, desc, ntiles, x, epi); break;
-            default: launch_stream_cfg<256, 8, 3, Epi>(h, D, desc, ntiles, x, epi); break;
+            case 1: launch_stream_cfg<256, 8, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+            case 2: launch_stream_cfg<512, 4, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+            case 3: launch_stream_cfg<256, 4, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+            case 4: launch_stream_cfg<256, 4, 3, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+            case 5: launch_stream_cfg<128, 8, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+            default: launch_stream_cfg<256, 8, 3, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
         }
     }
 }
@@ -528,8 +533,8 @@ int row_sums_halo(mgb_handle* h, int kind, int level, double bytes, const DevCsr
         cudaStreamWaitEvent(h->comm_stream, h->ev_fork, 0);
         rc = exchange_on(h, XL, x, h->comm_stream);
         cudaEventRecord(h->ev_join, h->comm_stream);
-        if (sub_desc) launch_stream<Epi>(h, D, x, epi, sub_desc, sub_int);
-        else launch_stream<Epi>(h, D, x, epi, D.sdesc + D.t_int0, D.t_int1 - D.t_int0);
+        if (sub_desc) launch_stream<Epi>(h, D, x, epi, sub_desc, sub_int, true);
+        else launch_stream<Epi>(h, D, x, epi, D.sdesc + D.t_int0, D.t_int1 - D.t_int0, true);
         cudaStreamWaitEvent(h->stream, h->ev_join, 0);
         if (sub_desc) launch_stream<Epi>(h, D, x, epi, sub_desc + sub_int, sub_bnd);
         else launch_stream<Epi>(h, D, x, epi, D.sdesc_bnd, D.n_bnd);
@@ -796,7 +801,7 @@ int run_cycle(mgb_handle* h, int top)
         if (rc != MGB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return fail(h, MGB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
         cudaGraphExec_t exec = nullptr;
-        e = cudaGraphInstantiate(&exec, graph, 0);
+        e = cudaGraphInstantiate(&exec, graph, h->dist ? cudaGraphInstantiateFlagUseNodePriority : 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return fail(h, MGB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
         h->graphs[top] = exec;
@@ -1026,7 +1031,9 @@ int mgb_dist_init(mgb_handle* h, int rank, int world, const void* unique_id, int
     ncclUniqueId id;
     std::memcpy(&id, unique_id, sizeof id);
     NC(g_nccl.CommInitRank(&h->comm, world, id, rank));
-    CU(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_hi));   // exchange kernels jump the queue
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     h->dist = true; h->rank = rank; h->world = world;
@@ -1163,23 +1170,43 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     return MGB_OK;
 }
 
-int mgb_finalize(mgb_handle* h)
+// everything mgb_finalize can reject without touching the device or the network (also exported as mgb_precheck so
+// that a row-sharded setup can agree on success BEFORE entering the collective part of mgb_finalize)
+static int validate_hierarchy(mgb_handle* h)
 {
-    if (!h) return MGB_ERR_INVALID;
     if (h->finalized) return fail(h, MGB_ERR_STATE, "already finalized");
     if (h->levels.empty()) return fail(h, MGB_ERR_STATE, "no levels set");
-    CU(cudaSetDevice(h->device));
     h->coarsest = h->levels.begin()->first;
     h->finest = h->levels.rbegin()->first;
     for (int l = h->coarsest; l <= h->finest; ++l) {
         Level* L = find_level(h, l);
         if (!L) return fail(h, MGB_ERR_STATE, "level %d missing (levels must be contiguous)", l);
         if (l > h->coarsest && !L->has_transfer) return fail(h, MGB_ERR_STATE, "transfer between levels %d and %d missing", l - 1, l);
+        if (h->dist && l > h->gather_level && L->has_transfer && (L->r_mode == MGB_R_FULL_WEIGHTING || L->r_mode == MGB_R_TRANSPOSE))
+            return fail(h, MGB_ERR_UNSUPPORTED, "row-sharded levels need the restriction rows explicitly (MGB_R_EXPLICIT) or injection");
+        if (L->device_born && h->smoother >= MGB_SM_GS_LEVEL)
+            return fail(h, MGB_ERR_UNSUPPORTED, "Gauss-Seidel needs the host copy of the level matrix; generated levels have none");
     }
     if (h->opt_iter && h->opt_iter != 1 && h->opt_iter != 2) return fail(h, MGB_ERR_INVALID, "tile_iter must be 1 or 2");
     if (h->opt_lpr && (h->opt_lpr & (h->opt_lpr - 1) || h->opt_lpr > 32)) return fail(h, MGB_ERR_INVALID, "lanes_per_row must be a power of two <= 32");
     if (h->dist && h->smoother >= MGB_SM_GS_LEVEL)
         return fail(h, MGB_ERR_UNSUPPORTED, "Gauss-Seidel smoothers are single-GPU only in this version (see DESIGN.md, multi-GPU)");
+    if (h->dist && h->world > 1 && h->gather_level == INT_MIN)
+        return fail(h, MGB_ERR_STATE, "row-sharded hierarchy without a gathered level (mgb_set_gather_level)");
+    return MGB_OK;
+}
+
+int mgb_precheck(mgb_handle* h)
+{
+    if (!h) return MGB_ERR_INVALID;
+    return validate_hierarchy(h);
+}
+
+int mgb_finalize(mgb_handle* h)
+{
+    if (!h) return MGB_ERR_INVALID;
+    TRY(validate_hierarchy(h));
+    CU(cudaSetDevice(h->device));
     for (auto& kv : h->levels) {
         Level& L = kv.second;
         const size_t n = (size_t)L.n;
@@ -1189,8 +1216,6 @@ int mgb_finalize(mgb_handle* h)
             for (double* p : {L.v, L.f}) CU(cudaMemsetAsync(p, 0, np * sizeof(double), h->stream));
             continue;
         }
-        if (h->dist && L.has_transfer && (L.r_mode == MGB_R_FULL_WEIGHTING || L.r_mode == MGB_R_TRANSPOSE))
-            return fail(h, MGB_ERR_UNSUPPORTED, "row-sharded levels need the restriction rows explicitly (MGB_R_EXPLICIT) or injection");
         const int64_t xo_self = (h->dist && L.n_ghost > 0) ? L.n : -1;       // operators reading this level's vectors
         if (L.device_born) {
             if (h->smoother >= MGB_SM_GS_LEVEL) return fail(h, MGB_ERR_UNSUPPORTED, "Gauss-Seidel needs the host copy of the level matrix; generated levels have none");

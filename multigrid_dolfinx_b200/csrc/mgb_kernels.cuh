@@ -302,8 +302,11 @@ struct StreamCfg {
 template <int THREADS, int EPT, int STAGES, bool NCX, class Epi>
 __global__ void __launch_bounds__(THREADS + 32)
 k_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, const double* __restrict__ vals,
-         const int4* __restrict__ desc, int ntiles, const double* x, Epi epi)
+         const int4* __restrict__ desc, int ntiles, int tpc, const double* x, Epi epi)
 {
+    // tpc == 0: persistent CTAs, tiles dealt round-robin (tile = blockIdx.x + i * gridDim.x).
+    // tpc  > 0: every CTA owns tpc consecutive tiles and then retires, so that a concurrently launched
+    //           high-priority kernel (the NCCL halo exchange) finds a free slot within a few microseconds.
     static_assert(Epi::CONTIG, "stream kernel needs contiguous epilogue operands");
     static_assert(STAGES <= 8, "barrier block holds 8 stages");
     constexpr int NIOPS = EpiNI<Epi>::value;
@@ -321,7 +324,9 @@ k_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int first = tpc > 0 ? (int)blockIdx.x * tpc : (int)blockIdx.x;
+    const int step = tpc > 0 ? 1 : (int)gridDim.x;
+    const int my_tiles = tpc > 0 ? min(tpc, ntiles - first) : (ntiles - first + step - 1) / step;
 
     if (tid >= THREADS) {                                   // ---- producer warp (one lane works)
         if (tid == THREADS) {
@@ -330,7 +335,7 @@ k_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, c
             for (int i = 0; i < my_tiles; ++i) {
                 const int s = i % STAGES;
                 if (i >= STAGES) mbar_wait(empty + s, (uint32_t)((i / STAGES - 1) & 1));
-                const int4 d = __ldg(desc + blockIdx.x + (size_t)i * gridDim.x);     // {row0, nrows, nz0a, nent}
+                const int4 d = __ldg(desc + first + (size_t)i * step);                   // {row0, nrows, nz0a, nent}
                 unsigned char* st = stage0 + (size_t)s * Cfg::STAGE_BYTES;
                 *reinterpret_cast<int4*>(st) = d;                                    // published by the arrive below (release)
                 const uint32_t b_cols = (uint32_t)d.w * 4u, b_vals = (uint32_t)d.w * 8u;

@@ -144,6 +144,9 @@ class MGEngine:
     def set_option(self, key, value):
         self._ck(self._lib.mgb_set_option(self._h, key.encode(), float(value)))
 
+    def precheck(self):
+        self._ck(self._lib.mgb_precheck(self._h))
+
     def finalize(self):
         self._ck(self._lib.mgb_finalize(self._h))
         self.finalized = True

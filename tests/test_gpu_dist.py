@@ -77,9 +77,11 @@ def test_sharded_equals_single_gpu(case):
     procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in procs]
+    res = [q.get(timeout=150) for _ in procs]
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=30)
+        if p.is_alive():
+            p.terminate()
     for rank, v, hist, err in res:
         assert err is None, err
     v = [r[1] for r in res if r[0] == 0][0]
