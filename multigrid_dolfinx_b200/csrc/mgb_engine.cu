@@ -127,7 +127,8 @@ struct mgb_handle {
     ncclComm_t comm = nullptr;
     cudaStream_t comm_stream = nullptr;      // halo exchanges run here while interior rows run on `stream`
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int overlap = 1;                         // option "overlap_halo"
+    int overlap = 0;                         // option "overlap_halo"
+    int overlap_waves = 2;                   // option "overlap_waves": waves of retiring CTAs in an overlapped interior launch
     int gather_level = INT_MIN;      // level that is gathered to rank 0 (INT_MIN: none)
     int sm_count = 148;
     int gs_coop_blocks_per_sm = 0;
@@ -373,7 +374,7 @@ void launch_stream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nti
     }
     int grid = std::min(ntiles, h->sm_count * occ), tpc = 0;
     if (chunked) {                       // CTAs that retire: about 8 waves of them (see k_stream)
-        tpc = std::max(1, std::min(64, ntiles / (h->sm_count * occ * 8)));
+        tpc = std::max(1, ntiles / (h->sm_count * occ * std::max(1, h->overlap_waves)));
         grid = (ntiles + tpc - 1) / tpc;
     }
     kern<<<grid, T + 32, smem, h->stream>>>(D.rowptr, D.cols, D.vals, desc, ntiles, tpc, x, epi);
@@ -1166,6 +1167,7 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "tile_iter" && pre) h->opt_iter = iv;
     else if (k == "stream_cfg" && pre) h->stream_cfg = iv;
     else if (k == "overlap_halo") { h->overlap = iv; drop_graphs(h); }
+    else if (k == "overlap_waves") { h->overlap_waves = iv; drop_graphs(h); }
     else return fail(h, pre ? MGB_ERR_INVALID : MGB_ERR_STATE, "option '%s' unknown or not settable %s finalize", key, pre ? "before" : "after");
     return MGB_OK;
 }

@@ -48,7 +48,8 @@ def run(args):
     t0 = time.perf_counter()
     src = ds.StructuredSource(dim, c, lc, lf)
     mg = ds.DistMG(src, device=local_rank, r_mode=args.restriction, smoother=args.smoother, gather_threshold=args.gather_threshold,
-                   options={"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg, "use_graph": args.use_graph},
+                   options={"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg, "use_graph": args.use_graph,
+                            "overlap_halo": args.overlap, "overlap_waves": args.overlap_waves},
                    device_gen=bool(args.device_gen) and args.restriction == "injection")
     setup_s = time.perf_counter() - t0
     eng = mg.eng
