@@ -234,6 +234,7 @@ def main():
     ap.add_argument("--use-graph", type=int, default=1)
     ap.add_argument("--overlap", type=int, default=0, help="overlap the halo exchange with interior rows (sharded runs)")
     ap.add_argument("--overlap-waves", type=int, default=2)
+    ap.add_argument("--p2p", type=int, default=1, help="halo exchange through NVLink peer memory (0: ncclSend/ncclRecv)")
     ap.add_argument("--device-gen", type=int, default=1, help="generate the sharded levels on the device (structured workloads)")
     ap.add_argument("--restriction", default="injection", choices=["injection", "full_weighting", "transpose"])
     ap.add_argument("--smoother", default="jacobi", choices=["jacobi", "jacobi_a", "gs", "gs_color"])

@@ -138,6 +138,12 @@ int mgb_set_level_local(mgb_handle* h, int level, int64_t n_owned, int64_t n_gho
  * number of ghost entries received from it (ghost slots are ordered neighbour after neighbour). */
 int mgb_set_halo(mgb_handle* h, int level, int npeers, const int32_t* peer_ranks, const int32_t* send_counts,
                  const int32_t* send_indices, const int32_t* recv_counts);
+/* Peer-memory halo exchange (NVLink, CUDA IPC) instead of ncclSend/ncclRecv: every rank exports a blob per sharded
+ * level (call with blob == NULL to get its size), the host side hands each neighbour's blob to mgb_p2p_import.
+ * Once all neighbours of a level are imported its halo exchange is two small kernels: a push that gathers and stores
+ * straight into the neighbours' memory, and a pull that waits for their arrival flags and fills the ghost section. */
+int mgb_p2p_export(mgb_handle* h, int level, void* blob, int capacity, int* size);
+int mgb_p2p_import(mgb_handle* h, int level, int peer_rank, const void* blob, int size);
 /* Declares `level` (and everything coarser) to live on rank 0 only.  offsets[world+1]: the slice of that level's
  * right-hand side each rank produces when restricting from level+1.  On rank 0 the level must already be set in
  * full (mgb_set_level); on other ranks it must not be set at all. */

@@ -48,6 +48,8 @@ SYMBOLS = {
     "mgb_set_level_local": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i, _vp, _vp]),
     "mgb_set_halo": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "mgb_set_gather_level": (_i, [_vp, _i, _i64, _vp]),
+    "mgb_p2p_export": (_i, [_vp, _i, _vp, _i, C.POINTER(_i)]),
+    "mgb_p2p_import": (_i, [_vp, _i, _i, _vp, _i]),
     "mgb_synth_poisson_level": (_i, [_vp, _i, _i, _i, _i64, _i64, _i64, _i64]),
     "mgb_synth_poisson_transfer": (_i, [_vp, _i, _i64, _i64]),
     "mgb_set_params": (_i, [_vp, _d, _i, _i, _i]),

@@ -51,6 +51,29 @@ struct DevCsr {
     bool present() const { return rowptr != nullptr; }
 };
 
+constexpr int P2P_MAX_PEERS = 16;
+constexpr int P2P_FLAG_SLOTS = 256;          // one arrival flag per sender rank
+struct P2PPlan {                             // passed to the halo kernels by value
+    int npeers = 0;
+    int send_off[P2P_MAX_PEERS + 1] = {0};   // prefix sums into send_idx
+    int recv_off[P2P_MAX_PEERS + 1] = {0};   // prefix sums into the ghost section
+    double* rstage[P2P_MAX_PEERS][2] = {};   // neighbour's staging copies, already offset to this rank's slot
+    unsigned long long* rflag[P2P_MAX_PEERS] = {};   // neighbour's arrival flag for this rank
+    int peer_rank[P2P_MAX_PEERS] = {0};
+    unsigned long long* counters = nullptr;  // see Level::p2p_counters
+    unsigned long long* flags = nullptr;     // this rank's arrival flags (indexed by sender rank)
+    double* stage = nullptr;                 // this rank's staging copies (2 x n_ghost)
+    int n_ghost = 0;
+};
+
+struct P2PBlob {                             // what a rank publishes per level (mgb_p2p_export)
+    cudaIpcMemHandle_t handle;
+    long long n_ghost;
+    int npeers;
+    int peer_rank[P2P_MAX_PEERS];
+    int recv_off[P2P_MAX_PEERS + 1];
+};
+
 struct Level {
     int level = 0;
     int64_t n = 0;
@@ -74,6 +97,14 @@ struct Level {
     int32_t* send_idx = nullptr;     // device: owned local indices to pack, peer after peer
     double* send_buf = nullptr;
     int64_t send_total = 0;
+    // peer-memory halo exchange (CUDA IPC over NVLink): flags + two staging copies of the ghost section live in one
+    // exported allocation; the neighbours write into it directly
+    void* p2p_arena = nullptr;       // [flags: 256 x u64][stage 0: n_ghost][stage 1: n_ghost]
+    unsigned long long* p2p_counters = nullptr;   // device: [0..15] send epochs, [16..31] recv epochs, [32] block counter x2
+    std::vector<void*> p2p_opened;   // peers' arenas mapped into this process
+    bool p2p_ready = false;
+    int p2p_imported = 0;
+    P2PPlan p2p;
 
     DevCsr A, RJ, P, R, G;           // G: Gauss-Seidel off-diagonal operator, rows in execution order
     double* dinv = nullptr;
@@ -489,8 +520,86 @@ __global__ void k_sqrt_inplace(double* x) { *x = sqrt(*x); }
 
 // Halo exchange of one level vector: pack the owned entries the neighbours need, one grouped
 // ncclSend/ncclRecv per neighbour; the ghost section of `vec` (behind the n owned entries) is the receive buffer.
+// ---- halo exchange through peer memory ------------------------------------------------------------------
+// push: gather the owned entries each neighbour needs and store them straight into that neighbour's staging copy
+// (NVLink peer stores), then -- last block only -- publish the new epoch in the neighbour's arrival flag.
+// pull: wait until every neighbour's flag shows the epoch, then copy the staging copy into the ghost section of
+// the vector.  Epochs live in device memory, so the pair replays correctly inside a CUDA graph.  Two staging
+// copies alternate: a neighbour can only push epoch e after it has received this rank's epoch e-1, which this rank
+// sent after finishing its pull of epoch e-2 -- so copy (e mod 2) is never overwritten while it is still read.
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_p2p_push(P2PPlan pl, const int32_t* __restrict__ send_idx, const double* __restrict__ vec)
+{
+    const int total = pl.send_off[pl.npeers];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        int p = 0;
+        while (k >= pl.send_off[p + 1]) ++p;
+        const int par = (int)((pl.counters[p] + 1) & 1);
+        pl.rstage[p][par][k - pl.send_off[p]] = vec[send_idx[k]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long prev = atomicAdd(&pl.counters[32], 1ULL);
+        if (prev == gridDim.x - 1) {                  // every block's stores are fenced: publish
+            pl.counters[32] = 0;
+            for (int p = 0; p < pl.npeers; ++p) {
+                const unsigned long long e = pl.counters[p] + 1;
+                pl.counters[p] = e;
+                st_flag(pl.rflag[p], e);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_p2p_pull(P2PPlan pl, double* __restrict__ vec, int n_owned)
+{
+    if (threadIdx.x < pl.npeers) {
+        const int p = threadIdx.x;
+        const unsigned long long want = pl.counters[16 + p] + 1;
+        const long long t0 = clock64();
+        while (ld_flag(pl.flags + pl.peer_rank[p]) < want)
+            if (clock64() - t0 > 4000000000LL) __trap();          // a lost neighbour must fault, never hang the GPU
+    }
+    __syncthreads();
+    const int par = (int)((pl.counters[16] + 1) & 1);
+    const double* src = pl.stage + (size_t)par * pl.n_ghost;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < pl.n_ghost; k += gridDim.x * blockDim.x)
+        vec[n_owned + k] = __ldcg(src + k);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long prev = atomicAdd(&pl.counters[33], 1ULL);
+        if (prev == gridDim.x - 1) {
+            pl.counters[33] = 0;
+            for (int p = 0; p < pl.npeers; ++p) pl.counters[16 + p] += 1;
+        }
+    }
+}
+
 int exchange_on(mgb_handle* h, Level& L, double* vec, cudaStream_t st)
 {
+    if (L.p2p_ready) {
+        const int total = (int)L.send_total;
+        const int gb = std::max(1, std::min(64, (total + 255) / 256));
+        k_p2p_push<<<gb, 256, 0, st>>>(L.p2p, L.send_idx, vec);
+        const int gp = std::max(1, std::min(64, ((int)L.n_ghost + 255) / 256));
+        k_p2p_pull<<<gp, 256, 0, st>>>(L.p2p, vec, (int)L.n);
+        h->launches += 1;
+        return MGB_OK;
+    }
     if (L.send_total > 0) k_pack<<<(int)((L.send_total + 255) / 256), 256, 0, st>>>((int)L.send_total, L.send_idx, vec, L.send_buf);
     ncclResult_t r = g_nccl.GroupStart();
     int64_t so = 0, ro = 0;
@@ -917,7 +1026,9 @@ int mgb_destroy(mgb_handle* h)
     for (auto& kv : h->levels) {
         Level& L = kv.second;
         free_csr(L.A); free_csr(L.RJ); free_csr(L.P); free_csr(L.R); free_csr(L.G);
-        cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.cmap); cudaFree(L.inj_desc); cudaFree(L.send_idx); cudaFree(L.send_buf); cudaFree(L.v); cudaFree(L.vtmp); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
+        cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.cmap); cudaFree(L.inj_desc); cudaFree(L.send_idx); cudaFree(L.send_buf); cudaFree(L.p2p_counters);
+        for (void* q : L.p2p_opened) cudaIpcCloseMemHandle(q);
+        cudaFree(L.p2p_arena); cudaFree(L.v); cudaFree(L.vtmp); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
         cudaFree(L.gs_order); cudaFree(L.gs_off); cudaFree(L.gs_diag);
     }
     cudaFree(h->coarse_inv); cudaFree(h->d_partial); cudaFree(h->d_hist);
@@ -1079,6 +1190,72 @@ int mgb_set_halo(mgb_handle* h, int level, int npeers, const int32_t* peer_ranks
     cudaFree(L->send_idx); cudaFree(L->send_buf);
     TRY(dev_upload(h, &L->send_idx, send_indices, (size_t)st));
     TRY(dev_alloc(h, &L->send_buf, (size_t)st));
+    return MGB_OK;
+}
+
+int mgb_p2p_export(mgb_handle* h, int level, void* blob, int capacity, int* size)
+{
+    if (!h || !size) return MGB_ERR_INVALID;
+    *size = (int)sizeof(P2PBlob);
+    if (!blob) return MGB_OK;
+    if (capacity < (int)sizeof(P2PBlob)) return fail(h, MGB_ERR_INVALID, "blob needs %d bytes", (int)sizeof(P2PBlob));
+    Level* L = find_level(h, level);
+    if (!L || !h->dist) return fail(h, MGB_ERR_STATE, "level %d has no halo plan", level);
+    if ((int)L->peers.size() > P2P_MAX_PEERS || h->world > P2P_FLAG_SLOTS) return fail(h, MGB_ERR_UNSUPPORTED, "too many neighbours for the peer-memory exchange");
+    CU(cudaSetDevice(h->device));
+    if (!L->p2p_arena) {
+        const size_t bytes = P2P_FLAG_SLOTS * sizeof(unsigned long long) + 2 * ((size_t)L->n_ghost + 2) * sizeof(double);
+        CU(cudaMalloc(&L->p2p_arena, bytes));
+        CU(cudaMemset(L->p2p_arena, 0, bytes));
+        TRY(dev_alloc(h, &L->p2p_counters, 64));
+        CU(cudaMemset(L->p2p_counters, 0, 64 * sizeof(unsigned long long)));
+    }
+    P2PBlob b{};
+    CU(cudaIpcGetMemHandle(&b.handle, L->p2p_arena));
+    b.n_ghost = L->n_ghost;
+    b.npeers = (int)L->peers.size();
+    int ro = 0;
+    for (int p = 0; p < b.npeers; ++p) { b.peer_rank[p] = L->peers[p]; b.recv_off[p] = ro; ro += L->recv_cnt[p]; }
+    b.recv_off[b.npeers] = ro;
+    std::memcpy(blob, &b, sizeof b);
+    return MGB_OK;
+}
+
+int mgb_p2p_import(mgb_handle* h, int level, int peer_rank, const void* blob, int size)
+{
+    if (!h || !blob || size < (int)sizeof(P2PBlob)) return MGB_ERR_INVALID;
+    Level* L = find_level(h, level);
+    if (!L || !L->p2p_arena) return fail(h, MGB_ERR_STATE, "mgb_p2p_export level %d first", level);
+    CU(cudaSetDevice(h->device));
+    P2PBlob b;
+    std::memcpy(&b, blob, sizeof b);
+    int mine = -1;                                     // this rank's slot in the neighbour's ghost section
+    for (int j = 0; j < b.npeers; ++j) if (b.peer_rank[j] == h->rank) mine = j;
+    int p = -1;
+    for (size_t j = 0; j < L->peers.size(); ++j) if (L->peers[j] == peer_rank) p = (int)j;
+    if (mine < 0 || p < 0) return fail(h, MGB_ERR_INVALID, "ranks %d and %d do not list each other as neighbours on level %d", h->rank, peer_rank, level);
+    if (b.recv_off[mine + 1] - b.recv_off[mine] != L->send_cnt[p]) return fail(h, MGB_ERR_INVALID, "send/receive counts of ranks %d and %d differ on level %d", h->rank, peer_rank, level);
+    void* base = nullptr;
+    CU(cudaIpcOpenMemHandle(&base, b.handle, cudaIpcMemLazyEnablePeerAccess));
+    L->p2p_opened.push_back(base);
+    unsigned long long* rflags = (unsigned long long*)base;
+    double* rstage = (double*)((char*)base + P2P_FLAG_SLOTS * sizeof(unsigned long long));
+    L->p2p.rflag[p] = rflags + h->rank;
+    L->p2p.rstage[p][0] = rstage + b.recv_off[mine];
+    L->p2p.rstage[p][1] = rstage + (size_t)b.n_ghost + b.recv_off[mine];
+    L->p2p.peer_rank[p] = peer_rank;
+    if (++L->p2p_imported == (int)L->peers.size()) {  // plan complete
+        P2PPlan& pl = L->p2p;
+        pl.npeers = (int)L->peers.size();
+        int so = 0, ro = 0;
+        for (int j = 0; j < pl.npeers; ++j) { pl.send_off[j] = so; pl.recv_off[j] = ro; so += L->send_cnt[j]; ro += L->recv_cnt[j]; }
+        pl.send_off[pl.npeers] = so; pl.recv_off[pl.npeers] = ro;
+        pl.counters = L->p2p_counters;
+        pl.flags = (unsigned long long*)L->p2p_arena;
+        pl.stage = (double*)((char*)L->p2p_arena + P2P_FLAG_SLOTS * sizeof(unsigned long long));
+        pl.n_ghost = (int)L->n_ghost;
+        L->p2p_ready = true;
+    }
     return MGB_OK;
 }
 

@@ -50,7 +50,7 @@ def run(args):
     mg = ds.DistMG(src, device=local_rank, r_mode=args.restriction, smoother=args.smoother, gather_threshold=args.gather_threshold,
                    options={"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg, "use_graph": args.use_graph,
                             "overlap_halo": args.overlap, "overlap_waves": args.overlap_waves},
-                   device_gen=bool(args.device_gen) and args.restriction == "injection")
+                   device_gen=bool(args.device_gen) and args.restriction == "injection", p2p=bool(args.p2p))
     setup_s = time.perf_counter() - t0
     eng = mg.eng
     stream = eng.torch_stream()

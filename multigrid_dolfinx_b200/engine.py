@@ -106,6 +106,16 @@ class MGEngine:
         rc = np.ascontiguousarray(recv_cnt, dtype=np.int32)
         self._ck(self._lib.mgb_set_halo(self._h, int(level), len(peers_a), peers_a.ctypes.data, sc.ctypes.data, si.ctypes.data, rc.ctypes.data))
 
+    def p2p_export(self, level):
+        size = C.c_int()
+        self._ck(self._lib.mgb_p2p_export(self._h, int(level), None, 0, C.byref(size)))
+        buf = C.create_string_buffer(size.value)
+        self._ck(self._lib.mgb_p2p_export(self._h, int(level), buf, size.value, C.byref(size)))
+        return bytes(buf.raw)
+
+    def p2p_import(self, level, peer_rank, blob):
+        self._ck(self._lib.mgb_p2p_import(self._h, int(level), int(peer_rank), blob, len(blob)))
+
     def set_gather_level(self, level, n_global, offsets):
         off = np.ascontiguousarray(offsets, dtype=np.int64)
         self._ck(self._lib.mgb_set_gather_level(self._h, int(level), int(n_global), off.ctypes.data))

@@ -36,7 +36,9 @@ def _worker(rank, world, port, case, q):
         else:
             H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=seed, with_dicts=False)
             src = ds.HierarchySource(H)
-        mg = ds.DistMG(src, device=rank, r_mode=r_mode, gather_level=glevel, options=opts, device_gen=seed == "generated")
+        opts = dict(opts)
+        p2p = bool(opts.pop("p2p", 1))
+        mg = ds.DistMG(src, device=rank, r_mode=r_mode, gather_level=glevel, options=opts, device_gen=seed == "generated", p2p=p2p)
         mg.load_rhs()
         hist = mg.cycles(4, history=True)
         v = mg.gather_solution()
@@ -52,6 +54,7 @@ def _worker(rank, world, port, case, q):
 
 CASES = [
     (2, 8, 4, None, "injection", 1, {}),
+    (2, 8, 4, None, "injection", 1, {"p2p": 0}),      # ncclSend/ncclRecv halo exchange
     (3, 2, 4, None, "injection", 1, {"use_graph": 0}),
     (3, 2, 3, None, "transpose", 0, {}),
     (3, 2, 4, None, "injection", 1, {"overlap_halo": 0}),
