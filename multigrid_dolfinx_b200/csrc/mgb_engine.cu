@@ -542,11 +542,21 @@ __global__ void __launch_bounds__(256)
 k_p2p_push(P2PPlan pl, const int32_t* __restrict__ send_idx, const double* __restrict__ vec)
 {
     const int total = pl.send_off[pl.npeers];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
-        int p = 0;
-        while (k >= pl.send_off[p + 1]) ++p;
-        const int par = (int)((pl.counters[p] + 1) & 1);
-        pl.rstage[p][par][k - pl.send_off[p]] = vec[send_idx[k]];
+    const int par = (int)((pl.counters[0] + 1) & 1);          // all neighbours of a level share one epoch count
+    const int stride = gridDim.x * blockDim.x;
+    for (int k0 = blockIdx.x * blockDim.x + threadIdx.x; k0 < total; k0 += 4 * stride) {
+        double val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int k = k0 + u * stride; if (k < total) val[u] = vec[send_idx[k]]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * stride;
+            if (k < total) {
+                int p = 0;
+                while (k >= pl.send_off[p + 1]) ++p;
+                pl.rstage[p][par][k - pl.send_off[p]] = val[u];
+            }
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -576,8 +586,14 @@ k_p2p_pull(P2PPlan pl, double* __restrict__ vec, int n_owned)
     __syncthreads();
     const int par = (int)((pl.counters[16] + 1) & 1);
     const double* src = pl.stage + (size_t)par * pl.n_ghost;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < pl.n_ghost; k += gridDim.x * blockDim.x)
-        vec[n_owned + k] = __ldcg(src + k);
+    const int stride = gridDim.x * blockDim.x;
+    for (int k0 = blockIdx.x * blockDim.x + threadIdx.x; k0 < pl.n_ghost; k0 += 4 * stride) {
+        double val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int k = k0 + u * stride; if (k < pl.n_ghost) val[u] = __ldcg(src + k); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int k = k0 + u * stride; if (k < pl.n_ghost) vec[n_owned + k] = val[u]; }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -593,9 +609,10 @@ int exchange_on(mgb_handle* h, Level& L, double* vec, cudaStream_t st)
 {
     if (L.p2p_ready) {
         const int total = (int)L.send_total;
-        const int gb = std::max(1, std::min(64, (total + 255) / 256));
+        const int wide = 4 * h->sm_count;          // NVLink stores and the local unpack need many SMs to reach bandwidth
+        const int gb = std::max(1, std::min(wide, (total + 1023) / 1024));
         k_p2p_push<<<gb, 256, 0, st>>>(L.p2p, L.send_idx, vec);
-        const int gp = std::max(1, std::min(64, ((int)L.n_ghost + 255) / 256));
+        const int gp = std::max(1, std::min(wide, ((int)L.n_ghost + 1023) / 1024));
         k_p2p_pull<<<gp, 256, 0, st>>>(L.p2p, vec, (int)L.n);
         h->launches += 1;
         return MGB_OK;
