@@ -67,9 +67,9 @@ def run(args):
         torch.cuda.synchronize()
         launches = eng.launch_count() - l0
         barrier()
-        if args.steps * 2e-3 < 1.0:
-            mg.cycles(200); torch.cuda.synchronize()
-    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)      # identical on every rank (the cycles are collective)
+        if ms * args.steps < 1000.0:         # ~1 s under load for the clock sampler
+            mg.cycles(int(min(2000, max(1, (1000.0 - ms * args.steps) / max(ms, 1e-3))))); torch.cuda.synchronize()
     hist = mg.cycles(1, history=True)
 
     # dominant kernel on rank 0, event-timed (all ranks run the same cycles: the halo exchanges are collective)

@@ -448,3 +448,164 @@ def build_hierarchy(dim=2, c=8, coarsest_level=0, finest_level=2, perm_seed=None
         H.P[l] = prolongation(Nc, dim, H.perms[l], H.perms[l + 1])
         H.inj[l] = injection(Nc, dim, H.perms[l], H.perms[l + 1])
     return H
+
+
+# --------------------------------------------------------------------------------------------
+# 3-D P2 (quadratic Lagrange) on the Kuhn mesh -- BASELINE config 4.  No reference text exists for
+# P2 (the reference is 2-D P1 only): element matrices and transfers below are the standard FE ones.
+# --------------------------------------------------------------------------------------------
+# DOFs: vertices and edge midpoints.  Every nonzero vector of {0,1}^3 is an edge direction of the Kuhn
+# triangulation, so the P2 DOFs of an m^3-cell mesh are exactly the points of the (2m+1)^3 lattice of half
+# cell widths ("doubled lattice"); numbering is lexicographic on that lattice, x fastest.
+
+_P2_EDGES = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+
+
+def _kuhn_tets_doubled(m):
+    """(ntet, 4, 3) vertex coordinates on the doubled lattice."""
+    i, j, k = np.meshgrid(np.arange(m), np.arange(m), np.arange(m), indexing="ij")
+    base = np.stack([i.ravel(), j.ravel(), k.ravel()], 1) * 2
+    out = []
+    eye = np.eye(3, dtype=np.int64) * 2
+    for s in itertools.permutations(range(3)):
+        v0 = base
+        v1 = v0 + eye[s[0]]
+        v2 = v1 + eye[s[1]]
+        v3 = v2 + eye[s[2]]
+        out.append(np.stack([v0, v1, v2, v3], 1))
+    return np.concatenate(out, 0)
+
+
+def _p2_element_int(verts2):
+    """Integer-scaled P2 stiffness of every tet: K_true = E * h / 120 (10 x 10, DOF order: 4 vertices, 6 edges).
+    With g_ab = grad(lambda_a).grad(lambda_b) in cell units and V = 1/6:
+      vertex-vertex  (3/5 V) g_ii, (-1/5 V) g_ij ;  vertex-edge 4 V [g_ik c(i,j) + g_ij c(i,k)], c = 3/20 (same) / -1/20 ;
+      edge-edge      16 V/20 [g_jl (1+d_ik) + g_jk (1+d_il) + g_il (1+d_jk) + g_ik (1+d_jl)]."""
+    X = verts2.astype(np.float64) / 2.0                       # cell units
+    Emat = X[:, 1:, :] - X[:, :1, :]
+    Einv = np.linalg.inv(Emat)
+    G = np.concatenate([-Einv.sum(axis=2, keepdims=True).transpose(0, 2, 1), Einv.transpose(0, 2, 1)], 1)   # grad lambda
+    g = np.rint(np.einsum("cad,cbd->cab", G, G))              # integers on the Kuhn mesh
+    nt = X.shape[0]
+    E = np.zeros((nt, 10, 10))
+    d = np.eye(4)
+    for a in range(4):
+        for b in range(4):
+            E[:, a, b] = (12.0 if a == b else -4.0) * g[:, a, b]                      # x (V/20) with V factored out below
+    for a in range(4):
+        for e, (j, k) in enumerate(_P2_EDGES):
+            cj = 3.0 if a == j else -1.0
+            ck = 3.0 if a == k else -1.0
+            val = 4.0 * (g[:, a, k] * cj + g[:, a, j] * ck)
+            E[:, a, 4 + e] = val
+            E[:, 4 + e, a] = val
+    for e1, (i, j) in enumerate(_P2_EDGES):
+        for e2, (k, l) in enumerate(_P2_EDGES):
+            E[:, 4 + e1, 4 + e2] = 16.0 * (g[:, j, l] * (1 + d[i, k]) + g[:, j, k] * (1 + d[i, l])
+                                           + g[:, i, l] * (1 + d[j, k]) + g[:, i, k] * (1 + d[j, l]))
+    return E            # K_true = E * (V/20) / h^2 * h^3 = E * h / 120   (V = 1/6 in cell units)
+
+
+def _p2_dofs(verts2, N):
+    """(ntet, 10) lexicographic DOF ids on the doubled lattice."""
+    pts = [verts2[:, a, :] for a in range(4)] + [(verts2[:, i, :] + verts2[:, j, :]) // 2 for i, j in _P2_EDGES]
+    return np.stack([p[:, 0] + N * p[:, 1] + N * N * p[:, 2] for p in pts], 1)
+
+
+def assemble_p2_3d(m, perm=None, bc=True, with_load=False):
+    """P2 Poisson stiffness on the m^3 Kuhn mesh, dolfinx-shaped: pattern = DOF connectivity through cells (stored
+    zeros kept), Dirichlet rows/columns zeroed in place with unit diagonal.  Returns (A, boundary mask[, load])
+    where load_i = integral of phi_i (for a constant source)."""
+    N = 2 * m + 1
+    n = N ** 3
+    h = 1.0 / m
+    verts2 = _kuhn_tets_doubled(m)
+    E = _p2_element_int(verts2)
+    dofs = _p2_dofs(verts2, N)
+    if perm is not None:
+        dofs = perm[dofs]
+    rows = np.repeat(dofs, 10, axis=1).ravel()
+    cols = np.tile(dofs, (1, 10)).ravel()
+    K = sp.coo_matrix((E.ravel(), (rows, cols)), shape=(n, n)).tocsr()
+    K.sum_duplicates(); K.sort_indices()
+    K.data = K.data * h / 120.0
+    mi = node_multi_index(N, 3)
+    bnd = np.zeros(n, dtype=bool)
+    for a in mi:
+        bnd |= (a == 0) | (a == N - 1)
+    if perm is not None:
+        b2 = np.zeros(n, dtype=bool); b2[perm] = bnd; bnd = b2
+    A = K.copy()
+    if bc:
+        r = np.repeat(np.arange(n), np.diff(A.indptr))
+        kill = bnd[r] | bnd[A.indices]
+        A.data[kill] = 0.0
+        A.data[(r == A.indices) & bnd[r]] = 1.0
+    A.data = A.data + 0.0
+    A.indices = A.indices.astype(np.int32); A.indptr = A.indptr.astype(np.int32)
+    if not with_load:
+        return A, bnd
+    V = h ** 3 / 6.0
+    w = np.concatenate([np.full(4, -V / 20.0), np.full(6, V / 5.0)])      # integral of the P2 basis functions
+    load = np.bincount(dofs.ravel(), weights=np.tile(w, dofs.shape[0]), minlength=n)
+    return A, bnd, load, K
+
+
+def prolongation_p2_3d(mc, perm_c=None, perm_f=None):
+    """P2 -> P2 interpolation between the nested Kuhn meshes mc^3 -> (2 mc)^3: fine DOF value = coarse FE function
+    evaluated at the fine DOF point.  Row entry order: the 4 vertex functions, then the 6 edge functions of the
+    containing coarse tet (zeros dropped)."""
+    Nc, Nf = 2 * mc + 1, 4 * mc + 1
+    nf, nc = Nf ** 3, Nc ** 3
+    mi = node_multi_index(Nf, 3)
+    p = np.stack(mi, 1).astype(np.float64) / 4.0                      # coarse cell units
+    cube = np.minimum(np.floor(p).astype(np.int64), mc - 1)
+    r = p - cube
+    order = np.argsort(-r, axis=1, kind="stable")                     # Kuhn tet: coordinates in descending order
+    rs = np.take_along_axis(r, order, axis=1)
+    lam = np.stack([1.0 - rs[:, 0], rs[:, 0] - rs[:, 1], rs[:, 1] - rs[:, 2], rs[:, 2]], 1)
+    eye2 = np.eye(3, dtype=np.int64) * 2
+    v = [cube * 2]
+    for s in range(3):
+        v.append(v[-1] + eye2[order[:, s]])
+    pts = v + [(v[i] + v[j]) // 2 for i, j in _P2_EDGES]
+    wts = [lam[:, a] * (2.0 * lam[:, a] - 1.0) for a in range(4)] + [4.0 * lam[:, i] * lam[:, j] for i, j in _P2_EDGES]
+    cols = np.stack([q[:, 0] + Nc * q[:, 1] + Nc * Nc * q[:, 2] for q in pts], 1)
+    W = np.stack(wts, 1)
+    keep = W != 0.0
+    counts = keep.sum(1)
+    indptr = np.zeros(nf + 1, dtype=np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    indices = cols[keep]
+    data = W[keep]
+    if perm_c is not None:
+        indices = perm_c[indices]
+    P = sp.csr_matrix((data, indices.astype(np.int32), indptr.astype(np.int32)), shape=(nf, nc))
+    if perm_f is not None:
+        inv = np.empty(nf, dtype=np.int64); inv[perm_f] = np.arange(nf)
+        P = P[inv]
+    return P
+
+
+def build_hierarchy_p2(c=2, coarsest_level=0, finest_level=2, perm_seed=None, mu0=2, mu1=2, mu2=2, omega=2.0 / 3.0, seed_rhs=0):
+    """3-D P2 hierarchy (BASELINE config 4: c=4, levels 0..4 -> DOF lattices 9^3 .. 129^3).  The right-hand side is a
+    seeded random vector with homogeneous Dirichlet values (no manufactured solution is needed for V-cycle parity)."""
+    H = Hierarchy(dim=3, coarsest_level_elements_per_dim=c, coarsest_level=coarsest_level, finest_level=finest_level,
+                  mu0=mu0, mu1=mu1, mu2=mu2, omega=omega)
+    for l in H.levels():
+        m = c * 2 ** l
+        N = 2 * m + 1
+        n = N ** 3
+        H.nodes_per_dim[l] = N
+        H.element_size[l] = 1 / m
+        perm = make_permutation(n, None if perm_seed is None else perm_seed + 1000 * l)
+        H.perms[l] = perm
+        A, bnd = assemble_p2_3d(m, perm)
+        H.A_sp_dict[l] = (A, l)
+        b = np.random.default_rng(seed_rhs + l).standard_normal(n)
+        b[bnd] = 0.0
+        H.b_dict[l] = b.reshape(n, 1)
+    for l in range(coarsest_level, finest_level):
+        H.P[l] = prolongation_p2_3d(c * 2 ** l, H.perms[l], H.perms[l + 1])
+        H.inj[l] = injection(H.nodes_per_dim[l], 3, H.perms[l], H.perms[l + 1])
+    return H

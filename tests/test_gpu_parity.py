@@ -315,3 +315,22 @@ def test_device_side_generation_matches_host_assembler(dim, c, lf, glevel):
     v0, h0 = ref.vcycle(lf, np.zeros_like(f), f, ncycles=3, history=True)
     assert np.array_equal(mg.local_solution(), v0) and np.array_equal(h1, h0)
     mg.close(); ref.close()
+
+
+@pytest.mark.parametrize("r_mode,opts", [("injection", {}), ("transpose", {}), ("transpose", {"kernel_family": 2}), ("full_weighting", {"stream_cfg": 0})])
+def test_p2_hierarchy_vs_oracle(r_mode, opts):
+    """BASELINE config 4 shape (3-D P2, rows of 10..65 entries, FE interpolation with negative weights), small instance."""
+    H = pr.build_hierarchy_p2(c=2, coarsest_level=0, finest_level=2, perm_seed=None)
+    eng = MGEngine.from_hierarchy(H, r_mode=r_mode, options=opts)
+    cm = co.from_hierarchy(H, r_mode=r_mode)
+    f = H.b_dict[2][:, 0]
+    vo, ho = cm.vcycle(np.zeros_like(f), f, ncycles=4, history=True)
+    vg, hg = eng.vcycle(2, np.zeros_like(f), f, ncycles=4, history=True)
+    r = float(np.abs(hg - ho).max() / ho.max()); s = relmax(vg, vo)
+    _report("p2_oracle", r_mode=r_mode, opts=str(opts), resnorm_rel=r, solution_rel=s)
+    assert r <= RTOL_RESNORM and s <= RTOL_SOLUTION
+    if "kernel_family" not in opts:
+        A = H.A_sp_dict[2][0]
+        x = np.random.default_rng(3).standard_normal(A.shape[0])
+        assert np.array_equal(eng.spmv(2, x), A.dot(x))                      # 65-entry rows, still bit-exact
+    eng.close()

@@ -79,3 +79,60 @@ def test_hierarchy_shapes_match_reference_objects():
         assert H.element_size[l] == 1 / (8 * 2 ** l)
         d = H.mesh_dof_list_dict[l]
         assert len(d) == 2 * H.n(l) and d[d[0]] == 0 and len(d[0]) == 3
+
+
+# ---- 3-D P2 (BASELINE config 4) ----------------------------------------------------------------------------
+
+def test_p2_pattern_matches_survey_probe():
+    """P2 on the Kuhn mesh, n = 4 and 8 cells: average row length 23.35 / 25.81, longest row 65, row lengths
+    drawn from {10,14,18,19,22,27,32,42,65}; the stiffness matrix is symmetric with zero row sums before boundary conditions."""
+    for m, avg in ((4, 23.35), (8, 25.81)):
+        A, bnd, load, K = pr.assemble_p2_3d(m, with_load=True)
+        cnt = np.diff(A.indptr)
+        assert abs(A.nnz / A.shape[0] - avg) < 0.01 and cnt.max() == 65
+        assert set(np.unique(cnt)) <= {10, 14, 18, 19, 22, 27, 32, 42, 65}
+        assert abs(K - K.T).max() == 0.0 and np.abs(K.sum(1)).max() < 1e-14
+        assert A.shape[0] == (2 * m + 1) ** 3
+
+
+def test_p2_is_exact_for_quadratics():
+    m = 4
+    A, bnd, load, K = pr.assemble_p2_3d(m, with_load=True)
+    N = 2 * m + 1
+    X = np.stack(pr.node_multi_index(N, 3), 1) / (N - 1)
+    u = 1 + X[:, 0] ** 2 + 2 * X[:, 1] ** 2 + 3 * X[:, 2] ** 2
+    rhs = -12.0 * load - K[:, bnd].dot(u[bnd])
+    rhs[bnd] = u[bnd]
+    uh = spl.spsolve(A.tocsc(), rhs)
+    assert np.abs(uh - u).max() < 1e-12
+
+
+@pytest.mark.parametrize("mc,seed", [(1, None), (2, None), (2, 4)])
+def test_p2_prolongation_reproduces_quadratics(mc, seed):
+    Nc, Nf = 2 * mc + 1, 4 * mc + 1
+    pc = pr.make_permutation(Nc ** 3, seed)
+    pf = pr.make_permutation(Nf ** 3, None if seed is None else seed + 1)
+    P = pr.prolongation_p2_3d(mc, pc, pf)
+    Xc = np.stack(pr.node_multi_index(Nc, 3), 1) / (Nc - 1)
+    Xf = np.stack(pr.node_multi_index(Nf, 3), 1) / (Nf - 1)
+
+    def q(X):
+        return 1 + X[:, 0] ** 2 + 2 * X[:, 1] * X[:, 2] + 3 * X[:, 2] ** 2 - X[:, 0] * X[:, 1]
+    uc, uf = q(Xc), q(Xf)
+    if pc is not None:
+        t = np.empty_like(uc); t[pc] = uc; uc = t
+        t = np.empty_like(uf); t[pf] = uf; uf = t
+    assert np.abs(P.dot(uc) - uf).max() < 1e-14
+    assert np.abs(np.asarray(P.sum(1)).ravel() - 1).max() < 1e-15
+    inj = pr.injection(Nc, 3, pc, pf)
+    import scipy.sparse as sp
+    assert (P.tocsr()[inj] != sp.identity(Nc ** 3)).nnz == 0
+
+
+def test_p2_vcycle_converges_with_transpose_restriction():
+    from oracle import c_oracle as co
+    H = pr.build_hierarchy_p2(c=1, coarsest_level=0, finest_level=2)
+    cm = co.from_hierarchy(H, r_mode="transpose")
+    f = H.b_dict[2][:, 0]
+    v, hist = cm.vcycle(np.zeros_like(f), f, ncycles=8, history=True)
+    assert hist[-1] < 1e-2 * hist[0]
