@@ -138,6 +138,7 @@ struct mgb_handle {
     int mu1 = 2, mu2 = 2, smoother = MGB_SM_JACOBI_RJ;
     // options
     int rj_reversed = 1, use_graph = 1, opt_family = 0, opt_lpr = 0, opt_iter = 0, coarse_refine = 0, fuse_restrict = 1;
+    int gs_cluster = 1;            // level-scheduled Gauss-Seidel inside one thread-block cluster when the levels are narrow
     int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
     bool allow_stream = true;      // false while borrowed user pointers are in play (no padding / alignment guarantee)
     int coarsest = 0, finest = 0;
@@ -707,6 +708,19 @@ int gs_sweep(mgb_handle* h, Level& L, double* v, const double* f)
 {
     const DevCsr& G = L.G;
     const double nb = 12.0 * (double)G.nnz + 8.0 * (double)L.n /*rowptr+order*/ + 8.0 * 3.0 * (double)L.n;
+    if (h->smoother == MGB_SM_GS_LEVEL && h->gs_cluster && L.gs_max_width <= 8 * 512 * 2) {
+        // narrow levels: one 8-CTA cluster, hardware cluster barrier between dependency levels
+        return launch(h, MGB_K_GS, L.level, nb, [&] {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(8); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, k_gs_levels_cluster, (const int32_t*)G.rowptr, (const int32_t*)G.cols, (const double*)G.vals,
+                               (const int32_t*)L.gs_order, (const double*)L.gs_diag, f, v, (const int32_t*)L.gs_off, L.gs_groups);
+        });
+    }
     if (h->smoother == MGB_SM_GS_LEVEL) {
         return launch(h, MGB_K_GS, L.level, nb, [&] {
             int blocks = std::max(1, std::min(h->gs_coop_blocks_per_sm * h->sm_count, (L.gs_max_width + 255) / 256));
@@ -1360,6 +1374,7 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "lanes_per_row" && pre) h->opt_lpr = iv;
     else if (k == "tile_iter" && pre) h->opt_iter = iv;
     else if (k == "stream_cfg" && pre) h->stream_cfg = iv;
+    else if (k == "gs_cluster") h->gs_cluster = iv;
     else if (k == "overlap_halo") { h->overlap = iv; drop_graphs(h); }
     else if (k == "overlap_waves") { h->overlap_waves = iv; drop_graphs(h); }
     else return fail(h, pre ? MGB_ERR_INVALID : MGB_ERR_STATE, "option '%s' unknown or not settable %s finalize", key, pre ? "before" : "after");
