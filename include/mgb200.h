@@ -186,6 +186,19 @@ int mgb_vcycle_debug(mgb_handle* h, int top_level, double* v, const double* f, i
  * no copy of any kind inside the call; resnorm_hist (host, nullable) forces a sync at the end. */
 int mgb_vcycle_resident(mgb_handle* h, int top_level, int ncycles, double* resnorm_hist);
 
+/* ---- the caller of the path: FullMultiGrid (multigrid.py:271-307) kept on the device --------------------------- */
+/* b_dict[level] (Multigrid_prototype.py:110): the re-discretised right-hand side FMG starts each level from. */
+int mgb_set_rhs(mgb_handle* h, int level, const double* b, int mem);
+/* optional mass matrix of a level: the stopping rule then uses sqrt(r^T M r), the L2(Omega) norm the reference
+ * assembles with dolfinx (res_calculator, multigrid.py:203-208); without it the l2 norm is used. */
+int mgb_set_mass_matrix(mgb_handle* h, int level, int64_t n, int64_t nnz, const void* indptr, int indptr_bytes,
+                        const int32_t* indices, const double* values);
+/* nested iteration: coarsest solve, interpolate up, mu0 V-cycles per intermediate level (multigrid.py:305-306), V-cycles on
+ * the finest level until the residual norm <= tol (multigrid.py:296) or max_cycles (the reference has no cap).
+ * v_out (nullable) receives the finest-level solution; resnorm_hist[0..min(cycles, hist_capacity)) the norms. */
+int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, int mem, int* cycles_done,
+            double* resnorm_hist, int hist_capacity);
+
 /* ---- per-operator entry points (parity tests, profiling) -------------------------------------- */
 int mgb_spmv(mgb_handle* h, int level, const double* x, double* y, int mem);                       /* A.dot(x), multigrid.py:244 */
 int mgb_residual(mgb_handle* h, int level, const double* v, const double* f, double* r, int mem); /* f - A v, multigrid.py:244  */

@@ -59,6 +59,9 @@ SYMBOLS = {
     "mgb_vcycle": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp]),
     "mgb_vcycle_debug": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "mgb_vcycle_resident": (_i, [_vp, _i, _i, _vp]),
+    "mgb_set_rhs": (_i, [_vp, _i, _vp, _i]),
+    "mgb_set_mass_matrix": (_i, [_vp, _i, _i64, _i64, _vp, _i, _vp, _vp]),
+    "mgb_fmg": (_i, [_vp, _i, _d, _i, _vp, _i, C.POINTER(_i), _vp, _i]),
     "mgb_spmv": (_i, [_vp, _i, _vp, _vp, _i]),
     "mgb_residual": (_i, [_vp, _i, _vp, _vp, _vp, _i]),
     "mgb_smooth": (_i, [_vp, _i, _vp, _vp, _i, _i]),

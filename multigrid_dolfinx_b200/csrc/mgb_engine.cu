@@ -115,6 +115,8 @@ struct Level {
     int inj_n_int = 0, inj_n_bnd = 0;   // sharded: the list is stored [interior tiles | boundary tiles]
     double inj_fraction = 1.0;       // share of A's entries in those tiles
     double *v = nullptr, *vtmp = nullptr, *f = nullptr, *r = nullptr, *g = nullptr;
+    double* b = nullptr;             // re-discretised right-hand side b_dict[l] (FMG, multigrid.py:279)
+    DevCsr M;                        // optional mass matrix for the L2(Omega) norm of the FMG stopping rule
     // Gauss-Seidel artefacts (host copies are what mgb_get_artifact returns)
     std::vector<int32_t> lev_of_row, lev_order, lev_off, col_of_row, col_order, col_off;
     int32_t* gs_order = nullptr;     // device: execution order actually used by G
@@ -1056,7 +1058,7 @@ int mgb_destroy(mgb_handle* h)
     drop_graphs(h);
     for (auto& kv : h->levels) {
         Level& L = kv.second;
-        free_csr(L.A); free_csr(L.RJ); free_csr(L.P); free_csr(L.R); free_csr(L.G);
+        free_csr(L.A); free_csr(L.RJ); free_csr(L.P); free_csr(L.R); free_csr(L.G); free_csr(L.M); cudaFree(L.b);
         cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.cmap); cudaFree(L.inj_desc); cudaFree(L.send_idx); cudaFree(L.send_buf); cudaFree(L.p2p_counters);
         for (void* q : L.p2p_opened) cudaIpcCloseMemHandle(q);
         cudaFree(L.p2p_arena); cudaFree(L.v); cudaFree(L.vtmp); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
@@ -1544,6 +1546,90 @@ int mgb_vcycle(mgb_handle* h, int top_level, double* v, const double* f, int mem
     TRY(cycles_on_buffers(h, top_level, ncycles, resnorm_hist));
     TRY(copy_out(h, v, T->v, T->n, mem));
     if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream));
+    return MGB_OK;
+}
+
+int mgb_set_rhs(mgb_handle* h, int level, const double* b, int mem)
+{
+    Level* L;
+    TRY(check_ready(h, level, &L));
+    if (!b) return fail(h, MGB_ERR_INVALID, "null right-hand side");
+    if (!L->b) TRY(dev_alloc(h, &L->b, (size_t)L->n + 16));
+    TRY(copy_in(h, L->b, b, L->n, mem));
+    if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream));
+    return MGB_OK;
+}
+
+int mgb_set_mass_matrix(mgb_handle* h, int level, int64_t n, int64_t nnz, const void* indptr, int indptr_bytes,
+                        const int32_t* indices, const double* values)
+{
+    Level* L;
+    TRY(check_ready(h, level, &L));
+    if (n != L->n) return fail(h, MGB_ERR_INVALID, "mass matrix has %lld rows, level %d has %lld", (long long)n, level, (long long)L->n);
+    HostCsr M;
+    std::string e = import_csr(M, n, n, nnz, indptr, indptr_bytes, indices, values);
+    if (!e.empty()) return fail(h, MGB_ERR_INVALID, "mass matrix: %s", e.c_str());
+    free_csr(L->M);
+    TRY(upload_csr(h, M, L->M));
+    CU(cudaStreamSynchronize(h->stream));
+    return MGB_OK;
+}
+
+// FullMultiGrid (multigrid.py:271-307) on the device: nested iteration from the re-discretised right-hand sides,
+// mu0 V-cycles per intermediate level, V-cycles on the finest level until the residual norm is <= tol (capped).
+// Norm: sqrt(r^T M r) if a mass matrix was set for the finest level (the reference's L2(Omega) norm, multigrid.py:203-208),
+// else the l2 norm.  Only the per-cycle scalar travels to the host.
+int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, int mem, int* cycles_done,
+            double* resnorm_hist, int hist_capacity)
+{
+    Level* T;
+    if (!h) return MGB_ERR_INVALID;
+    TRY(check_ready(h, h->finest, &T));
+    if (h->dist) return fail(h, MGB_ERR_UNSUPPORTED, "the FMG driver is single-GPU in this version");
+    if (mu0 < 0 || max_cycles < 0) return fail(h, MGB_ERR_INVALID, "negative cycle count");
+    for (int l = h->coarsest; l <= h->finest; ++l)
+        if (!h->levels[l].b) return fail(h, MGB_ERR_STATE, "mgb_set_rhs missing for level %d", l);
+    Level& C0 = h->levels[h->coarsest];
+    CU(cudaMemcpyAsync(C0.f, C0.b, sizeof(double) * (size_t)C0.n, cudaMemcpyDeviceToDevice, h->stream));
+    TRY(coarse_apply(h, C0, C0.f, C0.v));                                         // multigrid.py:274-277
+    int done = 0;
+    TRY(ensure_hist(h, 2));
+    for (int l = h->coarsest + 1; l <= h->finest; ++l) {
+        Level& L = h->levels[l];
+        Level& C = h->levels[l - 1];
+        CU(cudaMemsetAsync(L.v, 0, sizeof(double) * (size_t)L.n, h->stream));
+        TRY(prolong_add(h, L, C.v, L.v, nullptr));                                // v_h = Interpolation(v_2h), multigrid.py:283-284
+        CU(cudaMemcpyAsync(L.f, L.b, sizeof(double) * (size_t)L.n, cudaMemcpyDeviceToDevice, h->stream));
+        if (l < h->finest) {
+            for (int c = 0; c < mu0; ++c) TRY(run_cycle(h, l));                   // multigrid.py:305-306
+            continue;
+        }
+        while (done < max_cycles) {                                               // multigrid.py:288-302 (with a cap)
+            TRY(run_cycle(h, l));
+            ++done;
+            TRY(residual(h, L, L.v, L.f, L.r));                                   // multigrid.py:291
+            if (L.M.present()) {
+                EpiStore epi{L.vtmp};
+                TRY(row_sums(h, MGB_K_SPMV, l, bytes_rowsum(L.M, 2.0 * (double)L.n), L.M, L.r, epi));
+                TRY(launch(h, MGB_K_NORM, l, 16.0 * (double)L.n, [&] {
+                    k_dot_partial<<<h->norm_blocks, 256, 0, h->stream>>>(L.n, L.r, L.vtmp, h->d_partial);
+                    k_sumsq_final<<<1, 1024, 0, h->stream>>>(h->norm_blocks, h->d_partial, h->d_hist, 1);
+                }));
+            } else {
+                TRY(norm2_device(h, L.n, L.r, h->d_hist, l));
+            }
+            double nrm = 0.0;
+            CU(cudaMemcpyAsync(&nrm, h->d_hist, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            if (resnorm_hist && done <= hist_capacity) resnorm_hist[done - 1] = nrm;
+            if (nrm <= tol) break;                                                // multigrid.py:296
+        }
+    }
+    if (cycles_done) *cycles_done = done;
+    if (v_out) {
+        TRY(copy_out(h, v_out, T->v, T->n, mem));
+        if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream));
+    }
     return MGB_OK;
 }
 

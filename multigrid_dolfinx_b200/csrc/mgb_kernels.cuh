@@ -518,6 +518,23 @@ k_sumsq_partial(int64_t n, const double* __restrict__ x, double* __restrict__ pa
         partial[blockIdx.x] = t;
     }
 }
+// x . y with the same fixed trees (mass-matrix norm sqrt(r^T M r) of the FMG stopping rule, multigrid.py:203-208)
+__global__ void __launch_bounds__(256)
+k_dot_partial(int64_t n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ partial)
+{
+    __shared__ double sh[8];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s = fma(x[i], y[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+        partial[blockIdx.x] = t;
+    }
+}
 __global__ void k_sumsq_final(int nb, const double* __restrict__ partial, double* __restrict__ out, int take_root)
 {
     __shared__ double sh[32];

@@ -258,6 +258,26 @@ class MGEngine:
         col = (lambda a: a.reshape(-1, 1)) if np.asarray(v).ndim > 1 else (lambda a: a)
         return col(vv), col(f2), col(v2), col(e)
 
+    # -- FullMultiGrid on the device (multigrid.py:271-307) ------------------------------------------------------
+    def set_rhs(self, level, b):
+        bp, mem, keep = self._in(b, self.n[level], "b")
+        self._ck(self._lib.mgb_set_rhs(self._h, int(level), bp, mem))
+
+    def set_mass_matrix(self, level, M):
+        ip, ix, ax = _as_csr_arrays(M)
+        self._ck(self._lib.mgb_set_mass_matrix(self._h, int(level), M.shape[0], len(ax), ip.ctypes.data, ip.dtype.itemsize,
+                                               ix.ctypes.data, ax.ctypes.data))
+
+    def fmg(self, mu0=2, tol=1e-11, max_cycles=10000):
+        """-> (finest-level solution (n,), residual norms per finest-level cycle)."""
+        lf = max(self.n)
+        v = np.empty(self.n[lf])
+        hist = np.zeros(max(max_cycles, 1))
+        done = C.c_int()
+        self._ck(self._lib.mgb_fmg(self._h, int(mu0), float(tol), int(max_cycles), v.ctypes.data, L.MEM_HOST, C.byref(done),
+                                   hist.ctypes.data, len(hist)))
+        return v, hist[:done.value]
+
     def vcycle_resident(self, level, ncycles=1, history=False):
         """Cycles on the engine's own level buffers (see ``level_buffer``): no copies at all."""
         hist = np.zeros(ncycles) if history else None

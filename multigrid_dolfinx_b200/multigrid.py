@@ -278,31 +278,32 @@ def _is_device(x):
 
 
 def FullMultiGrid(A_h, f_h):
-    """multigrid.py:271-307: nested iteration; at the finest level cycles until the residual norm is
-    <= 1e-11 (capped at ``max_fmg_cycles``; the reference has no cap).  Norms use res_calculator's
-    substitution (V_fine_dolfx may be a mass matrix or None)."""
+    """multigrid.py:271-307: nested iteration; at the finest level V-cycles until the residual norm is <= 1e-11
+    (capped at ``max_fmg_cycles``; the reference has no cap).  Called with the finest level (the only way the
+    reference calls it, Multigrid_prototype.py:148) the whole driver runs on the device (``mgb_fmg``): only one scalar
+    per cycle comes back.  Norm: sqrt(r^T M r) when ``V_fine_dolfx`` is a mass matrix (the reference's L2(Omega)
+    norm, multigrid.py:203-208), else the l2 norm.  Called with an intermediate level it recurses like the reference."""
     current_level = A_h[2]
     eng = engine()
     if current_level == coarsest_level:
         return np.asarray(eng.coarse_solve(np.asarray(f_h, dtype=np.float64).reshape(-1))).reshape(-1, 1)
+    n = eng.n[current_level]
+    if current_level == finest_level:
+        for l in range(coarsest_level, finest_level):
+            eng.set_rhs(l, np.asarray(b_dict[l], dtype=np.float64).reshape(-1))
+        eng.set_rhs(finest_level, np.asarray(f_h, dtype=np.float64).reshape(-1))
+        if hasattr(V_fine_dolfx, "dot") and hasattr(V_fine_dolfx, "indptr"):
+            eng.set_mass_matrix(finest_level, V_fine_dolfx)
+        v, hist = eng.fmg(mu0, 1E-11, max_fmg_cycles)
+        residual_per_V_cycle_finest.extend(float(x) for x in hist)
+        if u_exact_fine is not None:
+            error_per_V_cycle_finest.append(err_calculator(v, u_exact_fine, V_fine_dolfx))
+        with open(f'iter_count_for_diff_num_elems_{finest_level - coarsest_level + 1}_levels.csv', mode='a') as file1:
+            csv.writer(file1, delimiter=',').writerow([coarsest_level_elements_per_dim * 2 ** finest_level, len(hist)])
+        return v.reshape(n, 1)
     f_2h = b_dict[current_level - 1]
     v_2h = FullMultiGrid(A_jacobi_sp_dict[current_level - 1], f_2h)
-    n = eng.n[current_level]
     v_h = eng.prolong_add(current_level, v_2h.reshape(-1), np.zeros(n)).reshape(n, 1)
-    if current_level == finest_level:
-        count = 0
-        while True:
-            v_h = V_cycle_scheme(A_h, v_h, f_h)
-            count += 1
-            res_h = eng.residual(current_level, v_h, f_h)
-            if u_exact_fine is not None:
-                error_per_V_cycle_finest.append(err_calculator(v_h, u_exact_fine, V_fine_dolfx))
-            res_norm = res_calculator(res_h, V_fine_dolfx)
-            residual_per_V_cycle_finest.append(res_norm)
-            if res_norm <= 1E-11 or count >= max_fmg_cycles:
-                with open(f'iter_count_for_diff_num_elems_{finest_level - coarsest_level + 1}_levels.csv', mode='a') as file1:
-                    csv.writer(file1, delimiter=',').writerow([coarsest_level_elements_per_dim * 2 ** finest_level, count])
-                return v_h
     for _ in range(mu0):
         v_h = V_cycle_scheme(A_h, v_h, f_h)
     return v_h

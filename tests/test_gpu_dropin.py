@@ -70,3 +70,28 @@ def test_fmg_driver_converges():
     A = H.A_sp_dict[3][0]
     assert np.linalg.norm(H.b_dict[3] - A.dot(u)) <= 1e-10
     assert H.residual_per_V_cycle_finest[-1] <= 1e-11
+
+
+@pytest.mark.parametrize("with_mass", [False, True])
+def test_device_fmg_matches_restated_fmg(with_mass):
+    """mgb_fmg (FullMultiGrid, multigrid.py:271-307, on the device) vs the numpy restatement: same cycle count, same
+    residual-norm history (1e-10 relative: the norms go down to 1e-11), same solution."""
+    import scipy.sparse as sp
+    from multigrid_dolfinx_b200.engine import MGEngine
+    from oracle import restated as rs
+    H = pr.build_hierarchy(dim=2, c=4, coarsest_level=0, finest_level=3, mu1=2, mu2=2, with_dicts=False)
+    mg_o = rs.from_hierarchy(H, r_mode="transpose")
+    n = H.n(3)
+    M = sp.diags(np.linspace(0.5, 1.5, n) / n, 0).tocsr() if with_mass else None      # any SPD "mass" matrix exercises the path
+    v_o, h_o = rs.fmg(mg_o, H.b_dict, H.mu0, tol=1e-11, max_cycles=200, M=M)
+    eng = MGEngine.from_hierarchy(H, r_mode="transpose")
+    for l in H.levels():
+        eng.set_rhs(l, H.b_dict[l])
+    if with_mass:
+        eng.set_mass_matrix(3, M)
+    v_g, h_g = eng.fmg(H.mu0, 1e-11, 200)
+    assert abs(len(h_g) - len(h_o)) <= 1 and h_g[-1] <= 1e-11          # (the last norms sit at the 1e-11 threshold)
+    k = min(len(h_g), len(h_o)) - 3
+    assert np.abs(h_g[:k] - np.array(h_o[:k])).max() <= 1e-9 * h_o[0]
+    assert np.abs(v_g - v_o[:, 0]).max() <= 1e-10 * np.abs(v_o).max()
+    eng.close()
