@@ -36,6 +36,7 @@ struct DevCsr {
     int ntiles = 0;
     int4* sdesc = nullptr;   // stream kernel: per-tile {row0, nrows, nz0a, nent}
     int sntiles = 0;
+    int scfg = 0;            // stream kernel configuration chosen for THIS operator (from its row lengths)
     std::vector<int4> sdesc_host;
     // row-sharded operators: stream tiles split into [boundary-low | interior | boundary-high]; interior rows reference
     // no ghost column, so they can run while the halo exchange is in flight
@@ -140,6 +141,7 @@ struct mgb_handle {
     int mu1 = 2, mu2 = 2, smoother = MGB_SM_JACOBI_RJ;
     // options
     int rj_reversed = 1, use_graph = 1, opt_family = 0, opt_lpr = 0, opt_iter = 0, coarse_refine = 0, fuse_restrict = 1;
+    int stream_auto = 0;           // pick the stream configuration per operator from its average row length (measured: no gain)
     int gs_cluster = 1;            // level-scheduled Gauss-Seidel inside one thread-block cluster when the levels are narrow
     int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
     bool allow_stream = true;      // false while borrowed user pointers are in play (no padding / alignment guarantee)
@@ -161,6 +163,7 @@ struct mgb_handle {
     ncclComm_t comm = nullptr;
     cudaStream_t comm_stream = nullptr;      // halo exchanges run here while interior rows run on `stream`
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int p2p_enable = 1;                      // option "p2p_enable": 0 forces ncclSend/ncclRecv even where peers are mapped
     int overlap = 0;                         // option "overlap_halo"
     int overlap_waves = 2;                   // option "overlap_waves": waves of retiring CTAs in an overlapped interior launch
     int gather_level = INT_MIN;      // level that is gathered to rank 0 (INT_MIN: none)
@@ -227,6 +230,7 @@ StreamChoice stream_choice(int cfg)
         case 3: return {256, 4, 2};      // 1024-entry tiles, 5 CTAs/SM
         case 4: return {256, 4, 3};      // 1024-entry tiles, 3 CTAs/SM
         case 5: return {128, 8, 2};      // 1024-entry tiles, 5 CTAs/SM
+        case 7: return {128, 4, 2};      // 512-entry tiles, ~10 CTAs/SM
         default: return {256, 8, 3};     // 2048-entry tiles, 1 CTA/SM, deep ring
     }
 }
@@ -257,7 +261,11 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
     }
     D.family = family; D.iter = iter;
     if (family == 1 && h->stream_cfg > 0 && breaks.empty()) {     // descriptors for the TMA stream kernel
-        const StreamChoice sc = stream_choice(h->stream_cfg);
+        // per-operator choice: short rows (P1 operators, transfers) -> many small CTAs; long rows (P2: 19..65 entries) ->
+        // 2048-entry tiles, so that the sequential per-row sums of phase B are amortised over twice the bytes
+        D.scfg = h->stream_cfg;
+        if (h->stream_auto && n > 0 && (double)nnz / (double)n > 16.0) D.scfg = 1;
+        const StreamChoice sc = stream_choice(D.scfg);
         const int cap = sc.threads * sc.ept;
         std::vector<int32_t> st, sbreaks, sbt;
         if (interior) {                          // interior row range [b0, b1), shrunk to multiples of 4 rows
@@ -421,12 +429,13 @@ void launch_stream(mgb_handle* h, const DevCsr& D, const double* x, const Epi& e
     if (!desc) { desc = D.sdesc; ntiles = D.sntiles; }
     if (ntiles <= 0) return;
     if constexpr (Epi::CONTIG) {
-        switch (h->stream_cfg) {
+        switch (D.scfg) {
             case 1: launch_stream_cfg<256, 8, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
             case 2: launch_stream_cfg<512, 4, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
             case 3: launch_stream_cfg<256, 4, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
             case 4: launch_stream_cfg<256, 4, 3, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
             case 5: launch_stream_cfg<128, 8, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+            case 7: launch_stream_cfg<128, 4, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
             default: launch_stream_cfg<256, 8, 3, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
         }
     }
@@ -610,7 +619,7 @@ k_p2p_pull(P2PPlan pl, double* __restrict__ vec, int n_owned)
 
 int exchange_on(mgb_handle* h, Level& L, double* vec, cudaStream_t st)
 {
-    if (L.p2p_ready) {
+    if (L.p2p_ready && h->p2p_enable) {
         const int total = (int)L.send_total;
         const int wide = 4 * h->sm_count;          // NVLink stores and the local unpack need many SMs to reach bandwidth
         const int gb = std::max(1, std::min(wide, (total + 1023) / 1024));
@@ -1376,7 +1385,9 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "lanes_per_row" && pre) h->opt_lpr = iv;
     else if (k == "tile_iter" && pre) h->opt_iter = iv;
     else if (k == "stream_cfg" && pre) h->stream_cfg = iv;
+    else if (k == "stream_auto" && pre) h->stream_auto = iv;
     else if (k == "gs_cluster") h->gs_cluster = iv;
+    else if (k == "p2p_enable") { h->p2p_enable = iv; drop_graphs(h); }
     else if (k == "overlap_halo") { h->overlap = iv; drop_graphs(h); }
     else if (k == "overlap_waves") { h->overlap_waves = iv; drop_graphs(h); }
     else return fail(h, pre ? MGB_ERR_INVALID : MGB_ERR_STATE, "option '%s' unknown or not settable %s finalize", key, pre ? "before" : "after");
@@ -1904,7 +1915,8 @@ int mgb_describe(mgb_handle* h, char* out, int64_t capacity)
     char buf[256];
     auto one = [&](const char* name, const DevCsr& D) {
         if (!D.present()) return;
-        if (D.family == 1) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d tile(cap=%d) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, tile_cap(D.iter), D.ntiles);
+        if (D.family == 1 && D.sdesc) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d stream(cfg=%d, %d x %d entries, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.scfg, stream_choice(D.scfg).threads, stream_choice(D.scfg).ept, stream_choice(D.scfg).stages, D.sntiles);
+        else if (D.family == 1) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d tile(cap=%d) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, tile_cap(D.iter), D.ntiles);
         else snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d subwarp(lanes=%d)\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.lpr);
         s += buf;
     };

@@ -27,6 +27,14 @@ VARIANTS = [
     ("stream5_128x8x2", {"stream_cfg": 5}),
     ("stream6_256x8x3", {"stream_cfg": 6}),
     ("tile_iter1_fused_restrict", {"tile_iter": 1, "stream_cfg": 0, "fuse_restrict": 1}),
+    ("auto", {}),
+    ("noauto_cfg3", {"stream_auto": 0, "stream_cfg": 3}),
+    ("noauto_cfg1", {"stream_auto": 0, "stream_cfg": 1}),
+    ("noauto_cfg2", {"stream_auto": 0, "stream_cfg": 2}),
+    ("noauto_cfg5", {"stream_auto": 0, "stream_cfg": 5}),
+    ("noauto_cfg7", {"stream_auto": 0, "stream_cfg": 7}),
+    ("noauto_subwarp8", {"kernel_family": 2, "lanes_per_row": 8}),
+    ("noauto_subwarp16", {"kernel_family": 2, "lanes_per_row": 16}),
 ]
 
 
@@ -61,7 +69,7 @@ def main():
                    "kernels": [{"k": f"{r['kind']}@{r['level']}", "us": round(r["ms_per_launch"] * 1e3, 2), "gbs": round(r["gbs"], 1), "n": r["launches"]}
                                for r in sorted(prof, key=lambda r: (-r["level"], r["kind"]))]}
             out.write(json.dumps(rec) + "\n"); out.flush()
-            top = [k for k in rec["kernels"] if k["k"].endswith(f"@{lf}")]
+            top = [k for k in rec["kernels"] if k["k"].endswith(f"@{lf}") and k["k"].split("@")[0] in ("jacobi", "residual", "prolong_add")]
             print(name, f"cycle {ms:.3f} ms", top, flush=True)
             eng.close()
 
