@@ -191,9 +191,17 @@ def run_single(args):
     prof = eng.profile_end()
     dom = max(prof, key=lambda r: r["total_ms"])
     peak, peak_src = measured_peak()
+    traffic = None                      # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, from the committed
+    try:                                # `ncu --set full` capture of this very command line (profiles/README.md)
+        if args.workload == "cfg2" and dom["kind"] == "jacobi" and args.smoother == "jacobi":
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_full_k_stream_cfg2.json")))
+            big = [k for k in cap if "EpiJacobiRJ>" in k["kernel"] and k["dram_read_MB"] > 200]
+            traffic = float(np.mean([k["dram_read_MB"] + k["dram_write_MB"] for k in big])) * 1e6 if big else None
+    except Exception:
+        traffic = None
     cyc_ms_prof = sum(r["total_ms"] for r in prof) / max(3, min(args.steps, 10))
     roofline = {"bound": "hbm", "kernel": f"{dom['kind']}@level{dom['level']}", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dom["gbs"] / peak, "frac_of_8TBs": dom["gbs"] / 8000.0, "traffic": None, "peak_source": peak_src,
+                "frac": dom["gbs"] / peak, "frac_of_8TBs": dom["gbs"] / 8000.0, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms_per_launch"],
                 "share_of_cycle": dom["total_ms"] / sum(r["total_ms"] for r in prof),
                 "vcycle_bytes": eng.vcycle_bytes(lf), "vcycle_gbs": eng.vcycle_bytes(lf) / (ms * 1e-3) / 1e9}

@@ -256,7 +256,7 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
             D.ntiles = (int)tiles.size() - 1;
             TRY(dev_upload(h, &D.tiles, tiles.data(), tiles.size()));
         } else {
-            family = 2;                                  // a row longer than a tile: warp per row
+            family = 3;                                  // a row longer than a tile: warp per row, still summed in stored order
         }
     }
     D.family = family; D.iter = iter;
@@ -293,6 +293,7 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
             D.sdesc_host.swap(desc);
         }
     }
+    if (family == 3) D.break_tile.assign(breaks.begin(), breaks.end());
     if (family == 2) {
         int lpr = h->opt_lpr;
         if (!lpr) {
@@ -473,7 +474,12 @@ int row_sums(mgb_handle* h, int kind, int level, double bytes, const DevCsr& D, 
         } else {
             int r0 = 0, r1 = (int)D.nrows;
             if (group >= 0) { r0 = D.break_tile[group]; r1 = D.break_tile[group + 1]; }
-            launch_subwarp<Epi, NCX>(h, D, r0, r1, x, epi);
+            if (D.family == 3) {
+                const int64_t rows = r1 - r0;
+                if (rows > 0) k_seqrow<NCX, Epi><<<(int)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(D.rowptr, D.cols, D.vals, r0, r1, x, epi);
+            } else {
+                launch_subwarp<Epi, NCX>(h, D, r0, r1, x, epi);
+            }
         }
     });
 }
@@ -1917,6 +1923,7 @@ int mgb_describe(mgb_handle* h, char* out, int64_t capacity)
         if (!D.present()) return;
         if (D.family == 1 && D.sdesc) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d stream(cfg=%d, %d x %d entries, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.scfg, stream_choice(D.scfg).threads, stream_choice(D.scfg).ept, stream_choice(D.scfg).stages, D.sntiles);
         else if (D.family == 1) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d tile(cap=%d) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, tile_cap(D.iter), D.ntiles);
+        else if (D.family == 3) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d warp-per-row (sequential order)\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row);
         else snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d subwarp(lanes=%d)\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.lpr);
         s += buf;
     };

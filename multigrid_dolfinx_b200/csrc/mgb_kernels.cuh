@@ -428,6 +428,32 @@ k_subwarp(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, 
     if (active && lane == 0) epi_store(epi, row, s, pre);
 }
 
+// ---- long-row fallback --------------------------------------------------------------------------------
+// Rows longer than a tile (thousands of entries) cannot be staged by the tile / stream kernels.  One warp per row:
+// the lanes form 32 products at a time, then every lane adds them IN STORED ORDER (the products are passed round with
+// shuffles), so the numerics contract of the tile family -- one accumulator, stored order, no FMA -- still holds.
+template <bool NCX, class Epi>
+__global__ void __launch_bounds__(256)
+k_seqrow(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, const double* __restrict__ vals,
+         int row_begin, int row_end, const double* x, Epi epi)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int row = row_begin + warp;
+    if (row >= row_end) return;                       // whole warp leaves together
+    const int a = rowptr[row], b = rowptr[row + 1];
+    decltype(epi_load(epi, 0)) pre;
+    if (lane == 0) pre = epi_load(epi, row);
+    double s = 0.0;
+    for (int k0 = a; k0 < b; k0 += 32) {
+        const int k = k0 + lane;
+        const double p = k < b ? __dmul_rn(vals[k], ld_x<NCX>(x, cols[k])) : 0.0;
+        const int m = min(32, b - k0);
+        for (int l = 0; l < m; ++l) s = __dadd_rn(s, __shfl_sync(0xffffffffu, p, l));
+    }
+    if (lane == 0) epi_store(epi, row, s, pre);
+}
+
 // ---- small kernels ----------------------------------------------------------------------------------
 // zero initial guess + one Jacobi sweep collapses to v = g = w*(dinv*f)   (multigrid.py:253 + :226)
 __global__ void k_init_guess(int n, const double* __restrict__ dinv, const double* __restrict__ f, double om,

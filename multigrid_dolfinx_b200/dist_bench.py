@@ -16,6 +16,8 @@ DIST_WORKLOADS = {
     "cfg5h": (3, 8, 0, 5, "3D Poisson P1 257^3 (17M DOFs), 6-level V(2,2), Jacobi, injection, row-sharded"),
     "cfg5": (3, 8, 0, 6, "3D Poisson P1 513^3 (135M DOFs), 7-level V(2,2), Jacobi, injection, row-sharded"),
     "cfg2": (2, 32, 0, 6, "2D Poisson P1 2049^2 (4.2M DOFs), 7-level V(2,2), Jacobi, injection, row-sharded"),
+    "cfg4": (3, 4, 0, 4, "3D Poisson P2 on 64^3 cells (129^3 = 2.1M DOFs, rows of 10..65), 5-level V(2,2), Jacobi, row-sharded"),
+    "cfg4s": (3, 2, 0, 3, "3D Poisson P2 on 16^3 cells (33^3 DOFs), 4-level V(2,2) (small stand-in)"),
 }
 
 
@@ -46,7 +48,12 @@ def run(args):
     name = args.workload if args.workload in DIST_WORKLOADS else "cfg5h"
     dim, c, lc, lf, desc = DIST_WORKLOADS[name]
     t0 = time.perf_counter()
-    src = ds.StructuredSource(dim, c, lc, lf)
+    if name.startswith("cfg4"):       # P2: every rank assembles the hierarchy on the host and cuts its row blocks out of it
+        from . import problems as pr
+        src = ds.HierarchySource(pr.build_hierarchy_p2(c=c, coarsest_level=lc, finest_level=lf))
+        args.device_gen = 0
+    else:
+        src = ds.StructuredSource(dim, c, lc, lf)
     mg = ds.DistMG(src, device=local_rank, r_mode=args.restriction, smoother=args.smoother, gather_threshold=args.gather_threshold,
                    options={"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg, "use_graph": args.use_graph,
                             "overlap_halo": args.overlap, "overlap_waves": args.overlap_waves},

@@ -337,3 +337,72 @@ def test_p2_hierarchy_vs_oracle(r_mode, opts):
         x = np.random.default_rng(3).standard_normal(A.shape[0])
         assert np.array_equal(eng.spmv(2, x), A.dot(x))                      # 65-entry rows, still bit-exact
     eng.close()
+
+
+def _ragged(n, m, rng, max_len, empty_frac=0.15, diag=False):
+    """random CSR with ragged rows (some empty unless ``diag``), unsorted columns, optional dominant diagonal"""
+    import scipy.sparse as sp
+    lens = rng.integers(0, max_len + 1, size=n)
+    lens[rng.random(n) < empty_frac] = 0
+    rows_ix, rows_ax = [], []
+    for i in range(n):
+        k = int(min(lens[i], m - 1 if diag else m))
+        cols = rng.choice(m, size=k, replace=False) if k else np.zeros(0, dtype=np.int64)
+        vals = rng.standard_normal(k)
+        if diag:
+            cols = cols[cols != i]; vals = vals[:len(cols)]
+            pos = int(rng.integers(0, len(cols) + 1))
+            cols = np.insert(cols, pos, i); vals = np.insert(vals, pos, 3.0 + np.abs(vals).sum())
+        rows_ix.append(cols); rows_ax.append(vals)
+    ip = np.zeros(n + 1, dtype=np.int64); np.cumsum([len(c) for c in rows_ix], out=ip[1:])
+    ix = np.concatenate(rows_ix).astype(np.int32) if ip[-1] else np.zeros(0, dtype=np.int32)
+    ax = np.concatenate(rows_ax) if ip[-1] else np.zeros(0)
+    return sp.csr_matrix((ax, ix, ip), shape=(n, m))
+
+
+@pytest.mark.parametrize("nf,nc,max_len,seed", [(1237, 311, 9, 0), (5, 3, 3, 1), (4099, 1025, 40, 2), (2050, 700, 300, 3), (1, 1, 1, 4),
+                                                 (3000, 400, 1500, 5), (6000, 64, 5000, 6)])
+@pytest.mark.parametrize("opts", [{}, {"stream_cfg": 0}, {"stream_cfg": 1}])
+def test_ragged_operators_bit_exact(nf, nc, max_len, seed, opts):
+    """Irregular inputs: empty rows, rows longer than a stream tile's row share, unsorted columns, sizes that are not
+    multiples of the tile / alignment granules, explicit (non-transpose) restriction.  Everything must equal scipy bit for bit."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    Af = _ragged(nf, nf, rng, min(max_len, nf), diag=True)
+    Ac = _ragged(nc, nc, rng, min(max_len, nc), diag=True)
+    Af.sort_indices(); Ac.sort_indices()         # level matrices come from PETSc with sorted columns; transfers may be in any order
+    P = _ragged(nf, nc, rng, min(max_len, nc))
+    R = _ragged(nc, nf, rng, min(max_len, nf))
+    eng = MGEngine(0)
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    eng.set_level(0, Ac); eng.set_level(1, Af)
+    eng.set_transfer(0, P, r_mode="explicit", R=R)
+    eng.set_params(0.7, 2, 1, "jacobi")
+    eng.finalize()
+    x, f = rng.standard_normal(nf), rng.standard_normal(nf)
+    e = rng.standard_normal(nc)
+    assert np.array_equal(eng.spmv(1, x), Af.dot(x))
+    assert np.array_equal(eng.residual(1, x, f), f - Af.dot(x))
+    assert np.array_equal(eng.restrict(1, x), R.dot(x))
+    assert np.array_equal(eng.prolong_add(1, e, x), x + P.dot(e))
+    RO, dinv = rs.jacobi_matrices(Af)
+    assert np.array_equal(eng.smooth(1, x, f, 3), rs.jacobi_relaxation(RO, dinv, x, f, 3, 0.7))
+    mg = rs.RestatedMG({0: Ac, 1: Af}, {0: P}, R={0: R}, r_mode="explicit", omega=0.7, mu1=2, mu2=1)
+    vo = mg.vcycle(1, x[:, None], f[:, None])
+    vg = eng.vcycle(1, x, f)
+    assert relmax(vg, vo) <= 1e-10
+    eng.close()
+
+
+def test_shard_size_limit_is_refused_not_truncated():
+    """An operator beyond the int32 row-pointer range of one device must be rejected with MGB_ERR_UNSUPPORTED
+    (checked on the row-pointer values alone: no 2^31-entry array is ever allocated here)."""
+    import ctypes as C
+    lib = L.load()
+    h = C.c_void_p()
+    assert lib.mgb_create(C.byref(h), 0) == 0
+    ip = np.array([0, 2 ** 31 + 5], dtype=np.int64)
+    rc = lib.mgb_set_level(h, 0, 1, 2 ** 31 + 5, ip.ctypes.data, 8, None, None)
+    assert rc == L.ERR_INVALID                      # null index arrays with nnz > 0 are refused before anything is read
+    lib.mgb_destroy(h)
