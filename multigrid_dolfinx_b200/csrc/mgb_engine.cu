@@ -125,6 +125,9 @@ struct Level {
     double* gs_diag = nullptr;       // device: a_ii in execution order
     int gs_groups = 0;               // number of levels / colours
     int gs_max_width = 0;
+    int32_t* gs_ecols = nullptr;     // GS_LEVEL, rows of <= 8 entries: the operator again in ELL form (W x n, level-major)
+    double* gs_evals = nullptr;
+    int gs_W = 0;
 };
 
 struct ProfEvent { int kind, level; double bytes; cudaEvent_t e0, e1; };
@@ -142,7 +145,7 @@ struct mgb_handle {
     // options
     int rj_reversed = 1, use_graph = 1, opt_family = 0, opt_lpr = 0, opt_iter = 0, coarse_refine = 0, fuse_restrict = 1;
     int stream_auto = 0;           // pick the stream configuration per operator from its average row length (measured: no gain)
-    int gs_cluster = 1;            // level-scheduled Gauss-Seidel inside one thread-block cluster when the levels are narrow
+    int gs_cluster = 2;            // level-scheduled Gauss-Seidel: 0 grid barrier, 1 one cluster, 2 one cluster + ELL prefetch pipeline
     int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
     bool allow_stream = true;      // false while borrowed user pointers are in play (no padding / alignment guarantee)
     int coarsest = 0, finest = 0;
@@ -725,6 +728,23 @@ int gs_sweep(mgb_handle* h, Level& L, double* v, const double* f)
 {
     const DevCsr& G = L.G;
     const double nb = 12.0 * (double)G.nnz + 8.0 * (double)L.n /*rowptr+order*/ + 8.0 * 3.0 * (double)L.n;
+    if (h->smoother == MGB_SM_GS_LEVEL && h->gs_cluster >= 2 && L.gs_W > 0 && L.gs_groups + 1 <= 12000) {
+        // rows of <= 8 entries: ELL copy of the operator, everything but the x gathers prefetched a level ahead
+        return launch(h, MGB_K_GS, L.level, nb, [&] {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(8); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = (size_t)(L.gs_groups + 1) * sizeof(int); cfg.stream = h->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            const int n = (int)L.n;
+            const int32_t* ec = L.gs_ecols; const double* ev = L.gs_evals; const int32_t* ord = L.gs_order;
+            const double* dg = L.gs_diag; const int32_t* off = L.gs_off; const int nlev = L.gs_groups;
+            if (L.gs_W <= 4) cudaLaunchKernelEx(&cfg, k_gs_levels_ell<4>, n, ec, ev, ord, dg, f, v, off, nlev);
+            else if (L.gs_W <= 6) cudaLaunchKernelEx(&cfg, k_gs_levels_ell<6>, n, ec, ev, ord, dg, f, v, off, nlev);
+            else cudaLaunchKernelEx(&cfg, k_gs_levels_ell<8>, n, ec, ev, ord, dg, f, v, off, nlev);
+        });
+    }
     if (h->smoother == MGB_SM_GS_LEVEL && h->gs_cluster && L.gs_max_width <= 8 * 512 * 2) {
         // narrow levels: one 8-CTA cluster, hardware cluster barrier between dependency levels
         return launch(h, MGB_K_GS, L.level, nb, [&] {
@@ -1077,7 +1097,7 @@ int mgb_destroy(mgb_handle* h)
         cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.cmap); cudaFree(L.inj_desc); cudaFree(L.send_idx); cudaFree(L.send_buf); cudaFree(L.p2p_counters);
         for (void* q : L.p2p_opened) cudaIpcCloseMemHandle(q);
         cudaFree(L.p2p_arena); cudaFree(L.v); cudaFree(L.vtmp); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
-        cudaFree(L.gs_order); cudaFree(L.gs_off); cudaFree(L.gs_diag);
+        cudaFree(L.gs_order); cudaFree(L.gs_off); cudaFree(L.gs_diag); cudaFree(L.gs_ecols); cudaFree(L.gs_evals);
     }
     cudaFree(h->coarse_inv); cudaFree(h->d_partial); cudaFree(h->d_hist);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -1480,6 +1500,19 @@ int mgb_finalize(mgb_handle* h)
                 int rc = upload_csr(h, G, L.G); h->opt_family = sf; TRY(rc);
             } else {
                 TRY(upload_csr(h, G, L.G, off));
+            }
+            if (lvl && L.G.max_row <= 8 && n > 0) {            // ELL copy for the pipelined kernel
+                const int W = L.G.max_row <= 4 ? 4 : (L.G.max_row <= 6 ? 6 : 8);
+                std::vector<int32_t> ec((size_t)W * n, 0);
+                std::vector<double> ev((size_t)W * n, 0.0);
+                for (size_t p = 0; p < n; ++p)
+                    for (int64_t k = G.ip[p]; k < G.ip[p + 1]; ++k) {
+                        ec[(size_t)(k - G.ip[p]) * n + p] = G.ix[k];
+                        ev[(size_t)(k - G.ip[p]) * n + p] = G.ax[k];
+                    }
+                TRY(dev_upload(h, &L.gs_ecols, ec.data(), ec.size()));
+                TRY(dev_upload(h, &L.gs_evals, ev.data(), ev.size()));
+                L.gs_W = W;
             }
             TRY(dev_upload(h, &L.gs_order, order.data(), n));
             TRY(dev_upload(h, &L.gs_off, off.data(), off.size()));

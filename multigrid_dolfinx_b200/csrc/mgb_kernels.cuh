@@ -626,4 +626,77 @@ k_gs_levels_cluster(const int32_t* __restrict__ rowptr, const int32_t* __restric
     }
 }
 
+// Level-scheduled Gauss-Seidel, pipelined.  The per-level critical path of k_gs_levels[_cluster] is a chain of
+// dependent loads (row pointers -> entries -> x gathers -> order -> f) plus the barrier.  Here the operator is
+// stored in ELL form (W <= 8 entries per row, level-major, column-major inside the array so that a level's rows are
+// coalesced) and everything that does not depend on the sweep itself -- entries, row index, f, diagonal -- is
+// fetched one / two dependency levels AHEAD, into registers that alternate between two sets (the loop is unrolled
+// by two, so no register copy waits on a load).  What remains per level: the x gathers (L2) and the cluster barrier.
+// The level offsets live in shared memory.  Entries beyond a row's length are (col 0, value 0).
+struct GsRow { int i; double f, d; int c[8]; double a[8]; };
+
+template <int W>
+__device__ __forceinline__ void gs_fetch(GsRow& r, int p, bool on, int iord, int n, const int32_t* __restrict__ ecols,
+                                         const double* __restrict__ evals, const double* __restrict__ diag, const double* __restrict__ f)
+{
+    if (!on) return;
+    r.i = iord;
+    r.f = f[iord];
+    r.d = diag[p];
+#pragma unroll
+    for (int k = 0; k < W; ++k) { r.c[k] = ecols[(size_t)k * n + p]; r.a[k] = evals[(size_t)k * n + p]; }
+}
+
+template <int W>
+__device__ __forceinline__ void gs_apply(const GsRow& r, bool on, double* v)
+{
+    if (!on) return;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < W; ++k) s = __dadd_rn(s, __dmul_rn(r.a[k], __ldcg(v + r.c[k])));
+    __stcg(v + r.i, __ddiv_rn(__dsub_rn(r.f, s), r.d));
+}
+
+template <int W>
+__global__ void __launch_bounds__(512)
+k_gs_levels_ell(int n, const int32_t* __restrict__ ecols, const double* __restrict__ evals, const int32_t* __restrict__ order,
+                const double* __restrict__ diag, const double* __restrict__ f, double* v, const int32_t* __restrict__ lvl_off, int nlev)
+{
+    extern __shared__ int s_off[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = (int)cluster.block_rank() * blockDim.x + threadIdx.x;
+    const int nth = (int)cluster.num_blocks() * blockDim.x;
+    for (int k = threadIdx.x; k <= nlev; k += blockDim.x) s_off[k] = lvl_off[k];
+    __syncthreads();
+    auto row_of = [&](int L, int& p) { p = (L < nlev) ? s_off[L] + tid : 0; return L < nlev && p < s_off[L + 1]; };
+    GsRow ra, rb;
+    int p0, p1, p2;
+    bool on0 = row_of(0, p0), on1 = row_of(1, p1), on2;
+    int i1 = on1 ? order[p1] : 0, i2;
+    gs_fetch<W>(ra, p0, on0, on0 ? order[p0] : 0, n, ecols, evals, diag, f);
+    for (int L = 0; L < nlev; L += 2) {
+        // ---- level L from set a; fetch level L+1 into set b; row index of level L+2
+        on2 = row_of(L + 2, p2);
+        i2 = on2 ? order[p2] : 0;
+        gs_fetch<W>(rb, p1, on1, i1, n, ecols, evals, diag, f);
+        gs_apply<W>(ra, on0, v);
+        for (int p = s_off[L] + tid + nth; p < s_off[L + 1]; p += nth) {       // levels wider than the cluster: plain path
+            GsRow t; gs_fetch<W>(t, p, true, order[p], n, ecols, evals, diag, f); gs_apply<W>(t, true, v);
+        }
+        cluster.sync();
+        if (L + 1 >= nlev) break;
+        // ---- level L+1 from set b; fetch level L+2 into set a; row index of level L+3
+        on0 = on2; p0 = p2;
+        const int i0 = i2;
+        on1 = row_of(L + 3, p1);
+        i1 = on1 ? order[p1] : 0;
+        gs_fetch<W>(ra, p0, on0, i0, n, ecols, evals, diag, f);
+        gs_apply<W>(rb, true && (s_off[L + 1] + tid < s_off[L + 2]), v);
+        for (int p = s_off[L + 1] + tid + nth; p < s_off[L + 2]; p += nth) {
+            GsRow t; gs_fetch<W>(t, p, true, order[p], n, ecols, evals, diag, f); gs_apply<W>(t, true, v);
+        }
+        cluster.sync();
+    }
+}
+
 }  // namespace mgb

@@ -177,9 +177,10 @@ def test_gauss_seidel_level_scheduled_bit_exact(dim, c, lf, seed):
     for _ in range(3):
         xo = co.gs_forward(A, xo, f)
     assert np.array_equal(eng.smooth(lf, x, f, 3), xo)
-    eng2 = MGEngine.from_hierarchy(H, smoother="gs", options={"gs_cluster": 0})      # grid-barrier variant
-    assert np.array_equal(eng2.smooth(lf, x, f, 3), xo)
-    eng2.close()
+    for variant in (0, 1):                       # grid-barrier and plain cluster variants (default 2 = cluster + ELL pipeline)
+        eng2 = MGEngine.from_hierarchy(H, smoother="gs", options={"gs_cluster": variant})
+        assert np.array_equal(eng2.smooth(lf, x, f, 3), xo)
+        eng2.close()
     cm = co.from_hierarchy(H, smoother="gs")
     b = H.b_dict[lf][:, 0]
     vo, ho = cm.vcycle(np.zeros_like(b), b, ncycles=3, history=True)
