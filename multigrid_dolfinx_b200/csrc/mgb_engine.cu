@@ -144,6 +144,7 @@ struct mgb_handle {
     int mu1 = 2, mu2 = 2, smoother = MGB_SM_JACOBI_RJ;
     // options
     int rj_reversed = 1, use_graph = 1, opt_family = 0, opt_lpr = 0, opt_iter = 0, coarse_refine = 0, fuse_restrict = 1;
+    int pdl = 0;                   // programmatic dependent launch between consecutive stream kernels (measured slower: off)
     int stream_auto = 0;           // pick the stream configuration per operator from its average row length (measured: no gain)
     int gs_cluster = 2;            // level-scheduled Gauss-Seidel: 0 grid barrier, 1 one cluster, 2 one cluster + ELL prefetch pipeline
     int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
@@ -423,7 +424,13 @@ void launch_stream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nti
         tpc = std::max(1, ntiles / (h->sm_count * occ * std::max(1, h->overlap_waves)));
         grid = (ntiles + tpc - 1) / tpc;
     }
-    kern<<<grid, T + 32, smem, h->stream>>>(D.rowptr, D.cols, D.vals, desc, ntiles, tpc, x, epi);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T + 32); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // see k_stream: overlap this kernel's prologue and first
+    at[0].val.programmaticStreamSerializationAllowed = 1;                // matrix tiles with the tail of the previous kernel
+    cfg.attrs = at; cfg.numAttrs = h->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, (const int32_t*)D.rowptr, (const int32_t*)D.cols, (const double*)D.vals, desc, ntiles, tpc, x, epi);
 }
 
 template <class Epi>
@@ -1413,6 +1420,7 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "stream_cfg" && pre) h->stream_cfg = iv;
     else if (k == "stream_auto" && pre) h->stream_auto = iv;
     else if (k == "gs_cluster") h->gs_cluster = iv;
+    else if (k == "pdl") { h->pdl = iv; drop_graphs(h); }
     else if (k == "p2p_enable") { h->p2p_enable = iv; drop_graphs(h); }
     else if (k == "overlap_halo") { h->overlap = iv; drop_graphs(h); }
     else if (k == "overlap_waves") { h->overlap_waves = iv; drop_graphs(h); }

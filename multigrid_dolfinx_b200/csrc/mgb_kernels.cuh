@@ -328,14 +328,18 @@ k_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, c
     const int step = tpc > 0 ? 1 : (int)gridDim.x;
     const int my_tiles = tpc > 0 ? min(tpc, ntiles - first) : (ntiles - first + step - 1) / step;
 
+    // Programmatic dependent launch: let the next kernel of the stream start its prologue while this one drains, and
+    // -- when this kernel was itself launched that way -- do everything that does not depend on the predecessor's
+    // output (barrier init above, the matrix part of the first STAGES tiles below) BEFORE waiting for it.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     if (tid >= THREADS) {                                   // ---- producer warp (one lane works)
         if (tid == THREADS) {
             uint64_t pol;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-            for (int i = 0; i < my_tiles; ++i) {
+            auto issue_matrix = [&](int i, int4& d) {
                 const int s = i % STAGES;
-                if (i >= STAGES) mbar_wait(empty + s, (uint32_t)((i / STAGES - 1) & 1));
-                const int4 d = __ldg(desc + first + (size_t)i * step);                   // {row0, nrows, nz0a, nent}
+                d = __ldg(desc + first + (size_t)i * step);                          // {row0, nrows, nz0a, nent}
                 unsigned char* st = stage0 + (size_t)s * Cfg::STAGE_BYTES;
                 *reinterpret_cast<int4*>(st) = d;                                    // published by the arrive below (release)
                 const uint32_t b_cols = (uint32_t)d.w * 4u, b_vals = (uint32_t)d.w * 8u;
@@ -345,14 +349,32 @@ k_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, c
                 unsigned char* p = st + Cfg::HDR_BYTES;
                 bulk_g2s_hint(p, cols + d.z, b_cols, full + s, pol);  p += Cfg::COLS_BYTES;
                 bulk_g2s_hint(p, vals + d.z, b_vals, full + s, pol);  p += Cfg::VALS_BYTES;
-                bulk_g2s(p, rowptr + d.x, b_rp, full + s);            p += Cfg::RP_BYTES;
+                bulk_g2s(p, rowptr + d.x, b_rp, full + s);
+            };
+            auto issue_operands = [&](int i, const int4& d) {                        // slices of vectors the predecessor may have written
+                const int s = i % STAGES;
+                const uint32_t b_op = (uint32_t)((d.y + 1) & ~1) * 8u, b_iop = (uint32_t)((d.y + 3) & ~3) * 4u;
+                unsigned char* p = stage0 + (size_t)s * Cfg::STAGE_BYTES + Cfg::HDR_BYTES + Cfg::COLS_BYTES + Cfg::VALS_BYTES + Cfg::RP_BYTES;
 #pragma unroll
                 for (int j = 0; j < Epi::NOPS; ++j) { bulk_g2s(p, epi.operand(j) + d.x, b_op, full + s); p += Cfg::OP_BYTES; }
                 if constexpr (NIOPS > 0) bulk_g2s(p, epi.ioperand() + d.x, b_iop, full + s);
+            };
+            int4 dpre[STAGES];
+            const int npre = my_tiles < STAGES ? my_tiles : STAGES;
+            for (int i = 0; i < npre; ++i) issue_matrix(i, dpre[i]);
+            asm volatile("griddepcontrol.wait;" ::: "memory");                       // predecessor's results are visible from here on
+            for (int i = 0; i < npre; ++i) issue_operands(i, dpre[i]);
+            for (int i = npre; i < my_tiles; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(empty + s, (uint32_t)((i / STAGES - 1) & 1));
+                int4 d;
+                issue_matrix(i, d);
+                issue_operands(i, d);
             }
         }
         return;
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // consumers gather x and store results: strictly after the predecessor
 
     for (int i = 0; i < my_tiles; ++i) {                     // ---- consumers
         const int s = i % STAGES;
