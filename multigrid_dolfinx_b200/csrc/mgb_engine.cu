@@ -22,158 +22,7 @@
 
 using namespace mgb;
 
-namespace {
-
-constexpr int THREADS = 256;
-thread_local std::string g_create_error;
-
-struct DevCsr {
-    int64_t nrows = 0, ncols = 0, nnz = 0;
-    int32_t* rowptr = nullptr;
-    int32_t* cols = nullptr;
-    double* vals = nullptr;
-    int32_t* tiles = nullptr;
-    int ntiles = 0;
-    int4* sdesc = nullptr;   // stream kernel: per-tile {row0, nrows, nz0a, nent}
-    int sntiles = 0;
-    int scfg = 0;            // stream kernel configuration chosen for THIS operator (from its row lengths)
-    std::vector<int4> sdesc_host;
-    // row-sharded operators: stream tiles split into [boundary-low | interior | boundary-high]; interior rows reference
-    // no ghost column, so they can run while the halo exchange is in flight
-    bool split = false;
-    int t_int0 = 0, t_int1 = 0;      // interior tiles = sdesc[t_int0 .. t_int1)
-    int4* sdesc_bnd = nullptr;       // boundary tiles, low block then high block
-    int n_bnd = 0;
-    int iter = 2;       // tile kernel: groups of 4 entries per thread
-    int family = 1;     // 1 tile, 2 sub-warp
-    int lpr = 4;        // sub-warp lanes per row
-    int max_row = 0;
-    std::vector<int32_t> break_tile;   // tile index at each row breakpoint (colour boundaries)
-    bool present() const { return rowptr != nullptr; }
-};
-
-constexpr int P2P_MAX_PEERS = 16;
-constexpr int P2P_FLAG_SLOTS = 256;          // one arrival flag per sender rank
-struct P2PPlan {                             // passed to the halo kernels by value
-    int npeers = 0;
-    int send_off[P2P_MAX_PEERS + 1] = {0};   // prefix sums into send_idx
-    int recv_off[P2P_MAX_PEERS + 1] = {0};   // prefix sums into the ghost section
-    double* rstage[P2P_MAX_PEERS][2] = {};   // neighbour's staging copies, already offset to this rank's slot
-    unsigned long long* rflag[P2P_MAX_PEERS] = {};   // neighbour's arrival flag for this rank
-    int peer_rank[P2P_MAX_PEERS] = {0};
-    unsigned long long* counters = nullptr;  // see Level::p2p_counters
-    unsigned long long* flags = nullptr;     // this rank's arrival flags (indexed by sender rank)
-    double* stage = nullptr;                 // this rank's staging copies (2 x n_ghost)
-    int n_ghost = 0;
-};
-
-struct P2PBlob {                             // what a rank publishes per level (mgb_p2p_export)
-    cudaIpcMemHandle_t handle;
-    long long n_ghost;
-    int npeers;
-    int peer_rank[P2P_MAX_PEERS];
-    int recv_off[P2P_MAX_PEERS + 1];
-};
-
-struct Level {
-    int level = 0;
-    int64_t n = 0;
-    HostCsr A_host;                  // released after finalize
-    HostCsr P_host, R_host;          // transfer from level-1 to this level (this level = fine side)
-    std::vector<int32_t> inj_host;
-    int r_mode = MGB_R_INJECTION;
-    int dim_fw = 2;
-    bool has_transfer = false;       // transfer pair (level-1, level) was set
-    int64_t n_coarse = 0;            // coarse rows this rank produces when restricting from this level
-    // ---- row-sharded (multi-GPU) state: this rank owns n rows; vectors hold n + n_ghost entries, ghosts last
-    int64_t n_ghost = 0;
-    bool stub = false;               // gathered level on a non-root rank: full-size vectors, no operators
-    bool device_born = false;        // operators were generated on the device (mgb_synth_*): no host copy exists
-    int syn_dim = 0, syn_m = 0;      // geometry of a generated level
-    int64_t row_begin = 0, row_end = 0, ghost_lo = 0, ghost_hi = 0;   // global row range owned / ghost ranges around it
-    bool gathered = false;           // first level that lives on rank 0 only; every rank owns a slice of its RHS
-    int64_t my_off = 0, my_cnt = 0;  // this rank's slice of the gathered level
-    std::vector<int64_t> gather_off; // world + 1 offsets of all slices
-    std::vector<int> peers, send_cnt, recv_cnt;
-    int32_t* send_idx = nullptr;     // device: owned local indices to pack, peer after peer
-    double* send_buf = nullptr;
-    int64_t send_total = 0;
-    // peer-memory halo exchange (CUDA IPC over NVLink): flags + two staging copies of the ghost section live in one
-    // exported allocation; the neighbours write into it directly
-    void* p2p_arena = nullptr;       // [flags: 256 x u64][stage 0: n_ghost][stage 1: n_ghost]
-    unsigned long long* p2p_counters = nullptr;   // device: [0..15] send epochs, [16..31] recv epochs, [32] block counter x2
-    std::vector<void*> p2p_opened;   // peers' arenas mapped into this process
-    bool p2p_ready = false;
-    int p2p_imported = 0;
-    P2PPlan p2p;
-
-    DevCsr A, RJ, P, R, G;           // G: Gauss-Seidel off-diagonal operator, rows in execution order
-    double* dinv = nullptr;
-    int32_t* inj = nullptr;
-    int32_t* cmap = nullptr;         // fine dof -> coarse dof or -1 (fused residual + injection)
-    int4* inj_desc = nullptr;        // the stream tiles of A that contain at least one injected row
-    int inj_ntiles = 0;
-    int inj_n_int = 0, inj_n_bnd = 0;   // sharded: the list is stored [interior tiles | boundary tiles]
-    double inj_fraction = 1.0;       // share of A's entries in those tiles
-    double *v = nullptr, *vtmp = nullptr, *f = nullptr, *r = nullptr, *g = nullptr;
-    double* b = nullptr;             // re-discretised right-hand side b_dict[l] (FMG, multigrid.py:279)
-    DevCsr M;                        // optional mass matrix for the L2(Omega) norm of the FMG stopping rule
-    // Gauss-Seidel artefacts (host copies are what mgb_get_artifact returns)
-    std::vector<int32_t> lev_of_row, lev_order, lev_off, col_of_row, col_order, col_off;
-    int32_t* gs_order = nullptr;     // device: execution order actually used by G
-    int32_t* gs_off = nullptr;       // device: level offsets (GS_LEVEL)
-    double* gs_diag = nullptr;       // device: a_ii in execution order
-    int gs_groups = 0;               // number of levels / colours
-    int gs_max_width = 0;
-    int32_t* gs_ecols = nullptr;     // GS_LEVEL, rows of <= 8 entries: the operator again in ELL form (W x n, level-major)
-    double* gs_evals = nullptr;
-    int gs_W = 0;
-};
-
-struct ProfEvent { int kind, level; double bytes; cudaEvent_t e0, e1; };
-
-}  // namespace
-
-struct mgb_handle {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    std::map<int, Level> levels;
-    bool finalized = false;
-    double omega = 2.0 / 3.0;
-    int mu1 = 2, mu2 = 2, smoother = MGB_SM_JACOBI_RJ;
-    // options
-    int rj_reversed = 1, use_graph = 1, opt_family = 0, opt_lpr = 0, opt_iter = 0, coarse_refine = 0, fuse_restrict = 1;
-    int pdl = 0;                   // programmatic dependent launch between consecutive stream kernels (measured slower: off)
-    int stream_auto = 0;           // pick the stream configuration per operator from its average row length (measured: no gain)
-    int gs_cluster = 2;            // level-scheduled Gauss-Seidel: 0 grid barrier, 1 one cluster, 2 one cluster + ELL prefetch pipeline
-    int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
-    bool allow_stream = true;      // false while borrowed user pointers are in play (no padding / alignment guarantee)
-    int coarsest = 0, finest = 0;
-    double* coarse_inv = nullptr;
-    std::vector<double> coarse_inv_host;
-    double *d_partial = nullptr, *d_hist = nullptr;
-    int hist_cap = 0;
-    int norm_blocks = 0;
-    std::map<int, cudaGraphExec_t> graphs;
-    std::map<int, int64_t> graph_kernels;
-    bool prof = false;
-    std::vector<ProfEvent> prof_events;
-    std::map<std::pair<int, int>, mgb_profile_record> prof_records;
-    int64_t launches = 0;
-    // ---- multi-GPU: one process per GPU, NCCL communicator created from a broadcast unique id
-    bool dist = false;
-    int rank = 0, world = 1;
-    ncclComm_t comm = nullptr;
-    cudaStream_t comm_stream = nullptr;      // halo exchanges run here while interior rows run on `stream`
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int p2p_enable = 1;                      // option "p2p_enable": 0 forces ncclSend/ncclRecv even where peers are mapped
-    int overlap = 0;                         // option "overlap_halo"
-    int overlap_waves = 2;                   // option "overlap_waves": waves of retiring CTAs in an overlapped interior launch
-    int gather_level = INT_MIN;      // level that is gathered to rank 0 (INT_MIN: none)
-    int sm_count = 148;
-    int gs_coop_blocks_per_sm = 0;
-};
+#include "mgb_types.cuh"
 
 namespace {
 
@@ -503,232 +352,7 @@ Level* find_level(mgb_handle* h, int level)
     return it == h->levels.end() ? nullptr : &it->second;
 }
 
-// ---- NCCL, loaded at run time (libnccl.so.2 of the process, i.e. the one torch already loaded) ---------------
-struct NcclApi {
-    void* lib = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    const char* (*GetErrorString)(ncclResult_t) = nullptr;
-};
-NcclApi g_nccl;
-
-const char* load_nccl()
-{
-    if (g_nccl.lib) return nullptr;
-    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) return "libnccl.so.2 not found";
-#define NCCL_SYM(name) *(void**)(&g_nccl.name) = dlsym(lib, "nccl" #name); if (!g_nccl.name) return "symbol nccl" #name " missing";
-    NCCL_SYM(GetUniqueId) NCCL_SYM(CommInitRank) NCCL_SYM(CommDestroy) NCCL_SYM(Send) NCCL_SYM(Recv) NCCL_SYM(Broadcast)
-    NCCL_SYM(AllReduce) NCCL_SYM(GroupStart) NCCL_SYM(GroupEnd) NCCL_SYM(GetErrorString)
-#undef NCCL_SYM
-    g_nccl.lib = lib;
-    return nullptr;
-}
-
-#define NC(call)                                                                                       \
-    do {                                                                                               \
-        ncclResult_t r_ = (call);                                                                      \
-        if (r_ != ncclSuccess) return fail(h, MGB_ERR_COMM, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
-    } while (0)
-
-__global__ void k_pack(int n, const int32_t* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) buf[i] = v[idx[i]];
-}
-__global__ void k_sqrt_inplace(double* x) { *x = sqrt(*x); }
-
-// Halo exchange of one level vector: pack the owned entries the neighbours need, one grouped
-// ncclSend/ncclRecv per neighbour; the ghost section of `vec` (behind the n owned entries) is the receive buffer.
-// ---- halo exchange through peer memory ------------------------------------------------------------------
-// push: gather the owned entries each neighbour needs and store them straight into that neighbour's staging copy
-// (NVLink peer stores), then -- last block only -- publish the new epoch in the neighbour's arrival flag.
-// pull: wait until every neighbour's flag shows the epoch, then copy the staging copy into the ghost section of
-// the vector.  Epochs live in device memory, so the pair replays correctly inside a CUDA graph.  Two staging
-// copies alternate: a neighbour can only push epoch e after it has received this rank's epoch e-1, which this rank
-// sent after finishing its pull of epoch e-2 -- so copy (e mod 2) is never overwritten while it is still read.
-__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_flag(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-__global__ void __launch_bounds__(256)
-k_p2p_push(P2PPlan pl, const int32_t* __restrict__ send_idx, const double* __restrict__ vec)
-{
-    const int total = pl.send_off[pl.npeers];
-    const int par = (int)((pl.counters[0] + 1) & 1);          // all neighbours of a level share one epoch count
-    const int stride = gridDim.x * blockDim.x;
-    for (int k0 = blockIdx.x * blockDim.x + threadIdx.x; k0 < total; k0 += 4 * stride) {
-        double val[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const int k = k0 + u * stride; if (k < total) val[u] = vec[send_idx[k]]; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int k = k0 + u * stride;
-            if (k < total) {
-                int p = 0;
-                while (k >= pl.send_off[p + 1]) ++p;
-                pl.rstage[p][par][k - pl.send_off[p]] = val[u];
-            }
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned long long prev = atomicAdd(&pl.counters[32], 1ULL);
-        if (prev == gridDim.x - 1) {                  // every block's stores are fenced: publish
-            pl.counters[32] = 0;
-            for (int p = 0; p < pl.npeers; ++p) {
-                const unsigned long long e = pl.counters[p] + 1;
-                pl.counters[p] = e;
-                st_flag(pl.rflag[p], e);
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_p2p_pull(P2PPlan pl, double* __restrict__ vec, int n_owned)
-{
-    if (threadIdx.x < pl.npeers) {
-        const int p = threadIdx.x;
-        const unsigned long long want = pl.counters[16 + p] + 1;
-        const long long t0 = clock64();
-        while (ld_flag(pl.flags + pl.peer_rank[p]) < want)
-            if (clock64() - t0 > 4000000000LL) __trap();          // a lost neighbour must fault, never hang the GPU
-    }
-    __syncthreads();
-    const int par = (int)((pl.counters[16] + 1) & 1);
-    const double* src = pl.stage + (size_t)par * pl.n_ghost;
-    const int stride = gridDim.x * blockDim.x;
-    for (int k0 = blockIdx.x * blockDim.x + threadIdx.x; k0 < pl.n_ghost; k0 += 4 * stride) {
-        double val[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const int k = k0 + u * stride; if (k < pl.n_ghost) val[u] = __ldcg(src + k); }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const int k = k0 + u * stride; if (k < pl.n_ghost) vec[n_owned + k] = val[u]; }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long prev = atomicAdd(&pl.counters[33], 1ULL);
-        if (prev == gridDim.x - 1) {
-            pl.counters[33] = 0;
-            for (int p = 0; p < pl.npeers; ++p) pl.counters[16 + p] += 1;
-        }
-    }
-}
-
-int exchange_on(mgb_handle* h, Level& L, double* vec, cudaStream_t st)
-{
-    if (L.p2p_ready && h->p2p_enable) {
-        const int total = (int)L.send_total;
-        const int wide = 4 * h->sm_count;          // NVLink stores and the local unpack need many SMs to reach bandwidth
-        const int gb = std::max(1, std::min(wide, (total + 1023) / 1024));
-        k_p2p_push<<<gb, 256, 0, st>>>(L.p2p, L.send_idx, vec);
-        const int gp = std::max(1, std::min(wide, ((int)L.n_ghost + 1023) / 1024));
-        k_p2p_pull<<<gp, 256, 0, st>>>(L.p2p, vec, (int)L.n);
-        h->launches += 1;
-        return MGB_OK;
-    }
-    if (L.send_total > 0) k_pack<<<(int)((L.send_total + 255) / 256), 256, 0, st>>>((int)L.send_total, L.send_idx, vec, L.send_buf);
-    ncclResult_t r = g_nccl.GroupStart();
-    int64_t so = 0, ro = 0;
-    for (size_t p = 0; p < L.peers.size() && r == ncclSuccess; ++p) {
-        if (L.send_cnt[p] > 0) r = g_nccl.Send(L.send_buf + so, (size_t)L.send_cnt[p], ncclDouble, L.peers[p], h->comm, st);
-        if (r == ncclSuccess && L.recv_cnt[p] > 0) r = g_nccl.Recv(vec + L.n + ro, (size_t)L.recv_cnt[p], ncclDouble, L.peers[p], h->comm, st);
-        so += L.send_cnt[p]; ro += L.recv_cnt[p];
-    }
-    ncclResult_t e = g_nccl.GroupEnd();
-    if (r == ncclSuccess) r = e;
-    if (r != ncclSuccess) return fail(h, MGB_ERR_COMM, "halo exchange on level %d: %s", L.level, g_nccl.GetErrorString(r));
-    return MGB_OK;
-}
-
-int exchange(mgb_handle* h, Level& L, double* vec)
-{
-    if (!h->dist || L.peers.empty()) return MGB_OK;
-    int rc = MGB_OK;
-    TRY(launch(h, MGB_K_HALO, L.level, 16.0 * (double)L.send_total, [&] { rc = exchange_on(h, L, vec, h->stream); }));
-    return rc;
-}
-
-// Row sums of a sharded operator whose input vector x lives on level XL: exchange XL's ghosts, overlapped with the
-// interior tiles when the operator has an interior / boundary split.
-template <class Epi>
-int row_sums_halo(mgb_handle* h, int kind, int level, double bytes, const DevCsr& D, Level& XL, double* x, const Epi& epi,
-                  const int4* sub_desc = nullptr, int sub_int = 0, int sub_bnd = 0)
-{
-    const bool need = h->dist && !XL.peers.empty();
-    const bool can_overlap = need && h->overlap && !h->prof && D.split && D.sdesc && h->stream_cfg > 0 && h->allow_stream && D.family == 1;
-    if (!can_overlap) {
-        if (need) TRY(exchange(h, XL, x));
-        if (sub_desc) {
-            return launch(h, kind, level, bytes, [&] { launch_stream<Epi>(h, D, x, epi, sub_desc, sub_int + sub_bnd); });
-        }
-        return row_sums(h, kind, level, bytes, D, x, epi);
-    }
-    int rc = MGB_OK;
-    TRY(launch(h, kind, level, bytes, [&] {
-        cudaEventRecord(h->ev_fork, h->stream);
-        cudaStreamWaitEvent(h->comm_stream, h->ev_fork, 0);
-        rc = exchange_on(h, XL, x, h->comm_stream);
-        cudaEventRecord(h->ev_join, h->comm_stream);
-        if (sub_desc) launch_stream<Epi>(h, D, x, epi, sub_desc, sub_int, true);
-        else launch_stream<Epi>(h, D, x, epi, D.sdesc + D.t_int0, D.t_int1 - D.t_int0, true);
-        cudaStreamWaitEvent(h->stream, h->ev_join, 0);
-        if (sub_desc) launch_stream<Epi>(h, D, x, epi, sub_desc + sub_int, sub_bnd);
-        else launch_stream<Epi>(h, D, x, epi, D.sdesc_bnd, D.n_bnd);
-    }));
-    h->launches += 2;
-    return rc;
-}
-
-// slices of the gathered level's right-hand side -> rank 0
-int gather_to_root(mgb_handle* h, Level& C, double* f)
-{
-    int rc = MGB_OK;
-    TRY(launch(h, MGB_K_HALO, C.level, 8.0 * (double)C.n, [&] {
-        ncclResult_t r = g_nccl.GroupStart();
-        if (h->rank == 0) {
-            for (int q = 1; q < h->world && r == ncclSuccess; ++q) {
-                const int64_t cnt = C.gather_off[q + 1] - C.gather_off[q];
-                if (cnt > 0) r = g_nccl.Recv(f + C.gather_off[q], (size_t)cnt, ncclDouble, q, h->comm, h->stream);
-            }
-        } else if (C.my_cnt > 0) {
-            r = g_nccl.Send(f + C.my_off, (size_t)C.my_cnt, ncclDouble, 0, h->comm, h->stream);
-        }
-        ncclResult_t e = g_nccl.GroupEnd();
-        if (r == ncclSuccess) r = e;
-        if (r != ncclSuccess) rc = fail(h, MGB_ERR_COMM, "gather to rank 0: %s", g_nccl.GetErrorString(r));
-    }));
-    return rc;
-}
-
-// coarse-grid correction of the gathered level: rank 0 -> everybody
-int bcast_from_root(mgb_handle* h, Level& C, const double* src, double* dst)
-{
-    int rc = MGB_OK;
-    TRY(launch(h, MGB_K_HALO, C.level, 8.0 * (double)C.n, [&] {
-        ncclResult_t r = g_nccl.Broadcast(src, dst, (size_t)C.n, ncclDouble, 0, h->comm, h->stream);
-        if (r != ncclSuccess) rc = fail(h, MGB_ERR_COMM, "broadcast from rank 0: %s", g_nccl.GetErrorString(r));
-    }));
-    return rc;
-}
+#include "mgb_dist.cuh"
 
 // ---- smoothers ---------------------------------------------------------------------------------------
 int gs_sweep(mgb_handle* h, Level& L, double* v, const double* f)

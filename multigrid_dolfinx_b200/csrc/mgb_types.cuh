@@ -1,0 +1,157 @@
+// Internal types of the engine (one translation unit: mgb_engine.cu): device CSR operators, the per-level state,
+// the peer-memory halo plan and the handle itself.  Nothing here is part of the C ABI.
+#pragma once
+
+namespace {
+
+constexpr int THREADS = 256;
+thread_local std::string g_create_error;
+
+struct DevCsr {
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    int32_t* rowptr = nullptr;
+    int32_t* cols = nullptr;
+    double* vals = nullptr;
+    int32_t* tiles = nullptr;
+    int ntiles = 0;
+    int4* sdesc = nullptr;   // stream kernel: per-tile {row0, nrows, nz0a, nent}
+    int sntiles = 0;
+    int scfg = 0;            // stream kernel configuration chosen for THIS operator (from its row lengths)
+    std::vector<int4> sdesc_host;
+    // row-sharded operators: stream tiles split into [boundary-low | interior | boundary-high]; interior rows reference
+    // no ghost column, so they can run while the halo exchange is in flight
+    bool split = false;
+    int t_int0 = 0, t_int1 = 0;      // interior tiles = sdesc[t_int0 .. t_int1)
+    int4* sdesc_bnd = nullptr;       // boundary tiles, low block then high block
+    int n_bnd = 0;
+    int iter = 2;       // tile kernel: groups of 4 entries per thread
+    int family = 1;     // 1 tile, 2 sub-warp
+    int lpr = 4;        // sub-warp lanes per row
+    int max_row = 0;
+    std::vector<int32_t> break_tile;   // tile index at each row breakpoint (colour boundaries)
+    bool present() const { return rowptr != nullptr; }
+};
+
+constexpr int P2P_MAX_PEERS = 16;
+constexpr int P2P_FLAG_SLOTS = 256;          // one arrival flag per sender rank
+struct P2PPlan {                             // passed to the halo kernels by value
+    int npeers = 0;
+    int send_off[P2P_MAX_PEERS + 1] = {0};   // prefix sums into send_idx
+    int recv_off[P2P_MAX_PEERS + 1] = {0};   // prefix sums into the ghost section
+    double* rstage[P2P_MAX_PEERS][2] = {};   // neighbour's staging copies, already offset to this rank's slot
+    unsigned long long* rflag[P2P_MAX_PEERS] = {};   // neighbour's arrival flag for this rank
+    int peer_rank[P2P_MAX_PEERS] = {0};
+    unsigned long long* counters = nullptr;  // see Level::p2p_counters
+    unsigned long long* flags = nullptr;     // this rank's arrival flags (indexed by sender rank)
+    double* stage = nullptr;                 // this rank's staging copies (2 x n_ghost)
+    int n_ghost = 0;
+};
+
+struct P2PBlob {                             // what a rank publishes per level (mgb_p2p_export)
+    cudaIpcMemHandle_t handle;
+    long long n_ghost;
+    int npeers;
+    int peer_rank[P2P_MAX_PEERS];
+    int recv_off[P2P_MAX_PEERS + 1];
+};
+
+struct Level {
+    int level = 0;
+    int64_t n = 0;
+    HostCsr A_host;                  // released after finalize
+    HostCsr P_host, R_host;          // transfer from level-1 to this level (this level = fine side)
+    std::vector<int32_t> inj_host;
+    int r_mode = MGB_R_INJECTION;
+    int dim_fw = 2;
+    bool has_transfer = false;       // transfer pair (level-1, level) was set
+    int64_t n_coarse = 0;            // coarse rows this rank produces when restricting from this level
+    // ---- row-sharded (multi-GPU) state: this rank owns n rows; vectors hold n + n_ghost entries, ghosts last
+    int64_t n_ghost = 0;
+    bool stub = false;               // gathered level on a non-root rank: full-size vectors, no operators
+    bool device_born = false;        // operators were generated on the device (mgb_synth_*): no host copy exists
+    int syn_dim = 0, syn_m = 0;      // geometry of a generated level
+    int64_t row_begin = 0, row_end = 0, ghost_lo = 0, ghost_hi = 0;   // global row range owned / ghost ranges around it
+    bool gathered = false;           // first level that lives on rank 0 only; every rank owns a slice of its RHS
+    int64_t my_off = 0, my_cnt = 0;  // this rank's slice of the gathered level
+    std::vector<int64_t> gather_off; // world + 1 offsets of all slices
+    std::vector<int> peers, send_cnt, recv_cnt;
+    int32_t* send_idx = nullptr;     // device: owned local indices to pack, peer after peer
+    double* send_buf = nullptr;
+    int64_t send_total = 0;
+    // peer-memory halo exchange (CUDA IPC over NVLink): flags + two staging copies of the ghost section live in one
+    // exported allocation; the neighbours write into it directly
+    void* p2p_arena = nullptr;       // [flags: 256 x u64][stage 0: n_ghost][stage 1: n_ghost]
+    unsigned long long* p2p_counters = nullptr;   // device: [0..15] send epochs, [16..31] recv epochs, [32] block counter x2
+    std::vector<void*> p2p_opened;   // peers' arenas mapped into this process
+    bool p2p_ready = false;
+    int p2p_imported = 0;
+    P2PPlan p2p;
+
+    DevCsr A, RJ, P, R, G;           // G: Gauss-Seidel off-diagonal operator, rows in execution order
+    double* dinv = nullptr;
+    int32_t* inj = nullptr;
+    int32_t* cmap = nullptr;         // fine dof -> coarse dof or -1 (fused residual + injection)
+    int4* inj_desc = nullptr;        // the stream tiles of A that contain at least one injected row
+    int inj_ntiles = 0;
+    int inj_n_int = 0, inj_n_bnd = 0;   // sharded: the list is stored [interior tiles | boundary tiles]
+    double inj_fraction = 1.0;       // share of A's entries in those tiles
+    double *v = nullptr, *vtmp = nullptr, *f = nullptr, *r = nullptr, *g = nullptr;
+    double* b = nullptr;             // re-discretised right-hand side b_dict[l] (FMG, multigrid.py:279)
+    DevCsr M;                        // optional mass matrix for the L2(Omega) norm of the FMG stopping rule
+    // Gauss-Seidel artefacts (host copies are what mgb_get_artifact returns)
+    std::vector<int32_t> lev_of_row, lev_order, lev_off, col_of_row, col_order, col_off;
+    int32_t* gs_order = nullptr;     // device: execution order actually used by G
+    int32_t* gs_off = nullptr;       // device: level offsets (GS_LEVEL)
+    double* gs_diag = nullptr;       // device: a_ii in execution order
+    int gs_groups = 0;               // number of levels / colours
+    int gs_max_width = 0;
+    int32_t* gs_ecols = nullptr;     // GS_LEVEL, rows of <= 8 entries: the operator again in ELL form (W x n, level-major)
+    double* gs_evals = nullptr;
+    int gs_W = 0;
+};
+
+struct ProfEvent { int kind, level; double bytes; cudaEvent_t e0, e1; };
+
+}  // namespace
+
+struct mgb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::map<int, Level> levels;
+    bool finalized = false;
+    double omega = 2.0 / 3.0;
+    int mu1 = 2, mu2 = 2, smoother = MGB_SM_JACOBI_RJ;
+    // options
+    int rj_reversed = 1, use_graph = 1, opt_family = 0, opt_lpr = 0, opt_iter = 0, coarse_refine = 0, fuse_restrict = 1;
+    int pdl = 0;                   // programmatic dependent launch between consecutive stream kernels (measured slower: off)
+    int stream_auto = 0;           // pick the stream configuration per operator from its average row length (measured: no gain)
+    int gs_cluster = 2;            // level-scheduled Gauss-Seidel: 0 grid barrier, 1 one cluster, 2 one cluster + ELL prefetch pipeline
+    int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
+    bool allow_stream = true;      // false while borrowed user pointers are in play (no padding / alignment guarantee)
+    int coarsest = 0, finest = 0;
+    double* coarse_inv = nullptr;
+    std::vector<double> coarse_inv_host;
+    double *d_partial = nullptr, *d_hist = nullptr;
+    int hist_cap = 0;
+    int norm_blocks = 0;
+    std::map<int, cudaGraphExec_t> graphs;
+    std::map<int, int64_t> graph_kernels;
+    bool prof = false;
+    std::vector<ProfEvent> prof_events;
+    std::map<std::pair<int, int>, mgb_profile_record> prof_records;
+    int64_t launches = 0;
+    // ---- multi-GPU: one process per GPU, NCCL communicator created from a broadcast unique id
+    bool dist = false;
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    cudaStream_t comm_stream = nullptr;      // halo exchanges run here while interior rows run on `stream`
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int p2p_enable = 1;                      // option "p2p_enable": 0 forces ncclSend/ncclRecv even where peers are mapped
+    int overlap = 0;                         // option "overlap_halo"
+    int overlap_waves = 2;                   // option "overlap_waves": waves of retiring CTAs in an overlapped interior launch
+    int gather_level = INT_MIN;      // level that is gathered to rank 0 (INT_MIN: none)
+    int sm_count = 148;
+    int gs_coop_blocks_per_sm = 0;
+};
+
