@@ -133,15 +133,24 @@ k_p2p_pull(P2PPlan pl, double* __restrict__ vec, int n_owned)
     }
 }
 
+void p2p_push(mgb_handle* h, Level& L, const double* vec, cudaStream_t st)
+{
+    const int wide = 4 * h->sm_count;              // NVLink stores and the local unpack need many SMs to reach bandwidth
+    const int gb = std::max(1, std::min(wide, ((int)L.send_total + 1023) / 1024));
+    k_p2p_push<<<gb, 256, 0, st>>>(L.p2p, L.send_idx, vec);
+}
+void p2p_pull(mgb_handle* h, Level& L, double* vec, cudaStream_t st)
+{
+    const int wide = 4 * h->sm_count;
+    const int gp = std::max(1, std::min(wide, ((int)L.n_ghost + 1023) / 1024));
+    k_p2p_pull<<<gp, 256, 0, st>>>(L.p2p, vec, (int)L.n);
+}
+
 int exchange_on(mgb_handle* h, Level& L, double* vec, cudaStream_t st)
 {
     if (L.p2p_ready && h->p2p_enable) {
-        const int total = (int)L.send_total;
-        const int wide = 4 * h->sm_count;          // NVLink stores and the local unpack need many SMs to reach bandwidth
-        const int gb = std::max(1, std::min(wide, (total + 1023) / 1024));
-        k_p2p_push<<<gb, 256, 0, st>>>(L.p2p, L.send_idx, vec);
-        const int gp = std::max(1, std::min(wide, ((int)L.n_ghost + 1023) / 1024));
-        k_p2p_pull<<<gp, 256, 0, st>>>(L.p2p, vec, (int)L.n);
+        p2p_push(h, L, vec, st);
+        p2p_pull(h, L, vec, st);
         h->launches += 1;
         return MGB_OK;
     }
@@ -174,7 +183,23 @@ int row_sums_halo(mgb_handle* h, int kind, int level, double bytes, const DevCsr
                   const int4* sub_desc = nullptr, int sub_int = 0, int sub_bnd = 0)
 {
     const bool need = h->dist && !XL.peers.empty();
-    const bool can_overlap = need && h->overlap && !h->prof && D.split && D.sdesc && h->stream_cfg > 0 && h->allow_stream && D.family == 1;
+    // overlap mode 2 (peer-memory exchange only): push -> interior tiles -> pull -> boundary tiles, all on one stream.
+    // The neighbours' data travels while the interior rows (which read no ghost entry) are being summed, so the pull
+    // finds its flags already set; no second stream and no co-residency with another kernel is needed.
+    if (need && h->overlap == 2 && !h->prof && XL.p2p_ready && h->p2p_enable && D.split && D.sdesc && h->stream_cfg > 0 &&
+        h->allow_stream && D.family == 1) {
+        TRY(launch(h, kind, level, bytes, [&] {
+            p2p_push(h, XL, x, h->stream);
+            if (sub_desc) launch_stream<Epi>(h, D, x, epi, sub_desc, sub_int);
+            else launch_stream<Epi>(h, D, x, epi, D.sdesc + D.t_int0, D.t_int1 - D.t_int0);
+            p2p_pull(h, XL, x, h->stream);
+            if (sub_desc) launch_stream<Epi>(h, D, x, epi, sub_desc + sub_int, sub_bnd);
+            else launch_stream<Epi>(h, D, x, epi, D.sdesc_bnd, D.n_bnd);
+        }));
+        h->launches += 3;
+        return MGB_OK;
+    }
+    const bool can_overlap = need && h->overlap == 1 && !h->prof && D.split && D.sdesc && h->stream_cfg > 0 && h->allow_stream && D.family == 1;
     if (!can_overlap) {
         if (need) TRY(exchange(h, XL, x));
         if (sub_desc) {

@@ -62,6 +62,8 @@ CASES = [
     (2, 8, 3, 7, "injection", 1, {}),                 # random numbering: ghosts everywhere, explicit injection rows
     (3, 4, 3, "structured", "injection", 1, {"stream_cfg": 0}),
     (3, 4, 4, "generated", "injection", 1, {}),       # sharded levels generated on the device, range ghosts
+    (3, 4, 4, "generated", "injection", 1, {"overlap_halo": 2}),   # push -> interior rows -> pull -> boundary rows
+    (3, 2, 4, None, "transpose", 1, {"overlap_halo": 2}),
     (2, 16, 4, "generated", "injection", 0, {}),
 ]
 
