@@ -1220,7 +1220,7 @@ int mgb_finalize(mgb_handle* h)
 
 int mgb_vcycle(mgb_handle* h, int top_level, double* v, const double* f, int mem, int ncycles, double* resnorm_hist)
 {
-    Level* T;
+    Level* T = nullptr;
     TRY(check_ready(h, top_level, &T));
     if (!v || !f || ncycles < 0) return fail(h, MGB_ERR_INVALID, "null vector or negative cycle count");
     TRY(copy_in(h, T->f, f, T->n, mem));
@@ -1233,7 +1233,7 @@ int mgb_vcycle(mgb_handle* h, int top_level, double* v, const double* f, int mem
 
 int mgb_set_rhs(mgb_handle* h, int level, const double* b, int mem)
 {
-    Level* L;
+    Level* L = nullptr;
     TRY(check_ready(h, level, &L));
     if (!b) return fail(h, MGB_ERR_INVALID, "null right-hand side");
     if (!L->b) TRY(dev_alloc(h, &L->b, (size_t)L->n + 16));
@@ -1245,7 +1245,7 @@ int mgb_set_rhs(mgb_handle* h, int level, const double* b, int mem)
 int mgb_set_mass_matrix(mgb_handle* h, int level, int64_t n, int64_t nnz, const void* indptr, int indptr_bytes,
                         const int32_t* indices, const double* values)
 {
-    Level* L;
+    Level* L = nullptr;
     TRY(check_ready(h, level, &L));
     if (n != L->n) return fail(h, MGB_ERR_INVALID, "mass matrix has %lld rows, level %d has %lld", (long long)n, level, (long long)L->n);
     HostCsr M;
@@ -1264,7 +1264,7 @@ int mgb_set_mass_matrix(mgb_handle* h, int level, int64_t n, int64_t nnz, const 
 int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, int mem, int* cycles_done,
             double* resnorm_hist, int hist_capacity)
 {
-    Level* T;
+    Level* T = nullptr;
     if (!h) return MGB_ERR_INVALID;
     TRY(check_ready(h, h->finest, &T));
     if (h->dist) return fail(h, MGB_ERR_UNSUPPORTED, "the FMG driver is single-GPU in this version");
@@ -1317,7 +1317,7 @@ int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, i
 
 int mgb_vcycle_resident(mgb_handle* h, int top_level, int ncycles, double* resnorm_hist)
 {
-    Level* T;
+    Level* T = nullptr;
     TRY(check_ready(h, top_level, &T));
     if (ncycles < 0) return fail(h, MGB_ERR_INVALID, "negative cycle count");
     return cycles_on_buffers(h, top_level, ncycles, resnorm_hist);
@@ -1325,7 +1325,7 @@ int mgb_vcycle_resident(mgb_handle* h, int top_level, int ncycles, double* resno
 
 int mgb_vcycle_debug(mgb_handle* h, int top_level, double* v, const double* f, int mem, double* f2h, double* v2h, double* err_h)
 {
-    Level* T;
+    Level* T = nullptr;
     TRY(check_ready(h, top_level, &T));
     if (top_level == h->coarsest) return fail(h, MGB_ERR_INVALID, "the debug outputs need a level above the coarsest");
     if (!v || !f) return fail(h, MGB_ERR_INVALID, "null vector");
@@ -1345,7 +1345,7 @@ int mgb_vcycle_debug(mgb_handle* h, int top_level, double* v, const double* f, i
 
 int mgb_spmv(mgb_handle* h, int level, const double* x, double* y, int mem)
 {
-    Level* L;
+    Level* L = nullptr;
     TRY(check_ready(h, level, &L));
     BorrowGuard guard(h, mem);
     const double* xd = x; double* yd = y;
@@ -1358,7 +1358,7 @@ int mgb_spmv(mgb_handle* h, int level, const double* x, double* y, int mem)
 
 int mgb_residual(mgb_handle* h, int level, const double* v, const double* f, double* r, int mem)
 {
-    Level* L;
+    Level* L = nullptr;
     TRY(check_ready(h, level, &L));
     BorrowGuard guard(h, mem);
     const double *vd = v, *fd = f; double* rd = r;
@@ -1370,7 +1370,7 @@ int mgb_residual(mgb_handle* h, int level, const double* v, const double* f, dou
 
 int mgb_smooth(mgb_handle* h, int level, double* v, const double* f, int nsweeps, int mem)
 {
-    Level* L;
+    Level* L = nullptr;
     TRY(check_ready(h, level, &L));
     BorrowGuard guard(h, mem);
     if (level == h->coarsest && h->smoother >= MGB_SM_GS_LEVEL) return fail(h, MGB_ERR_STATE, "no Gauss-Seidel operator on the coarsest level");
@@ -1386,7 +1386,7 @@ int mgb_smooth(mgb_handle* h, int level, double* v, const double* f, int nsweeps
 
 int mgb_restrict(mgb_handle* h, int fine_level, const double* r_fine, double* f_coarse, int mem)
 {
-    Level* L;
+    Level* L = nullptr;
     TRY(check_ready(h, fine_level, &L));
     BorrowGuard guard(h, mem);
     if (!L->has_transfer) return fail(h, MGB_ERR_INVALID, "level %d has no coarser neighbour", fine_level);
@@ -1400,7 +1400,7 @@ int mgb_restrict(mgb_handle* h, int fine_level, const double* r_fine, double* f_
 
 int mgb_prolong_add(mgb_handle* h, int fine_level, const double* e_coarse, double* v_fine, int mem)
 {
-    Level* L;
+    Level* L = nullptr;
     TRY(check_ready(h, fine_level, &L));
     BorrowGuard guard(h, mem);
     if (!L->has_transfer) return fail(h, MGB_ERR_INVALID, "level %d has no coarser neighbour", fine_level);
@@ -1414,7 +1414,7 @@ int mgb_prolong_add(mgb_handle* h, int fine_level, const double* e_coarse, doubl
 
 int mgb_coarse_solve(mgb_handle* h, const double* f, double* u, int mem)
 {
-    Level* C;
+    Level* C = nullptr;
     if (!h) return MGB_ERR_INVALID;
     TRY(check_ready(h, h->coarsest, &C));
     BorrowGuard guard(h, mem);
@@ -1442,7 +1442,7 @@ int mgb_norm2(mgb_handle* h, int64_t n, const double* x, int mem, double* out_ho
 
 int mgb_get_artifact(mgb_handle* h, int level, int kind, void* out, int64_t capacity_bytes, int64_t* size_bytes)
 {
-    Level* L;
+    Level* L = nullptr;
     TRY(check_ready(h, level, &L));
     const void* src = nullptr; bool on_device = true; int64_t bytes = 0;
     auto host_vec = [&](const std::vector<int32_t>& v) { src = v.data(); bytes = (int64_t)v.size() * 4; on_device = false; };
@@ -1486,7 +1486,7 @@ int mgb_get_artifact(mgb_handle* h, int level, int kind, void* out, int64_t capa
 
 int mgb_level_buffer(mgb_handle* h, int level, int which, void** device_ptr, int64_t* n)
 {
-    Level* L;
+    Level* L = nullptr;
     TRY(check_ready(h, level, &L));
     if (!device_ptr) return MGB_ERR_INVALID;
     switch (which) {
@@ -1558,7 +1558,7 @@ int mgb_profile_get(mgb_handle* h, mgb_profile_record* out, int capacity, int* c
 
 int mgb_vcycle_bytes(mgb_handle* h, int top_level, double* bytes)
 {
-    Level* T;
+    Level* T = nullptr;
     TRY(check_ready(h, top_level, &T));
     if (!bytes) return MGB_ERR_INVALID;
     double b = 0.0;
