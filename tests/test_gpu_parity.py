@@ -407,3 +407,73 @@ def test_shard_size_limit_is_refused_not_truncated():
     rc = lib.mgb_set_level(h, 0, 1, 2 ** 31 + 5, ip.ctypes.data, 8, None, None)
     assert rc == L.ERR_INVALID                      # null index arrays with nnz > 0 are refused before anything is read
     lib.mgb_destroy(h)
+
+
+@pytest.mark.parametrize("name", ["oracle_3d_p1_inj", "oracle_3d_p1_perm_transpose", "oracle_2d_gs", "oracle_2d_gs_color_perm", "oracle_3d_p2_transpose"])
+def test_against_committed_oracle_fixtures(name):
+    """Parts of the path without reference text (3-D, P2, Gauss-Seidel): GPU vs the frozen oracle outputs in tests/golden/."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_oracle_fixtures", os.path.join(ROOT, "tests", "golden", "gen_oracle_fixtures.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    kw, r_mode, smoother, K = m.CASES[name]
+    H = m.build(kw)
+    lf = H.finest_level
+    d = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    eng = MGEngine.from_hierarchy(H, r_mode=r_mode, smoother=smoother)
+    f = H.b_dict[lf][:, 0]
+    v, hist = eng.vcycle(lf, np.zeros_like(f), f, ncycles=K, history=True)
+    assert np.abs(hist - d["resnorm"]).max() <= RTOL_RESNORM * d["resnorm"].max()
+    assert relmax(v, d["v"]) <= RTOL_SOLUTION
+    if smoother.startswith("gs"):
+        assert np.array_equal(eng.artifact(lf, L.ART_LEVEL_OF_ROW), d["level_of_row"])
+        assert np.array_equal(eng.artifact(lf, L.ART_LEVEL_OFFSETS), d["level_offsets"])
+        assert np.array_equal(eng.artifact(lf, L.ART_COLOUR_OF_ROW), d["colour_of_row"])
+        assert np.array_equal(eng.artifact(lf, L.ART_COLOUR_OFFSETS), d["colour_offsets"])
+    eng.close()
+
+
+def test_full_size_properties_config3():
+    """BASELINE config 3 (129^3 tetrahedral P1, 5 levels): oracle parity at full size + linearity + determinism."""
+    H = pr.build_hierarchy(dim=3, c=8, coarsest_level=0, finest_level=4, with_dicts=False)
+    assert H.n(4) == 129 ** 3 and H.A_sp_dict[4][0].nnz == 31802497
+    eng = MGEngine.from_hierarchy(H)
+    f = H.b_dict[4][:, 0]
+    v1, h1 = eng.vcycle(4, np.zeros_like(f), f, ncycles=3, history=True)
+    v2, h2 = eng.vcycle(4, np.zeros_like(f), 0.5 * f, ncycles=3, history=True)
+    assert np.array_equal(0.5 * v1, v2) and np.array_equal(0.5 * h1, h2)
+    assert np.array_equal(eng.vcycle(4, np.zeros_like(f), f, ncycles=3), v1)
+    cm = co.from_hierarchy(H)
+    vo, ho = cm.vcycle(np.zeros_like(f), f, ncycles=3, history=True)
+    r = float(np.abs(h1 - ho).max() / ho.max()); s = relmax(v1, vo)
+    _report("config3_full", resnorm_rel=r, solution_rel=s)
+    assert r <= RTOL_RESNORM and s <= RTOL_SOLUTION
+    eng.close()
+
+
+def test_full_size_properties_config5():
+    """BASELINE config 5 (513^3, 135 M DOFs, 2.0e9 stored entries, generated on the device): the CPU oracle cannot hold it,
+    so size-independent properties: V-cycles are linear in f (exact for a power-of-two scale), deterministic, identical with
+    and without graph replay, the residual history decreases and equals an independently computed ||f - A v||."""
+    import torch
+    from multigrid_dolfinx_b200 import dist as ds
+    if torch.cuda.mem_get_info(0)[0] < 80e9:
+        pytest.skip("needs ~60 GB of free device memory")
+    src = ds.StructuredSource(3, 8, 0, 6)
+    mg = ds.DistMG(src, device=0, device_gen=True)
+    eng, lf = mg.eng, 6
+    assert eng.n[lf] == 513 ** 3
+    mg.load_rhs()
+    h1 = mg.cycles(3, history=True)
+    v1 = eng.level_buffer(lf, "v").clone()
+    eng.level_buffer(lf, "f").mul_(4.0); eng.level_buffer(lf, "v").zero_(); torch.cuda.synchronize()
+    h2 = mg.cycles(3, history=True)
+    assert torch.equal(eng.level_buffer(lf, "v"), 4.0 * v1) and np.array_equal(h2, 4.0 * h1)
+    eng.set_option("use_graph", 0)
+    eng.level_buffer(lf, "f").mul_(0.25); eng.level_buffer(lf, "v").zero_(); torch.cuda.synchronize()
+    h3 = mg.cycles(3, history=True)
+    assert torch.equal(eng.level_buffer(lf, "v"), v1) and np.array_equal(h3, h1)
+    assert h1[2] < h1[1] < h1[0]
+    r = eng.residual(lf, eng.level_buffer(lf, "v"), eng.level_buffer(lf, "f"))          # per-operator entry point, tile kernel path
+    assert abs(float(torch.linalg.vector_norm(r)) - h1[2]) <= 1e-12 * h1[2]
+    _report("config5_full", hist=[float(x) for x in h1])
+    mg.close()

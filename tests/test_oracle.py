@@ -2,10 +2,12 @@
 vectors the reference itself produced (tests/golden/gen_golden.py), (2) where /root/reference is
 present it is re-run live, (3) the C restatement equals scipy per operator bit for bit and the reference's
 V-cycle to ~1e-15 (it replaces SuperLU by a dense LU on the coarsest level)."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, GOLDEN_SMALL, load_golden
+from conftest import GOLDEN_CASES, GOLDEN_SMALL, ROOT, load_golden
 from multigrid_dolfinx_b200 import problems as pr
 from oracle import c_oracle as co
 from oracle import reference_import as ri
@@ -141,3 +143,32 @@ def test_c_oracle_other_restrictions_match_restated(r_mode):
     assert np.allclose(h1, h2, rtol=1e-12, atol=0)
     assert np.abs(v1[:, 0] - v2).max() < 1e-13
     assert h1[-1] < h1[0]
+
+
+def _oracle_fixture_cases():
+    import importlib.util
+    p = os.path.join(ROOT, "tests", "golden", "gen_oracle_fixtures.py")
+    spec = importlib.util.spec_from_file_location("gen_oracle_fixtures", p)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("name", ["oracle_3d_p1_inj", "oracle_3d_p1_perm_transpose", "oracle_2d_gs", "oracle_2d_gs_color_perm", "oracle_3d_p2_transpose"])
+def test_oracle_reproduces_its_committed_fixtures(name):
+    """The parts without reference text (3-D, P2, Gauss-Seidel): the oracle's outputs are frozen in tests/golden/oracle_*.npz."""
+    m = _oracle_fixture_cases()
+    kw, r_mode, smoother, K = m.CASES[name]
+    H = m.build(kw)
+    lf = H.finest_level
+    d = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    cm = co.from_hierarchy(H, r_mode=r_mode, smoother=smoother)
+    f = H.b_dict[lf][:, 0]
+    v, hist = cm.vcycle(np.zeros_like(f), f, ncycles=K, history=True)
+    assert np.array_equal(v, d["v"]) and np.array_equal(hist, d["resnorm"])
+    if smoother.startswith("gs"):
+        A = H.A_sp_dict[lf][0]
+        lev, order, off = co.level_sets(A)
+        col, corder, coff = co.greedy_colouring(A)
+        assert np.array_equal(lev, d["level_of_row"]) and np.array_equal(off, d["level_offsets"])
+        assert np.array_equal(col, d["colour_of_row"]) and np.array_equal(coff, d["colour_offsets"])
