@@ -80,17 +80,17 @@ StreamChoice stream_choice(int cfg)
     switch (cfg) {
         case 1: return {256, 8, 2};      // 2048-entry tiles, 2 CTAs/SM
         case 2: return {512, 4, 2};      // 2048-entry tiles, 2 CTAs/SM, twice the consumer threads
-        case 3: return {256, 4, 2};      // 1024-entry tiles, 5 CTAs/SM
+        case 3: return {256, 4, 2};      // 1024-entry tiles, 4 CTAs/SM (592 persistent CTAs) -- the default, fastest measured
         case 4: return {256, 4, 3};      // 1024-entry tiles, 3 CTAs/SM
-        case 5: return {128, 8, 2};      // 1024-entry tiles, 5 CTAs/SM
+        case 5: return {128, 8, 2};      // 1024-entry tiles, half the consumer threads
         case 7: return {128, 4, 2};      // 512-entry tiles, ~10 CTAs/SM
-        default: return {256, 8, 3};     // 2048-entry tiles, 1 CTA/SM, deep ring
+        default: return {256, 8, 3};     // 2048-entry tiles, 1 CTA/SM, deep ring (consumer-bound: slowest)
     }
 }
 
-// Upload a host CSR and choose the kernel family / tile shape for it.
 // Kernel family, row tiles and stream descriptors of an operator whose arrays are already on the device.
-// Needs only the row pointers on the host (ip).
+// Needs only the row pointers on the host (ip).  interior (optional): row range [b0, b1) that references no ghost
+// column -> the stream tiles are additionally split into boundary-low | interior | boundary-high.
 int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const std::vector<int32_t>& breaks = {},
                const int64_t* interior = nullptr)
 {
@@ -114,8 +114,8 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
     }
     D.family = family; D.iter = iter;
     if (family == 1 && h->stream_cfg > 0 && breaks.empty()) {     // descriptors for the TMA stream kernel
-        // per-operator choice: short rows (P1 operators, transfers) -> many small CTAs; long rows (P2: 19..65 entries) ->
-        // 2048-entry tiles, so that the sequential per-row sums of phase B are amortised over twice the bytes
+        // one configuration for all operators by default; "stream_auto" switches long-row operators (> 16 entries per
+        // row on average, i.e. P2) to 2048-entry tiles -- measured slower, hence off
         D.scfg = h->stream_cfg;
         if (h->stream_auto && n > 0 && (double)nnz / (double)n > 16.0) D.scfg = 1;
         const StreamChoice sc = stream_choice(D.scfg);
@@ -269,7 +269,7 @@ void launch_stream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nti
         if (occ < 1) occ = 1;
     }
     int grid = std::min(ntiles, h->sm_count * occ), tpc = 0;
-    if (chunked) {                       // CTAs that retire: about 8 waves of them (see k_stream)
+    if (chunked) {                       // CTAs that retire after tpc tiles: `overlap_waves` waves of them (see k_stream)
         tpc = std::max(1, ntiles / (h->sm_count * occ * std::max(1, h->overlap_waves)));
         grid = (ntiles + tpc - 1) / tpc;
     }
