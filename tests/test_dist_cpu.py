@@ -193,3 +193,40 @@ def test_partition_follows_injection():
             assert len(g) == 0 or (g.min() >= off[l + 1][r] and g.max() < off[l + 1][r + 1])
         assert aligned[l]
     assert ds.choose_gather_level(src, 1000) == 1 and ds.choose_gather_level(src, 10) == 0
+
+
+@pytest.mark.parametrize("dim,c,lf,world", [(3, 2, 3, 4), (2, 8, 3, 3), (3, 4, 2, 8)])
+def test_range_halo_plan_covers_the_real_ghosts_and_is_consistent(dim, c, lf, world):
+    """The device-side generator describes ghosts as two index ranges one bandwidth wide.  They must contain every column
+    the operators of that rank really reference, and what rank a sends to b must be exactly what b expects from a."""
+    src = ds.StructuredSource(dim, c, 0, lf)
+    g = 0
+    offsets, aligned = ds.plan_offsets(src, world, g)
+    needs = [None] * world
+
+    class Stop(Exception):
+        pass
+
+    for r in range(world):                      # first pass: collect every rank's ghost requests (emulates the all-gather)
+        def grab(obj, r=r):
+            needs[r] = obj
+            raise Stop
+        try:
+            ds.build_local(src, r, world, gather_level=g, allgather=grab)
+        except Stop:
+            pass
+    for r in range(world):
+        loc = ds.build_local(src, r, world, gather_level=g, allgather=lambda o: needs)
+        for l, L in loc["levels"].items():
+            glo, ghi, peers, send, recv = ds.range_halo_plan(offsets[l], r, src.n(l), ds.bandwidth(src.N(l), dim))
+            gh = L.ghosts
+            assert np.all(((gh >= glo) & (gh < L.s)) | ((gh >= L.e) & (gh < ghi)))
+            assert sum(recv) == (L.s - glo) + (ghi - L.e)
+    for l in range(g + 1, lf + 1):
+        plans = [ds.range_halo_plan(offsets[l], r, src.n(l), ds.bandwidth(src.N(l), dim)) for r in range(world)]
+        for r in range(world):
+            _, _, peers, send, recv = plans[r]
+            for p, q in enumerate(peers):
+                _, _, pq, sq, rq = plans[q]
+                j = pq.index(r)
+                assert len(send[p]) == rq[j] and recv[p] == len(sq[j])
