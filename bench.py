@@ -271,8 +271,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     if multi or args.workload == "cfg5":          # 513^3 never exists on the host: same code path as the sharded arm, world = 1
-        from multigrid_dolfinx_b200 import dist_bench
-        return dist_bench.run(args)
+        import bench_dist
+        return bench_dist.run(args)
     return run_single(args)
 
 

@@ -24,7 +24,7 @@ DIST_WORKLOADS = {
 def run(args):
     import torch
     import torch.distributed as td
-    from . import dist as ds
+    from multigrid_dolfinx_b200 import dist as ds
     import bench as B
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -49,7 +49,7 @@ def run(args):
     dim, c, lc, lf, desc = DIST_WORKLOADS[name]
     t0 = time.perf_counter()
     if name.startswith("cfg4"):       # P2: every rank assembles the hierarchy on the host and cuts its row blocks out of it
-        from . import problems as pr
+        from multigrid_dolfinx_b200 import problems as pr
         src = ds.HierarchySource(pr.build_hierarchy_p2(c=c, coarsest_level=lc, finest_level=lf))
         args.device_gen = 0
     else:
