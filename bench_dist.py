@@ -56,7 +56,8 @@ def run(args):
         src = ds.StructuredSource(dim, c, lc, lf)
     mg = ds.DistMG(src, device=local_rank, r_mode=args.restriction, smoother=args.smoother, gather_threshold=args.gather_threshold,
                    options={"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg, "use_graph": args.use_graph,
-                            "overlap_halo": args.overlap, "overlap_waves": args.overlap_waves},
+                            "overlap_halo": args.overlap, "overlap_waves": args.overlap_waves,
+                            "compress": getattr(args, "compress", 1), "code_cfg": getattr(args, "code_cfg", 1)},
                    device_gen=bool(args.device_gen) and args.restriction == "injection", p2p=bool(args.p2p))
     setup_s = time.perf_counter() - t0
     eng = mg.eng
@@ -106,19 +107,20 @@ def run(args):
         line = {"metric": B.METRIC, "value": dofu / (ms * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{name}: {desc}", "restriction": args.restriction, "smoother": args.smoother, "fine_dofs": n_glob,
-                           "levels": lf - lc + 1, "mu1": src.mu1, "mu2": src.mu2, "generated_on_device": bool(mg.device_gen),
+                           "levels": lf - lc + 1, "mu1": src.mu1, "mu2": src.mu2, "generated_on_device": bool(mg.device_gen), "compress": getattr(args, "compress", 1),
                            "parallelism": f"row-sharded x{world}, levels <= {mg.gather_level} on rank 0" if multi else "single GPU",
                            "l2": "per-rank fine-level operators exceed the 126 MB L2" if n_glob / world > 2e6 else "fine level partly L2-resident", "setup_s": setup_s},
                 "fine_dof_cycles_per_s": n_glob / (ms * 1e-3), "resnorm_after": float(hist[0]),
                 "roofline": {"bound": "hbm", "kernel": f"{dom['kind']}@level{dom['level']} (rank 0 shard)", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
                              "frac": dom["gbs"] / peak, "frac_of_8TBs": dom["gbs"] / 8000.0, "traffic": None, "peak_source": peak_src,
-                             "bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms_per_launch"]},
+                             "bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms_per_launch"],
+                             "moved_bytes_per_launch": dom["moved_bytes"], "moved_achieved": dom["moved_gbs"], "moved_frac": dom["moved_gbs"] / peak},
                 "halo_ms_per_cycle_rank0": halo_ms, "profiled_cycle_ms_rank0": tot_ms,
                 "cpu_baseline": None,
                 "e2e": {"value": dofu / e2e_s, "unit": B.UNIT, "h2d_bytes_per_step": 16 * n_glob, "d2h_bytes_per_step": 8 * n_glob, "ms_per_step": e2e_s * 1e3,
                         "api": "mgb_vcycle(mem=MGB_MEM_HOST) on every rank's row block, pinned host buffers"},
                 "gpu_launches": int(launches), "clocks": clk.summary(),
-                "kernels": [{"k": f"{r['kind']}@{r['level']}", "ms": round(r["ms_per_launch"], 5), "n": r["launches"], "gbs": round(r["gbs"], 1)}
+                "kernels": [{"k": f"{r['kind']}@{r['level']}", "ms": round(r["ms_per_launch"], 5), "n": r["launches"], "gbs": round(r["gbs"], 1), "moved_gbs": round(r["moved_gbs"], 1)}
                             for r in sorted(prof, key=lambda r: -r["total_ms"])[:10]]}
         print(json.dumps(line), flush=True)
     barrier()

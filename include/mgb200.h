@@ -98,7 +98,9 @@ typedef struct {
     int32_t level;
     int64_t launches;
     double total_ms;     /* CUDA-event time summed over launches                */
-    double bytes;        /* algorithmic bytes of ONE launch   */
+    double bytes;        /* algorithmic bytes of ONE launch (CSR form) */
+    double moved_bytes;  /* bytes the chosen kernel streams per launch: equal to `bytes` unless the operator is
+                            dictionary-coded (option "compress"), then 1 (or 5) instead of 12 bytes per stored entry */
 } mgb_profile_record;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -164,7 +166,10 @@ int mgb_synth_poisson_transfer(mgb_handle* h, int coarse_level, int64_t inj_coar
 int mgb_set_params(mgb_handle* h, double omega, int mu1, int mu2, int smoother);
 /* named numeric options, see DESIGN.md:  "rj_order" (0 = as stored in A, 1 = reversed = scipy's
  * DIA*CSR product order, default 1), "use_graph" (default 1), "kernel_family" (0 auto, 1 tile, 2 sub-warp),
- * "lanes_per_row" (0 auto), "coarse_refine" (0/1), "fuse_restrict" (0/1) */
+ * "lanes_per_row" (0 auto), "coarse_refine" (0/1), "fuse_restrict" (0/1), "stream_cfg" (TMA stream kernel shape),
+ * "compress" (default 1: operators whose stored entries repeat -- few distinct values and column offsets, as on the
+ * uniform meshes of the reference -- are additionally kept as one byte per entry + a dictionary, verified lossless on the
+ * device, and streamed in that form; results are bit-identical either way), "code_cfg" (row-stream kernel shape) */
 int mgb_set_option(mgb_handle* h, const char* key, double value);
 /* builds R_omega and D^-1 (getJacobiMatrices, multigrid.py:48-56), R from P, the dense inverse of the
  * coarsest matrix (replaces spsolve, multigrid.py:239), level sets / colours when a GS smoother is
@@ -220,6 +225,8 @@ int mgb_profile_end(mgb_handle* h);
 int mgb_profile_get(mgb_handle* h, mgb_profile_record* out, int capacity, int* count);
 /* algorithmic bytes of one V-cycle at top_level with the current parameters */
 int mgb_vcycle_bytes(mgb_handle* h, int top_level, double* bytes);
+/* the same sum with the bytes the chosen kernels actually stream (dictionary-coded operators move fewer) */
+int mgb_vcycle_bytes_moved(mgb_handle* h, int top_level, double* bytes);
 /* human-readable description of the kernel variant chosen for each (level, operator) */
 int mgb_describe(mgb_handle* h, char* out, int64_t capacity);
 

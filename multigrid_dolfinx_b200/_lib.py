@@ -31,7 +31,7 @@ SMOOTHERS = {"jacobi": SM_JACOBI_RJ, "jacobi_rj": SM_JACOBI_RJ, "jacobi_a": SM_J
 
 class ProfileRecord(C.Structure):
     _fields_ = [("kind", C.c_int32), ("level", C.c_int32), ("launches", C.c_int64), ("total_ms", C.c_double),
-                ("bytes", C.c_double)]
+                ("bytes", C.c_double), ("moved_bytes", C.c_double)]
 
 
 # every symbol include/mgb200.h declares: (name, restype, argtypes)
@@ -78,6 +78,7 @@ SYMBOLS = {
     "mgb_profile_end": (_i, [_vp]),
     "mgb_profile_get": (_i, [_vp, C.POINTER(ProfileRecord), _i, C.POINTER(_i)]),
     "mgb_vcycle_bytes": (_i, [_vp, _i, C.POINTER(_d)]),
+    "mgb_vcycle_bytes_moved": (_i, [_vp, _i, C.POINTER(_d)]),
     "mgb_describe": (_i, [_vp, C.c_char_p, _i64]),
     "mgb_host_build_rj": (_i, [_i64, _vp, _vp, _vp, _i, C.POINTER(_i64), _vp, _vp, _vp, _vp]),
     "mgb_host_level_sets": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _i64]),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgb200.so")
 SOURCES = ["mgb_engine.cu", "mgb_setup.cpp"]
-HEADERS = ["mgb_kernels.cuh", "mgb_internal.h", "mgb_types.cuh", "mgb_dist.cuh", "mgb_synth.cuh",
+HEADERS = ["mgb_kernels.cuh", "mgb_internal.h", "mgb_types.cuh", "mgb_dist.cuh", "mgb_synth.cuh", "mgb_code.cuh",
            os.path.join("..", "..", "include", "mgb200.h")]
 
 

@@ -1,0 +1,250 @@
+// Lossless dictionary coding of device-resident CSR operators (included by mgb_engine.cu inside its anonymous
+// namespace).  Set-up work only -- the coded copy is consumed by k_rowstream (mgb_kernels.cuh).
+//
+// The operators the reference hands over come from uniform meshes (Multigrid_prototype.py:63-66), so their stored
+// entries repeat: few distinct values (R_omega of the P1 Laplacian holds a single one) and, for square operators in a
+// banded numbering, few distinct column offsets.  try_encode() discovers that ON THE DEVICE, from the arrays as they
+// are (nothing is assumed about geometry):
+//   1. k_code_collect   distinct value bit patterns / distinct (col - row) into two small lock-free hash tables
+//                       (atomicCAS on the key itself); more than 256 of either -> that dictionary is abandoned;
+//   2. k_code_pairs     which (offset, value) combinations occur (byte map over 256 x 256);
+//   3. k_code_encode    one byte per stored entry;
+//   4. k_code_verify    decodes every entry again and compares column and value BITS with the CSR arrays; any
+//                       mismatch discards the coding (the operator then simply runs through the uncoded kernels).
+// Dictionaries are sorted (values by bit pattern, offsets ascending, pairs by (offset, value) index), so the coding
+// is a deterministic function of the operator.
+#pragma once
+
+constexpr int CODE_SLOTS = 1024;                     // hash-table slots (power of two, > 256)
+constexpr unsigned long long CODE_VEMPTY = ~0ULL;    // an all-ones NaN never appears as a stored value we accept
+constexpr int CODE_DEMPTY = (int)0x80808080;         // memset-able "no offset" marker
+
+__device__ __forceinline__ unsigned code_hash(unsigned long long k)
+{
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return (unsigned)k;
+}
+
+// flags: [0] values abandoned, [1] offsets abandoned, [2] distinct values, [3] distinct offsets
+__device__ __forceinline__ void code_insert_value(unsigned long long* tbl, int* flags, unsigned long long key)
+{
+    if (key == CODE_VEMPTY) { flags[0] = 1; return; }
+    unsigned s = code_hash(key) & (CODE_SLOTS - 1);
+    for (int p = 0; p < CODE_SLOTS; ++p) {
+        unsigned long long cur = tbl[s];                 // may be a stale "empty" from L1: the CAS below is authoritative
+        if (cur == key) return;
+        if (cur == CODE_VEMPTY) {
+            cur = atomicCAS(tbl + s, CODE_VEMPTY, key);
+            if (cur == key) return;
+            if (cur == CODE_VEMPTY) { if (atomicAdd(flags + 2, 1) >= 256) flags[0] = 1; return; }
+        }
+        s = (s + 1) & (CODE_SLOTS - 1);
+    }
+    flags[0] = 1;
+}
+__device__ __forceinline__ void code_insert_delta(int* tbl, int* flags, int key)
+{
+    if (key == CODE_DEMPTY) { flags[1] = 1; return; }
+    unsigned s = code_hash((unsigned long long)(unsigned)key) & (CODE_SLOTS - 1);
+    for (int p = 0; p < CODE_SLOTS; ++p) {
+        int cur = tbl[s];
+        if (cur == key) return;
+        if (cur == CODE_DEMPTY) {
+            cur = atomicCAS(tbl + s, CODE_DEMPTY, key);
+            if (cur == key) return;
+            if (cur == CODE_DEMPTY) { if (atomicAdd(flags + 3, 1) >= 256) flags[1] = 1; return; }
+        }
+        s = (s + 1) & (CODE_SLOTS - 1);
+    }
+    flags[1] = 1;
+}
+
+__global__ void __launch_bounds__(256)
+k_code_collect(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, const double* __restrict__ vals,
+               unsigned long long* vtbl, int* dtbl, int* flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    volatile int* vf = flags;
+    if (vf[0]) return;
+    const bool want_delta = vf[1] == 0;
+    unsigned long long last_v = CODE_VEMPTY;
+    int last_d = CODE_DEMPTY;
+    for (int k = rp[i]; k < rp[i + 1]; ++k) {
+        const unsigned long long vb = (unsigned long long)__double_as_longlong(vals[k]);
+        if (vb != last_v) { code_insert_value(vtbl, flags, vb); last_v = vb; }
+        if (want_delta) {
+            const int dl = cols[k] - i;
+            if (dl != last_d) { code_insert_delta(dtbl, flags, dl); last_d = dl; }
+        }
+    }
+}
+
+struct CodeDicts {                       // sorted dictionaries, passed by value (3 KB) and staged in shared memory
+    unsigned long long v[256];
+    int d[256];
+    int nv, nd;
+};
+
+__device__ __forceinline__ int code_find_value(const unsigned long long* v, int nv, unsigned long long key)
+{
+    int lo = 0, hi = nv;                 // first index with v[idx] >= key
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (v[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;                            // (caller guarantees presence; k_code_verify catches anything else)
+}
+__device__ __forceinline__ int code_find_delta(const int* d, int nd, int key)
+{
+    int lo = 0, hi = nd;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (d[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// mode 1: lut == nullptr -> mark present[offset index * 256 + value index]; else codes[k] = lut[...]
+// mode 2: codes[k] = value index
+__global__ void __launch_bounds__(256)
+k_code_encode(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, const double* __restrict__ vals,
+              const CodeDicts* __restrict__ dicts, int mode, unsigned char* __restrict__ present,
+              const unsigned char* __restrict__ lut, unsigned char* __restrict__ codes)
+{
+    __shared__ unsigned long long sv[256];
+    __shared__ int sd[256];
+    sv[threadIdx.x] = dicts->v[threadIdx.x];
+    sd[threadIdx.x] = dicts->d[threadIdx.x];
+    const int nv = dicts->nv, nd = dicts->nd;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = rp[i]; k < rp[i + 1]; ++k) {
+        const int vi = code_find_value(sv, nv, (unsigned long long)__double_as_longlong(vals[k])) & 255;
+        if (mode == 2) { codes[k] = (unsigned char)vi; continue; }
+        const int di = code_find_delta(sd, nd, cols[k] - i) & 255;
+        if (lut) codes[k] = lut[di * 256 + vi];
+        else present[di * 256 + vi] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_code_verify(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, const double* __restrict__ vals,
+              const unsigned char* __restrict__ codes, const DictEnt* __restrict__ dict, int mode, int* __restrict__ bad)
+{
+    __shared__ DictEnt sdict[256];
+    sdict[threadIdx.x] = dict[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool ok = true;
+    for (int k = rp[i]; k < rp[i + 1]; ++k) {
+        const DictEnt de = sdict[codes[k]];
+        ok = ok && __double_as_longlong(de.val) == __double_as_longlong(vals[k]);
+        if (mode == 1) ok = ok && (i + de.delta == cols[k]);
+    }
+    if (!ok) *bad = 1;
+}
+
+void free_coded(Coded& c)
+{
+    cudaFree(c.codes); cudaFree(c.dict);
+    c = Coded();
+}
+
+// Try to dictionary-code D (arrays already on the device).  Leaves D.cd.mode == 0 when the operator does not
+// compress; only CUDA failures are errors.
+int try_encode(mgb_handle* h, DevCsr& D)
+{
+    free_coded(D.cd);
+    if (!h->compress || D.nrows <= 0 || D.nnz <= 0) return MGB_OK;
+    if ((double)D.nnz / (double)D.nrows > 24.0) return MGB_OK;          // long rows: thread-per-row does not pay (P2)
+    const int n = (int)D.nrows;
+    const int grid = (n + 255) / 256;
+    unsigned long long* vtbl = nullptr; int* dtbl = nullptr; int* flags = nullptr;
+    CodeDicts* ddicts = nullptr; unsigned char* present = nullptr; unsigned char* lut = nullptr; int* bad = nullptr;
+    auto cleanup = [&] { cudaFree(vtbl); cudaFree(dtbl); cudaFree(flags); cudaFree(ddicts); cudaFree(present); cudaFree(lut); cudaFree(bad); };
+#define CUC(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) { cleanup(); free_coded(D.cd); return fail(h, MGB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } \
+    } while (0)
+    CUC(cudaMalloc((void**)&vtbl, CODE_SLOTS * sizeof(unsigned long long)));
+    CUC(cudaMalloc((void**)&dtbl, CODE_SLOTS * sizeof(int)));
+    CUC(cudaMalloc((void**)&flags, 4 * sizeof(int)));
+    CUC(cudaMemsetAsync(vtbl, 0xFF, CODE_SLOTS * sizeof(unsigned long long), h->stream));
+    CUC(cudaMemsetAsync(dtbl, 0x80, CODE_SLOTS * sizeof(int), h->stream));
+    CUC(cudaMemsetAsync(flags, 0, 4 * sizeof(int), h->stream));
+    k_code_collect<<<grid, 256, 0, h->stream>>>(n, D.rowptr, D.cols, D.vals, vtbl, dtbl, flags);
+    CUC(cudaGetLastError());
+    std::vector<unsigned long long> hv(CODE_SLOTS);
+    std::vector<int> hd(CODE_SLOTS);
+    int hf[4] = {0, 0, 0, 0};
+    CUC(cudaMemcpyAsync(hv.data(), vtbl, CODE_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CUC(cudaMemcpyAsync(hd.data(), dtbl, CODE_SLOTS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUC(cudaMemcpyAsync(hf, flags, sizeof hf, cudaMemcpyDeviceToHost, h->stream));
+    CUC(cudaStreamSynchronize(h->stream));
+    CodeDicts dd{};
+    std::vector<unsigned long long> V;
+    std::vector<int> Dl;
+    for (unsigned long long x : hv) if (x != CODE_VEMPTY) V.push_back(x);
+    for (int x : hd) if (x != CODE_DEMPTY) Dl.push_back(x);
+    if (hf[0] || V.empty() || V.size() > 256) { cleanup(); return MGB_OK; }
+    bool pair = !hf[1] && !Dl.empty() && Dl.size() <= 256;
+    std::sort(V.begin(), V.end());
+    std::sort(Dl.begin(), Dl.end());
+    dd.nv = (int)V.size(); dd.nd = pair ? (int)Dl.size() : 0;
+    for (int k = 0; k < 256; ++k) { dd.v[k] = k < dd.nv ? V[(size_t)k] : ~0ULL; dd.d[k] = k < dd.nd ? Dl[(size_t)k] : INT_MAX; }
+    CUC(cudaMalloc((void**)&ddicts, sizeof(CodeDicts)));
+    CUC(cudaMemcpyAsync(ddicts, &dd, sizeof dd, cudaMemcpyHostToDevice, h->stream));
+    std::vector<DictEnt> dict(256, DictEnt{0.0, 0, 0});
+    std::vector<unsigned char> hlut;
+    int ndict = 0;
+    if (pair) {
+        CUC(cudaMalloc((void**)&present, 65536));
+        CUC(cudaMemsetAsync(present, 0, 65536, h->stream));
+        k_code_encode<<<grid, 256, 0, h->stream>>>(n, D.rowptr, D.cols, D.vals, ddicts, 1, present, nullptr, nullptr);
+        CUC(cudaGetLastError());
+        std::vector<unsigned char> hp(65536);
+        CUC(cudaMemcpyAsync(hp.data(), present, 65536, cudaMemcpyDeviceToHost, h->stream));
+        CUC(cudaStreamSynchronize(h->stream));
+        hlut.assign(65536, 0);
+        for (int key = 0; key < 65536 && ndict <= 256; ++key) {
+            if (!hp[(size_t)key]) continue;
+            if (ndict < 256) {
+                double val; const unsigned long long bits = V[(size_t)(key & 255)];
+                std::memcpy(&val, &bits, sizeof val);
+                dict[(size_t)ndict] = DictEnt{val, Dl[(size_t)(key >> 8)], 0};
+                hlut[(size_t)key] = (unsigned char)ndict;
+            }
+            ++ndict;
+        }
+        if (ndict > 256) { pair = false; ndict = 0; }
+    }
+    const int mode = pair ? 1 : 2;
+    if (!pair) {
+        ndict = dd.nv;
+        for (int k = 0; k < ndict; ++k) {
+            double val; std::memcpy(&val, &V[(size_t)k], sizeof val);
+            dict[(size_t)k] = DictEnt{val, 0, 0};
+        }
+    }
+    CUC(cudaMalloc((void**)&D.cd.dict, 256 * sizeof(DictEnt)));
+    CUC(cudaMemcpyAsync(D.cd.dict, dict.data(), 256 * sizeof(DictEnt), cudaMemcpyHostToDevice, h->stream));
+    const size_t cbytes = ((size_t)D.nnz + 15) / 16 * 16 + 64;             // bulk copies read whole 16-byte groups
+    CUC(cudaMalloc((void**)&D.cd.codes, cbytes));
+    CUC(cudaMemsetAsync(D.cd.codes, 0, cbytes, h->stream));
+    if (pair) {
+        CUC(cudaMalloc((void**)&lut, 65536));
+        CUC(cudaMemcpyAsync(lut, hlut.data(), 65536, cudaMemcpyHostToDevice, h->stream));
+    }
+    k_code_encode<<<grid, 256, 0, h->stream>>>(n, D.rowptr, D.cols, D.vals, ddicts, mode, nullptr, lut, D.cd.codes);
+    CUC(cudaGetLastError());
+    CUC(cudaMalloc((void**)&bad, sizeof(int)));
+    CUC(cudaMemsetAsync(bad, 0, sizeof(int), h->stream));
+    k_code_verify<<<grid, 256, 0, h->stream>>>(n, D.rowptr, D.cols, D.vals, D.cd.codes, D.cd.dict, mode, bad);
+    CUC(cudaGetLastError());
+    int hb = 0;
+    CUC(cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUC(cudaStreamSynchronize(h->stream));
+    cleanup();
+#undef CUC
+    if (hb) { free_coded(D.cd); return MGB_OK; }          // never trust an unverified coding
+    D.cd.mode = mode; D.cd.ndict = ndict; D.cd.nvals = dd.nv; D.cd.ndeltas = (int)Dl.size();
+    return MGB_OK;
+}

@@ -180,8 +180,11 @@ int exchange(mgb_handle* h, Level& L, double* vec)
 // interior tiles when the operator has an interior / boundary split.
 template <class Epi>
 int row_sums_halo(mgb_handle* h, int kind, int level, double bytes, const DevCsr& D, Level& XL, double* x, const Epi& epi,
-                  const int4* sub_desc = nullptr, int sub_int = 0, int sub_bnd = 0)
+                  const int4* sub_desc = nullptr, int sub_int = 0, int sub_bnd = 0, double sub_moved = -1.0)
 {
+    // bytes actually streamed (profile records): the tile subset's own figure, else CSR bytes minus the coding's saving
+    const bool streamable = Epi::CONTIG && D.family == 1 && D.sdesc && h->stream_cfg > 0 && h->allow_stream;
+    const double moved = sub_desc ? sub_moved : (streamable ? bytes - coded_saving(D) : -1.0);
     const bool need = h->dist && !XL.peers.empty();
     // overlap mode 2 (peer-memory exchange only): push -> interior tiles -> pull -> boundary tiles, all on one stream.
     // The neighbours' data travels while the interior rows (which read no ghost entry) are being summed, so the pull
@@ -195,7 +198,7 @@ int row_sums_halo(mgb_handle* h, int kind, int level, double bytes, const DevCsr
             p2p_pull(h, XL, x, h->stream);
             if (sub_desc) launch_stream<Epi>(h, D, x, epi, sub_desc + sub_int, sub_bnd);
             else launch_stream<Epi>(h, D, x, epi, D.sdesc_bnd, D.n_bnd);
-        }));
+        }, moved));
         h->launches += 3;
         return MGB_OK;
     }
@@ -203,7 +206,7 @@ int row_sums_halo(mgb_handle* h, int kind, int level, double bytes, const DevCsr
     if (!can_overlap) {
         if (need) TRY(exchange(h, XL, x));
         if (sub_desc) {
-            return launch(h, kind, level, bytes, [&] { launch_stream<Epi>(h, D, x, epi, sub_desc, sub_int + sub_bnd); });
+            return launch(h, kind, level, bytes, [&] { launch_stream<Epi>(h, D, x, epi, sub_desc, sub_int + sub_bnd); }, moved);
         }
         return row_sums(h, kind, level, bytes, D, x, epi);
     }

@@ -67,6 +67,7 @@ int dev_upload(mgb_handle* h, T** p, const T* src, size_t count, size_t pad = 0)
 
 void free_csr(DevCsr& D)
 {
+    cudaFree(D.cd.codes); cudaFree(D.cd.dict);
     cudaFree(D.rowptr); cudaFree(D.cols); cudaFree(D.vals); cudaFree(D.tiles); cudaFree(D.sdesc); cudaFree(D.sdesc_bnd);
     D = DevCsr();
 }
@@ -87,6 +88,22 @@ StreamChoice stream_choice(int cfg)
         default: return {256, 8, 3};     // 2048-entry tiles, 1 CTA/SM, deep ring (consumer-bound: slowest)
     }
 }
+
+// Row-stream kernel configurations for dictionary-coded operators (option "code_cfg"): consumer threads, rows per
+// thread, entries per row the stage has room for, stages
+struct CodeChoice { int threads, rpt, epr, stages; };
+CodeChoice code_choice(int cfg)
+{
+    switch (cfg) {
+        case 2: return {256, 4, 8, 2};       // 1024-row tiles
+        case 3: return {256, 2, 8, 3};       // 512-row tiles, deeper ring
+        case 4: return {128, 4, 8, 2};       // 512-row tiles, half the consumer threads
+        default: return {256, 2, 8, 2};      // 512-row tiles of <= 4096 entries -- the default
+    }
+}
+
+int try_encode(mgb_handle* h, DevCsr& D);
+void free_coded(Coded& c);
 
 // Kernel family, row tiles and stream descriptors of an operator whose arrays are already on the device.
 // Needs only the row pointers on the host (ip).  interior (optional): row range [b0, b1) that references no ghost
@@ -113,24 +130,39 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
         }
     }
     D.family = family; D.iter = iter;
-    if (family == 1 && h->stream_cfg > 0 && breaks.empty()) {     // descriptors for the TMA stream kernel
+    if (family == 1 && h->stream_cfg > 0 && breaks.empty()) {     // descriptors for the TMA stream kernels
         // one configuration for all operators by default; "stream_auto" switches long-row operators (> 16 entries per
         // row on average, i.e. P2) to 2048-entry tiles -- measured slower, hence off
         D.scfg = h->stream_cfg;
         if (h->stream_auto && n > 0 && (double)nnz / (double)n > 16.0) D.scfg = 1;
-        const StreamChoice sc = stream_choice(D.scfg);
-        const int cap = sc.threads * sc.ept;
         std::vector<int32_t> st, sbreaks, sbt;
         if (interior) {                          // interior row range [b0, b1), shrunk to multiples of 4 rows
             const int64_t b0 = (interior[0] + 3) & ~(int64_t)3, b1 = interior[1] == n ? n : (interior[1] & ~(int64_t)3);
             if (b1 > b0) sbreaks = {(int32_t)b0, (int32_t)b1};
         }
-        if (make_tiles(ip, cap, cap / 4, sbreaks, st, &sbt, 4)) {
+        // dictionary-coded copy (mgb_code.cuh) when the operator's entries are repetitive: row tiles for k_rowstream,
+        // entries counted from a 16-entry aligned start (16-byte bulk copies of one-byte codes)
+        bool tiled = false;
+        int64_t align_mask = 7;
+        TRY(try_encode(h, D));
+        if (D.cd.mode) {
+            D.ccfg = h->code_cfg;
+            const CodeChoice cc = code_choice(D.ccfg);
+            const int64_t rowcap = (int64_t)cc.threads * cc.rpt;
+            tiled = make_tiles(ip, rowcap * cc.epr - 8, rowcap, sbreaks, st, &sbt, 4);
+            if (tiled) align_mask = 15; else free_coded(D.cd);
+        }
+        if (!tiled) {
+            const StreamChoice sc = stream_choice(D.scfg);
+            const int cap = sc.threads * sc.ept;
+            tiled = make_tiles(ip, cap, cap / 4, sbreaks, st, &sbt, 4);
+        }
+        if (tiled) {
             std::vector<int4> desc(st.size() - 1);
             for (size_t t = 0; t + 1 < st.size(); ++t) {
                 const int64_t r0 = st[t], r1 = st[t + 1];
-                const int64_t z0 = ip[r0] & ~(int64_t)7, z1 = ip[r1];
-                desc[t] = make_int4((int)r0, (int)(r1 - r0), (int)z0, (int)((z1 - z0 + 7) & ~(int64_t)7));
+                const int64_t z0 = ip[r0] & ~align_mask, z1 = ip[r1];
+                desc[t] = make_int4((int)r0, (int)(r1 - r0), (int)z0, (int)((z1 - z0 + align_mask) & ~align_mask));
             }
             D.sntiles = (int)desc.size();
             if (D.sntiles > 0) TRY(dev_upload(h, &D.sdesc, desc.data(), desc.size()));
@@ -228,10 +260,12 @@ int fetch_rowptr(mgb_handle* h, const DevCsr& D, std::vector<int64_t>& ip)
 #include "mgb_synth.cuh"
 
 // ---- launch bookkeeping -------------------------------------------------------------------------------
+// bytes: algorithmic bytes of the launch (CSR form); moved: what the chosen kernel actually streams
+// (smaller for dictionary-coded operators); < 0: same as bytes
 template <class F>
-int launch(mgb_handle* h, int kind, int level, double bytes, F&& fn)
+int launch(mgb_handle* h, int kind, int level, double bytes, F&& fn, double moved = -1.0)
 {
-    ProfEvent pe{kind, level, bytes, nullptr, nullptr};
+    ProfEvent pe{kind, level, bytes, moved < 0.0 ? bytes : moved, nullptr, nullptr};
     if (h->prof) {
         CU(cudaEventCreate(&pe.e0)); CU(cudaEventCreate(&pe.e1));
         CU(cudaEventRecord(pe.e0, h->stream));
@@ -282,6 +316,43 @@ void launch_stream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nti
     cudaLaunchKernelEx(&cfg, kern, (const int32_t*)D.rowptr, (const int32_t*)D.cols, (const double*)D.vals, desc, ntiles, tpc, x, epi);
 }
 
+template <int T, int RPT, int EPR, int S, int MODE, class Epi>
+void launch_rowstream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
+{
+    auto kern = k_rowstream<T, RPT, EPR, S, MODE, Epi>;
+    constexpr int smem = RowCfg<T, RPT, EPR, Epi::NOPS, EpiNI<Epi>::value, MODE>::smem_bytes(S);
+    static int occ = -1;                 // per instantiation (one device per process)
+    if (occ < 0) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T + 32, smem);
+        if (occ < 1) occ = 1;
+    }
+    int grid = std::min(ntiles, h->sm_count * occ), tpc = 0;
+    if (chunked) {
+        tpc = std::max(1, ntiles / (h->sm_count * occ * std::max(1, h->overlap_waves)));
+        grid = (ntiles + tpc - 1) / tpc;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T + 32); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, (const int32_t*)D.rowptr, (const int32_t*)D.cols, (const unsigned char*)D.cd.codes,
+                       (const DictEnt*)D.cd.dict, desc, ntiles, tpc, x, epi);
+}
+
+template <int MODE, class Epi>
+void launch_rowstream(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
+{
+    switch (D.ccfg) {                    // code_choice()
+        case 2: launch_rowstream_cfg<256, 4, 8, 2, MODE, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        case 3: launch_rowstream_cfg<256, 2, 8, 3, MODE, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        case 4: launch_rowstream_cfg<128, 4, 8, 2, MODE, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        default: launch_rowstream_cfg<256, 2, 8, 2, MODE, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+    }
+}
+
 template <class Epi>
 void launch_stream(mgb_handle* h, const DevCsr& D, const double* x, const Epi& epi, const int4* desc = nullptr, int ntiles = 0,
                    bool chunked = false)
@@ -289,6 +360,8 @@ void launch_stream(mgb_handle* h, const DevCsr& D, const double* x, const Epi& e
     if (!desc) { desc = D.sdesc; ntiles = D.sntiles; }
     if (ntiles <= 0) return;
     if constexpr (Epi::CONTIG) {
+        if (D.cd.mode == 1) return launch_rowstream<1, Epi>(h, D, desc, ntiles, x, epi, chunked);
+        if (D.cd.mode == 2) return launch_rowstream<2, Epi>(h, D, desc, ntiles, x, epi, chunked);
         switch (D.scfg) {
             case 1: launch_stream_cfg<256, 8, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
             case 2: launch_stream_cfg<512, 4, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
@@ -318,13 +391,17 @@ void launch_subwarp(mgb_handle* h, const DevCsr& D, int r0, int r1, const double
     }
 }
 
+// bytes a dictionary-coded operator does NOT move per pass, relative to its CSR form (12 per stored entry)
+double coded_saving(const DevCsr& D) { return D.cd.mode == 1 ? 11.0 * (double)D.nnz : (D.cd.mode == 2 ? 7.0 * (double)D.nnz : 0.0); }
+
 // all rows of D (group < 0) or the rows of one breakpoint group (colour)
 template <class Epi, bool NCX = true>
 int row_sums(mgb_handle* h, int kind, int level, double bytes, const DevCsr& D, const double* x, const Epi& epi, int group = -1)
 {
     if (D.nrows == 0) return MGB_OK;
+    const bool streamed = Epi::CONTIG && NCX && D.family == 1 && group < 0 && D.sdesc && h->stream_cfg > 0 && h->allow_stream;
     return launch(h, kind, level, bytes, [&] {
-        if (Epi::CONTIG && NCX && D.family == 1 && group < 0 && D.sdesc && h->stream_cfg > 0 && h->allow_stream) {
+        if (streamed) {
             launch_stream<Epi>(h, D, x, epi);
         } else if (D.family == 1) {
             int t0 = 0, t1 = D.ntiles;
@@ -340,7 +417,7 @@ int row_sums(mgb_handle* h, int kind, int level, double bytes, const DevCsr& D, 
                 launch_subwarp<Epi, NCX>(h, D, r0, r1, x, epi);
             }
         }
-    });
+    }, streamed ? bytes - coded_saving(D) : -1.0);
 }
 
 // ---- algorithmic byte counts (SURVEY 8d / DESIGN.md) ---------------------------------------------------
@@ -353,6 +430,7 @@ Level* find_level(mgb_handle* h, int level)
 }
 
 #include "mgb_dist.cuh"
+#include "mgb_code.cuh"
 
 // ---- smoothers ---------------------------------------------------------------------------------------
 int gs_sweep(mgb_handle* h, Level& L, double* v, const double* f)
@@ -459,11 +537,12 @@ int residual_injected(mgb_handle* h, Level& L, const double* v, const double* f,
 {
     const int64_t nc = L.n_coarse;
     const double avg = L.A.nrows ? (double)L.A.nnz / (double)L.A.nrows : 0.0;
-    if (L.inj_desc && L.inj_fraction < 0.8 && h->stream_cfg > 0 && h->allow_stream) {
+    if (L.inj_desc && (L.inj_fraction < 0.8 || L.A.cd.mode) && h->stream_cfg > 0 && h->allow_stream) {
         // stream only the tiles of A that hold injected rows; every row of such a tile is summed, injected ones are stored
         const double nb = L.inj_fraction * (12.0 * (double)L.A.nnz + (4.0 + 8.0 + 4.0) * (double)L.n) + 8.0 * (double)L.n + 8.0 * (double)nc;
         EpiResidualInject epi{f, L.cmap, f_coarse};
-        return row_sums_halo(h, MGB_K_RESIDUAL, L.level, nb, L.A, L, const_cast<double*>(v), epi, L.inj_desc, L.inj_n_int, L.inj_n_bnd);
+        return row_sums_halo(h, MGB_K_RESIDUAL, L.level, nb, L.A, L, const_cast<double*>(v), epi, L.inj_desc, L.inj_n_int, L.inj_n_bnd,
+                             nb - L.inj_fraction * coded_saving(L.A));
     }
     TRY(exchange(h, L, const_cast<double*>(v)));
     return launch(h, MGB_K_RESIDUAL, L.level, (12.0 * avg + 4.0 + 8.0 + 4.0 + 8.0 + 8.0) * (double)nc + 8.0 * (double)L.n, [&] {
@@ -1043,6 +1122,8 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "tile_iter" && pre) h->opt_iter = iv;
     else if (k == "stream_cfg" && pre) h->stream_cfg = iv;
     else if (k == "stream_auto" && pre) h->stream_auto = iv;
+    else if (k == "compress" && pre) h->compress = iv;
+    else if (k == "code_cfg" && pre) h->code_cfg = iv;
     else if (k == "gs_cluster") h->gs_cluster = iv;
     else if (k == "pdl") { h->pdl = iv; drop_graphs(h); }
     else if (k == "p2p_enable") { h->p2p_enable = iv; drop_graphs(h); }
@@ -1538,7 +1619,7 @@ int mgb_profile_end(mgb_handle* h)
         float ms = 0.f;
         cudaEventElapsedTime(&ms, pe.e0, pe.e1);
         mgb_profile_record& r = h->prof_records[{pe.kind, pe.level}];
-        r.kind = pe.kind; r.level = pe.level; r.launches++; r.total_ms += ms; r.bytes = pe.bytes;
+        r.kind = pe.kind; r.level = pe.level; r.launches++; r.total_ms += ms; r.bytes = pe.bytes; r.moved_bytes = pe.moved;
         cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1);
     }
     h->prof_events.clear();
@@ -1556,11 +1637,19 @@ int mgb_profile_get(mgb_handle* h, mgb_profile_record* out, int capacity, int* c
     return MGB_OK;
 }
 
-int mgb_vcycle_bytes(mgb_handle* h, int top_level, double* bytes)
+static int vcycle_bytes_impl(mgb_handle* h, int top_level, double* bytes, bool moved);
+int mgb_vcycle_bytes(mgb_handle* h, int top_level, double* bytes) { return vcycle_bytes_impl(h, top_level, bytes, false); }
+int mgb_vcycle_bytes_moved(mgb_handle* h, int top_level, double* bytes) { return vcycle_bytes_impl(h, top_level, bytes, true); }
+
+static int vcycle_bytes_impl(mgb_handle* h, int top_level, double* bytes, bool moved)
 {
     Level* T = nullptr;
+    if (!h) return MGB_ERR_INVALID;
     TRY(check_ready(h, top_level, &T));
     if (!bytes) return MGB_ERR_INVALID;
+    auto bytes_rowsum = [&](const DevCsr& D, double vec_terms) {
+        return ::bytes_rowsum(D, vec_terms) - (moved && h->stream_cfg > 0 ? coded_saving(D) : 0.0);
+    };
     double b = 0.0;
     for (int l = h->coarsest + 1; l <= top_level; ++l) {
         Level& L = h->levels[l];
@@ -1586,7 +1675,8 @@ int mgb_describe(mgb_handle* h, char* out, int64_t capacity)
     char buf[256];
     auto one = [&](const char* name, const DevCsr& D) {
         if (!D.present()) return;
-        if (D.family == 1 && D.sdesc) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d stream(cfg=%d, %d x %d entries, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.scfg, stream_choice(D.scfg).threads, stream_choice(D.scfg).ept, stream_choice(D.scfg).stages, D.sntiles);
+        if (D.family == 1 && D.sdesc && D.cd.mode) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowstream(coded mode=%d: %d dictionary entries, %d values, %d offsets; cfg=%d, %d x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.mode, D.cd.ndict, D.cd.nvals, D.cd.ndeltas, D.ccfg, code_choice(D.ccfg).threads, code_choice(D.ccfg).rpt, code_choice(D.ccfg).stages, D.sntiles);
+        else if (D.family == 1 && D.sdesc) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d stream(cfg=%d, %d x %d entries, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.scfg, stream_choice(D.scfg).threads, stream_choice(D.scfg).ept, stream_choice(D.scfg).stages, D.sntiles);
         else if (D.family == 1) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d tile(cap=%d) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, tile_cap(D.iter), D.ntiles);
         else if (D.family == 3) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d warp-per-row (sequential order)\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row);
         else snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d subwarp(lanes=%d)\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.lpr);

@@ -428,6 +428,164 @@ k_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, c
     }
 }
 
+// ---- row-stream family: dictionary-coded operators ------------------------------------------------------
+// On the uniform meshes the reference works on, an operator's stored entries repeat: a handful of distinct values
+// and -- for square operators in a banded numbering -- a handful of distinct column offsets (col - row).  Such an
+// operator is kept a second time as ONE BYTE per stored entry, an index into a dictionary of <= 256
+// (col - row, value) pairs (MODE 1), or as the int32 columns plus one byte per value (MODE 2: transfer operators,
+// unstructured numberings).  The coding is lossless and verified entry by entry on the device when it is built
+// (mgb_code.cuh); row sums are formed exactly as before -- one accumulator, stored order, separately rounded multiply
+// and add -- so results stay bit-identical while the matrix stream shrinks from 12 to 1 (or 5) bytes per entry.
+//
+// Same producer / consumer structure as k_stream (one lane issues bulk copies of the tile's codes, columns,
+// row-pointer slice and epilogue operand slices into a ring of stages), but the consumers are thread-per-row: with
+// <= ~16 entries per row there is nothing to balance, consecutive rows gather consecutive x entries (coalesced), and
+// no product buffer or mid-tile barrier is needed.  Every consumer thread arrives on the stage's "empty" barrier
+// itself, so warps drift apart freely.
+struct DictEnt { double val; int delta; int pad; };
+
+template <int THREADS, int RPT, int EPR, int NOPS, int NIOPS, int MODE>
+struct RowCfg {
+    static constexpr int ROWCAP = THREADS * RPT;         // rows per tile
+    static constexpr int ENTCAP = ROWCAP * EPR;          // stored entries per tile (from a 16-entry aligned start)
+    static constexpr int HDR_BYTES = 128;
+    static constexpr int CODE_BYTES = ENTCAP;
+    static constexpr int COLS_BYTES = MODE == 2 ? ENTCAP * 4 : 0;
+    static constexpr int RP_BYTES = ((ROWCAP + 4) * 4 + 127) / 128 * 128;
+    static constexpr int OP_BYTES = ROWCAP * 8;
+    static constexpr int IOP_BYTES = ROWCAP * 4;
+    static constexpr int STAGE_BYTES = HDR_BYTES + CODE_BYTES + COLS_BYTES + RP_BYTES + NOPS * OP_BYTES + NIOPS * IOP_BYTES;
+    static constexpr int DICT_BYTES = 256 * (int)sizeof(DictEnt);
+    static constexpr int BAR_BYTES = 128;
+    static constexpr int smem_bytes(int stages) { return BAR_BYTES + DICT_BYTES + stages * STAGE_BYTES; }
+    static_assert(ENTCAP % 128 == 0 && ROWCAP % 32 == 0, "stage sections must stay 128-byte aligned");
+};
+
+// W entries of one row, starting at stage-local entry k0 (< b): all W gathers are issued unconditionally (entries past
+// the row's end repeat its last entry -- a cache hit -- so that no load waits behind a predicate), then the products
+// are added to the running sum in stored order.
+template <int W, int MODE>
+__device__ __forceinline__ double coded_chunk(double sum, int k0, int b, int row, const unsigned char* scodes, const int32_t* scols,
+                                              const DictEnt* sdict, const double* x)
+{
+    double xv[W], vv[W];
+    int col[W];
+#pragma unroll
+    for (int e = 0; e < W; ++e) {                          // shared-memory look-ups first ...
+        const int k = min(k0 + e, b - 1);
+        const DictEnt de = sdict[scodes[k]];
+        if constexpr (MODE == 1) col[e] = row + de.delta; else col[e] = scols[k];
+        vv[e] = de.val;
+    }
+#pragma unroll
+    for (int e = 0; e < W; ++e) xv[e] = ld_x<true>(x, col[e]);   // ... then the gathers back to back
+#pragma unroll
+    for (int e = 0; e < W; ++e)
+        if (k0 + e < b) sum = __dadd_rn(sum, __dmul_rn(vv[e], xv[e]));
+    return sum;
+}
+
+template <int THREADS, int RPT, int EPR, int STAGES, int MODE, class Epi>
+__global__ void __launch_bounds__(THREADS + 32, 1024 / THREADS)
+k_rowstream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, const unsigned char* __restrict__ codes,
+            const DictEnt* __restrict__ dict, const int4* __restrict__ desc, int ntiles, int tpc, const double* x, Epi epi)
+{
+    static_assert(Epi::CONTIG, "row-stream kernel needs contiguous epilogue operands");
+    static_assert(STAGES <= 8, "barrier block holds 8 stages");
+    static_assert(MODE == 1 || MODE == 2, "MODE 1: pair codes, MODE 2: value codes + columns");
+    constexpr int NIOPS = EpiNI<Epi>::value;
+    using Cfg = RowCfg<THREADS, RPT, EPR, Epi::NOPS, NIOPS, MODE>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + 8;
+    DictEnt* sdict = reinterpret_cast<DictEnt*>(smem + Cfg::BAR_BYTES);
+    unsigned char* stage0 = smem + Cfg::BAR_BYTES + Cfg::DICT_BYTES;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, THREADS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int k = tid; k < 256; k += THREADS + 32) sdict[k] = dict[k];
+    __syncthreads();
+    const int first = tpc > 0 ? (int)blockIdx.x * tpc : (int)blockIdx.x;
+    const int step = tpc > 0 ? 1 : (int)gridDim.x;
+    const int my_tiles = tpc > 0 ? min(tpc, ntiles - first) : (ntiles - first + step - 1) / step;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (tid >= THREADS) {                                   // ---- producer warp (one lane works)
+        if (tid == THREADS) {
+            uint64_t pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            auto issue_matrix = [&](int i, int4& d) {
+                const int s = i % STAGES;
+                d = __ldg(desc + first + (size_t)i * step);                          // {row0, nrows, nz0a, nent}
+                unsigned char* st = stage0 + (size_t)s * Cfg::STAGE_BYTES;
+                *reinterpret_cast<int4*>(st) = d;                                    // published by the arrive below (release)
+                const uint32_t b_code = (uint32_t)d.w, b_cols = MODE == 2 ? (uint32_t)d.w * 4u : 0u;
+                const uint32_t b_rp = (uint32_t)((d.y + 1 + 3) & ~3) * 4u, b_op = (uint32_t)((d.y + 1) & ~1) * 8u;
+                const uint32_t b_iop = (uint32_t)((d.y + 3) & ~3) * 4u;
+                mbar_expect_tx(full + s, b_code + b_cols + b_rp + (uint32_t)Epi::NOPS * b_op + (uint32_t)NIOPS * b_iop);
+                unsigned char* p = st + Cfg::HDR_BYTES;
+                if (b_code) bulk_g2s_hint(p, codes + d.z, b_code, full + s, pol);
+                p += Cfg::CODE_BYTES;
+                if constexpr (MODE == 2) { if (b_cols) bulk_g2s_hint(p, cols + d.z, b_cols, full + s, pol);  p += Cfg::COLS_BYTES; }
+                bulk_g2s(p, rowptr + d.x, b_rp, full + s);
+            };
+            auto issue_operands = [&](int i, const int4& d) {                        // slices of vectors the predecessor may have written
+                const int s = i % STAGES;
+                const uint32_t b_op = (uint32_t)((d.y + 1) & ~1) * 8u, b_iop = (uint32_t)((d.y + 3) & ~3) * 4u;
+                unsigned char* p = stage0 + (size_t)s * Cfg::STAGE_BYTES + Cfg::HDR_BYTES + Cfg::CODE_BYTES + Cfg::COLS_BYTES + Cfg::RP_BYTES;
+#pragma unroll
+                for (int j = 0; j < Epi::NOPS; ++j) { bulk_g2s(p, epi.operand(j) + d.x, b_op, full + s); p += Cfg::OP_BYTES; }
+                if constexpr (NIOPS > 0) bulk_g2s(p, epi.ioperand() + d.x, b_iop, full + s);
+            };
+            int4 dpre[STAGES];
+            const int npre = my_tiles < STAGES ? my_tiles : STAGES;
+            for (int i = 0; i < npre; ++i) issue_matrix(i, dpre[i]);
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            for (int i = 0; i < npre; ++i) issue_operands(i, dpre[i]);
+            for (int i = npre; i < my_tiles; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(empty + s, (uint32_t)((i / STAGES - 1) & 1));
+                int4 d;
+                issue_matrix(i, d);
+                issue_operands(i, d);
+            }
+        }
+        return;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    for (int i = 0; i < my_tiles; ++i) {                     // ---- consumers: thread per row
+        const int s = i % STAGES;
+        mbar_wait(full + s, (uint32_t)((i / STAGES) & 1));
+        const unsigned char* st = stage0 + (size_t)s * Cfg::STAGE_BYTES;
+        const int4 d = *reinterpret_cast<const int4*>(st);
+        const unsigned char* scodes = st + Cfg::HDR_BYTES;
+        const int32_t* scols = reinterpret_cast<const int32_t*>(st + Cfg::HDR_BYTES + Cfg::CODE_BYTES);
+        const int32_t* srp = reinterpret_cast<const int32_t*>(st + Cfg::HDR_BYTES + Cfg::CODE_BYTES + Cfg::COLS_BYTES);
+        const double* sops = reinterpret_cast<const double*>(st + Cfg::HDR_BYTES + Cfg::CODE_BYTES + Cfg::COLS_BYTES + Cfg::RP_BYTES);
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int r = tid + j * THREADS;
+            if (r < d.y) {
+                const int a = srp[r] - d.z, b = srp[r + 1] - d.z;
+                double o[Epi::NOPS > 0 ? Epi::NOPS : 1];
+#pragma unroll
+                for (int q = 0; q < Epi::NOPS; ++q) o[q] = sops[q * Cfg::ROWCAP + r];
+                double sum = 0.0;
+                for (int k0 = a; k0 < b;) {                  // W independent gathers in flight, then the ordered sum
+                    if (b - k0 <= 4) { sum = coded_chunk<4, MODE>(sum, k0, b, d.x + r, scodes, scols, sdict, x); k0 += 4; }
+                    else { sum = coded_chunk<8, MODE>(sum, k0, b, d.x + r, scodes, scols, sdict, x); k0 += 8; }
+                }
+                if constexpr (NIOPS > 0) epi.store_i(d.x + r, sum, o, reinterpret_cast<const int32_t*>(sops + Epi::NOPS * Cfg::ROWCAP)[r]);
+                else epi.store(d.x + r, sum, o);
+            }
+        }
+        mbar_arrive(empty + s);                              // every consumer thread releases the stage itself
+    }
+}
+
 // ---- sub-warp family --------------------------------------------------------------------------------
 // LPR lanes cooperate on one row (LPR = 32: warp per row), partial sums combined with a shuffle tree.
 template <int LPR, bool NCX, class Epi>

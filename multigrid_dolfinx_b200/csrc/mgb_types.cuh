@@ -7,8 +7,20 @@ namespace {
 constexpr int THREADS = 256;
 thread_local std::string g_create_error;
 
+// Lossless dictionary coding of an operator's (column, value) stream (mgb_code.cuh).  The CSR arrays stay on the
+// device (artefacts, fallback kernels); the coded copy is what the row-stream kernel moves through HBM.
+struct Coded {
+    int mode = 0;                    // 0 none, 1 pair codes: entry -> (col - row, value), 2 value codes (+ the int32 columns)
+    unsigned char* codes = nullptr;  // u8[nnz + pad]: index into dict
+    DictEnt* dict = nullptr;         // device, 256 entries
+    int ndict = 0;                   // entries in use
+    int nvals = 0, ndeltas = 0;      // distinct values / distinct (col - row) found
+};
+
 struct DevCsr {
     int64_t nrows = 0, ncols = 0, nnz = 0;
+    Coded cd;
+    int ccfg = 0;            // row-stream kernel configuration (code_choice) when cd.mode != 0
     int32_t* rowptr = nullptr;
     int32_t* cols = nullptr;
     double* vals = nullptr;
@@ -110,7 +122,7 @@ struct Level {
     int gs_W = 0;
 };
 
-struct ProfEvent { int kind, level; double bytes; cudaEvent_t e0, e1; };
+struct ProfEvent { int kind, level; double bytes, moved; cudaEvent_t e0, e1; };
 
 }  // namespace
 
@@ -128,6 +140,8 @@ struct mgb_handle {
     int stream_auto = 0;           // pick the stream configuration per operator from its average row length (measured: no gain)
     int gs_cluster = 2;            // level-scheduled Gauss-Seidel: 0 grid barrier, 1 one cluster, 2 one cluster + ELL prefetch pipeline
     int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
+    int compress = 1;              // dictionary-code operators whose (col - row, value) stream is repetitive (mgb_code.cuh)
+    int code_cfg = 1;              // row-stream kernel configuration for coded operators (code_choice)
     bool allow_stream = true;      // false while borrowed user pointers are in play (no padding / alignment guarantee)
     int coarsest = 0, finest = 0;
     double* coarse_inv = nullptr;

@@ -390,6 +390,12 @@ class MGEngine:
         self._ck(self._lib.mgb_vcycle_bytes(self._h, int(level), C.byref(b)))
         return b.value
 
+    def vcycle_bytes_moved(self, level):
+        """Bytes the chosen kernels stream per V-cycle (fewer than ``vcycle_bytes`` for dictionary-coded operators)."""
+        b = C.c_double()
+        self._ck(self._lib.mgb_vcycle_bytes_moved(self._h, int(level), C.byref(b)))
+        return b.value
+
     def describe(self):
         buf = C.create_string_buffer(1 << 16)
         self._ck(self._lib.mgb_describe(self._h, buf, len(buf)))
@@ -399,7 +405,8 @@ class MGEngine:
         self._ck(self._lib.mgb_profile_begin(self._h))
 
     def profile_end(self):
-        """-> list of dicts {kind, level, launches, total_ms, bytes, gbs}."""
+        """-> list of dicts {kind, level, launches, total_ms, bytes, gbs, moved_bytes, moved_gbs}: ``bytes`` are the
+        algorithmic bytes of the CSR form, ``moved_bytes`` what the chosen kernel streams (dictionary-coded operators)."""
         self._ck(self._lib.mgb_profile_end(self._h))
         cnt = C.c_int()
         self._ck(self._lib.mgb_profile_get(self._h, None, 0, C.byref(cnt)))
@@ -410,7 +417,8 @@ class MGEngine:
             r = arr[i]
             ms = r.total_ms / max(r.launches, 1)
             out.append({"kind": L.KERNEL_KINDS[r.kind], "level": r.level, "launches": r.launches, "total_ms": r.total_ms,
-                        "ms_per_launch": ms, "bytes": r.bytes, "gbs": (r.bytes / (ms * 1e-3) / 1e9) if ms > 0 else 0.0})
+                        "ms_per_launch": ms, "bytes": r.bytes, "gbs": (r.bytes / (ms * 1e-3) / 1e9) if ms > 0 else 0.0,
+                        "moved_bytes": r.moved_bytes, "moved_gbs": (r.moved_bytes / (ms * 1e-3) / 1e9) if ms > 0 else 0.0})
         return out
 
 

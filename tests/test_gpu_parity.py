@@ -477,3 +477,92 @@ def test_full_size_properties_config5():
     assert abs(float(torch.linalg.vector_norm(r)) - h1[2]) <= 1e-12 * h1[2]
     _report("config5_full", hist=[float(x) for x in h1])
     mg.close()
+
+
+# ---- dictionary-coded operators (option "compress", mgb_code.cuh / k_rowstream) ---------------------------------------
+@pytest.mark.parametrize("dim,c,lf,seed,r_mode", [(2, 8, 4, None, "injection"), (2, 8, 4, 1, "injection"), (3, 2, 4, None, "injection"),
+                                                   (3, 2, 3, 5, "transpose"), (2, 5, 3, None, "full_weighting"), (2, 32, 2, None, "transpose")])
+def test_coded_operators_bit_identical_to_uncoded(dim, c, lf, seed, r_mode):
+    """The one-byte-per-entry coding is lossless: every operator and the whole cycle give the same BITS with compress = 0
+    (CSR stream kernel), with the register-staged tile kernel, and with every row-stream kernel shape."""
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=seed, with_dicts=False)
+    n, nc = H.n(lf), H.n(lf - 1)
+    rng = np.random.default_rng(17)
+    x, f, e = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(nc)
+    A = H.A_sp_dict[lf][0]
+    outs = []
+    for opts in [{"compress": 0}, {"stream_cfg": 0}, {"compress": 1}, {"code_cfg": 2}, {"code_cfg": 3}, {"code_cfg": 4}]:
+        eng = MGEngine.from_hierarchy(H, r_mode=r_mode, options=opts)
+        desc = eng.describe()
+        coded = "coded" in desc
+        assert coded == (opts.get("compress", 1) == 1 and opts.get("stream_cfg", 3) != 0), desc
+        if coded and seed is None:              # lexicographic numbering: few column offsets -> pair codes for the level matrices
+            assert "A   " in desc and all("coded mode=1" in ln for ln in desc.splitlines() if ln.strip().startswith(("A ", "RJ ")) and f"rows={n} " in ln), desc
+        if coded:
+            assert all("coded mode=2" in ln for ln in desc.splitlines() if ln.strip().startswith("P ")), desc
+        b = H.b_dict[lf][:, 0]
+        v, hist = eng.vcycle(lf, np.zeros_like(b), b, ncycles=3, history=True)
+        outs.append((eng.spmv(lf, x), eng.residual(lf, x, f), eng.smooth(lf, x, f, 3), eng.prolong_add(lf, e, x), eng.restrict(lf, x), v, hist))
+        if coded:
+            eng.profile_begin(); eng.vcycle(lf, np.zeros_like(b), b); prof = eng.profile_end()
+            jac = [r for r in prof if r["kind"] == "jacobi" and r["level"] == lf][0]
+            assert jac["moved_bytes"] < 0.75 * jac["bytes"]
+            assert eng.vcycle_bytes_moved(lf) < eng.vcycle_bytes(lf)
+        eng.close()
+    assert np.array_equal(outs[0][0], A.dot(x)) and np.array_equal(outs[0][1], f - A.dot(x))
+    for o in outs[1:]:
+        for a, b_ in zip(outs[0], o):
+            assert np.array_equal(a, b_)
+
+
+@pytest.mark.parametrize("nvals,expect", [(1, "coded mode=2"), (7, "coded mode=2"), (256, "coded mode=2"), (257, None)])
+@pytest.mark.parametrize("banded", [False, True])
+def test_coded_ragged_few_values(nvals, expect, banded):
+    """Value dictionary on irregular operators: ragged rows (empty ones included), unsorted columns, values drawn from a
+    small set (signed zeros, a denormal and a huge value among them).  <= 256 distinct values -> coded; 257 -> CSR kernel."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(nvals + 1000 * banded)
+    table = np.concatenate([[0.0, -0.0, 1.0, -1.0, 2.0 ** -1070, 1e150, 0.25], rng.standard_normal(300)])[:nvals] if nvals >= 7 else np.array([0.25])
+    table = np.unique(table.view(np.int64)).view(np.float64)
+    if len(table) < nvals:
+        table = np.concatenate([table, 10.0 + np.arange(nvals - len(table))])
+
+    def draw(M):
+        M = M.copy()
+        idx = np.arange(M.nnz) % nvals                  # every table entry is used
+        rng.shuffle(idx)
+        M.data = table[idx]
+        return M
+    nf, nc = 3001, 777
+    if banded:                                          # few column offsets as well -> pair codes
+        offs = np.array([-40, -1, 0, 1, 40])
+        rows = np.repeat(np.arange(nf), len(offs)); cols = rows + np.tile(offs, nf)
+        keep = (cols >= 0) & (cols < nf)
+        Af = sp.csr_matrix((np.ones(keep.sum()), (rows[keep], cols[keep])), shape=(nf, nf))
+        Af.sort_indices()
+    else:
+        Af = _ragged(nf, nf, rng, 20, diag=True); Af.sort_indices()
+    Af = draw(Af)
+    rows_of = np.repeat(np.arange(nf), np.diff(Af.indptr))
+    Af.data[Af.indices == rows_of] = 1.0 if nvals >= 7 else 0.25                   # a benign diagonal (1 / d stays finite)
+    Ac = _ragged(nc, nc, rng, 12, diag=True); Ac.sort_indices()
+    P, R = draw(_ragged(nf, nc, rng, 15)), draw(_ragged(nc, nf, rng, 22))
+    eng = MGEngine(0)
+    eng.set_level(0, Ac); eng.set_level(1, Af)
+    eng.set_transfer(0, P, r_mode="explicit", R=R)
+    eng.set_params(0.7, 2, 1, "jacobi")
+    eng.finalize()
+    desc = eng.describe()
+    pl = [ln for ln in desc.splitlines() if ln.strip().startswith("P ")][0]
+    assert (expect in pl) if expect else ("coded" not in pl), desc
+    if banded and nvals <= 7:
+        al = [ln for ln in desc.splitlines() if ln.strip().startswith("A ") and f"rows={nf} " in ln][0]
+        assert "coded mode=1" in al, desc
+    x, f, e = rng.standard_normal(nf), rng.standard_normal(nf), rng.standard_normal(nc)
+    assert np.array_equal(eng.spmv(1, x), Af.dot(x))
+    assert np.array_equal(eng.residual(1, x, f), f - Af.dot(x))
+    assert np.array_equal(eng.restrict(1, x), R.dot(x))
+    assert np.array_equal(eng.prolong_add(1, e, x), x + P.dot(e))
+    RO, dinv = rs.jacobi_matrices(Af)
+    assert np.array_equal(eng.smooth(1, x, f, 3), rs.jacobi_relaxation(RO, dinv, x, f, 3, 0.7))
+    eng.close()

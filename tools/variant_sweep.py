@@ -15,6 +15,11 @@ import bench  # noqa: E402
 from multigrid_dolfinx_b200.engine import MGEngine  # noqa: E402
 
 VARIANTS = [
+    ("coded1_256x2", {"code_cfg": 1}),
+    ("coded2_256x4", {"code_cfg": 2}),
+    ("coded3_256x2x3", {"code_cfg": 3}),
+    ("coded4_128x4", {"code_cfg": 4}),
+    ("csr_stream3", {"compress": 0}),
     ("tile_iter1", {"tile_iter": 1, "stream_cfg": 0, "fuse_restrict": 0}),
     ("stream1_nofuse", {"stream_cfg": 1, "fuse_restrict": 0}),
     ("tile_iter2", {"tile_iter": 2, "stream_cfg": 0}),
@@ -66,7 +71,7 @@ def main():
             ms = e0.elapsed_time(e1) / args.cycles
             eng.profile_begin(); eng.vcycle_resident(lf, args.cycles); prof = eng.profile_end()
             rec = {"workload": args.workload, "variant": name, "opts": opts, "cycle_ms_graph": ms, "vcycle_gbs": eng.vcycle_bytes(lf) / ms / 1e6,
-                   "kernels": [{"k": f"{r['kind']}@{r['level']}", "us": round(r["ms_per_launch"] * 1e3, 2), "gbs": round(r["gbs"], 1), "n": r["launches"]}
+                   "kernels": [{"k": f"{r['kind']}@{r['level']}", "us": round(r["ms_per_launch"] * 1e3, 2), "gbs": round(r["gbs"], 1), "moved_gbs": round(r["moved_gbs"], 1), "n": r["launches"]}
                                for r in sorted(prof, key=lambda r: (-r["level"], r["kind"]))]}
             out.write(json.dumps(rec) + "\n"); out.flush()
             top = [k for k in rec["kernels"] if k["k"].endswith(f"@{lf}") and k["k"].split("@")[0] in ("jacobi", "residual", "prolong_add")]
