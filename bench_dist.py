@@ -57,7 +57,7 @@ def run(args):
     mg = ds.DistMG(src, device=local_rank, r_mode=args.restriction, smoother=args.smoother, gather_threshold=args.gather_threshold,
                    options={"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg, "use_graph": args.use_graph,
                             "overlap_halo": args.overlap, "overlap_waves": args.overlap_waves,
-                            "compress": getattr(args, "compress", 1), "code_cfg": getattr(args, "code_cfg", 1)},
+                            "compress": getattr(args, "compress", 2), "code_cfg": getattr(args, "code_cfg", 1)},
                    device_gen=bool(args.device_gen) and args.restriction == "injection", p2p=bool(args.p2p))
     setup_s = time.perf_counter() - t0
     eng = mg.eng
@@ -107,7 +107,7 @@ def run(args):
         line = {"metric": B.METRIC, "value": dofu / (ms * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{name}: {desc}", "restriction": args.restriction, "smoother": args.smoother, "fine_dofs": n_glob,
-                           "levels": lf - lc + 1, "mu1": src.mu1, "mu2": src.mu2, "generated_on_device": bool(mg.device_gen), "compress": getattr(args, "compress", 1),
+                           "levels": lf - lc + 1, "mu1": src.mu1, "mu2": src.mu2, "generated_on_device": bool(mg.device_gen), "compress": getattr(args, "compress", 2),
                            "parallelism": f"row-sharded x{world}, levels <= {mg.gather_level} on rank 0" if multi else "single GPU",
                            "l2": "per-rank fine-level operators exceed the 126 MB L2" if n_glob / world > 2e6 else "fine level partly L2-resident", "setup_s": setup_s},
                 "fine_dof_cycles_per_s": n_glob / (ms * 1e-3), "resnorm_after": float(hist[0]),

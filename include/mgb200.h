@@ -100,7 +100,7 @@ typedef struct {
     double total_ms;     /* CUDA-event time summed over launches                */
     double bytes;        /* algorithmic bytes of ONE launch (CSR form) */
     double moved_bytes;  /* bytes the chosen kernel streams per launch: equal to `bytes` unless the operator is
-                            dictionary-coded (option "compress"), then 1 (or 5) instead of 12 bytes per stored entry */
+                            dictionary-coded (option "compress"): 1 (or 5) instead of 12 bytes per stored entry, or 1 byte per row */
 } mgb_profile_record;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -167,9 +167,10 @@ int mgb_set_params(mgb_handle* h, double omega, int mu1, int mu2, int smoother);
 /* named numeric options, see DESIGN.md:  "rj_order" (0 = as stored in A, 1 = reversed = scipy's
  * DIA*CSR product order, default 1), "use_graph" (default 1), "kernel_family" (0 auto, 1 tile, 2 sub-warp),
  * "lanes_per_row" (0 auto), "coarse_refine" (0/1), "fuse_restrict" (0/1), "stream_cfg" (TMA stream kernel shape),
- * "compress" (default 1: operators whose stored entries repeat -- few distinct values and column offsets, as on the
- * uniform meshes of the reference -- are additionally kept as one byte per entry + a dictionary, verified lossless on the
- * device, and streamed in that form; results are bit-identical either way), "code_cfg" (row-stream kernel shape) */
+ * "compress" (0 off; 1: operators whose stored entries repeat -- few distinct values and column offsets, as on the
+ * uniform meshes of the reference -- are additionally kept as one byte per entry + a dictionary; 2, the default: also
+ * one byte per ROW + a table of row patterns where whole rows repeat.  Every coding is verified lossless on the device
+ * before it is used and results are bit-identical either way), "code_cfg" (row-stream kernel shape) */
 int mgb_set_option(mgb_handle* h, const char* key, double value);
 /* builds R_omega and D^-1 (getJacobiMatrices, multigrid.py:48-56), R from P, the dense inverse of the
  * coarsest matrix (replaces spsolve, multigrid.py:239), level sets / colours when a GS smoother is

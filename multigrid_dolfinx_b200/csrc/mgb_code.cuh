@@ -13,6 +13,14 @@
 //                       mismatch discards the coding (the operator then simply runs through the uncoded kernels).
 // Dictionaries are sorted (values by bit pattern, offsets ascending, pairs by (offset, value) index), so the coding
 // is a deterministic function of the operator.
+//
+// Row patterns (mode 3, tried first for operators with at least as many columns as rows): on a uniform mesh whole ROWS
+// repeat -- the list of (col - row, value) pairs of an interior row is the same for every interior row.  try_patterns()
+// hashes every row's list on the device (k_pat_collect, lock-free table keyed by the 64-bit hash, smallest row index kept
+// as the representative), builds the pattern table from the representatives' actual entries (patterns numbered by
+// representative row, each padded to a multiple of 8 entries), codes every row as one byte (k_pat_encode) and verifies
+// every entry of every row against the CSR arrays (k_pat_verify) -- a hash collision can therefore only cost the
+// coding, never a wrong result.  The kernel then needs neither row pointers nor per-entry codes.
 #pragma once
 
 constexpr int CODE_SLOTS = 1024;                     // hash-table slots (power of two, > 256)
@@ -143,8 +151,175 @@ k_code_verify(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__
 
 void free_coded(Coded& c)
 {
-    cudaFree(c.codes); cudaFree(c.dict);
+    cudaFree(c.codes); cudaFree(c.dict); cudaFree(c.phead);
     c = Coded();
+}
+
+// ---- row patterns --------------------------------------------------------------------------------------
+constexpr int PAT_MAX_ENTRIES = 2048;                // pattern-table entries the kernel keeps in shared memory (32 KB)
+constexpr int PAT_REP_EMPTY = 0x7F7F7F7F;
+
+__device__ __forceinline__ unsigned long long pat_row_hash(int i, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols,
+                                                           const double* __restrict__ vals)
+{
+    const int a = rp[i], b = rp[i + 1];
+    unsigned long long h = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)(unsigned)(b - a);
+    for (int k = a; k < b; ++k) {
+        h ^= (unsigned long long)(unsigned)(cols[k] - i);
+        h *= 0xff51afd7ed558ccdULL; h ^= h >> 32;
+        h ^= (unsigned long long)__double_as_longlong(vals[k]);
+        h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 29;
+    }
+    return h == CODE_VEMPTY ? h - 1 : h;
+}
+
+// flags: [0] abandoned (more than 256 distinct hashes), [2] distinct hashes
+__global__ void __launch_bounds__(256)
+k_pat_collect(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, const double* __restrict__ vals,
+              unsigned long long* htbl, int* rep, int* flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (((volatile int*)flags)[0]) return;
+    const unsigned long long key = pat_row_hash(i, rp, cols, vals);
+    unsigned s = code_hash(key) & (CODE_SLOTS - 1);
+    for (int p = 0; p < CODE_SLOTS; ++p) {
+        unsigned long long cur = htbl[s];
+        if (cur == CODE_VEMPTY) {
+            cur = atomicCAS(htbl + s, CODE_VEMPTY, key);
+            if (cur == CODE_VEMPTY) { if (atomicAdd(flags + 2, 1) >= 256) flags[0] = 1; cur = key; }
+        }
+        if (cur == key) { atomicMin(rep + s, i); return; }
+        s = (s + 1) & (CODE_SLOTS - 1);
+    }
+    flags[0] = 1;
+}
+
+struct PatDicts { unsigned long long h[256]; int id[256]; int n; };      // hashes ascending -> pattern number
+
+__global__ void __launch_bounds__(256)
+k_pat_encode(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, const double* __restrict__ vals,
+             const PatDicts* __restrict__ pd, unsigned char* __restrict__ rcodes)
+{
+    __shared__ unsigned long long sh[256];
+    __shared__ int sid[256];
+    sh[threadIdx.x] = pd->h[threadIdx.x];
+    sid[threadIdx.x] = pd->id[threadIdx.x];
+    const int np = pd->n;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int pos = code_find_value(sh, np, pat_row_hash(i, rp, cols, vals)) & 255;
+    rcodes[i] = (unsigned char)sid[pos];
+}
+
+__global__ void __launch_bounds__(256)
+k_pat_verify(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, const double* __restrict__ vals,
+             const unsigned char* __restrict__ rcodes, const int2* __restrict__ phead, const DictEnt* __restrict__ pent, int* __restrict__ bad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 ph = phead[rcodes[i]];
+    const int a = rp[i], len = rp[i + 1] - a;
+    bool ok = ph.y == len;
+    for (int e = 0; ok && e < len; ++e) {
+        const DictEnt de = pent[ph.x + e];
+        ok = (i + de.delta == cols[a + e]) && __double_as_longlong(de.val) == __double_as_longlong(vals[a + e]);
+    }
+    if (!ok) *bad = 1;
+}
+
+// Row-pattern coding of D (mode 3).  ip: the operator's row pointers on the host.  Leaves D.cd.mode == 0 when it does not apply.
+int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip)
+{
+    free_coded(D.cd);
+    if (h->compress < 2 || D.nrows <= 0 || D.nnz <= 0 || D.ncols < D.nrows) return MGB_OK;
+    if ((double)D.nnz / (double)D.nrows > 24.0) return MGB_OK;
+    const int n = (int)D.nrows;
+    const int grid = (n + 255) / 256;
+    unsigned long long* htbl = nullptr; int* rep = nullptr; int* flags = nullptr; PatDicts* dpd = nullptr; int* bad = nullptr;
+    auto cleanup = [&] { cudaFree(htbl); cudaFree(rep); cudaFree(flags); cudaFree(dpd); cudaFree(bad); };
+#define CUC(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) { cleanup(); free_coded(D.cd); return fail(h, MGB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } \
+    } while (0)
+    CUC(cudaMalloc((void**)&htbl, CODE_SLOTS * sizeof(unsigned long long)));
+    CUC(cudaMalloc((void**)&rep, CODE_SLOTS * sizeof(int)));
+    CUC(cudaMalloc((void**)&flags, 4 * sizeof(int)));
+    CUC(cudaMemsetAsync(htbl, 0xFF, CODE_SLOTS * sizeof(unsigned long long), h->stream));
+    CUC(cudaMemsetAsync(rep, 0x7F, CODE_SLOTS * sizeof(int), h->stream));
+    CUC(cudaMemsetAsync(flags, 0, 4 * sizeof(int), h->stream));
+    k_pat_collect<<<grid, 256, 0, h->stream>>>(n, D.rowptr, D.cols, D.vals, htbl, rep, flags);
+    CUC(cudaGetLastError());
+    std::vector<unsigned long long> hh(CODE_SLOTS);
+    std::vector<int> hr(CODE_SLOTS);
+    int hf[4] = {0, 0, 0, 0};
+    CUC(cudaMemcpyAsync(hh.data(), htbl, CODE_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CUC(cudaMemcpyAsync(hr.data(), rep, CODE_SLOTS * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUC(cudaMemcpyAsync(hf, flags, sizeof hf, cudaMemcpyDeviceToHost, h->stream));
+    CUC(cudaStreamSynchronize(h->stream));
+    std::vector<std::pair<int, unsigned long long>> pats;               // (representative row, hash)
+    for (int s = 0; s < CODE_SLOTS; ++s)
+        if (hh[(size_t)s] != CODE_VEMPTY && hr[(size_t)s] != PAT_REP_EMPTY) pats.push_back({hr[(size_t)s], hh[(size_t)s]});
+    if (hf[0] || pats.empty() || pats.size() > 256) { cleanup(); return MGB_OK; }
+    std::sort(pats.begin(), pats.end());                                  // patterns numbered by representative row
+    std::vector<int2> phead(256, make_int2(0, 0));
+    int total = 0;
+    for (size_t p = 0; p < pats.size(); ++p) {
+        const int r = pats[p].first;
+        if (r < 0 || r >= n) { cleanup(); return MGB_OK; }
+        const int len = (int)(ip[(size_t)r + 1] - ip[(size_t)r]);
+        phead[p] = make_int2(total, len);
+        total += std::max(8, (len + 7) / 8 * 8);
+    }
+    if (total > PAT_MAX_ENTRIES) { cleanup(); return MGB_OK; }
+    std::vector<DictEnt> pent((size_t)total, DictEnt{0.0, 0, 0});
+    std::vector<int32_t> rc; std::vector<double> rv;
+    for (size_t p = 0; p < pats.size(); ++p) {
+        const int r = pats[p].first, len = phead[p].y, off = phead[p].x;
+        rc.resize((size_t)len); rv.resize((size_t)len);
+        if (len > 0) {
+            CUC(cudaMemcpyAsync(rc.data(), D.cols + ip[(size_t)r], sizeof(int32_t) * (size_t)len, cudaMemcpyDeviceToHost, h->stream));
+            CUC(cudaMemcpyAsync(rv.data(), D.vals + ip[(size_t)r], sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, h->stream));
+            CUC(cudaStreamSynchronize(h->stream));
+        }
+        for (int e = 0; e < len; ++e) pent[(size_t)(off + e)] = DictEnt{rv[(size_t)e], rc[(size_t)e] - r, 0};
+        const int padded = std::max(8, (len + 7) / 8 * 8);
+        for (int e = len; e < padded; ++e)                                // copies of the last entry; (0, 0.0) for an empty row
+            pent[(size_t)(off + e)] = len > 0 ? pent[(size_t)(off + len - 1)] : DictEnt{0.0, 0, 0};
+    }
+    PatDicts pd{};
+    {
+        std::vector<std::pair<unsigned long long, int>> byhash;
+        for (size_t p = 0; p < pats.size(); ++p) byhash.push_back({pats[p].second, (int)p});
+        std::sort(byhash.begin(), byhash.end());
+        pd.n = (int)byhash.size();
+        for (int k = 0; k < 256; ++k) { pd.h[k] = k < pd.n ? byhash[(size_t)k].first : ~0ULL; pd.id[k] = k < pd.n ? byhash[(size_t)k].second : 0; }
+    }
+    CUC(cudaMalloc((void**)&dpd, sizeof(PatDicts)));
+    CUC(cudaMemcpyAsync(dpd, &pd, sizeof pd, cudaMemcpyHostToDevice, h->stream));
+    CUC(cudaMalloc((void**)&D.cd.phead, 256 * sizeof(int2)));
+    CUC(cudaMemcpyAsync(D.cd.phead, phead.data(), 256 * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    CUC(cudaMalloc((void**)&D.cd.dict, (size_t)total * sizeof(DictEnt)));
+    CUC(cudaMemcpyAsync(D.cd.dict, pent.data(), (size_t)total * sizeof(DictEnt), cudaMemcpyHostToDevice, h->stream));
+    const size_t cbytes = ((size_t)n + 15) / 16 * 16 + 64;
+    CUC(cudaMalloc((void**)&D.cd.codes, cbytes));
+    CUC(cudaMemsetAsync(D.cd.codes, 0, cbytes, h->stream));
+    k_pat_encode<<<grid, 256, 0, h->stream>>>(n, D.rowptr, D.cols, D.vals, dpd, D.cd.codes);
+    CUC(cudaGetLastError());
+    CUC(cudaMalloc((void**)&bad, sizeof(int)));
+    CUC(cudaMemsetAsync(bad, 0, sizeof(int), h->stream));
+    k_pat_verify<<<grid, 256, 0, h->stream>>>(n, D.rowptr, D.cols, D.vals, D.cd.codes, D.cd.phead, D.cd.dict, bad);
+    CUC(cudaGetLastError());
+    int hb = 0;
+    CUC(cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUC(cudaStreamSynchronize(h->stream));
+    cleanup();
+#undef CUC
+    if (hb) { free_coded(D.cd); return MGB_OK; }          // never trust an unverified coding
+    D.cd.mode = 3; D.cd.ndict = (int)pats.size(); D.cd.npent = total;
+    return MGB_OK;
 }
 
 // Try to dictionary-code D (arrays already on the device).  Leaves D.cd.mode == 0 when the operator does not

@@ -67,7 +67,7 @@ int dev_upload(mgb_handle* h, T** p, const T* src, size_t count, size_t pad = 0)
 
 void free_csr(DevCsr& D)
 {
-    cudaFree(D.cd.codes); cudaFree(D.cd.dict);
+    cudaFree(D.cd.codes); cudaFree(D.cd.dict); cudaFree(D.cd.phead);
     cudaFree(D.rowptr); cudaFree(D.cols); cudaFree(D.vals); cudaFree(D.tiles); cudaFree(D.sdesc); cudaFree(D.sdesc_bnd);
     D = DevCsr();
 }
@@ -95,14 +95,14 @@ struct CodeChoice { int threads, rpt, epr, stages; };
 CodeChoice code_choice(int cfg)
 {
     switch (cfg) {
-        case 2: return {256, 4, 8, 2};       // 1024-row tiles
+        case 2: return {256, 1, 16, 2};      // 256-row tiles, one row per thread
         case 3: return {256, 2, 8, 3};       // 512-row tiles, deeper ring
-        case 4: return {128, 4, 8, 2};       // 512-row tiles, half the consumer threads
         default: return {256, 2, 8, 2};      // 512-row tiles of <= 4096 entries -- the default
     }
 }
 
 int try_encode(mgb_handle* h, DevCsr& D);
+int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip);
 void free_coded(Coded& c);
 
 // Kernel family, row tiles and stream descriptors of an operator whose arrays are already on the device.
@@ -136,20 +136,22 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
         D.scfg = h->stream_cfg;
         if (h->stream_auto && n > 0 && (double)nnz / (double)n > 16.0) D.scfg = 1;
         std::vector<int32_t> st, sbreaks, sbt;
-        if (interior) {                          // interior row range [b0, b1), shrunk to multiples of 4 rows
-            const int64_t b0 = (interior[0] + 3) & ~(int64_t)3, b1 = interior[1] == n ? n : (interior[1] & ~(int64_t)3);
+        if (interior) {                          // interior row range [b0, b1), shrunk to multiples of 16 rows
+            const int64_t b0 = (interior[0] + 15) & ~(int64_t)15, b1 = interior[1] == n ? n : (interior[1] & ~(int64_t)15);
             if (b1 > b0) sbreaks = {(int32_t)b0, (int32_t)b1};
         }
         // dictionary-coded copy (mgb_code.cuh) when the operator's entries are repetitive: row tiles for k_rowstream,
         // entries counted from a 16-entry aligned start (16-byte bulk copies of one-byte codes)
         bool tiled = false;
         int64_t align_mask = 7;
-        TRY(try_encode(h, D));
+        TRY(try_patterns(h, D, ip));             // whole rows repeat (uniform mesh, banded numbering): one byte per ROW
+        if (!D.cd.mode) TRY(try_encode(h, D));   // else one byte per stored entry
         if (D.cd.mode) {
             D.ccfg = h->code_cfg;
             const CodeChoice cc = code_choice(D.ccfg);
             const int64_t rowcap = (int64_t)cc.threads * cc.rpt;
-            tiled = make_tiles(ip, rowcap * cc.epr - 8, rowcap, sbreaks, st, &sbt, 4);
+            if (D.cd.mode == 3) tiled = make_tiles(ip, (int64_t)1 << 40, rowcap, sbreaks, st, &sbt, 16);    // rows only; 16-byte aligned code slices
+            else tiled = make_tiles(ip, rowcap * cc.epr - 8, rowcap, sbreaks, st, &sbt, 4);
             if (tiled) align_mask = 15; else free_coded(D.cd);
         }
         if (!tiled) {
@@ -162,7 +164,8 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
             for (size_t t = 0; t + 1 < st.size(); ++t) {
                 const int64_t r0 = st[t], r1 = st[t + 1];
                 const int64_t z0 = ip[r0] & ~align_mask, z1 = ip[r1];
-                desc[t] = make_int4((int)r0, (int)(r1 - r0), (int)z0, (int)((z1 - z0 + align_mask) & ~align_mask));
+                if (D.cd.mode == 3) desc[t] = make_int4((int)r0, (int)(r1 - r0), 0, (int)(ip[r1] - ip[r0]));   // (entry count: accounting only)
+                else desc[t] = make_int4((int)r0, (int)(r1 - r0), (int)z0, (int)((z1 - z0 + align_mask) & ~align_mask));
             }
             D.sntiles = (int)desc.size();
             if (D.sntiles > 0) TRY(dev_upload(h, &D.sdesc, desc.data(), desc.size()));
@@ -316,40 +319,45 @@ void launch_stream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nti
     cudaLaunchKernelEx(&cfg, kern, (const int32_t*)D.rowptr, (const int32_t*)D.cols, (const double*)D.vals, desc, ntiles, tpc, x, epi);
 }
 
-template <int T, int RPT, int EPR, int S, int MODE, class Epi>
+template <int T, int RPT, int EPR, int S, int MODE, int JW, class Epi>
 void launch_rowstream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
 {
-    auto kern = k_rowstream<T, RPT, EPR, S, MODE, Epi>;
-    constexpr int smem = RowCfg<T, RPT, EPR, Epi::NOPS, EpiNI<Epi>::value, MODE>::smem_bytes(S);
-    static int occ = -1;                 // per instantiation (one device per process)
-    if (occ < 0) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T + 32, smem);
-        if (occ < 1) occ = 1;
+    auto kern = k_rowstream<T, RPT, EPR, S, MODE, JW, Epi>;
+    const int npent = MODE == 3 ? D.cd.npent : 0;            // the pattern table's size decides the shared-memory footprint
+    const int smem = RowCfg<T, RPT, EPR, Epi::NOPS, EpiNI<Epi>::value, MODE>::smem_bytes(S, npent * (int)sizeof(DictEnt));
+    static std::map<int, int> occ_by_smem;                   // per instantiation (one device per process)
+    static int smem_attr = 0;
+    if (smem > smem_attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_attr = smem; }
+    auto it = occ_by_smem.find(smem);
+    if (it == occ_by_smem.end()) {
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, T + 32, smem);
+        it = occ_by_smem.emplace(smem, std::max(o, 1)).first;
     }
+    const int occ = it->second;
     int grid = std::min(ntiles, h->sm_count * occ), tpc = 0;
     if (chunked) {
         tpc = std::max(1, ntiles / (h->sm_count * occ * std::max(1, h->overlap_waves)));
         grid = (ntiles + tpc - 1) / tpc;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T + 32); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T + 32); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = h->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = h->pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kern, (const int32_t*)D.rowptr, (const int32_t*)D.cols, (const unsigned char*)D.cd.codes,
-                       (const DictEnt*)D.cd.dict, desc, ntiles, tpc, x, epi);
+                       (const DictEnt*)D.cd.dict, (const int2*)D.cd.phead, npent, desc, ntiles, tpc, x, epi);
 }
 
-template <int MODE, class Epi>
+// MODE: the coding (pair / value codes); JW: gathers issued up front per row (4 when no row is longer, else 8)
+template <int MODE, int JW, class Epi>
 void launch_rowstream(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
 {
     switch (D.ccfg) {                    // code_choice()
-        case 2: launch_rowstream_cfg<256, 4, 8, 2, MODE, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
-        case 3: launch_rowstream_cfg<256, 2, 8, 3, MODE, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
-        case 4: launch_rowstream_cfg<128, 4, 8, 2, MODE, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
-        default: launch_rowstream_cfg<256, 2, 8, 2, MODE, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        case 2: launch_rowstream_cfg<256, 1, 16, 2, MODE, JW, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        case 3: launch_rowstream_cfg<256, 2, 8, 3, MODE, JW, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        default: launch_rowstream_cfg<256, 2, 8, 2, MODE, JW, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
     }
 }
 
@@ -360,8 +368,12 @@ void launch_stream(mgb_handle* h, const DevCsr& D, const double* x, const Epi& e
     if (!desc) { desc = D.sdesc; ntiles = D.sntiles; }
     if (ntiles <= 0) return;
     if constexpr (Epi::CONTIG) {
-        if (D.cd.mode == 1) return launch_rowstream<1, Epi>(h, D, desc, ntiles, x, epi, chunked);
-        if (D.cd.mode == 2) return launch_rowstream<2, Epi>(h, D, desc, ntiles, x, epi, chunked);
+        if (D.cd.mode == 3 && D.max_row <= 4) return launch_rowstream<3, 4, Epi>(h, D, desc, ntiles, x, epi, chunked);
+        if (D.cd.mode == 3) return launch_rowstream<3, 8, Epi>(h, D, desc, ntiles, x, epi, chunked);
+        if (D.cd.mode == 1 && D.max_row <= 4) return launch_rowstream<1, 4, Epi>(h, D, desc, ntiles, x, epi, chunked);
+        if (D.cd.mode == 1) return launch_rowstream<1, 8, Epi>(h, D, desc, ntiles, x, epi, chunked);
+        if (D.cd.mode == 2 && D.max_row <= 4) return launch_rowstream<2, 4, Epi>(h, D, desc, ntiles, x, epi, chunked);
+        if (D.cd.mode == 2) return launch_rowstream<2, 8, Epi>(h, D, desc, ntiles, x, epi, chunked);
         switch (D.scfg) {
             case 1: launch_stream_cfg<256, 8, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
             case 2: launch_stream_cfg<512, 4, 2, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
@@ -392,7 +404,16 @@ void launch_subwarp(mgb_handle* h, const DevCsr& D, int r0, int r1, const double
 }
 
 // bytes a dictionary-coded operator does NOT move per pass, relative to its CSR form (12 per stored entry)
-double coded_saving(const DevCsr& D) { return D.cd.mode == 1 ? 11.0 * (double)D.nnz : (D.cd.mode == 2 ? 7.0 * (double)D.nnz : 0.0); }
+// (mode 3: one byte per row replaces the stored entries AND the row pointers)
+double coded_saving(const DevCsr& D)
+{
+    switch (D.cd.mode) {
+        case 1: return 11.0 * (double)D.nnz;
+        case 2: return 7.0 * (double)D.nnz;
+        case 3: return 12.0 * (double)D.nnz + 3.0 * (double)D.nrows;
+        default: return 0.0;
+    }
+}
 
 // all rows of D (group < 0) or the rows of one breakpoint group (colour)
 template <class Epi, bool NCX = true>
@@ -1675,7 +1696,8 @@ int mgb_describe(mgb_handle* h, char* out, int64_t capacity)
     char buf[256];
     auto one = [&](const char* name, const DevCsr& D) {
         if (!D.present()) return;
-        if (D.family == 1 && D.sdesc && D.cd.mode) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowstream(coded mode=%d: %d dictionary entries, %d values, %d offsets; cfg=%d, %d x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.mode, D.cd.ndict, D.cd.nvals, D.cd.ndeltas, D.ccfg, code_choice(D.ccfg).threads, code_choice(D.ccfg).rpt, code_choice(D.ccfg).stages, D.sntiles);
+        if (D.family == 1 && D.sdesc && D.cd.mode == 3) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowstream(coded mode=3: %d row patterns, %d table entries; cfg=%d, %d x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.ccfg, code_choice(D.ccfg).threads, code_choice(D.ccfg).rpt, code_choice(D.ccfg).stages, D.sntiles);
+        else if (D.family == 1 && D.sdesc && D.cd.mode) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowstream(coded mode=%d: %d dictionary entries, %d values, %d offsets; cfg=%d, %d x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.mode, D.cd.ndict, D.cd.nvals, D.cd.ndeltas, D.ccfg, code_choice(D.ccfg).threads, code_choice(D.ccfg).rpt, code_choice(D.ccfg).stages, D.sntiles);
         else if (D.family == 1 && D.sdesc) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d stream(cfg=%d, %d x %d entries, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.scfg, stream_choice(D.scfg).threads, stream_choice(D.scfg).ept, stream_choice(D.scfg).stages, D.sntiles);
         else if (D.family == 1) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d tile(cap=%d) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, tile_cap(D.iter), D.ntiles);
         else if (D.family == 3) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d warp-per-row (sequential order)\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row);

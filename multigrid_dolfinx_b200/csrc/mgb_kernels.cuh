@@ -440,7 +440,7 @@ k_stream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, c
 // Same producer / consumer structure as k_stream (one lane issues bulk copies of the tile's codes, columns,
 // row-pointer slice and epilogue operand slices into a ring of stages), but the consumers are thread-per-row: with
 // <= ~16 entries per row there is nothing to balance, consecutive rows gather consecutive x entries (coalesced), and
-// no product buffer or mid-tile barrier is needed.  Every consumer thread arrives on the stage's "empty" barrier
+// no product buffer or mid-tile barrier is needed.  Every consumer warp arrives on the stage's "empty" barrier
 // itself, so warps drift apart freely.
 struct DictEnt { double val; int delta; int pad; };
 
@@ -449,15 +449,19 @@ struct RowCfg {
     static constexpr int ROWCAP = THREADS * RPT;         // rows per tile
     static constexpr int ENTCAP = ROWCAP * EPR;          // stored entries per tile (from a 16-entry aligned start)
     static constexpr int HDR_BYTES = 128;
-    static constexpr int CODE_BYTES = ENTCAP;
+    static constexpr int CODE_BYTES = MODE == 3 ? ROWCAP : ENTCAP;       // MODE 3: one code per ROW
     static constexpr int COLS_BYTES = MODE == 2 ? ENTCAP * 4 : 0;
-    static constexpr int RP_BYTES = ((ROWCAP + 4) * 4 + 127) / 128 * 128;
+    static constexpr int RP_BYTES = MODE == 3 ? 0 : ((ROWCAP + 4) * 4 + 127) / 128 * 128;
     static constexpr int OP_BYTES = ROWCAP * 8;
     static constexpr int IOP_BYTES = ROWCAP * 4;
     static constexpr int STAGE_BYTES = HDR_BYTES + CODE_BYTES + COLS_BYTES + RP_BYTES + NOPS * OP_BYTES + NIOPS * IOP_BYTES;
-    static constexpr int DICT_BYTES = 256 * (int)sizeof(DictEnt);
+    static constexpr int DICT_BYTES = 256 * (int)sizeof(DictEnt);        // MODE 3: 256 pattern heads (int2) + the pattern entries
+    static constexpr int PHEAD_BYTES = 256 * 8;
     static constexpr int BAR_BYTES = 128;
-    static constexpr int smem_bytes(int stages) { return BAR_BYTES + DICT_BYTES + stages * STAGE_BYTES; }
+    static constexpr int smem_bytes(int stages, int pent_bytes = 0)
+    {
+        return BAR_BYTES + (MODE == 3 ? PHEAD_BYTES + pent_bytes : DICT_BYTES) + stages * STAGE_BYTES;
+    }
     static_assert(ENTCAP % 128 == 0 && ROWCAP % 32 == 0, "stage sections must stay 128-byte aligned");
 };
 
@@ -485,27 +489,34 @@ __device__ __forceinline__ double coded_chunk(double sum, int k0, int b, int row
     return sum;
 }
 
-template <int THREADS, int RPT, int EPR, int STAGES, int MODE, class Epi>
+template <int THREADS, int RPT, int EPR, int STAGES, int MODE, int JW, class Epi>
 __global__ void __launch_bounds__(THREADS + 32, 1024 / THREADS)
 k_rowstream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, const unsigned char* __restrict__ codes,
-            const DictEnt* __restrict__ dict, const int4* __restrict__ desc, int ntiles, int tpc, const double* x, Epi epi)
+            const DictEnt* __restrict__ dict, const int2* __restrict__ phead, int npent,
+            const int4* __restrict__ desc, int ntiles, int tpc, const double* x, Epi epi)
 {
     static_assert(Epi::CONTIG, "row-stream kernel needs contiguous epilogue operands");
     static_assert(STAGES <= 8, "barrier block holds 8 stages");
-    static_assert(MODE == 1 || MODE == 2, "MODE 1: pair codes, MODE 2: value codes + columns");
+    static_assert(MODE >= 1 && MODE <= 3, "MODE 1: pair codes, MODE 2: value codes + columns, MODE 3: row-pattern codes");
+    static_assert(JW == 4 || JW == 8, "first-chunk width");
     constexpr int NIOPS = EpiNI<Epi>::value;
     using Cfg = RowCfg<THREADS, RPT, EPR, Epi::NOPS, NIOPS, MODE>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + 8;
-    DictEnt* sdict = reinterpret_cast<DictEnt*>(smem + Cfg::BAR_BYTES);
-    unsigned char* stage0 = smem + Cfg::BAR_BYTES + Cfg::DICT_BYTES;
+    // MODE 1/2: [barriers | 256 dictionary entries | stages]; MODE 3: [barriers | 256 pattern heads | npent pattern entries | stages]
+    DictEnt* sdict = reinterpret_cast<DictEnt*>(smem + Cfg::BAR_BYTES + (MODE == 3 ? Cfg::PHEAD_BYTES : 0));
+    const int2* sphead = reinterpret_cast<const int2*>(smem + Cfg::BAR_BYTES);
+    const int ndict = MODE == 3 ? npent : 256;               // npent is a multiple of 8: the stages stay 128-byte aligned
+    unsigned char* stage0 = smem + Cfg::BAR_BYTES + (MODE == 3 ? Cfg::PHEAD_BYTES + npent * (int)sizeof(DictEnt) : Cfg::DICT_BYTES);
     const int tid = threadIdx.x;
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, THREADS); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int k = tid; k < 256; k += THREADS + 32) sdict[k] = dict[k];
+    for (int k = tid; k < ndict; k += THREADS + 32) sdict[k] = dict[k];
+    if constexpr (MODE == 3)
+        for (int k = tid; k < 256; k += THREADS + 32) const_cast<int2*>(sphead)[k] = phead[k];
     __syncthreads();
     const int first = tpc > 0 ? (int)blockIdx.x * tpc : (int)blockIdx.x;
     const int step = tpc > 0 ? 1 : (int)gridDim.x;
@@ -516,20 +527,20 @@ k_rowstream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols
         if (tid == THREADS) {
             uint64_t pol;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-            auto issue_matrix = [&](int i, int4& d) {
+            auto issue_matrix = [&](int i, const int4& d) {                          // d = {row0, nrows, nz0a, nent}
                 const int s = i % STAGES;
-                d = __ldg(desc + first + (size_t)i * step);                          // {row0, nrows, nz0a, nent}
                 unsigned char* st = stage0 + (size_t)s * Cfg::STAGE_BYTES;
                 *reinterpret_cast<int4*>(st) = d;                                    // published by the arrive below (release)
-                const uint32_t b_code = (uint32_t)d.w, b_cols = MODE == 2 ? (uint32_t)d.w * 4u : 0u;
-                const uint32_t b_rp = (uint32_t)((d.y + 1 + 3) & ~3) * 4u, b_op = (uint32_t)((d.y + 1) & ~1) * 8u;
+                // MODE 3: one code per row, rows [d.x, d.x + d.y), d.x a multiple of 16; no row pointers are needed
+                const uint32_t b_code = MODE == 3 ? (uint32_t)((d.y + 15) & ~15) : (uint32_t)d.w, b_cols = MODE == 2 ? (uint32_t)d.w * 4u : 0u;
+                const uint32_t b_rp = MODE == 3 ? 0u : (uint32_t)((d.y + 1 + 3) & ~3) * 4u, b_op = (uint32_t)((d.y + 1) & ~1) * 8u;
                 const uint32_t b_iop = (uint32_t)((d.y + 3) & ~3) * 4u;
                 mbar_expect_tx(full + s, b_code + b_cols + b_rp + (uint32_t)Epi::NOPS * b_op + (uint32_t)NIOPS * b_iop);
                 unsigned char* p = st + Cfg::HDR_BYTES;
-                if (b_code) bulk_g2s_hint(p, codes + d.z, b_code, full + s, pol);
+                if (b_code) bulk_g2s_hint(p, codes + (MODE == 3 ? d.x : d.z), b_code, full + s, pol);
                 p += Cfg::CODE_BYTES;
                 if constexpr (MODE == 2) { if (b_cols) bulk_g2s_hint(p, cols + d.z, b_cols, full + s, pol);  p += Cfg::COLS_BYTES; }
-                bulk_g2s(p, rowptr + d.x, b_rp, full + s);
+                if constexpr (MODE != 3) bulk_g2s(p, rowptr + d.x, b_rp, full + s);
             };
             auto issue_operands = [&](int i, const int4& d) {                        // slices of vectors the predecessor may have written
                 const int s = i % STAGES;
@@ -541,13 +552,17 @@ k_rowstream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols
             };
             int4 dpre[STAGES];
             const int npre = my_tiles < STAGES ? my_tiles : STAGES;
+            for (int i = 0; i < npre; ++i) dpre[i] = __ldg(desc + first + (size_t)i * step);
+            int4 dn = make_int4(0, 0, 0, 0);                                         // descriptor of the next tile, fetched one tile ahead
+            if (npre < my_tiles) dn = __ldg(desc + first + (size_t)npre * step);
             for (int i = 0; i < npre; ++i) issue_matrix(i, dpre[i]);
             asm volatile("griddepcontrol.wait;" ::: "memory");
             for (int i = 0; i < npre; ++i) issue_operands(i, dpre[i]);
             for (int i = npre; i < my_tiles; ++i) {
                 const int s = i % STAGES;
+                const int4 d = dn;
+                if (i + 1 < my_tiles) dn = __ldg(desc + first + (size_t)(i + 1) * step);   // in flight while the stage drains
                 mbar_wait(empty + s, (uint32_t)((i / STAGES - 1) & 1));
-                int4 d;
                 issue_matrix(i, d);
                 issue_operands(i, d);
             }
@@ -556,7 +571,7 @@ k_rowstream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    for (int i = 0; i < my_tiles; ++i) {                     // ---- consumers: thread per row
+    for (int i = 0; i < my_tiles; ++i) {                     // ---- consumers: thread per row, RPT rows per thread
         const int s = i % STAGES;
         mbar_wait(full + s, (uint32_t)((i / STAGES) & 1));
         const unsigned char* st = stage0 + (size_t)s * Cfg::STAGE_BYTES;
@@ -565,24 +580,91 @@ k_rowstream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols
         const int32_t* scols = reinterpret_cast<const int32_t*>(st + Cfg::HDR_BYTES + Cfg::CODE_BYTES);
         const int32_t* srp = reinterpret_cast<const int32_t*>(st + Cfg::HDR_BYTES + Cfg::CODE_BYTES + Cfg::COLS_BYTES);
         const double* sops = reinterpret_cast<const double*>(st + Cfg::HDR_BYTES + Cfg::CODE_BYTES + Cfg::COLS_BYTES + Cfg::RP_BYTES);
+        if constexpr (MODE == 3) {
+            // row-pattern codes: the row's whole entry list {(col - row, value)} comes from the pattern table; every
+            // pattern is padded to a multiple of 8 entries with copies of its last entry ((0, 0.0) for an empty row),
+            // so the gathers need neither a clamp nor a predicate.  Threads past the tile's end redo its last row.
+            const DictEnt* pe[RPT];
+            int len[RPT];
+            double xv[RPT][JW];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                const int rr = min(tid + j * THREADS, d.y - 1);
+                const int2 ph = sphead[scodes[rr]];
+                pe[j] = sdict + ph.x; len[j] = ph.y;
+                const int row = d.x + rr;
+#pragma unroll
+                for (int e = 0; e < JW; ++e) xv[j][e] = ld_x<true>(x, row + pe[j][e].delta);
+            }
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                const int r = tid + j * THREADS;
+                if (r < d.y) {
+                    double o[Epi::NOPS > 0 ? Epi::NOPS : 1];
+#pragma unroll
+                    for (int q = 0; q < Epi::NOPS; ++q) o[q] = sops[q * Cfg::ROWCAP + r];
+                    double sum = 0.0;                        // one accumulator, stored order
+#pragma unroll
+                    for (int e = 0; e < JW; ++e)
+                        if (e < len[j]) sum = __dadd_rn(sum, __dmul_rn(pe[j][e].val, xv[j][e]));
+                    for (int e0 = JW; e0 < len[j]; e0 += JW) {   // rows longer than JW entries
+                        double xw[JW];
+#pragma unroll
+                        for (int e = 0; e < JW; ++e) xw[e] = ld_x<true>(x, d.x + r + pe[j][e0 + e].delta);
+#pragma unroll
+                        for (int e = 0; e < JW; ++e)
+                            if (e0 + e < len[j]) sum = __dadd_rn(sum, __dmul_rn(pe[j][e0 + e].val, xw[e]));
+                    }
+                    if constexpr (NIOPS > 0) epi.store_i(d.x + r, sum, o, reinterpret_cast<const int32_t*>(sops + Epi::NOPS * Cfg::ROWCAP)[r]);
+                    else epi.store(d.x + r, sum, o);
+                }
+            }
+        } else {
+        int a[RPT], b[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int r = tid + j * THREADS;
+            const bool on = r < d.y;
+            a[j] = on ? srp[r] - d.z : 0;
+            b[j] = on ? srp[r + 1] - d.z : 0;
+        }
+        // the first JW entries of all RPT rows: RPT * JW gathers issued back to back, unconditionally (entries past a
+        // row's end repeat its last entry, an empty row reads x[0]), so that none of them waits behind a predicate
+        double xv[RPT][JW];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int row = d.x + tid + j * THREADS;
+            const bool any = b[j] > a[j];
+#pragma unroll
+            for (int e = 0; e < JW; ++e) {
+                const int k = any ? min(a[j] + e, b[j] - 1) : 0;
+                int col;
+                if constexpr (MODE == 1) col = row + sdict[scodes[k]].delta; else col = scols[k];
+                xv[j][e] = ld_x<true>(x, any ? col : 0);
+            }
+        }
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
             const int r = tid + j * THREADS;
             if (r < d.y) {
-                const int a = srp[r] - d.z, b = srp[r + 1] - d.z;
                 double o[Epi::NOPS > 0 ? Epi::NOPS : 1];
 #pragma unroll
                 for (int q = 0; q < Epi::NOPS; ++q) o[q] = sops[q * Cfg::ROWCAP + r];
-                double sum = 0.0;
-                for (int k0 = a; k0 < b;) {                  // W independent gathers in flight, then the ordered sum
-                    if (b - k0 <= 4) { sum = coded_chunk<4, MODE>(sum, k0, b, d.x + r, scodes, scols, sdict, x); k0 += 4; }
-                    else { sum = coded_chunk<8, MODE>(sum, k0, b, d.x + r, scodes, scols, sdict, x); k0 += 8; }
+                double sum = 0.0;                            // one accumulator, stored order
+#pragma unroll
+                for (int e = 0; e < JW; ++e)
+                    if (a[j] + e < b[j]) sum = __dadd_rn(sum, __dmul_rn(sdict[scodes[a[j] + e]].val, xv[j][e]));
+                for (int k0 = a[j] + JW; k0 < b[j];) {       // rows longer than JW entries
+                    if (b[j] - k0 <= 4) { sum = coded_chunk<4, MODE>(sum, k0, b[j], d.x + r, scodes, scols, sdict, x); k0 += 4; }
+                    else { sum = coded_chunk<8, MODE>(sum, k0, b[j], d.x + r, scodes, scols, sdict, x); k0 += 8; }
                 }
                 if constexpr (NIOPS > 0) epi.store_i(d.x + r, sum, o, reinterpret_cast<const int32_t*>(sops + Epi::NOPS * Cfg::ROWCAP)[r]);
                 else epi.store(d.x + r, sum, o);
             }
         }
-        mbar_arrive(empty + s);                              // every consumer thread releases the stage itself
+        }   // MODE 1 / 2
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(empty + s);         // one arrival per consumer warp releases the stage
     }
 }
 

@@ -10,10 +10,13 @@ thread_local std::string g_create_error;
 // Lossless dictionary coding of an operator's (column, value) stream (mgb_code.cuh).  The CSR arrays stay on the
 // device (artefacts, fallback kernels); the coded copy is what the row-stream kernel moves through HBM.
 struct Coded {
-    int mode = 0;                    // 0 none, 1 pair codes: entry -> (col - row, value), 2 value codes (+ the int32 columns)
-    unsigned char* codes = nullptr;  // u8[nnz + pad]: index into dict
-    DictEnt* dict = nullptr;         // device, 256 entries
-    int ndict = 0;                   // entries in use
+    int mode = 0;                    // 0 none, 1 pair codes: entry -> (col - row, value), 2 value codes (+ the int32 columns),
+                                     // 3 row-pattern codes: row -> its whole list of (col - row, value)
+    unsigned char* codes = nullptr;  // u8[nnz + pad]: index into dict (mode 3: u8[nrows + pad]: index into phead)
+    DictEnt* dict = nullptr;         // device, 256 entries (mode 3: npent pattern entries)
+    int2* phead = nullptr;           // mode 3: device, 256 x {first entry, length}
+    int npent = 0;                   // mode 3: entries in the pattern table (multiple of 8)
+    int ndict = 0;                   // entries (mode 3: patterns) in use
     int nvals = 0, ndeltas = 0;      // distinct values / distinct (col - row) found
 };
 
@@ -140,7 +143,7 @@ struct mgb_handle {
     int stream_auto = 0;           // pick the stream configuration per operator from its average row length (measured: no gain)
     int gs_cluster = 2;            // level-scheduled Gauss-Seidel: 0 grid barrier, 1 one cluster, 2 one cluster + ELL prefetch pipeline
     int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
-    int compress = 1;              // dictionary-code operators whose (col - row, value) stream is repetitive (mgb_code.cuh)
+    int compress = 2;              // lossless coding of repetitive operators (mgb_code.cuh): 0 off, 1 per-entry codes, 2 + row patterns
     int code_cfg = 1;              // row-stream kernel configuration for coded operators (code_choice)
     bool allow_stream = true;      // false while borrowed user pointers are in play (no padding / alignment guarantee)
     int coarsest = 0, finest = 0;

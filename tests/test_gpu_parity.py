@@ -491,15 +491,17 @@ def test_coded_operators_bit_identical_to_uncoded(dim, c, lf, seed, r_mode):
     x, f, e = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(nc)
     A = H.A_sp_dict[lf][0]
     outs = []
-    for opts in [{"compress": 0}, {"stream_cfg": 0}, {"compress": 1}, {"code_cfg": 2}, {"code_cfg": 3}, {"code_cfg": 4}]:
+    for opts in [{"compress": 0}, {"stream_cfg": 0}, {"compress": 1}, {"compress": 2}, {"code_cfg": 2}, {"code_cfg": 3}, {"compress": 1, "code_cfg": 3}]:
         eng = MGEngine.from_hierarchy(H, r_mode=r_mode, options=opts)
         desc = eng.describe()
         coded = "coded" in desc
-        assert coded == (opts.get("compress", 1) == 1 and opts.get("stream_cfg", 3) != 0), desc
-        if coded and seed is None:              # lexicographic numbering: few column offsets -> pair codes for the level matrices
-            assert "A   " in desc and all("coded mode=1" in ln for ln in desc.splitlines() if ln.strip().startswith(("A ", "RJ ")) and f"rows={n} " in ln), desc
-        if coded:
-            assert all("coded mode=2" in ln for ln in desc.splitlines() if ln.strip().startswith("P ")), desc
+        assert coded == (opts.get("compress", 2) >= 1 and opts.get("stream_cfg", 3) != 0), desc
+        if coded and seed is None:              # lexicographic numbering: whole rows repeat -> row patterns (compress = 2, the
+            want = "coded mode=3" if opts.get("compress", 2) == 2 else "coded mode=1"      # default), else pair codes per entry
+            assert "A   " in desc and all(want in ln for ln in desc.splitlines() if ln.strip().startswith(("A ", "RJ ")) and f"rows={n} " in ln), desc
+        if coded:                               # transfers: value codes (+ columns); tiny ones may still fit the pair dictionary
+            assert all("coded" in ln for ln in desc.splitlines() if ln.strip().startswith("P ")), desc
+            assert all("coded mode=2" in ln for ln in desc.splitlines() if ln.strip().startswith("P ") and f"rows={n} " in ln), desc
         b = H.b_dict[lf][:, 0]
         v, hist = eng.vcycle(lf, np.zeros_like(b), b, ncycles=3, history=True)
         outs.append((eng.spmv(lf, x), eng.residual(lf, x, f), eng.smooth(lf, x, f, 3), eng.prolong_add(lf, e, x), eng.restrict(lf, x), v, hist))
@@ -522,7 +524,7 @@ def test_coded_ragged_few_values(nvals, expect, banded):
     small set (signed zeros, a denormal and a huge value among them).  <= 256 distinct values -> coded; 257 -> CSR kernel."""
     import scipy.sparse as sp
     rng = np.random.default_rng(nvals + 1000 * banded)
-    table = np.concatenate([[0.0, -0.0, 1.0, -1.0, 2.0 ** -1070, 1e150, 0.25], rng.standard_normal(300)])[:nvals] if nvals >= 7 else np.array([0.25])
+    table = np.concatenate([[0.0, -0.0, 1.0, -1.0, 2.0 ** -1070, 1e60, 0.25], rng.standard_normal(300)])[:nvals] if nvals >= 7 else np.array([0.25])
     table = np.unique(table.view(np.int64)).view(np.float64)
     if len(table) < nvals:
         table = np.concatenate([table, 10.0 + np.arange(nvals - len(table))])
@@ -555,9 +557,9 @@ def test_coded_ragged_few_values(nvals, expect, banded):
     desc = eng.describe()
     pl = [ln for ln in desc.splitlines() if ln.strip().startswith("P ")][0]
     assert (expect in pl) if expect else ("coded" not in pl), desc
-    if banded and nvals <= 7:
+    if banded and nvals <= 7:                           # few offsets and values, but rows do not repeat: pair codes per entry
         al = [ln for ln in desc.splitlines() if ln.strip().startswith("A ") and f"rows={nf} " in ln][0]
-        assert "coded mode=1" in al, desc
+        assert ("coded mode=1" in al) or (nvals == 1 and "coded mode=3" in al), desc
     x, f, e = rng.standard_normal(nf), rng.standard_normal(nf), rng.standard_normal(nc)
     assert np.array_equal(eng.spmv(1, x), Af.dot(x))
     assert np.array_equal(eng.residual(1, x, f), f - Af.dot(x))
@@ -565,4 +567,72 @@ def test_coded_ragged_few_values(nvals, expect, banded):
     assert np.array_equal(eng.prolong_add(1, e, x), x + P.dot(e))
     RO, dinv = rs.jacobi_matrices(Af)
     assert np.array_equal(eng.smooth(1, x, f, 3), rs.jacobi_relaxation(RO, dinv, x, f, 3, 0.7))
+    eng.close()
+
+
+def test_row_pattern_coding_long_and_empty_rows():
+    """Row-pattern codes (mode 3) on operators whose rows repeat but are neither short nor uniform: 19-entry rows (first
+    8 gathers + two continuation chunks), truncated boundary rows, periodically EMPTY rows and a rectangular operator."""
+    import scipy.sparse as sp
+    nf, nc = 5003, 1201
+    offs = np.arange(-90, 91, 10)                        # 19 offsets, 0 among them
+    vals = {int(o): (4.0 if o == 0 else -1.0 / (1 + abs(o) // 10)) for o in offs}
+    rows = np.repeat(np.arange(nf), len(offs)); cols = rows + np.tile(offs, nf)
+    keep = (cols >= 0) & (cols < nf)
+    data = np.array([vals[int(o)] for o in np.tile(offs, nf)])
+    Af = sp.csr_matrix((data[keep], (rows[keep], cols[keep])), shape=(nf, nf)); Af.sort_indices()
+    Ac = sp.diags([-1.0, 2.5, -1.0], [-1, 0, 1], shape=(nc, nc)).tocsr()
+    # R (nc x nf): row i couples fine columns 4i + {0, 1, 2, 5, 9, 14, 20, 27, 35, 44, 54}; every 5th row is empty, every 7th short
+    roffs = np.array([0, 1, 2, 5, 9, 14, 20, 27, 35, 44, 54])
+    r_i, r_j, r_v = [], [], []
+    for i in range(nc):
+        if i % 5 == 3:
+            continue
+        use = roffs[:3] if i % 7 == 2 else roffs
+        for q, o in enumerate(use):
+            j = 4 * i + int(o)
+            if j < nf:
+                r_i.append(i); r_j.append(j); r_v.append(0.5 ** (q % 4))
+    R = sp.csr_matrix((r_v, (r_i, r_j)), shape=(nc, nf)); R.sort_indices()
+    rng = np.random.default_rng(5)
+    P = _ragged(nf, nc, rng, 9)
+    eng = MGEngine(0)
+    eng.set_level(0, Ac); eng.set_level(1, Af)
+    eng.set_transfer(0, P, r_mode="explicit", R=R)
+    eng.set_params(0.7, 2, 1, "jacobi")
+    eng.finalize()
+    desc = eng.describe()
+    for tag, rows_ in (("A ", nf), ("RJ ", nf)):
+        ln = [l for l in desc.splitlines() if l.strip().startswith(tag) and f"rows={rows_} " in l][0]
+        assert "coded mode=3" in ln, desc
+    # R's rows are not translates of each other in (col - row) terms (columns advance by 4 per row): no pattern coding, but
+    # its four values still give the value dictionary
+    assert "coded mode=2" in [l for l in desc.splitlines() if l.strip().startswith("R ")][0], desc
+    x, f = rng.standard_normal(nf), rng.standard_normal(nf)
+    assert np.array_equal(eng.spmv(1, x), Af.dot(x))
+    assert np.array_equal(eng.residual(1, x, f), f - Af.dot(x))
+    assert np.array_equal(eng.restrict(1, x), R.dot(x))
+    RO, dinv = rs.jacobi_matrices(Af)
+    assert np.array_equal(eng.smooth(1, x, f, 3), rs.jacobi_relaxation(RO, dinv, x, f, 3, 0.7))
+    eng.close()
+    # a square operator with periodically empty and short rows, used as the level matrix of a one-level "hierarchy" is not
+    # possible (Jacobi needs the diagonal), so the same rows go in as the mass matrix of the FMG norm: M r through mode 3
+    m_i, m_j, m_v = [], [], []
+    for i in range(nf):
+        if i % 5 == 3:
+            continue
+        for q, o in enumerate((-7, 0, 3) if i % 7 == 2 else (-50, -7, -1, 0, 1, 3, 11, 23, 40, 77)):
+            if 0 <= i + o < nf:
+                m_i.append(i); m_j.append(i + o); m_v.append(40.0 if o == 0 else 1.0 + 0.25 * q)     # dominant diagonal: r^T M r > 0
+    M = sp.csr_matrix((m_v, (m_i, m_j)), shape=(nf, nf)); M.sort_indices()
+    eng = MGEngine(0)
+    eng.set_level(0, Ac); eng.set_level(1, Af)
+    eng.set_transfer(0, P, r_mode="explicit", R=R)
+    eng.set_params(0.7, 1, 1, "jacobi")
+    eng.finalize()
+    eng.set_mass_matrix(1, M)
+    eng.set_rhs(0, np.ones(nc)); eng.set_rhs(1, f)
+    v, hist = eng.fmg(mu0=1, tol=0.0, max_cycles=1)
+    r = f - Af.dot(v)
+    assert abs(hist[0] - np.sqrt(abs(r @ M.dot(r)))) <= 1e-12 * max(hist[0], 1e-300)
     eng.close()

@@ -15,10 +15,12 @@ import bench  # noqa: E402
 from multigrid_dolfinx_b200.engine import MGEngine  # noqa: E402
 
 VARIANTS = [
-    ("coded1_256x2", {"code_cfg": 1}),
-    ("coded2_256x4", {"code_cfg": 2}),
-    ("coded3_256x2x3", {"code_cfg": 3}),
-    ("coded4_128x4", {"code_cfg": 4}),
+    ("pattern1_256x2", {"code_cfg": 1}),
+    ("pattern2_256x1", {"code_cfg": 2}),
+    ("pattern3_256x2x3", {"code_cfg": 3}),
+    ("coded1_256x2", {"compress": 1, "code_cfg": 1}),
+    ("coded2_256x1", {"compress": 1, "code_cfg": 2}),
+    ("coded3_256x2x3", {"compress": 1, "code_cfg": 3}),
     ("csr_stream3", {"compress": 0}),
     ("tile_iter1", {"tile_iter": 1, "stream_cfg": 0, "fuse_restrict": 0}),
     ("stream1_nofuse", {"stream_cfg": 1, "fuse_restrict": 0}),
