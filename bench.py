@@ -157,7 +157,7 @@ def run_single(args):
     lf = H.finest_level
     eng = MGEngine.from_hierarchy(H, r_mode=args.restriction, smoother=args.smoother, device=0,
                                   options={"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg,
-                                           "compress": args.compress, "code_cfg": args.code_cfg})
+                                           "compress": args.compress, "pdl": "coded kernels (default)", "code_cfg": args.code_cfg})
     n = H.n(lf)
     f_host = H.b_dict[lf][:, 0]
     t_setup = time.perf_counter() - t_setup
@@ -241,7 +241,7 @@ def run_single(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "restriction": args.restriction, "smoother": args.smoother,
                        "fine_dofs": n, "levels": lf - H.coarsest_level + 1, "mu1": H.mu1, "mu2": H.mu2, "omega": H.omega,
-                       "compress": args.compress,
+                       "compress": args.compress, "pdl": "coded kernels (default)",
                        "l2": "fine-level operators (>= 550 MB) exceed the 126 MB L2; no flush needed", "setup_s": t_setup},
             "fine_dof_cycles_per_s": n / (ms * 1e-3), "resnorm_after": float(hist[0]),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),

@@ -97,6 +97,8 @@ CodeChoice code_choice(int cfg)
     switch (cfg) {
         case 2: return {256, 1, 16, 2};      // 256-row tiles, one row per thread
         case 3: return {256, 2, 8, 3};       // 512-row tiles, deeper ring
+        case 4: return {256, 4, 8, 2};       // 1024-row tiles, four rows per thread
+        case 5: return {256, 2, 8, 2};       // as the default, register budget for 5 CTAs per SM where rows have <= 4 entries
         default: return {256, 2, 8, 2};      // 512-row tiles of <= 4096 entries -- the default
     }
 }
@@ -315,14 +317,14 @@ void launch_stream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nti
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // see k_stream: overlap this kernel's prologue and first
     at[0].val.programmaticStreamSerializationAllowed = 1;                // matrix tiles with the tail of the previous kernel
-    cfg.attrs = at; cfg.numAttrs = h->pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = h->pdl == 1 ? 1 : 0;        // CSR stream kernel: only when forced (measured slower)
     cudaLaunchKernelEx(&cfg, kern, (const int32_t*)D.rowptr, (const int32_t*)D.cols, (const double*)D.vals, desc, ntiles, tpc, x, epi);
 }
 
-template <int T, int RPT, int EPR, int S, int MODE, int JW, class Epi>
+template <int T, int RPT, int EPR, int S, int MODE, int JW, int MINB, class Epi>
 void launch_rowstream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
 {
-    auto kern = k_rowstream<T, RPT, EPR, S, MODE, JW, Epi>;
+    auto kern = k_rowstream<T, RPT, EPR, S, MODE, JW, MINB, Epi>;
     const int npent = MODE == 3 ? D.cd.npent : 0;            // the pattern table's size decides the shared-memory footprint
     const int smem = RowCfg<T, RPT, EPR, Epi::NOPS, EpiNI<Epi>::value, MODE>::smem_bytes(S, npent * (int)sizeof(DictEnt));
     static std::map<int, int> occ_by_smem;                   // per instantiation (one device per process)
@@ -345,7 +347,7 @@ void launch_rowstream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int 
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = h->pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = h->pdl != 0 ? 1 : 0;        // on by default for the coded kernels (measured: cfg2 0.280 -> 0.264 ms)
     cudaLaunchKernelEx(&cfg, kern, (const int32_t*)D.rowptr, (const int32_t*)D.cols, (const unsigned char*)D.cd.codes,
                        (const DictEnt*)D.cd.dict, (const int2*)D.cd.phead, npent, desc, ntiles, tpc, x, epi);
 }
@@ -355,9 +357,11 @@ template <int MODE, int JW, class Epi>
 void launch_rowstream(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
 {
     switch (D.ccfg) {                    // code_choice()
-        case 2: launch_rowstream_cfg<256, 1, 16, 2, MODE, JW, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
-        case 3: launch_rowstream_cfg<256, 2, 8, 3, MODE, JW, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
-        default: launch_rowstream_cfg<256, 2, 8, 2, MODE, JW, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        case 2: launch_rowstream_cfg<256, 1, 16, 2, MODE, JW, 4, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        case 3: launch_rowstream_cfg<256, 2, 8, 3, MODE, JW, 4, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        case 4: launch_rowstream_cfg<256, 4, 8, 2, MODE, JW, 4, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        case 5: launch_rowstream_cfg<256, 2, 8, 2, MODE, JW, (JW == 4 ? 5 : 4), Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        default: launch_rowstream_cfg<256, 2, 8, 2, MODE, JW, 4, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
     }
 }
 

@@ -489,8 +489,10 @@ __device__ __forceinline__ double coded_chunk(double sum, int k0, int b, int row
     return sum;
 }
 
-template <int THREADS, int RPT, int EPR, int STAGES, int MODE, int JW, class Epi>
-__global__ void __launch_bounds__(THREADS + 32, 1024 / THREADS)
+// MINB: resident CTAs per SM the register budget is sized for (4 x 288 threads -> 56 registers; 5 -> 40, enough when
+// only RPT * JW = 8 gathers are kept in flight)
+template <int THREADS, int RPT, int EPR, int STAGES, int MODE, int JW, int MINB, class Epi>
+__global__ void __launch_bounds__(THREADS + 32, MINB)
 k_rowstream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, const unsigned char* __restrict__ codes,
             const DictEnt* __restrict__ dict, const int2* __restrict__ phead, int npent,
             const int4* __restrict__ desc, int ntiles, int tpc, const double* x, Epi epi)

@@ -139,7 +139,9 @@ struct mgb_handle {
     int mu1 = 2, mu2 = 2, smoother = MGB_SM_JACOBI_RJ;
     // options
     int rj_reversed = 1, use_graph = 1, opt_family = 0, opt_lpr = 0, opt_iter = 0, coarse_refine = 0, fuse_restrict = 1;
-    int pdl = 0;                   // programmatic dependent launch between consecutive stream kernels (measured slower: off)
+    int pdl = -1;                  // programmatic dependent launch: a kernel's barrier set-up, dictionary load and first matrix
+                                   // tiles overlap the tail of its predecessor.  -1 (default): row-stream kernels of coded operators
+                                   // only (measured faster); 1: the CSR stream kernels too (measured slower); 0: never
     int stream_auto = 0;           // pick the stream configuration per operator from its average row length (measured: no gain)
     int gs_cluster = 2;            // level-scheduled Gauss-Seidel: 0 grid barrier, 1 one cluster, 2 one cluster + ELL prefetch pipeline
     int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)

@@ -134,7 +134,7 @@ def test_subwarp_family_within_tolerance(family, lanes):
 
 @pytest.mark.parametrize("opts", [{"tile_iter": 1}, {"tile_iter": 2}, {"use_graph": 0}, {"fuse_restrict": 1}, {"rj_order": 0},
                                   {"stream_cfg": 1}, {"stream_cfg": 2}, {"stream_cfg": 3}, {"stream_cfg": 4}, {"stream_cfg": 5}, {"stream_cfg": 6},
-                                  {"stream_cfg": 1, "fuse_restrict": 0}, {"pdl": 1}, {"stream_cfg": 7}])
+                                  {"stream_cfg": 1, "fuse_restrict": 0}, {"pdl": 1}, {"pdl": 0}, {"pdl": 1, "compress": 0}, {"stream_cfg": 7}, {"code_cfg": 4}, {"code_cfg": 5}])
 def test_kernel_options_do_not_change_results(opts):
     for dim, c, lf, seed, r_mode in [(2, 8, 4, 1, "injection"), (3, 2, 3, None, "transpose"), (2, 5, 3, None, "full_weighting")]:
         H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=seed, with_dicts=False)

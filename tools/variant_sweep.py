@@ -18,6 +18,10 @@ VARIANTS = [
     ("pattern1_256x2", {"code_cfg": 1}),
     ("pattern2_256x1", {"code_cfg": 2}),
     ("pattern3_256x2x3", {"code_cfg": 3}),
+    ("pattern4_256x4", {"code_cfg": 4}),
+    ("pattern5_occ5", {"code_cfg": 5}),
+    ("pattern1_pdl", {"code_cfg": 1, "pdl": 1}),
+    ("pattern5_pdl", {"code_cfg": 5, "pdl": 1}),
     ("coded1_256x2", {"compress": 1, "code_cfg": 1}),
     ("coded2_256x1", {"compress": 1, "code_cfg": 2}),
     ("coded3_256x2x3", {"compress": 1, "code_cfg": 3}),
