@@ -157,7 +157,7 @@ def run_single(args):
     lf = H.finest_level
     eng = MGEngine.from_hierarchy(H, r_mode=args.restriction, smoother=args.smoother, device=0,
                                   options={"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg,
-                                           "compress": args.compress, "pdl": "coded kernels (default)", "code_cfg": args.code_cfg})
+                                           "compress": args.compress, "code_cfg": args.code_cfg})
     n = H.n(lf)
     f_host = H.b_dict[lf][:, 0]
     t_setup = time.perf_counter() - t_setup

@@ -189,7 +189,10 @@ k_pat_collect(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__
             cur = atomicCAS(htbl + s, CODE_VEMPTY, key);
             if (cur == CODE_VEMPTY) { if (atomicAdd(flags + 2, 1) >= 256) flags[0] = 1; cur = key; }
         }
-        if (cur == key) { atomicMin(rep + s, i); return; }
+        if (cur == key) {                                 // representative = smallest row; rows arrive roughly in order, so a
+            if (i < ((volatile int*)rep)[s]) atomicMin(rep + s, i);      // plain read filters almost every atomic (a stale value is only larger)
+            return;
+        }
         s = (s + 1) & (CODE_SLOTS - 1);
     }
     flags[0] = 1;
