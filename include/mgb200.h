@@ -170,7 +170,9 @@ int mgb_set_params(mgb_handle* h, double omega, int mu1, int mu2, int smoother);
  * "compress" (0 off; 1: operators whose stored entries repeat -- few distinct values and column offsets, as on the
  * uniform meshes of the reference -- are additionally kept as one byte per entry + a dictionary; 2, the default: also
  * one byte per ROW + a table of row patterns where whole rows repeat.  Every coding is verified lossless on the device
- * before it is used and results are bit-identical either way), "code_cfg" (row-stream kernel shape) */
+ * before it is used and results are bit-identical either way), "code_cfg" (row-stream kernel shape),
+ * "pdl" (programmatic dependent launch: -1, the default, for the row-stream kernels of coded operators; 1 also for the CSR
+ * stream kernels; 0 never) */
 int mgb_set_option(mgb_handle* h, const char* key, double value);
 /* builds R_omega and D^-1 (getJacobiMatrices, multigrid.py:48-56), R from P, the dense inverse of the
  * coarsest matrix (replaces spsolve, multigrid.py:239), level sets / colours when a GS smoother is
