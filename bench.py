@@ -209,6 +209,9 @@ def run_single(args):
                 "frac": dom["gbs"] / peak, "frac_of_8TBs": dom["gbs"] / 8000.0, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms_per_launch"],
                 "moved_bytes_per_launch": dom["moved_bytes"], "moved_achieved": dom["moved_gbs"], "moved_frac": dom["moved_gbs"] / peak,
+                "note": "achieved/frac: algorithmic CSR bytes (SURVEY 8d) over the event-timed duration; the operators are streamed in a "
+                        "lossless coded form (DESIGN 4.1), so frac may exceed 1 -- moved_* uses the bytes actually streamed, traffic the "
+                        "DRAM bytes ncu measured for the same launch" if args.compress else "",
                 "share_of_cycle": dom["total_ms"] / sum(r["total_ms"] for r in prof),
                 "vcycle_bytes": eng.vcycle_bytes(lf), "vcycle_gbs": eng.vcycle_bytes(lf) / (ms * 1e-3) / 1e9,
                 "vcycle_moved_bytes": eng.vcycle_bytes_moved(lf), "vcycle_moved_gbs": eng.vcycle_bytes_moved(lf) / (ms * 1e-3) / 1e9}

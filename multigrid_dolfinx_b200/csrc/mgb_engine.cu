@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -327,16 +328,21 @@ void launch_rowstream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int 
     auto kern = k_rowstream<T, RPT, EPR, S, MODE, JW, MINB, Epi>;
     const int npent = MODE == 3 ? D.cd.npent : 0;            // the pattern table's size decides the shared-memory footprint
     const int smem = RowCfg<T, RPT, EPR, Epi::NOPS, EpiNI<Epi>::value, MODE>::smem_bytes(S, npent * (int)sizeof(DictEnt));
-    static std::map<int, int> occ_by_smem;                   // per instantiation (one device per process)
-    static int smem_attr = 0;
-    if (smem > smem_attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_attr = smem; }
-    auto it = occ_by_smem.find(smem);
-    if (it == occ_by_smem.end()) {
-        int o = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, T + 32, smem);
-        it = occ_by_smem.emplace(smem, std::max(o, 1)).first;
+    int occ = 1;
+    {   // per-instantiation cache (one device per process); handles are independent, so guard it against concurrent first use
+        static std::mutex mu;
+        static std::map<int, int> occ_by_smem;
+        static int smem_attr = 0;
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > smem_attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_attr = smem; }
+        auto it = occ_by_smem.find(smem);
+        if (it == occ_by_smem.end()) {
+            int o = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, T + 32, smem);
+            it = occ_by_smem.emplace(smem, std::max(o, 1)).first;
+        }
+        occ = it->second;
     }
-    const int occ = it->second;
     int grid = std::min(ntiles, h->sm_count * occ), tpc = 0;
     if (chunked) {
         tpc = std::max(1, ntiles / (h->sm_count * occ * std::max(1, h->overlap_waves)));
