@@ -28,3 +28,68 @@ def test_reference_arm_is_silent_on_other_ranks():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "cfg1"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_gpu_arm_json_assembly_with_a_stub_engine(monkeypatch, capsys):
+    """The GPU arm's bookkeeping (everything in run_single that is not a kernel: byte accounting, roofline / moved-bytes
+    fields, e2e and cpu_baseline objects, the JSON line itself) run on the CPU against a stub engine.  Numbers are
+    meaningless here; the point is that the line the driver parses keeps every contract key."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    import multigrid_dolfinx_b200.engine as E
+
+    class Ev:
+        def __init__(self, enable_timing=False): pass
+        def record(self, s=None): pass
+        def elapsed_time(self, other): return 12.5
+
+    class Lib:
+        def mgb_vcycle(self, *a): return 0
+
+    class Eng:
+        def __init__(self, H): self.H, self._lib, self._h, self.bufs, self.count = H, Lib(), None, {}, 0
+        def torch_stream(self): return None
+        def level_buffer(self, l, w): return self.bufs.setdefault((l, w), torch.zeros(self.H.n(l), dtype=torch.float64))
+        def vcycle_resident(self, lf, n, history=False):
+            self.count += 37 * n
+            return np.ones(n) if history else None
+        def synchronize(self): pass
+        def launch_count(self): return self.count
+        def profile_begin(self): pass
+        def profile_end(self):
+            return [{"kind": "jacobi", "level": 2, "launches": 4, "total_ms": 0.1, "ms_per_launch": 0.025, "bytes": 3e8, "gbs": 1.2e4,
+                     "moved_bytes": 1e8, "moved_gbs": 4e3},
+                    {"kind": "residual", "level": 2, "launches": 1, "total_ms": 0.02, "ms_per_launch": 0.02, "bytes": 4e8, "gbs": 2e4,
+                     "moved_bytes": 7e7, "moved_gbs": 3.5e3}]
+        def vcycle_bytes(self, l): return 2.6e9
+        def vcycle_bytes_moved(self, l): return 0.9e9
+        def _ck(self, rc): assert rc == 0
+        def close(self): pass
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(E.MGEngine, "from_hierarchy", classmethod(lambda cls, H, **kw: Eng(H)))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "cfg1", "--steps", "3", "--warmup", "3"])
+    bench.main()
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    r = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in r, k
+    assert r["n_gpus"] == 1 and r["dtype"] == "f64" and r["vs_baseline"] is None and r["data"] == "synthetic" and "workload" in r["config"]
+    rf = r["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "moved_bytes_per_launch", "moved_achieved", "moved_frac"):
+        assert k in rf, k
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert rf["kernel"] == "jacobi@level2" and rf["moved_bytes_per_launch"] == 1e8
+    cb = r["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb and cb["unit"] == r["unit"]
+    e = r["e2e"]
+    n = r["config"]["fine_dofs"]
+    assert e["h2d_bytes_per_step"] == 16 * n and e["d2h_bytes_per_step"] == 8 * n and e["unit"] == r["unit"] and e["value"] > 0
+    assert r["gpu_launches"] == 37 * 3
