@@ -242,6 +242,15 @@ int mgb_host_level_sets(int64_t n, const int64_t* indptr, const int32_t* indices
 int mgb_host_colouring(int64_t n, const int64_t* indptr, const int32_t* indices, const double* values,
                        int32_t* colour_of_row, int32_t* order, int64_t* ncolours, int32_t* offsets, int64_t offsets_capacity);
 int mgb_host_dense_inverse(int64_t n, const int64_t* indptr, const int32_t* indices, const double* values, double* inv_row_major);
+/* The lossless operator coding of DESIGN.md 4.1 as a host routine: the definition of what mgb_finalize builds (and verifies
+ * entry by entry) on the device.  *mode_out: 0 none, 1 pair codes, 2 value codes, 3 row patterns (tried only if allow_patterns).
+ * codes: uint8[nrows] (mode 3) or uint8[nnz] (modes 1, 2).  table: 16-byte entries {double value; int32 col_minus_row; int32 0},
+ * 256 of them (modes 1, 2) or *table_entries <= 2048 (mode 3: every pattern padded to a multiple of 8 entries).
+ * pattern_head (mode 3): int32 {first entry, length} x 256.  *ndict_out: dictionary entries / patterns in use.
+ * codes, table, pattern_head may be NULL to query the mode and the counts only. */
+int mgb_host_code_operator(int64_t nrows, int64_t ncols, const int64_t* indptr, const int32_t* indices, const double* values,
+                           int allow_patterns, int* mode_out, int* ndict_out, uint8_t* codes, void* table, int* table_entries,
+                           int32_t* pattern_head);
 
 #ifdef __cplusplus
 }

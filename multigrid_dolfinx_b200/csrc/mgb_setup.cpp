@@ -7,7 +7,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <numeric>
+#include <set>
 
 #include "../../include/mgb200.h"
 
@@ -330,5 +332,144 @@ extern "C" int mgb_host_dense_inverse(int64_t n, const int64_t* indptr, const in
     std::vector<double> inv;
     if (!dense_inverse(A, inv)) return MGB_ERR_SINGULAR;
     std::copy(inv.begin(), inv.end(), inv_row_major);
+    return MGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lossless operator coding on the host: the DEFINITION of the artefact.  mgb_finalize builds the same
+// dictionaries and codes on the device (csrc/mgb_code.cuh: hash tables instead of ordered maps, then an exact
+// verification pass); this routine states what they must be, in plain C++, so that CPU tests can pin the definition
+// against an independent numpy restatement (oracle/coding.py) without a GPU.
+//   mode 3  row patterns : operators with ncols >= nrows whose rows repeat.  A pattern = a row's list of
+//           (col - row, value bits); patterns are numbered by their first row; <= 256 patterns; each pattern's entries
+//           are padded to a multiple of 8 (at least 8) with copies of its last entry ((0, 0.0) for an empty row); the
+//           padded table holds <= 2048 entries.  codes[i] = pattern of row i.
+//   mode 1  pair codes   : <= 256 distinct values (by bit pattern, all-ones excluded), <= 256 distinct (col - row)
+//           (0x80808080 excluded), <= 256 distinct pairs.  Pairs are numbered by (offset rank, value rank), offsets
+//           ascending, values ascending as unsigned 64-bit patterns.  codes[k] = pair of stored entry k.
+//   mode 2  value codes  : <= 256 distinct values; codes[k] = rank of the value's bit pattern.
+//   mode 0  otherwise (also: empty operators, more than 24 stored entries per row on average).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct HostDictEnt { double val; int32_t delta; int32_t pad; };
+static_assert(sizeof(HostDictEnt) == 16, "same layout as the device dictionary entry");
+uint64_t bits_of(double v) { uint64_t b; std::memcpy(&b, &v, sizeof b); return b; }
+}  // namespace
+
+extern "C" int mgb_host_code_operator(int64_t nrows, int64_t ncols, const int64_t* indptr, const int32_t* indices, const double* values,
+                                      int allow_patterns, int* mode_out, int* ndict_out, uint8_t* codes, void* table,
+                                      int* table_entries, int32_t* pattern_head)
+{
+    if (nrows < 0 || ncols < 0 || !indptr || !mode_out) return MGB_ERR_INVALID;
+    const int64_t nnz = indptr[nrows];
+    if (nnz > 0 && (!indices || !values)) return MGB_ERR_INVALID;
+    *mode_out = 0;
+    if (ndict_out) *ndict_out = 0;
+    if (table_entries) *table_entries = 0;
+    if (nrows == 0 || nnz == 0 || (double)nnz / (double)nrows > 24.0) return MGB_OK;
+    HostDictEnt* tab = (HostDictEnt*)table;
+    // ---- row patterns
+    if (allow_patterns && ncols >= nrows) {
+        typedef std::vector<std::pair<int32_t, uint64_t>> Row;
+        std::map<Row, int64_t> first;                       // pattern -> first row showing it
+        bool ok = true;
+        Row key;
+        for (int64_t i = 0; i < nrows && ok; ++i) {
+            key.clear();
+            for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) key.push_back({(int32_t)(indices[k] - i), bits_of(values[k])});
+            first.emplace(key, i);                          // rows ascend: the first insertion is the smallest row
+            ok = first.size() <= 256;
+        }
+        if (ok) {
+            std::vector<std::pair<int64_t, const Row*>> order;
+            for (auto& kv : first) order.push_back({kv.second, &kv.first});
+            std::sort(order.begin(), order.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+            int total = 0;
+            for (auto& o : order) total += std::max<int>(8, ((int)o.second->size() + 7) / 8 * 8);
+            if (total <= 2048) {
+                if (codes && tab && pattern_head) {
+                    std::map<Row, int> id;
+                    int off = 0;
+                    for (int p = 0; p < 256; ++p) { pattern_head[2 * p] = 0; pattern_head[2 * p + 1] = 0; }
+                    for (size_t p = 0; p < order.size(); ++p) {
+                        const Row& r = *order[p].second;
+                        const int len = (int)r.size(), padded = std::max(8, (len + 7) / 8 * 8);
+                        pattern_head[2 * p] = off; pattern_head[2 * p + 1] = len;
+                        for (int e = 0; e < padded; ++e) {
+                            HostDictEnt d{0.0, 0, 0};
+                            if (len > 0) { const auto& q = r[(size_t)std::min(e, len - 1)]; std::memcpy(&d.val, &q.second, 8); d.delta = q.first; }
+                            tab[off + e] = d;
+                        }
+                        off += padded;
+                        id[r] = (int)p;
+                    }
+                    for (int64_t i = 0; i < nrows; ++i) {
+                        key.clear();
+                        for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) key.push_back({(int32_t)(indices[k] - i), bits_of(values[k])});
+                        codes[i] = (uint8_t)id[key];
+                    }
+                }
+                *mode_out = 3;
+                if (ndict_out) *ndict_out = (int)order.size();
+                if (table_entries) *table_entries = total;
+                return MGB_OK;
+            }
+        }
+    }
+    // ---- per-entry codes
+    std::set<uint64_t> vs;
+    std::set<int32_t> dset;
+    bool dfail = false;
+    for (int64_t i = 0; i < nrows; ++i)
+        for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) {
+            const uint64_t b = bits_of(values[k]);
+            if (b == ~(uint64_t)0) return MGB_OK;           // the device tables use this pattern as "empty"
+            vs.insert(b);
+            if (vs.size() > 256) return MGB_OK;
+            if (!dfail) {
+                const int32_t d = (int32_t)(indices[k] - i);
+                if (d == (int32_t)0x80808080) dfail = true; else dset.insert(d);
+                if (dset.size() > 256) dfail = true;
+            }
+        }
+    std::vector<uint64_t> V(vs.begin(), vs.end());          // ascending as unsigned bit patterns
+    std::vector<int32_t> Dl(dset.begin(), dset.end());
+    auto vrank = [&](double v) { return (int)(std::lower_bound(V.begin(), V.end(), bits_of(v)) - V.begin()); };
+    bool pair = !dfail && !Dl.empty();
+    std::vector<int> lut;
+    int npair = 0;
+    if (pair) {
+        std::vector<unsigned char> present(65536, 0);
+        for (int64_t i = 0; i < nrows; ++i)
+            for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) {
+                const int di = (int)(std::lower_bound(Dl.begin(), Dl.end(), (int32_t)(indices[k] - i)) - Dl.begin());
+                present[(size_t)(di * 256 + vrank(values[k]))] = 1;
+            }
+        lut.assign(65536, -1);
+        for (int key = 0; key < 65536; ++key) if (present[(size_t)key]) lut[(size_t)key] = npair++;
+        if (npair > 256) pair = false;
+    }
+    if (tab) for (int k = 0; k < 256; ++k) tab[k] = HostDictEnt{0.0, 0, 0};
+    if (pair) {
+        if (tab)
+            for (int key = 0; key < 65536; ++key)
+                if (lut[(size_t)key] >= 0) { HostDictEnt d{0.0, Dl[(size_t)(key >> 8)], 0}; std::memcpy(&d.val, &V[(size_t)(key & 255)], 8); tab[lut[(size_t)key]] = d; }
+        if (codes)
+            for (int64_t i = 0; i < nrows; ++i)
+                for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) {
+                    const int di = (int)(std::lower_bound(Dl.begin(), Dl.end(), (int32_t)(indices[k] - i)) - Dl.begin());
+                    codes[k] = (uint8_t)lut[(size_t)(di * 256 + vrank(values[k]))];
+                }
+        *mode_out = 1;
+        if (ndict_out) *ndict_out = npair;
+    } else {
+        if (tab) for (size_t k = 0; k < V.size(); ++k) { HostDictEnt d{0.0, 0, 0}; std::memcpy(&d.val, &V[k], 8); tab[k] = d; }
+        if (codes)
+            for (int64_t i = 0; i < nrows; ++i)
+                for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) codes[k] = (uint8_t)vrank(values[k]);
+        *mode_out = 2;
+        if (ndict_out) *ndict_out = (int)V.size();
+    }
+    if (table_entries) *table_entries = 256;
     return MGB_OK;
 }

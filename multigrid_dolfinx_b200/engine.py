@@ -469,3 +469,27 @@ def host_dense_inverse(A):
     if rc != L.OK:
         raise L.MGBError(rc, "singular matrix")
     return inv
+
+
+CODE_TABLE_DTYPE = np.dtype([("val", "<f8"), ("delta", "<i4"), ("pad", "<i4")])
+
+
+def host_code_operator(A, allow_patterns=True):
+    """The lossless operator coding of DESIGN.md 4.1, computed by the library's host routine (the definition of what
+    ``mgb_finalize`` builds on the device).  -> dict(mode, ndict, codes, table, head): ``codes`` uint8 per row (mode 3) or per
+    stored entry (modes 1, 2); ``table`` structured array {val, delta}; ``head`` (mode 3) int32 (256, 2) {first entry, length}."""
+    lib = L.load()
+    ip = np.ascontiguousarray(A.indptr, dtype=np.int64); ix = np.ascontiguousarray(A.indices, dtype=np.int32)
+    ax = np.ascontiguousarray(A.data, dtype=np.float64)
+    n, m = A.shape
+    mode, ndict, nent = C.c_int(), C.c_int(), C.c_int()
+    codes = np.zeros(max(n, len(ax), 1), dtype=np.uint8)
+    table = np.zeros(2048, dtype=CODE_TABLE_DTYPE)
+    head = np.zeros((256, 2), dtype=np.int32)
+    rc = lib.mgb_host_code_operator(n, m, ip.ctypes.data, ix.ctypes.data, ax.ctypes.data, int(bool(allow_patterns)), C.byref(mode), C.byref(ndict),
+                                    codes.ctypes.data, table.ctypes.data, C.byref(nent), head.ctypes.data)
+    if rc != L.OK:
+        raise L.MGBError(rc, "mgb_host_code_operator failed")
+    ncodes = {0: 0, 3: n}.get(mode.value, len(ax))
+    return {"mode": mode.value, "ndict": ndict.value, "codes": codes[:ncodes].copy(), "table": table[:nent.value].copy(),
+            "head": head if mode.value == 3 else None}
