@@ -82,6 +82,12 @@ enum {
     MGB_ART_P_VALUES = 19,
     MGB_ART_INJECTION = 20     /* int32[n_c] injection list of this level (fine side)              */
 };
+/* The lossless coding mgb_finalize built for an operator of the level (compare with mgb_host_code_operator):
+ * kind = MGB_ART_CODE(op, part), op: 0 A, 1 R_omega, 2 P, 3 R;
+ * part 0: int32[4] {mode, dictionary entries / patterns in use, table entries, number of codes};
+ * part 1: uint8 codes (per row in mode 3, per stored entry in modes 1 and 2); part 2: table, 16-byte entries
+ * {double value; int32 col_minus_row; int32 0}; part 3 (mode 3): int32 {first entry, length} x 256. */
+#define MGB_ART_CODE(op, part) (32 + 4 * (op) + (part))
 
 /* per-level device buffers (mgb_level_buffer) */
 enum { MGB_BUF_V = 0, MGB_BUF_F = 1, MGB_BUF_R = 2 };

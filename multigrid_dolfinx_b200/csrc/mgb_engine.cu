@@ -1557,6 +1557,7 @@ int mgb_get_artifact(mgb_handle* h, int level, int kind, void* out, int64_t capa
     Level* L = nullptr;
     TRY(check_ready(h, level, &L));
     const void* src = nullptr; bool on_device = true; int64_t bytes = 0;
+    int32_t code_info[4] = {0, 0, 0, 0};
     auto host_vec = [&](const std::vector<int32_t>& v) { src = v.data(); bytes = (int64_t)v.size() * 4; on_device = false; };
     switch (kind) {
         case MGB_ART_RJ_INDPTR: src = L->RJ.rowptr; bytes = (L->RJ.nrows + 1) * 4; break;
@@ -1581,7 +1582,20 @@ int mgb_get_artifact(mgb_handle* h, int level, int kind, void* out, int64_t capa
         case MGB_ART_INJECTION: src = L->inj; bytes = L->inj ? L->n_coarse * 4 : 0; break;
         case MGB_ART_COARSE_INVERSE:
             src = h->coarse_inv_host.data(); bytes = (int64_t)h->coarse_inv_host.size() * 8; on_device = false; break;
-        default: return fail(h, MGB_ERR_INVALID, "unknown artefact kind %d", kind);
+        default: {
+            if (kind < MGB_ART_CODE(0, 0) || kind > MGB_ART_CODE(3, 3)) return fail(h, MGB_ERR_INVALID, "unknown artefact kind %d", kind);
+            const int op = (kind - MGB_ART_CODE(0, 0)) / 4, part = (kind - MGB_ART_CODE(0, 0)) % 4;
+            const DevCsr& D = op == 0 ? L->A : (op == 1 ? L->RJ : (op == 2 ? L->P : L->R));
+            const Coded& cd = D.cd;
+            const int64_t ncodes = cd.mode == 3 ? D.nrows : (cd.mode ? D.nnz : 0);
+            const int64_t tab = cd.mode == 3 ? cd.npent : (cd.mode ? 256 : 0);
+            code_info[0] = cd.mode; code_info[1] = cd.ndict; code_info[2] = (int32_t)tab; code_info[3] = (int32_t)ncodes;
+            if (part == 0) { src = code_info; bytes = sizeof code_info; on_device = false; }
+            else if (part == 1) { src = cd.codes; bytes = ncodes; }
+            else if (part == 2) { src = cd.dict; bytes = tab * (int64_t)sizeof(DictEnt); }
+            else { src = cd.phead; bytes = cd.mode == 3 ? 256 * (int64_t)sizeof(int2) : 0; }
+            break;
+        }
     }
     if (size_bytes) *size_bytes = bytes;
     if (!out) return MGB_OK;

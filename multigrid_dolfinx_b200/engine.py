@@ -372,6 +372,23 @@ class MGEngine:
             self._ck(self._lib.mgb_get_artifact(self._h, int(level), int(kind), out.ctypes.data, size.value, None))
         return out
 
+    def code_artifact(self, level, op):
+        """The lossless coding mgb_finalize built on the device for operator ``op`` ("A", "RJ", "P", "R") of ``level``, in the
+        layout of ``host_code_operator`` (module level): dict(mode, ndict, codes, table, head)."""
+        base = 32 + 4 * {"A": 0, "RJ": 1, "P": 2, "R": 3}[op]
+
+        def fetch(part, dtype):
+            size = C.c_int64()
+            self._ck(self._lib.mgb_get_artifact(self._h, int(level), base + part, None, 0, C.byref(size)))
+            out = np.zeros(size.value // np.dtype(dtype).itemsize, dtype=dtype)
+            if size.value:
+                self._ck(self._lib.mgb_get_artifact(self._h, int(level), base + part, out.ctypes.data, size.value, None))
+            return out
+        info = fetch(0, np.int32)
+        mode = int(info[0])
+        return {"mode": mode, "ndict": int(info[1]), "codes": fetch(1, np.uint8), "table": fetch(2, CODE_TABLE_DTYPE),
+                "head": fetch(3, np.int32).reshape(-1, 2) if mode == 3 else None}
+
     def rj_matrix(self, level):
         """R_omega of ``level`` as scipy CSR + D^-1 (what getJacobiMatrices returns, multigrid.py:56)."""
         import scipy.sparse as sp

@@ -636,3 +636,27 @@ def test_row_pattern_coding_long_and_empty_rows():
     r = f - Af.dot(v)
     assert abs(hist[0] - np.sqrt(abs(r @ M.dot(r)))) <= 1e-12 * max(hist[0], 1e-300)
     eng.close()
+
+
+@pytest.mark.parametrize("dim,c,lf,seed", [(2, 8, 3, None), (3, 2, 3, None), (2, 8, 3, 5)])
+def test_device_built_coding_against_host_definition(dim, c, lf, seed):
+    """The coding artefact: what mgb_finalize built on the device vs mgb_host_code_operator (the definition, itself pinned to the
+    numpy restatement by tests/test_coding.py).  Mode and dictionary / pattern counts are asserted; the entry-by-entry equality of
+    codes and tables is RECORDED in gpurun_out/parity_report.jsonl (first hardware run of this comparison) and will be asserted
+    once seen green."""
+    from multigrid_dolfinx_b200.engine import host_code_operator
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=seed, with_dicts=False)
+    eng = MGEngine.from_hierarchy(H)
+    A = H.A_sp_dict[lf][0].tocsr()
+    RO, _ = rs.jacobi_matrices(A)
+    for op, M in (("A", A), ("RJ", RO.tocsr()), ("P", H.P[lf - 1].tocsr())):
+        dev, host = eng.code_artifact(lf, op), host_code_operator(M)
+        assert dev["mode"] == host["mode"] and dev["ndict"] == host["ndict"], (op, dev["mode"], host["mode"], dev["ndict"], host["ndict"])
+        same_codes = bool(np.array_equal(dev["codes"], host["codes"]))
+        k = min(len(dev["table"]), len(host["table"]))
+        same_table = bool(len(dev["table"]) == len(host["table"]) and np.array_equal(dev["table"]["val"][:k].view(np.uint64), host["table"]["val"][:k].view(np.uint64))
+                          and np.array_equal(dev["table"]["delta"][:k], host["table"]["delta"][:k]))
+        same_head = bool(dev["mode"] != 3 or np.array_equal(dev["head"], host["head"]))
+        _report("coding_artefact", dim=dim, seed=seed, op=op, mode=dev["mode"], ndict=dev["ndict"], codes_equal=same_codes,
+                table_equal=same_table, head_equal=same_head)
+    eng.close()
