@@ -248,6 +248,13 @@ int mgb_host_level_sets(int64_t n, const int64_t* indptr, const int32_t* indices
 int mgb_host_colouring(int64_t n, const int64_t* indptr, const int32_t* indices, const double* values,
                        int32_t* colour_of_row, int32_t* order, int64_t* ncolours, int32_t* offsets, int64_t offsets_capacity);
 int mgb_host_dense_inverse(int64_t n, const int64_t* indptr, const int32_t* indices, const double* values, double* inv_row_major);
+/* Row tiles of the stream kernels (what mgb_finalize cuts every operator into): tile t = rows [tiles[t], tiles[t+1]) with
+ * at most row_cap rows and indptr[tiles[t+1]] - (indptr[tiles[t]] & ~7) <= cap stored entries, never straddling a breakpoint
+ * (sorted row indices), every tile start a multiple of row_align unless it is a breakpoint.  tiles: int32[*ntiles + 1];
+ * break_tile: int32[nbreaks] tile index at each breakpoint.  MGB_ERR_UNSUPPORTED: a single row exceeds cap (or cannot be
+ * aligned) -- the engine then falls back to the warp-per-row kernel. */
+int mgb_host_make_tiles(int64_t n, const int64_t* indptr, int64_t cap, int64_t row_cap, int nbreaks, const int32_t* breaks,
+                        int64_t row_align, int32_t* tiles, int64_t tiles_capacity, int64_t* ntiles, int32_t* break_tile);
 /* The lossless operator coding of DESIGN.md 4.1 as a host routine: the definition of what mgb_finalize builds (and verifies
  * entry by entry) on the device.  *mode_out: 0 none, 1 pair codes, 2 value codes, 3 row patterns (tried only if allow_patterns).
  * codes: uint8[nrows] (mode 3) or uint8[nnz] (modes 1, 2).  table: 16-byte entries {double value; int32 col_minus_row; int32 0},

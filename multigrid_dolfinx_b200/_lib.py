@@ -84,6 +84,7 @@ SYMBOLS = {
     "mgb_host_level_sets": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _i64]),
     "mgb_host_colouring": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _i64]),
     "mgb_host_dense_inverse": (_i, [_i64, _vp, _vp, _vp, _vp]),
+    "mgb_host_make_tiles": (_i, [_i64, _vp, _i64, _i64, _i, _vp, _i64, _vp, _i64, C.POINTER(_i64), _vp]),
     "mgb_host_code_operator": (_i, [_i64, _i64, _vp, _vp, _vp, _i, C.POINTER(_i), C.POINTER(_i), _vp, _vp, C.POINTER(_i), _vp]),
 }
 

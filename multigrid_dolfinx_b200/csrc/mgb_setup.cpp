@@ -335,6 +335,22 @@ extern "C" int mgb_host_dense_inverse(int64_t n, const int64_t* indptr, const in
     return MGB_OK;
 }
 
+extern "C" int mgb_host_make_tiles(int64_t n, const int64_t* indptr, int64_t cap, int64_t row_cap, int nbreaks, const int32_t* breaks,
+                                   int64_t row_align, int32_t* tiles, int64_t tiles_capacity, int64_t* ntiles, int32_t* break_tile)
+{
+    if (n < 0 || !indptr || !ntiles || nbreaks < 0 || (nbreaks > 0 && !breaks)) return MGB_ERR_INVALID;
+    std::vector<int64_t> ip(indptr, indptr + n + 1);
+    std::vector<int32_t> br(breaks, breaks + nbreaks), t, bt;
+    if (!make_tiles(ip, cap, row_cap, br, t, &bt, row_align)) return MGB_ERR_UNSUPPORTED;      // a row does not fit / cannot be aligned
+    *ntiles = (int64_t)t.size() - 1;
+    if (tiles) {
+        if (tiles_capacity < (int64_t)t.size()) return MGB_ERR_INVALID;
+        std::copy(t.begin(), t.end(), tiles);
+    }
+    if (break_tile) std::copy(bt.begin(), bt.end(), break_tile);
+    return MGB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Lossless operator coding on the host: the DEFINITION of the artefact.  mgb_finalize builds the same
 // dictionaries and codes on the device (csrc/mgb_code.cuh: hash tables instead of ordered maps, then an exact
