@@ -96,11 +96,10 @@ struct CodeChoice { int threads, rpt, epr, stages; };
 CodeChoice code_choice(int cfg)
 {
     switch (cfg) {
-        case 2: return {256, 1, 16, 2};      // 256-row tiles, one row per thread
-        case 3: return {256, 2, 8, 3};       // 512-row tiles, deeper ring
-        case 4: return {256, 4, 8, 2};       // 1024-row tiles, four rows per thread
-        case 5: return {256, 2, 8, 2};       // as the default, register budget for 5 CTAs per SM where rows have <= 4 entries
-        default: return {256, 2, 8, 2};      // 512-row tiles of <= 4096 entries -- the default
+        // measured and removed (profiles/r1_variant_sweep_cfg2_coded.jsonl): 256-row tiles with one row per thread (32.9 us per
+        // fine-level sweep against 28.2), 1024-row tiles with four rows per thread (29.1), a register budget for 5 CTAs per SM (28.1)
+        case 3: return {256, 2, 8, 3};       // 512-row tiles, deeper ring (27.8 us, but the prolongation loses: 43 against 32 us)
+        default: return {256, 2, 8, 2};      // 512-row tiles of <= 4096 entries, two rows per thread, two stages -- the default
     }
 }
 
@@ -363,10 +362,7 @@ template <int MODE, int JW, class Epi>
 void launch_rowstream(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
 {
     switch (D.ccfg) {                    // code_choice()
-        case 2: launch_rowstream_cfg<256, 1, 16, 2, MODE, JW, 4, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
         case 3: launch_rowstream_cfg<256, 2, 8, 3, MODE, JW, 4, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
-        case 4: launch_rowstream_cfg<256, 4, 8, 2, MODE, JW, 4, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
-        case 5: launch_rowstream_cfg<256, 2, 8, 2, MODE, JW, (JW == 4 ? 5 : 4), Epi>(h, D, desc, ntiles, x, epi, chunked); break;
         default: launch_rowstream_cfg<256, 2, 8, 2, MODE, JW, 4, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
     }
 }

@@ -16,14 +16,10 @@ from multigrid_dolfinx_b200.engine import MGEngine  # noqa: E402
 
 VARIANTS = [
     ("pattern1_256x2", {"code_cfg": 1}),
-    ("pattern2_256x1", {"code_cfg": 2}),
     ("pattern3_256x2x3", {"code_cfg": 3}),
-    ("pattern4_256x4", {"code_cfg": 4}),
-    ("pattern5_occ5", {"code_cfg": 5}),
     ("pattern1_pdl", {"code_cfg": 1, "pdl": 1}),
-    ("pattern5_pdl", {"code_cfg": 5, "pdl": 1}),
+    ("pattern1_nopdl", {"code_cfg": 1, "pdl": 0}),
     ("coded1_256x2", {"compress": 1, "code_cfg": 1}),
-    ("coded2_256x1", {"compress": 1, "code_cfg": 2}),
     ("coded3_256x2x3", {"compress": 1, "code_cfg": 3}),
     ("csr_stream3", {"compress": 0}),
     ("tile_iter1", {"tile_iter": 1, "stream_cfg": 0, "fuse_restrict": 0}),
