@@ -178,7 +178,8 @@ int mgb_set_params(mgb_handle* h, double omega, int mu1, int mu2, int smoother);
  * one byte per ROW + a table of row patterns where whole rows repeat.  Every coding is verified lossless on the device
  * before it is used and results are bit-identical either way), "code_cfg" (row-stream kernel shape),
  * "pdl" (programmatic dependent launch: -1, the default, for the row-stream kernels of coded operators; 1 also for the CSR
- * stream kernels; 0 never) */
+ * stream kernels; 0 never), "stage_x" (EXPERIMENTAL, default 0: x staged in shared memory for row-pattern-coded operators;
+ * written at the end of round 1 and not yet measured) */
 int mgb_set_option(mgb_handle* h, const char* key, double value);
 /* builds R_omega and D^-1 (getJacobiMatrices, multigrid.py:48-56), R from P, the dense inverse of the
  * coarsest matrix (replaces spsolve, multigrid.py:239), level sets / colours when a GS smoother is

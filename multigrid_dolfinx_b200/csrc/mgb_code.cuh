@@ -151,7 +151,7 @@ k_code_verify(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__
 
 void free_coded(Coded& c)
 {
-    cudaFree(c.codes); cudaFree(c.dict); cudaFree(c.phead);
+    cudaFree(c.codes); cudaFree(c.dict); cudaFree(c.phead); cudaFree(c.dict_sx);
     c = Coded();
 }
 
@@ -322,6 +322,43 @@ int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip)
 #undef CUC
     if (hb) { free_coded(D.cd); return MGB_OK; }          // never trust an unverified coding
     D.cd.mode = 3; D.cd.ndict = (int)pats.size(); D.cd.npent = total;
+    if (h->stage_x) {
+        // EXPERIMENTAL (k_rowstream_sx): group the distinct offsets, re-express every table entry as a slot of the stage's x area
+        std::vector<int> offs;
+        for (size_t p = 0; p < pats.size(); ++p)
+            for (int e = 0; e < phead[p].y; ++e) offs.push_back(pent[(size_t)(phead[p].x + e)].delta);
+        std::sort(offs.begin(), offs.end());
+        offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
+        SxGroups G{};
+        bool ok = !offs.empty();
+        for (size_t k = 0; k < offs.size() && ok; ++k) {
+            if (G.ng > 0 && offs[k] - G.gmin[G.ng - 1] <= SX_SPAN) { G.gspan[G.ng - 1] = offs[k] - G.gmin[G.ng - 1]; continue; }
+            if (G.ng == SX_MAX_GROUPS) { ok = false; break; }
+            G.gmin[G.ng] = offs[k] & ~1;                                    // even: slices start 16-byte aligned (tile starts are multiples of 16)
+            G.gspan[G.ng] = offs[k] - G.gmin[G.ng];
+            ++G.ng;
+        }
+        if (ok) {
+            constexpr int SL = SxCfg<256, 2, 0, 0>::SL_DOUBLES;            // (same for every epilogue: depends on the tile's row capacity only)
+            std::vector<DictEnt> sx(pent);
+            for (size_t p = 0; p < pats.size(); ++p) {
+                const int len = phead[p].y, off = phead[p].x, padded = std::max(8, (len + 7) / 8 * 8);
+                for (int e = 0; e < padded; ++e) {
+                    DictEnt& d = sx[(size_t)(off + e)];
+                    if (len == 0) { d.delta = 0; continue; }                // empty row: slot 0 (its value is never used)
+                    int g = 0;
+                    while (g + 1 < G.ng && d.delta >= G.gmin[g + 1]) ++g;
+                    d.delta = g * SL + (d.delta - G.gmin[g]);
+                }
+            }
+            G.xlen = (int)((D.ncols + 16) & ~(int64_t)1);                  // engine vectors carry 16 padding entries behind ncols
+            cudaError_t e1 = cudaMalloc((void**)&D.cd.dict_sx, (size_t)total * sizeof(DictEnt));
+            if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(D.cd.dict_sx, sx.data(), (size_t)total * sizeof(DictEnt), cudaMemcpyHostToDevice, h->stream);
+            if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(h->stream);
+            if (e1 == cudaSuccess) D.cd.sx = G;
+            else { cudaFree(D.cd.dict_sx); D.cd.dict_sx = nullptr; (void)cudaGetLastError(); }
+        }
+    }
     return MGB_OK;
 }
 

@@ -68,7 +68,7 @@ int dev_upload(mgb_handle* h, T** p, const T* src, size_t count, size_t pad = 0)
 
 void free_csr(DevCsr& D)
 {
-    cudaFree(D.cd.codes); cudaFree(D.cd.dict); cudaFree(D.cd.phead);
+    cudaFree(D.cd.codes); cudaFree(D.cd.dict); cudaFree(D.cd.phead); cudaFree(D.cd.dict_sx);
     cudaFree(D.rowptr); cudaFree(D.cols); cudaFree(D.vals); cudaFree(D.tiles); cudaFree(D.sdesc); cudaFree(D.sdesc_bnd);
     D = DevCsr();
 }
@@ -357,6 +357,43 @@ void launch_rowstream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int 
                        (const DictEnt*)D.cd.dict, (const int2*)D.cd.phead, npent, desc, ntiles, tpc, x, epi);
 }
 
+// EXPERIMENTAL (option "stage_x"): row patterns with x staged in shared memory; 512-row tiles, two stages
+template <int JW, class Epi>
+void launch_rowstream_sx(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
+{
+    constexpr int T = 256, RPT = 2, S = 2;
+    auto kern = k_rowstream_sx<T, RPT, S, JW, Epi>;
+    const int smem = SxCfg<T, RPT, Epi::NOPS, EpiNI<Epi>::value>::smem_bytes(S, D.cd.npent, D.cd.sx.ng);
+    int occ = 1;
+    {
+        static std::mutex mu;
+        static std::map<int, int> occ_by_smem;
+        static int smem_attr = 0;
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > smem_attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_attr = smem; }
+        auto it = occ_by_smem.find(smem);
+        if (it == occ_by_smem.end()) {
+            int o = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, T + 32, smem);
+            it = occ_by_smem.emplace(smem, std::max(o, 1)).first;
+        }
+        occ = it->second;
+    }
+    int grid = std::min(ntiles, h->sm_count * occ), tpc = 0;
+    if (chunked) {
+        tpc = std::max(1, ntiles / (h->sm_count * occ * std::max(1, h->overlap_waves)));
+        grid = (ntiles + tpc - 1) / tpc;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T + 32); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->pdl != 0 ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, (const unsigned char*)D.cd.codes, (const DictEnt*)D.cd.dict_sx, (const int2*)D.cd.phead, D.cd.npent, D.cd.sx,
+                       desc, ntiles, tpc, x, epi);
+}
+
 // MODE: the coding (pair / value codes); JW: gathers issued up front per row (4 when no row is longer, else 8)
 template <int MODE, int JW, class Epi>
 void launch_rowstream(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
@@ -374,6 +411,10 @@ void launch_stream(mgb_handle* h, const DevCsr& D, const double* x, const Epi& e
     if (!desc) { desc = D.sdesc; ntiles = D.sntiles; }
     if (ntiles <= 0) return;
     if constexpr (Epi::CONTIG) {
+        if (D.cd.mode == 3 && h->stage_x && D.cd.sx.ng > 0 && D.cd.dict_sx && code_choice(D.ccfg).threads * code_choice(D.ccfg).rpt == 512) {
+            if (D.max_row <= 4) return launch_rowstream_sx<4, Epi>(h, D, desc, ntiles, x, epi, chunked);
+            return launch_rowstream_sx<8, Epi>(h, D, desc, ntiles, x, epi, chunked);
+        }
         if (D.cd.mode == 3 && D.max_row <= 4) return launch_rowstream<3, 4, Epi>(h, D, desc, ntiles, x, epi, chunked);
         if (D.cd.mode == 3) return launch_rowstream<3, 8, Epi>(h, D, desc, ntiles, x, epi, chunked);
         if (D.cd.mode == 1 && D.max_row <= 4) return launch_rowstream<1, 4, Epi>(h, D, desc, ntiles, x, epi, chunked);
@@ -1151,6 +1192,7 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "stream_auto" && pre) h->stream_auto = iv;
     else if (k == "compress" && pre) h->compress = iv;
     else if (k == "code_cfg" && pre) h->code_cfg = iv;
+    else if (k == "stage_x" && pre) h->stage_x = iv;
     else if (k == "gs_cluster") h->gs_cluster = iv;
     else if (k == "pdl") { h->pdl = iv; drop_graphs(h); }
     else if (k == "p2p_enable") { h->p2p_enable = iv; drop_graphs(h); }

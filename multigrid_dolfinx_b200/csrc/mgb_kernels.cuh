@@ -670,6 +670,155 @@ k_rowstream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols
     }
 }
 
+// ---- row-stream kernel with x staged in shared memory -----------------------------------------------------
+// EXPERIMENTAL (option "stage_x", default off): written at the end of round 1 after the GPU budget was spent -- it compiles, it has
+// NOT run on hardware yet, nothing uses it by default.  Design: DESIGN.md section 8.  For a row-pattern-coded operator the distinct
+// column offsets fall into a few groups of neighbouring offsets; a tile of consecutive rows needs, per group, ONE contiguous slice
+// of x, which the producer lane fetches with a bulk copy next to the operand slices.  The consumers then read x from shared
+// memory only: the pattern entries of this variant hold, instead of (col - row), the index of the entry's x value inside the
+// stage's x area for row 0 of the tile (group * SL_DOUBLES + (col - row) - group minimum); adding the row gives the slot.
+struct SxGroups { int ng; int xlen; int gmin[8]; int gspan[8]; };     // gmin even; slice of group g = x[row0 + gmin .. row0 + nrows - 1 + gmin + gspan]
+constexpr int SX_SPAN = 64;              // neighbouring offsets are merged while a group spans at most this many columns
+constexpr int SX_MAX_GROUPS = 8;
+
+template <int THREADS, int RPT, int NOPS, int NIOPS>
+struct SxCfg {
+    static constexpr int ROWCAP = THREADS * RPT;
+    static constexpr int HDR_BYTES = 128;
+    static constexpr int CODE_BYTES = ROWCAP;
+    static constexpr int OP_BYTES = ROWCAP * 8;
+    static constexpr int IOP_BYTES = ROWCAP * 4;
+    static constexpr int SL_DOUBLES = (ROWCAP + SX_SPAN + 4 + 15) / 16 * 16;      // one group's slice (rows + span + alignment slack)
+    static constexpr int SL_BYTES = SL_DOUBLES * 8;
+    static constexpr int PHEAD_BYTES = 256 * 8;
+    static constexpr int BAR_BYTES = 128;
+    static constexpr int X_OFF = HDR_BYTES + CODE_BYTES + NOPS * OP_BYTES + NIOPS * IOP_BYTES;
+    static constexpr int stage_bytes(int ng) { return X_OFF + ng * SL_BYTES; }
+    static constexpr int smem_bytes(int stages, int npent, int ng) { return BAR_BYTES + PHEAD_BYTES + npent * (int)sizeof(DictEnt) + stages * stage_bytes(ng); }
+    static_assert(ROWCAP % 32 == 0 && SL_BYTES % 128 == 0, "stage sections must stay 128-byte aligned");
+};
+
+template <int THREADS, int RPT, int STAGES, int JW, class Epi>
+__global__ void __launch_bounds__(THREADS + 32, 3)
+k_rowstream_sx(const unsigned char* __restrict__ rcodes, const DictEnt* __restrict__ pent, const int2* __restrict__ phead, int npent,
+               SxGroups G, const int4* __restrict__ desc, int ntiles, int tpc, const double* x, Epi epi)
+{
+    static_assert(Epi::CONTIG, "row-stream kernel needs contiguous epilogue operands");
+    static_assert(STAGES <= 8, "barrier block holds 8 stages");
+    static_assert(JW == 4 || JW == 8, "first-chunk width");
+    constexpr int NIOPS = EpiNI<Epi>::value;
+    using Cfg = SxCfg<THREADS, RPT, Epi::NOPS, NIOPS>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + 8;
+    int2* sphead = reinterpret_cast<int2*>(smem + Cfg::BAR_BYTES);
+    DictEnt* spent = reinterpret_cast<DictEnt*>(smem + Cfg::BAR_BYTES + Cfg::PHEAD_BYTES);
+    unsigned char* stage0 = smem + Cfg::BAR_BYTES + Cfg::PHEAD_BYTES + npent * (int)sizeof(DictEnt);
+    const int stage_bytes = Cfg::X_OFF + G.ng * Cfg::SL_BYTES;          // = SxCfg::stage_bytes(G.ng)
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int k = tid; k < npent; k += THREADS + 32) spent[k] = pent[k];
+    for (int k = tid; k < 256; k += THREADS + 32) sphead[k] = phead[k];
+    __syncthreads();
+    const int first = tpc > 0 ? (int)blockIdx.x * tpc : (int)blockIdx.x;
+    const int step = tpc > 0 ? 1 : (int)gridDim.x;
+    const int my_tiles = tpc > 0 ? min(tpc, ntiles - first) : (ntiles - first + step - 1) / step;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (tid >= THREADS) {                                   // ---- producer warp (one lane works)
+        if (tid == THREADS) {
+            uint64_t pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            // slice of group g for tile d: x[lo, hi), landing (lo - start) doubles into the group's area (start may be < 0 on the first tiles)
+            auto slice = [&](const int4& d, int g, int& lo, int& hi, int& start) {
+                start = d.x + G.gmin[g];
+                const int len = (d.y + G.gspan[g] + 1) & ~1;
+                lo = max(start, 0);
+                hi = min(start + len, G.xlen);
+            };
+            auto issue_matrix = [&](int i, const int4& d) {                          // d = {row0, nrows, -, -}
+                const int s = i % STAGES;
+                unsigned char* st = stage0 + (size_t)s * stage_bytes;
+                *reinterpret_cast<int4*>(st) = d;
+                const uint32_t b_code = (uint32_t)((d.y + 15) & ~15), b_op = (uint32_t)((d.y + 1) & ~1) * 8u, b_iop = (uint32_t)((d.y + 3) & ~3) * 4u;
+                uint32_t b_x = 0;
+                for (int g = 0; g < G.ng; ++g) { int lo, hi, st0; slice(d, g, lo, hi, st0); if (hi > lo) b_x += (uint32_t)(hi - lo) * 8u; }
+                mbar_expect_tx(full + s, b_code + (uint32_t)Epi::NOPS * b_op + (uint32_t)NIOPS * b_iop + b_x);
+                bulk_g2s_hint(st + Cfg::HDR_BYTES, rcodes + d.x, b_code, full + s, pol);
+            };
+            auto issue_operands = [&](int i, const int4& d) {                        // everything the predecessor may have written
+                const int s = i % STAGES;
+                const uint32_t b_op = (uint32_t)((d.y + 1) & ~1) * 8u, b_iop = (uint32_t)((d.y + 3) & ~3) * 4u;
+                unsigned char* st = stage0 + (size_t)s * stage_bytes;
+                unsigned char* p = st + Cfg::HDR_BYTES + Cfg::CODE_BYTES;
+#pragma unroll
+                for (int j = 0; j < Epi::NOPS; ++j) { bulk_g2s(p, epi.operand(j) + d.x, b_op, full + s); p += Cfg::OP_BYTES; }
+                if constexpr (NIOPS > 0) bulk_g2s(p, epi.ioperand() + d.x, b_iop, full + s);
+                for (int g = 0; g < G.ng; ++g) {
+                    int lo, hi, st0;
+                    slice(d, g, lo, hi, st0);
+                    if (hi > lo) bulk_g2s(st + Cfg::X_OFF + (size_t)g * Cfg::SL_BYTES + (size_t)(lo - st0) * 8, x + lo, (uint32_t)(hi - lo) * 8u, full + s);
+                }
+            };
+            int4 dpre[STAGES];
+            const int npre = my_tiles < STAGES ? my_tiles : STAGES;
+            for (int i = 0; i < npre; ++i) dpre[i] = __ldg(desc + first + (size_t)i * step);
+            int4 dn = make_int4(0, 0, 0, 0);
+            if (npre < my_tiles) dn = __ldg(desc + first + (size_t)npre * step);
+            for (int i = 0; i < npre; ++i) issue_matrix(i, dpre[i]);
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            for (int i = 0; i < npre; ++i) issue_operands(i, dpre[i]);
+            for (int i = npre; i < my_tiles; ++i) {
+                const int s = i % STAGES;
+                const int4 d = dn;
+                if (i + 1 < my_tiles) dn = __ldg(desc + first + (size_t)(i + 1) * step);
+                mbar_wait(empty + s, (uint32_t)((i / STAGES - 1) & 1));
+                issue_matrix(i, d);
+                issue_operands(i, d);
+            }
+        }
+        return;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    for (int i = 0; i < my_tiles; ++i) {                     // ---- consumers: thread per row, x from shared memory
+        const int s = i % STAGES;
+        mbar_wait(full + s, (uint32_t)((i / STAGES) & 1));
+        const unsigned char* st = stage0 + (size_t)s * stage_bytes;
+        const int4 d = *reinterpret_cast<const int4*>(st);
+        const unsigned char* scodes = st + Cfg::HDR_BYTES;
+        const double* sops = reinterpret_cast<const double*>(st + Cfg::HDR_BYTES + Cfg::CODE_BYTES);
+        const double* xs = reinterpret_cast<const double*>(st + Cfg::X_OFF);
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int r = tid + j * THREADS;
+            if (r < d.y) {
+                const int2 ph = sphead[scodes[r]];
+                const DictEnt* pe = spent + ph.x;
+                double o[Epi::NOPS > 0 ? Epi::NOPS : 1];
+#pragma unroll
+                for (int q = 0; q < Epi::NOPS; ++q) o[q] = sops[q * Cfg::ROWCAP + r];
+                double sum = 0.0;                            // one accumulator, stored order
+                for (int e0 = 0; e0 < ph.y; e0 += JW) {      // (patterns are padded to multiples of 8 entries: no clamp needed)
+                    double xw[JW], vw[JW];
+#pragma unroll
+                    for (int e = 0; e < JW; ++e) { const DictEnt de = pe[e0 + e]; vw[e] = de.val; xw[e] = xs[de.delta + r]; }
+#pragma unroll
+                    for (int e = 0; e < JW; ++e)
+                        if (e0 + e < ph.y) sum = __dadd_rn(sum, __dmul_rn(vw[e], xw[e]));
+                }
+                if constexpr (NIOPS > 0) epi.store_i(d.x + r, sum, o, reinterpret_cast<const int32_t*>(sops + Epi::NOPS * Cfg::ROWCAP)[r]);
+                else epi.store(d.x + r, sum, o);
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(empty + s);
+    }
+}
+
 // ---- sub-warp family --------------------------------------------------------------------------------
 // LPR lanes cooperate on one row (LPR = 32: warp per row), partial sums combined with a shuffle tree.
 template <int LPR, bool NCX, class Epi>

@@ -16,6 +16,8 @@ struct Coded {
     DictEnt* dict = nullptr;         // device, 256 entries (mode 3: npent pattern entries)
     int2* phead = nullptr;           // mode 3: device, 256 x {first entry, length}
     int npent = 0;                   // mode 3: entries in the pattern table (multiple of 8)
+    DictEnt* dict_sx = nullptr;      // mode 3, option "stage_x" (experimental): the pattern table again, with the slot of each entry's x
+    SxGroups sx{};                   // value in the stage's staged-x area instead of (col - row); sx.ng == 0: not available
     int ndict = 0;                   // entries (mode 3: patterns) in use
     int nvals = 0, ndeltas = 0;      // distinct values / distinct (col - row) found
 };
@@ -147,6 +149,7 @@ struct mgb_handle {
     int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
     int compress = 2;              // lossless coding of repetitive operators (mgb_code.cuh): 0 off, 1 per-entry codes, 2 + row patterns
     int code_cfg = 1;              // row-stream kernel configuration for coded operators (code_choice)
+    int stage_x = 0;               // EXPERIMENTAL, unmeasured: x staged in shared memory by TMA for row-pattern-coded operators (k_rowstream_sx)
     bool allow_stream = true;      // false while borrowed user pointers are in play (no padding / alignment guarantee)
     int coarsest = 0, finest = 0;
     double* coarse_inv = nullptr;

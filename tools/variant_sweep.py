@@ -19,6 +19,7 @@ VARIANTS = [
     ("pattern3_256x2x3", {"code_cfg": 3}),
     ("pattern1_pdl", {"code_cfg": 1, "pdl": 1}),
     ("pattern1_nopdl", {"code_cfg": 1, "pdl": 0}),
+    ("pattern1_stage_x", {"code_cfg": 1, "stage_x": 1}),        # experimental: x staged in shared memory (unmeasured so far)
     ("coded1_256x2", {"compress": 1, "code_cfg": 1}),
     ("coded3_256x2x3", {"compress": 1, "code_cfg": 3}),
     ("csr_stream3", {"compress": 0}),
