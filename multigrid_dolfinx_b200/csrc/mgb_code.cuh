@@ -151,7 +151,7 @@ k_code_verify(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__
 
 void free_coded(Coded& c)
 {
-    cudaFree(c.codes); cudaFree(c.dict); cudaFree(c.phead); cudaFree(c.dict_sx);
+    cudaFree(c.codes); cudaFree(c.dict); cudaFree(c.phead); cudaFree(c.dict_win);
     c = Coded();
 }
 
@@ -322,41 +322,67 @@ int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip)
 #undef CUC
     if (hb) { free_coded(D.cd); return MGB_OK; }          // never trust an unverified coding
     D.cd.mode = 3; D.cd.ndict = (int)pats.size(); D.cd.npent = total;
-    if (h->stage_x) {
-        // EXPERIMENTAL (k_rowstream_sx): group the distinct offsets, re-express every table entry as a slot of the stage's x area
+    {   // the most frequent ("hot") pattern -- mode of 1024 evenly spaced codes -- travels to the row-direct / row-window
+        // kernels as kernel parameters
+        std::vector<unsigned char> smp(1024);
+        const size_t stride = std::max<size_t>(1, (size_t)n / 1024), cnt = std::min<size_t>(1024, (size_t)n / stride);
+        cudaError_t e1 = cudaMemcpy2DAsync(smp.data(), 1, D.cd.codes, stride, 1, cnt, cudaMemcpyDeviceToHost, h->stream);
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(h->stream);
+        if (e1 != cudaSuccess) { free_coded(D.cd); return fail(h, MGB_ERR_CUDA, "sampling the row codes failed: %s", cudaGetErrorString(e1)); }
+        int hist[256] = {0};
+        for (size_t k = 0; k < cnt; ++k) hist[smp[k]]++;
+        HotPlan& H = D.cd.hotplan;
+        H = HotPlan{};
+        H.hot = (int)(std::max_element(hist, hist + 256) - hist);
+        H.hotlen = phead[(size_t)H.hot].y;
+        for (int e = 0; e < WIN_HOT; ++e) {
+            const bool in = e < H.hotlen && H.hotlen <= WIN_HOT;
+            H.hd[e] = in ? pent[(size_t)(phead[(size_t)H.hot].x + e)].delta : 0;
+            H.hv[e] = in ? pent[(size_t)(phead[(size_t)H.hot].x + e)].val : 0.0;
+        }
+    }
+    if (h->stage_x == 1) {
+        // row-window kernel (k_rowwin): merge the distinct offsets into windows and re-express every table entry as
+        // (window, offset inside the window)
         std::vector<int> offs;
         for (size_t p = 0; p < pats.size(); ++p)
             for (int e = 0; e < phead[p].y; ++e) offs.push_back(pent[(size_t)(phead[p].x + e)].delta);
+        offs.push_back(0);                                                  // x[row] itself: the aliased epilogue operand
         std::sort(offs.begin(), offs.end());
         offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
-        SxGroups G{};
-        bool ok = !offs.empty();
+        WinPlan G{};
+        bool ok = true;
         for (size_t k = 0; k < offs.size() && ok; ++k) {
-            if (G.ng > 0 && offs[k] - G.gmin[G.ng - 1] <= SX_SPAN) { G.gspan[G.ng - 1] = offs[k] - G.gmin[G.ng - 1]; continue; }
-            if (G.ng == SX_MAX_GROUPS) { ok = false; break; }
+            if (G.ng > 0 && offs[k] - G.gmin[G.ng - 1] <= WIN_SPAN) { G.gspan[G.ng - 1] = offs[k] - G.gmin[G.ng - 1]; continue; }
+            if (G.ng == WIN_MAX) { ok = false; break; }
             G.gmin[G.ng] = offs[k] & ~1;                                    // even: slices start 16-byte aligned (tile starts are multiples of 16)
             G.gspan[G.ng] = offs[k] - G.gmin[G.ng];
             ++G.ng;
         }
         if (ok) {
-            constexpr int SL = SxCfg<256, 2, 0, 0>::SL_DOUBLES;            // (same for every epilogue: depends on the tile's row capacity only)
-            std::vector<DictEnt> sx(pent);
+            auto window_of = [&](int delta) { int g = 0; while (g + 1 < G.ng && delta >= G.gmin[g + 1]) ++g; return g; };
+            std::vector<DictEnt> wt(pent);
             for (size_t p = 0; p < pats.size(); ++p) {
                 const int len = phead[p].y, off = phead[p].x, padded = std::max(8, (len + 7) / 8 * 8);
                 for (int e = 0; e < padded; ++e) {
-                    DictEnt& d = sx[(size_t)(off + e)];
-                    if (len == 0) { d.delta = 0; continue; }                // empty row: slot 0 (its value is never used)
-                    int g = 0;
-                    while (g + 1 < G.ng && d.delta >= G.gmin[g + 1]) ++g;
-                    d.delta = g * SL + (d.delta - G.gmin[g]);
+                    DictEnt& d = wt[(size_t)(off + e)];
+                    const int g = window_of(d.delta);                       // (empty row: delta 0, value never used)
+                    d.delta = (g << WIN_GSHIFT) | (d.delta - G.gmin[g]);
                 }
             }
+            G.vslot = window_of(0);                                         // window holding offset 0; the slot is fixed at launch (needs the tile size)
             G.xlen = (int)((D.ncols + 16) & ~(int64_t)1);                  // engine vectors carry 16 padding entries behind ncols
-            cudaError_t e1 = cudaMalloc((void**)&D.cd.dict_sx, (size_t)total * sizeof(DictEnt));
-            if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(D.cd.dict_sx, sx.data(), (size_t)total * sizeof(DictEnt), cudaMemcpyHostToDevice, h->stream);
+            G.hot = D.cd.hotplan.hot; G.hotlen = D.cd.hotplan.hotlen;
+            for (int e = 0; e < WIN_HOT; ++e) {                             // (window, offset): resolved at launch
+                const bool in = e < G.hotlen && G.hotlen <= WIN_HOT;
+                G.hs[e] = in ? wt[(size_t)(phead[(size_t)G.hot].x + e)].delta : 0;
+                G.hv[e] = D.cd.hotplan.hv[e];
+            }
+            cudaError_t e1 = cudaMalloc((void**)&D.cd.dict_win, (size_t)total * sizeof(DictEnt));
+            if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(D.cd.dict_win, wt.data(), (size_t)total * sizeof(DictEnt), cudaMemcpyHostToDevice, h->stream);
             if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(h->stream);
-            if (e1 == cudaSuccess) D.cd.sx = G;
-            else { cudaFree(D.cd.dict_sx); D.cd.dict_sx = nullptr; (void)cudaGetLastError(); }
+            if (e1 == cudaSuccess) D.cd.win = G;
+            else { cudaFree(D.cd.dict_win); D.cd.dict_win = nullptr; (void)cudaGetLastError(); }
         }
     }
     return MGB_OK;

@@ -68,7 +68,7 @@ int dev_upload(mgb_handle* h, T** p, const T* src, size_t count, size_t pad = 0)
 
 void free_csr(DevCsr& D)
 {
-    cudaFree(D.cd.codes); cudaFree(D.cd.dict); cudaFree(D.cd.phead); cudaFree(D.cd.dict_sx);
+    cudaFree(D.cd.codes); cudaFree(D.cd.dict); cudaFree(D.cd.phead); cudaFree(D.cd.dict_win);
     cudaFree(D.rowptr); cudaFree(D.cols); cudaFree(D.vals); cudaFree(D.tiles); cudaFree(D.sdesc); cudaFree(D.sdesc_bnd);
     D = DevCsr();
 }
@@ -100,6 +100,18 @@ CodeChoice code_choice(int cfg)
         // fine-level sweep against 28.2), 1024-row tiles with four rows per thread (29.1), a register budget for 5 CTAs per SM (28.1)
         case 3: return {256, 2, 8, 3};       // 512-row tiles, deeper ring (27.8 us, but the prolongation loses: 43 against 32 us)
         default: return {256, 2, 8, 2};      // 512-row tiles of <= 4096 entries, two rows per thread, two stages -- the default
+    }
+}
+
+// Row-window kernel configurations (option "win_cfg"): rows per thread (x 256 consumer threads = rows per tile), stages
+struct WinChoice { int rpt, stages; };
+WinChoice win_choice(int cfg)
+{
+    switch (cfg) {
+        case 2: return {4, 2};           // 1024-row tiles, two stages, registers for 2 CTAs per SM
+        case 3: return {2, 3};           // 512-row tiles, three stages, registers for 3 CTAs per SM
+        case 4: return {4, 3};           // 1024-row tiles, three stages, registers for 2 CTAs per SM
+        default: return {2, 2};          // 512-row tiles, two stages, registers for 4 CTAs per SM
     }
 }
 
@@ -151,7 +163,12 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
         if (D.cd.mode) {
             D.ccfg = h->code_cfg;
             const CodeChoice cc = code_choice(D.ccfg);
-            const int64_t rowcap = (int64_t)cc.threads * cc.rpt;
+            int64_t rowcap = (int64_t)cc.threads * cc.rpt;
+            D.wcfg = 0;
+            if (D.cd.mode == 3 && h->stage_x == 1 && D.cd.win.ng > 0 && D.cd.dict_win) {          // row-window kernel: its own tile size
+                D.wcfg = std::max(1, h->win_cfg);
+                rowcap = 256 * (int64_t)win_choice(D.wcfg).rpt;
+            }
             if (D.cd.mode == 3) tiled = make_tiles(ip, (int64_t)1 << 40, rowcap, sbreaks, st, &sbt, 16);    // rows only; 16-byte aligned code slices
             else tiled = make_tiles(ip, rowcap * cc.epr - 8, rowcap, sbreaks, st, &sbt, 4);
             if (tiled) align_mask = 15; else free_coded(D.cd);
@@ -357,25 +374,37 @@ void launch_rowstream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int 
                        (const DictEnt*)D.cd.dict, (const int2*)D.cd.phead, npent, desc, ntiles, tpc, x, epi);
 }
 
-// EXPERIMENTAL (option "stage_x"): row patterns with x staged in shared memory; 512-row tiles, two stages
-template <int JW, class Epi>
-void launch_rowstream_sx(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
+// Row patterns with x staged in shared memory (k_rowwin).  The window plan of the operator is completed here for the
+// tile size of the chosen configuration (where each window's slice sits inside a stage, the hot pattern's slots).
+template <int RPT, int S, int MINB, int HOTN, class Epi>
+void launch_rowwin_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
 {
-    constexpr int T = 256, RPT = 2, S = 2;
-    auto kern = k_rowstream_sx<T, RPT, S, JW, Epi>;
-    const int smem = SxCfg<T, RPT, Epi::NOPS, EpiNI<Epi>::value>::smem_bytes(S, D.cd.npent, D.cd.sx.ng);
+    constexpr int T = 256;
+    using Cfg = WinCfg<T, RPT, Epi::NOPS, EpiNI<Epi>::value>;
+    auto kern = k_rowwin<T, RPT, S, HOTN, MINB, Epi>;
+    WinPlan W = D.cd.win;
+    int xd = 0;
+    for (int g = 0; g < W.ng; ++g) { W.goff[g] = xd; xd += (Cfg::ROWCAP + W.gspan[g] + 1) & ~1; }
+    W.xdoubles = xd;
+    const int gv = W.vslot;                                  // window holding offset 0 (try_patterns) -> slot
+    W.vslot = W.goff[gv] - W.gmin[gv];
+    for (int e = 0; e < WIN_HOT; ++e) W.hs[e] = W.goff[W.hs[e] >> WIN_GSHIFT] + (W.hs[e] & ((1 << WIN_GSHIFT) - 1));
+    constexpr int XOP = EpiXop<Epi>::value;
+    bool alias = false;
+    if constexpr (XOP >= 0) alias = epi.operand(XOP) == x;
+    const int smem = Cfg::smem_bytes(S, D.cd.npent, Epi::NOPS - (alias ? 1 : 0), xd);
     int occ = 1;
     {
         static std::mutex mu;
-        static std::map<int, int> occ_by_smem;
-        static int smem_attr = 0;
+        static std::map<std::pair<int, int>, int> occ_by_smem;      // (device, bytes)
+        static std::map<int, int> smem_attr;                        // device -> largest size configured
         std::lock_guard<std::mutex> lock(mu);
-        if (smem > smem_attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_attr = smem; }
-        auto it = occ_by_smem.find(smem);
+        if (smem > smem_attr[h->device]) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_attr[h->device] = smem; }
+        auto it = occ_by_smem.find({h->device, smem});
         if (it == occ_by_smem.end()) {
             int o = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, T + 32, smem);
-            it = occ_by_smem.emplace(smem, std::max(o, 1)).first;
+            it = occ_by_smem.emplace(std::make_pair(h->device, smem), std::max(o, 1)).first;
         }
         occ = it->second;
     }
@@ -390,8 +419,35 @@ void launch_rowstream_sx(mgb_handle* h, const DevCsr& D, const int4* desc, int n
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = h->pdl != 0 ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kern, (const unsigned char*)D.cd.codes, (const DictEnt*)D.cd.dict_sx, (const int2*)D.cd.phead, D.cd.npent, D.cd.sx,
-                       desc, ntiles, tpc, x, epi);
+    cudaLaunchKernelEx(&cfg, kern, (const unsigned char*)D.cd.codes, (const DictEnt*)D.cd.dict_win, (const int2*)D.cd.phead, D.cd.npent, W,
+                       desc, ntiles, tpc, h->win_prefetch, x, epi);
+}
+
+template <int HOTN, class Epi>
+void launch_rowwin_hot(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
+{
+    switch (D.wcfg) {                    // win_choice()
+        case 2: launch_rowwin_cfg<4, 2, 2, HOTN, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        case 3: launch_rowwin_cfg<2, 3, 3, HOTN, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        case 4: launch_rowwin_cfg<4, 3, 2, HOTN, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+        default: launch_rowwin_cfg<2, 2, 4, HOTN, Epi>(h, D, desc, ntiles, x, epi, chunked); break;
+    }
+}
+
+// The straight-line body exists for the pattern lengths of the operators this engine is built for: the smoother matrix of
+// the P1 Laplacian (4 couplings per row in 2-D, 6 in 3-D) and the level matrix as exported (7 / 15 stored entries).
+template <class Epi>
+void launch_rowwin(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
+{
+    const int hl = D.cd.win.hotlen;
+    if constexpr (std::is_same<Epi, EpiJacobiRJ>::value || std::is_same<Epi, EpiJacobiRJFirst>::value) {
+        if (hl == 4) return launch_rowwin_hot<4, Epi>(h, D, desc, ntiles, x, epi, chunked);
+        if (hl == 6) return launch_rowwin_hot<6, Epi>(h, D, desc, ntiles, x, epi, chunked);
+    } else if constexpr (!std::is_same<Epi, EpiProlongAdd>::value) {
+        if (hl == 7) return launch_rowwin_hot<7, Epi>(h, D, desc, ntiles, x, epi, chunked);
+        if (hl == 15) return launch_rowwin_hot<15, Epi>(h, D, desc, ntiles, x, epi, chunked);
+    }
+    launch_rowwin_hot<0, Epi>(h, D, desc, ntiles, x, epi, chunked);
 }
 
 // MODE: the coding (pair / value codes); JW: gathers issued up front per row (4 when no row is longer, else 8)
@@ -411,9 +467,8 @@ void launch_stream(mgb_handle* h, const DevCsr& D, const double* x, const Epi& e
     if (!desc) { desc = D.sdesc; ntiles = D.sntiles; }
     if (ntiles <= 0) return;
     if constexpr (Epi::CONTIG) {
-        if (D.cd.mode == 3 && h->stage_x && D.cd.sx.ng > 0 && D.cd.dict_sx && code_choice(D.ccfg).threads * code_choice(D.ccfg).rpt == 512) {
-            if (D.max_row <= 4) return launch_rowstream_sx<4, Epi>(h, D, desc, ntiles, x, epi, chunked);
-            return launch_rowstream_sx<8, Epi>(h, D, desc, ntiles, x, epi, chunked);
+        if (D.cd.mode == 3 && D.wcfg > 0) {              // x staged in shared memory (tiles were cut for this configuration)
+            return launch_rowwin<Epi>(h, D, desc, ntiles, x, epi, chunked);
         }
         if (D.cd.mode == 3 && D.max_row <= 4) return launch_rowstream<3, 4, Epi>(h, D, desc, ntiles, x, epi, chunked);
         if (D.cd.mode == 3) return launch_rowstream<3, 8, Epi>(h, D, desc, ntiles, x, epi, chunked);
@@ -1193,6 +1248,8 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "compress" && pre) h->compress = iv;
     else if (k == "code_cfg" && pre) h->code_cfg = iv;
     else if (k == "stage_x" && pre) h->stage_x = iv;
+    else if (k == "win_cfg" && pre) h->win_cfg = iv;
+    else if (k == "win_prefetch") { h->win_prefetch = iv; drop_graphs(h); }
     else if (k == "gs_cluster") h->gs_cluster = iv;
     else if (k == "pdl") { h->pdl = iv; drop_graphs(h); }
     else if (k == "p2p_enable") { h->p2p_enable = iv; drop_graphs(h); }
@@ -1758,7 +1815,8 @@ int mgb_describe(mgb_handle* h, char* out, int64_t capacity)
     char buf[256];
     auto one = [&](const char* name, const DevCsr& D) {
         if (!D.present()) return;
-        if (D.family == 1 && D.sdesc && D.cd.mode == 3) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowstream(coded mode=3: %d row patterns, %d table entries; cfg=%d, %d x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.ccfg, code_choice(D.ccfg).threads, code_choice(D.ccfg).rpt, code_choice(D.ccfg).stages, D.sntiles);
+        if (D.family == 1 && D.sdesc && D.cd.mode == 3 && D.wcfg > 0) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowwin(coded mode=3: %d row patterns, %d table entries, %d x-windows, hot pattern %d; cfg=%d, 256 x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.cd.win.ng, D.cd.win.hot, D.wcfg, win_choice(D.wcfg).rpt, win_choice(D.wcfg).stages, D.sntiles);
+        else if (D.family == 1 && D.sdesc && D.cd.mode == 3) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowstream(coded mode=3: %d row patterns, %d table entries; cfg=%d, %d x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.ccfg, code_choice(D.ccfg).threads, code_choice(D.ccfg).rpt, code_choice(D.ccfg).stages, D.sntiles);
         else if (D.family == 1 && D.sdesc && D.cd.mode) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowstream(coded mode=%d: %d dictionary entries, %d values, %d offsets; cfg=%d, %d x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.mode, D.cd.ndict, D.cd.nvals, D.cd.ndeltas, D.ccfg, code_choice(D.ccfg).threads, code_choice(D.ccfg).rpt, code_choice(D.ccfg).stages, D.sntiles);
         else if (D.family == 1 && D.sdesc) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d stream(cfg=%d, %d x %d entries, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.scfg, stream_choice(D.scfg).threads, stream_choice(D.scfg).ept, stream_choice(D.scfg).stages, D.sntiles);
         else if (D.family == 1) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d tile(cap=%d) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, tile_cap(D.iter), D.ntiles);

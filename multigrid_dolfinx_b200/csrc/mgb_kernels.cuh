@@ -42,21 +42,21 @@ __device__ __forceinline__ D4 ld_stream_d4(const double* p)
 struct EpiStore {
     static constexpr int NOPS = 0; static constexpr bool CONTIG = true;
     double* y;
-    __device__ __forceinline__ const double* operand(int) const { return nullptr; }
+    __host__ __device__ __forceinline__ const double* operand(int) const { return nullptr; }
     __device__ __forceinline__ void store(int i, double s, const double*) const { y[i] = s; }
 };
 // r = f - A v                                               (multigrid.py:244)
 struct EpiResidual {
     static constexpr int NOPS = 1; static constexpr bool CONTIG = true;
     const double* f; double* r;
-    __device__ __forceinline__ const double* operand(int) const { return f; }
+    __host__ __device__ __forceinline__ const double* operand(int) const { return f; }
     __device__ __forceinline__ void store(int i, double s, const double* o) const { r[i] = __dsub_rn(o[0], s); }
 };
 // weighted Jacobi, reference form (multigrid.py:226): out = ((1-w)*v + g) - w*s, g = w*(dinv*f)
 struct EpiJacobiRJ {
-    static constexpr int NOPS = 2; static constexpr bool CONTIG = true;
+    static constexpr int NOPS = 2; static constexpr bool CONTIG = true; static constexpr int XOP = 0;
     const double* v; const double* g; double* out; double om1, om;
-    __device__ __forceinline__ const double* operand(int j) const { return j == 0 ? v : g; }
+    __host__ __device__ __forceinline__ const double* operand(int j) const { return j == 0 ? v : g; }
     __device__ __forceinline__ void store(int i, double s, const double* o) const
     {
         out[i] = __dsub_rn(__dadd_rn(__dmul_rn(om1, o[0]), o[1]), __dmul_rn(om, s));
@@ -65,9 +65,9 @@ struct EpiJacobiRJ {
 // same, first sweep of a relaxation call: also produces g (multigrid.py:226 recomputes w*(Dinv f) per sweep;
 // the product is identical every time, so it is formed once and kept)
 struct EpiJacobiRJFirst {
-    static constexpr int NOPS = 3; static constexpr bool CONTIG = true;
+    static constexpr int NOPS = 3; static constexpr bool CONTIG = true; static constexpr int XOP = 0;
     const double* v; const double* dinv; const double* f; double* g; double* out; double om1, om;
-    __device__ __forceinline__ const double* operand(int j) const { return j == 0 ? v : (j == 1 ? dinv : f); }
+    __host__ __device__ __forceinline__ const double* operand(int j) const { return j == 0 ? v : (j == 1 ? dinv : f); }
     __device__ __forceinline__ void store(int i, double s, const double* o) const
     {
         const double gi = __dmul_rn(om, __dmul_rn(o[1], o[2]));
@@ -77,9 +77,9 @@ struct EpiJacobiRJFirst {
 };
 // single-matrix Jacobi: out = v + w*(dinv*(f - s)), s = (A v)_i
 struct EpiJacobiA {
-    static constexpr int NOPS = 3; static constexpr bool CONTIG = true;
+    static constexpr int NOPS = 3; static constexpr bool CONTIG = true; static constexpr int XOP = 0;
     const double* v; const double* dinv; const double* f; double* out; double om;
-    __device__ __forceinline__ const double* operand(int j) const { return j == 0 ? v : (j == 1 ? dinv : f); }
+    __host__ __device__ __forceinline__ const double* operand(int j) const { return j == 0 ? v : (j == 1 ? dinv : f); }
     __device__ __forceinline__ void store(int i, double s, const double* o) const
     {
         out[i] = __dadd_rn(o[0], __dmul_rn(om, __dmul_rn(o[1], __dsub_rn(o[2], s))));
@@ -89,7 +89,7 @@ struct EpiJacobiA {
 struct EpiProlongAdd {
     static constexpr int NOPS = 1; static constexpr bool CONTIG = true;
     double* v; double* err;
-    __device__ __forceinline__ const double* operand(int) const { return v; }
+    __host__ __device__ __forceinline__ const double* operand(int) const { return v; }
     __device__ __forceinline__ void store(int i, double s, const double* o) const
     {
         if (err) err[i] = s;
@@ -110,7 +110,7 @@ struct EpiGaussSeidel {
 struct EpiResidualInject {
     static constexpr int NOPS = 1; static constexpr bool CONTIG = true; static constexpr int NIOPS = 1;
     const double* f; const int32_t* cmap; double* out;
-    __device__ __forceinline__ const double* operand(int) const { return f; }
+    __host__ __device__ __forceinline__ const double* operand(int) const { return f; }
     __device__ __forceinline__ const int32_t* ioperand() const { return cmap; }
     __device__ __forceinline__ void store_i(int, double s, const double* o, int c) const { if (c >= 0) out[c] = __dsub_rn(o[0], s); }
 };
@@ -670,83 +670,144 @@ k_rowstream(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols
     }
 }
 
-// ---- row-stream kernel with x staged in shared memory -----------------------------------------------------
-// EXPERIMENTAL (option "stage_x", default off): written at the end of round 1 after the GPU budget was spent -- it compiles, it has
-// NOT run on hardware yet, nothing uses it by default.  Design: DESIGN.md section 8.  For a row-pattern-coded operator the distinct
-// column offsets fall into a few groups of neighbouring offsets; a tile of consecutive rows needs, per group, ONE contiguous slice
-// of x, which the producer lane fetches with a bulk copy next to the operand slices.  The consumers then read x from shared
-// memory only: the pattern entries of this variant hold, instead of (col - row), the index of the entry's x value inside the
-// stage's x area for row 0 of the tile (group * SL_DOUBLES + (col - row) - group minimum); adding the row gives the slot.
-struct SxGroups { int ng; int xlen; int gmin[8]; int gspan[8]; };     // gmin even; slice of group g = x[row0 + gmin .. row0 + nrows - 1 + gmin + gspan]
-constexpr int SX_SPAN = 64;              // neighbouring offsets are merged while a group spans at most this many columns
-constexpr int SX_MAX_GROUPS = 8;
+// ---- row-window family: row patterns with x staged in shared memory ("stage_x") -------------------------------
+// For a row-pattern-coded operator (MODE 3) in a banded numbering the distinct column offsets (col - row) over all patterns
+// fall into a few WINDOWS of neighbouring offsets (3-D P1 Laplacian, N^3 nodes: {-N^2}, {-N .. +N}, {+N^2}).  A tile of
+// consecutive rows [r0, r0 + nr) then needs, per window g, ONE contiguous slice x[r0 + gmin_g, r0 + nr + gmin_g + gspan_g):
+// the producer lane fetches it with a 1-D bulk copy next to the code and operand slices, and the consumers read x from
+// shared memory only -- no global gather, no L2 latency on the consumers' critical path.  The pattern table of this
+// family holds, instead of (col - row), the SLOT of the entry's x value in the stage's x area for row 0 of the tile
+// (window base + (col - row) - gmin); adding the row gives the slot.  Where offset 0 lies inside a window, the operand
+// of the epilogue that aliases x (the old iterate of a Jacobi sweep) is read from that window too and not copied a
+// second time.
+// What the kernel is bound by is instruction issue (ncu: profiles/r2_ncu_rowwin_*.json), so the common case is stripped
+// down: the most frequent ("hot") pattern travels as KERNEL PARAMETERS -- its values become constant-bank operands of the
+// multiplies, its slots uniform-register offsets of the shared loads, its length a template parameter -- and a warp whose
+// rows all carry it runs a straight-line body of (load, multiply, add) per entry.  Any other warp takes the table path.
+// DRAM latency is covered by L2 prefetches (cp.async.bulk.prefetch.L2) PF tiles ahead instead of by more stages.
+// Numerics are unchanged: one accumulator per row, stored order, separately rounded multiply and add.
+constexpr int WIN_MAX = 8;               // windows per operator
+constexpr int WIN_SPAN = 1536;           // neighbouring offsets are merged while a window spans at most this many columns
+constexpr int WIN_GSHIFT = 20;           // pattern-table entry of this family: (window << WIN_GSHIFT) | (offset - gmin)
+constexpr int WIN_HOT = 16;              // the hot pattern holds at most this many entries
+struct WinPlan {
+    int ng;                              // windows
+    int xlen;                            // x holds xlen (even) readable entries
+    int xdoubles;                        // doubles in a stage's x area = sum over windows of (ROWCAP + span, rounded up to even)
+    int vslot;                           // slot of offset 0 (x[row] itself) or -1 when no window contains it
+    int hot, hotlen;                     // most frequent pattern and its length
+    int gmin[WIN_MAX];                   // even; slice of window g for a tile = x[row0 + gmin, row0 + nrows + gmin + gspan)
+    int gspan[WIN_MAX];
+    int goff[WIN_MAX];                   // first double of window g inside the x area
+    int hs[WIN_HOT];                     // hot pattern: slot of every entry (filled at launch) ...
+    double hv[WIN_HOT];                  // ... and its value
+};
 
 template <int THREADS, int RPT, int NOPS, int NIOPS>
-struct SxCfg {
+struct WinCfg {
     static constexpr int ROWCAP = THREADS * RPT;
     static constexpr int HDR_BYTES = 128;
     static constexpr int CODE_BYTES = ROWCAP;
     static constexpr int OP_BYTES = ROWCAP * 8;
     static constexpr int IOP_BYTES = ROWCAP * 4;
-    static constexpr int SL_DOUBLES = (ROWCAP + SX_SPAN + 4 + 15) / 16 * 16;      // one group's slice (rows + span + alignment slack)
-    static constexpr int SL_BYTES = SL_DOUBLES * 8;
     static constexpr int PHEAD_BYTES = 256 * 8;
     static constexpr int BAR_BYTES = 128;
-    static constexpr int X_OFF = HDR_BYTES + CODE_BYTES + NOPS * OP_BYTES + NIOPS * IOP_BYTES;
-    static constexpr int stage_bytes(int ng) { return X_OFF + ng * SL_BYTES; }
-    static constexpr int smem_bytes(int stages, int npent, int ng) { return BAR_BYTES + PHEAD_BYTES + npent * (int)sizeof(DictEnt) + stages * stage_bytes(ng); }
-    static_assert(ROWCAP % 32 == 0 && SL_BYTES % 128 == 0, "stage sections must stay 128-byte aligned");
+    // nops: operands that are really copied (the one aliasing x is not, when a window holds offset 0)
+    __host__ __device__ static constexpr int x_off(int nops) { return HDR_BYTES + CODE_BYTES + nops * OP_BYTES + NIOPS * IOP_BYTES; }
+    static int stage_bytes(int nops, int xdoubles) { return (x_off(nops) + xdoubles * 8 + 127) / 128 * 128; }
+    static int smem_bytes(int stages, int npent, int nops, int xdoubles) { return BAR_BYTES + PHEAD_BYTES + npent * (int)sizeof(DictEnt) + stages * stage_bytes(nops, xdoubles); }
+    static_assert(ROWCAP % 32 == 0, "stage sections must stay 128-byte aligned");
 };
 
-template <int THREADS, int RPT, int STAGES, int JW, class Epi>
-__global__ void __launch_bounds__(THREADS + 32, 3)
-k_rowstream_sx(const unsigned char* __restrict__ rcodes, const DictEnt* __restrict__ pent, const int2* __restrict__ phead, int npent,
-               SxGroups G, const int4* __restrict__ desc, int ntiles, int tpc, const double* x, Epi epi)
+template <class Epi, class = void> struct EpiXop { static constexpr int value = -1; };
+template <class Epi> struct EpiXop<Epi, decltype((void)Epi::XOP)> { static constexpr int value = Epi::XOP; };
+
+// consumers' wait: first probe inline, then a spin of (potentially blocking) try_waits bounded by an iteration count --
+// no clock reads on the fast path (the 2 s clock bound of mbar_wait costs six instructions per probe)
+__device__ __forceinline__ void mbar_wait_light(uint64_t* b, uint32_t parity)
 {
-    static_assert(Epi::CONTIG, "row-stream kernel needs contiguous epilogue operands");
+    const uint32_t addr = smem_u32(b);
+    uint32_t ok = 0;
+    for (uint32_t it = 0; ; ++it) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) break;
+        if (it > (1u << 24)) __trap();                      // a lost copy must fault, never hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// HOTN: exact length of the hot pattern served by the straight-line body (0: table path only)
+template <int THREADS, int RPT, int STAGES, int HOTN, int MINB, class Epi>
+__global__ void __launch_bounds__(THREADS + 32, MINB)
+k_rowwin(const unsigned char* __restrict__ rcodes, const DictEnt* __restrict__ pent, const int2* __restrict__ phead, int npent,
+         const __grid_constant__ WinPlan W, const int4* __restrict__ desc, int ntiles, int tpc, int pf, const double* x, Epi epi)
+{
+    static_assert(Epi::CONTIG, "row-window kernel needs contiguous epilogue operands");
     static_assert(STAGES <= 8, "barrier block holds 8 stages");
-    static_assert(JW == 4 || JW == 8, "first-chunk width");
+    static_assert(HOTN >= 0 && HOTN <= WIN_HOT, "hot pattern length");
     constexpr int NIOPS = EpiNI<Epi>::value;
-    using Cfg = SxCfg<THREADS, RPT, Epi::NOPS, NIOPS>;
+    constexpr int XOP = EpiXop<Epi>::value;
+    constexpr int RB = HOTN > 8 ? 1 : 2;                     // rows whose x values are fetched back to back
+    static_assert(RPT % RB == 0, "rows per thread");
+    using Cfg = WinCfg<THREADS, RPT, Epi::NOPS, NIOPS>;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + 8;
     int2* sphead = reinterpret_cast<int2*>(smem + Cfg::BAR_BYTES);
     DictEnt* spent = reinterpret_cast<DictEnt*>(smem + Cfg::BAR_BYTES + Cfg::PHEAD_BYTES);
     unsigned char* stage0 = smem + Cfg::BAR_BYTES + Cfg::PHEAD_BYTES + npent * (int)sizeof(DictEnt);
-    const int stage_bytes = Cfg::X_OFF + G.ng * Cfg::SL_BYTES;          // = SxCfg::stage_bytes(G.ng)
+    const bool alias = XOP >= 0 && W.vslot >= 0 && epi.operand(XOP < 0 ? 0 : XOP) == x;      // operand XOP comes out of a window
+    const int nops = Epi::NOPS - (alias ? 1 : 0);
+    const int x_off = Cfg::x_off(nops);
+    const int stage_bytes = (x_off + W.xdoubles * 8 + 127) / 128 * 128;
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, THREADS / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int k = tid; k < npent; k += THREADS + 32) spent[k] = pent[k];
-    for (int k = tid; k < 256; k += THREADS + 32) sphead[k] = phead[k];
-    __syncthreads();
+    __shared__ int s_gmin[WIN_MAX], s_gspan[WIN_MAX], s_goff[WIN_MAX];      // (dynamic indexing of a kernel parameter would go through local memory)
+    constexpr int DCACHE = 512;
+    __shared__ int2 s_desc[DCACHE];                          // {row0, nrows} of this CTA's first DCACHE tiles: the producer never waits for a descriptor
     const int first = tpc > 0 ? (int)blockIdx.x * tpc : (int)blockIdx.x;
     const int step = tpc > 0 ? 1 : (int)gridDim.x;
     const int my_tiles = tpc > 0 ? min(tpc, ntiles - first) : (ntiles - first + step - 1) / step;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int g = 0; g < WIN_MAX; ++g) { s_gmin[g] = W.gmin[g]; s_gspan[g] = W.gspan[g]; s_goff[g] = W.goff[g]; }
+    }
+    for (int k = tid; k < min(my_tiles, DCACHE); k += THREADS + 32) { const int4 q = __ldg(desc + first + (size_t)k * step); s_desc[k] = make_int2(q.x, q.y); }
+    __syncthreads();
+    for (int k = tid; k < npent; k += THREADS + 32) {        // (window, offset) -> slot in the x area
+        DictEnt d = pent[k];
+        d.delta = s_goff[d.delta >> WIN_GSHIFT] + (d.delta & ((1 << WIN_GSHIFT) - 1));
+        spent[k] = d;
+    }
+    for (int k = tid; k < 256; k += THREADS + 32) sphead[k] = phead[k];
+    __syncthreads();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (tid >= THREADS) {                                   // ---- producer warp (one lane works)
         if (tid == THREADS) {
             uint64_t pol;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-            // slice of group g for tile d: x[lo, hi), landing (lo - start) doubles into the group's area (start may be < 0 on the first tiles)
+            const int ng = W.ng;
+            // slice of window g for tile d: x[lo, hi), landing (lo - start) doubles into the window's area (start < 0 on the first tiles)
             auto slice = [&](const int4& d, int g, int& lo, int& hi, int& start) {
-                start = d.x + G.gmin[g];
-                const int len = (d.y + G.gspan[g] + 1) & ~1;
+                start = d.x + s_gmin[g];
+                const int len = (d.y + s_gspan[g] + 1) & ~1;
                 lo = max(start, 0);
-                hi = min(start + len, G.xlen);
+                hi = min(start + len, W.xlen);
             };
             auto issue_matrix = [&](int i, const int4& d) {                          // d = {row0, nrows, -, -}
                 const int s = i % STAGES;
                 unsigned char* st = stage0 + (size_t)s * stage_bytes;
-                *reinterpret_cast<int4*>(st) = d;
+                *reinterpret_cast<int4*>(st) = d;                                    // published by the arrive below (release)
                 const uint32_t b_code = (uint32_t)((d.y + 15) & ~15), b_op = (uint32_t)((d.y + 1) & ~1) * 8u, b_iop = (uint32_t)((d.y + 3) & ~3) * 4u;
                 uint32_t b_x = 0;
-                for (int g = 0; g < G.ng; ++g) { int lo, hi, st0; slice(d, g, lo, hi, st0); if (hi > lo) b_x += (uint32_t)(hi - lo) * 8u; }
-                mbar_expect_tx(full + s, b_code + (uint32_t)Epi::NOPS * b_op + (uint32_t)NIOPS * b_iop + b_x);
+                for (int g = 0; g < ng; ++g) { int lo, hi, st0; slice(d, g, lo, hi, st0); if (hi > lo) b_x += (uint32_t)(hi - lo) * 8u; }
+                mbar_expect_tx(full + s, b_code + (uint32_t)nops * b_op + (uint32_t)NIOPS * b_iop + b_x);
                 bulk_g2s_hint(st + Cfg::HDR_BYTES, rcodes + d.x, b_code, full + s, pol);
             };
             auto issue_operands = [&](int i, const int4& d) {                        // everything the predecessor may have written
@@ -755,26 +816,46 @@ k_rowstream_sx(const unsigned char* __restrict__ rcodes, const DictEnt* __restri
                 unsigned char* st = stage0 + (size_t)s * stage_bytes;
                 unsigned char* p = st + Cfg::HDR_BYTES + Cfg::CODE_BYTES;
 #pragma unroll
-                for (int j = 0; j < Epi::NOPS; ++j) { bulk_g2s(p, epi.operand(j) + d.x, b_op, full + s); p += Cfg::OP_BYTES; }
+                for (int j = 0; j < Epi::NOPS; ++j) {
+                    if (alias && j == XOP) continue;
+                    bulk_g2s(p, epi.operand(j) + d.x, b_op, full + s); p += Cfg::OP_BYTES;
+                }
                 if constexpr (NIOPS > 0) bulk_g2s(p, epi.ioperand() + d.x, b_iop, full + s);
-                for (int g = 0; g < G.ng; ++g) {
+                for (int g = 0; g < ng; ++g) {
                     int lo, hi, st0;
                     slice(d, g, lo, hi, st0);
-                    if (hi > lo) bulk_g2s(st + Cfg::X_OFF + (size_t)g * Cfg::SL_BYTES + (size_t)(lo - st0) * 8, x + lo, (uint32_t)(hi - lo) * 8u, full + s);
+                    if (hi > lo) bulk_g2s(st + x_off + ((size_t)s_goff[g] + (size_t)(lo - st0)) * 8, x + lo, (uint32_t)(hi - lo) * 8u, full + s);
                 }
             };
-            int4 dpre[STAGES];
+            auto tile_desc = [&](int i) {
+                if (i < DCACHE) { const int2 q = s_desc[i]; return make_int4(q.x, q.y, 0, 0); }
+                return __ldg(desc + first + (size_t)i * step);
+            };
+            // L2 prefetch of what a tile streams from DRAM for the first time: codes, operand slices, the window of the largest offsets
+            auto prefetch = [&](int i) {
+                if (i >= my_tiles) return;
+                const int4 d = tile_desc(i);
+                const uint32_t b_code = (uint32_t)((d.y + 15) & ~15), b_op = (uint32_t)((d.y + 1) & ~1) * 8u, b_iop = (uint32_t)((d.y + 3) & ~3) * 4u;
+                bulk_prefetch_l2(rcodes + d.x, b_code);
+#pragma unroll
+                for (int j = 0; j < Epi::NOPS; ++j) {
+                    if (alias && j == XOP) continue;
+                    bulk_prefetch_l2(epi.operand(j) + d.x, b_op);
+                }
+                if constexpr (NIOPS > 0) bulk_prefetch_l2(epi.ioperand() + d.x, b_iop);
+                int lo, hi, st0;
+                slice(d, ng - 1, lo, hi, st0);
+                if (hi > lo) bulk_prefetch_l2(x + lo, (uint32_t)(hi - lo) * 8u);
+            };
             const int npre = my_tiles < STAGES ? my_tiles : STAGES;
-            for (int i = 0; i < npre; ++i) dpre[i] = __ldg(desc + first + (size_t)i * step);
-            int4 dn = make_int4(0, 0, 0, 0);
-            if (npre < my_tiles) dn = __ldg(desc + first + (size_t)npre * step);
-            for (int i = 0; i < npre; ++i) issue_matrix(i, dpre[i]);
+            for (int i = 0; i < npre; ++i) issue_matrix(i, tile_desc(i));
             asm volatile("griddepcontrol.wait;" ::: "memory");
-            for (int i = 0; i < npre; ++i) issue_operands(i, dpre[i]);
+            for (int i = 0; i < npre; ++i) issue_operands(i, tile_desc(i));
+            for (int i = npre; i < npre + pf; ++i) prefetch(i);
             for (int i = npre; i < my_tiles; ++i) {
                 const int s = i % STAGES;
-                const int4 d = dn;
-                if (i + 1 < my_tiles) dn = __ldg(desc + first + (size_t)(i + 1) * step);
+                const int4 d = tile_desc(i);
+                if (pf > 0) prefetch(i + pf);
                 mbar_wait(empty + s, (uint32_t)((i / STAGES - 1) & 1));
                 issue_matrix(i, d);
                 issue_operands(i, d);
@@ -786,38 +867,92 @@ k_rowstream_sx(const unsigned char* __restrict__ rcodes, const DictEnt* __restri
 
     for (int i = 0; i < my_tiles; ++i) {                     // ---- consumers: thread per row, x from shared memory
         const int s = i % STAGES;
-        mbar_wait(full + s, (uint32_t)((i / STAGES) & 1));
+        mbar_wait_light(full + s, (uint32_t)((i / STAGES) & 1));
         const unsigned char* st = stage0 + (size_t)s * stage_bytes;
-        const int4 d = *reinterpret_cast<const int4*>(st);
+        const int nrows = reinterpret_cast<const int4*>(st)->y, row0 = reinterpret_cast<const int4*>(st)->x;
         const unsigned char* scodes = st + Cfg::HDR_BYTES;
         const double* sops = reinterpret_cast<const double*>(st + Cfg::HDR_BYTES + Cfg::CODE_BYTES);
-        const double* xs = reinterpret_cast<const double*>(st + Cfg::X_OFF);
+        const double* xs = reinterpret_cast<const double*>(st + x_off);
 #pragma unroll
-        for (int j = 0; j < RPT; ++j) {
-            const int r = tid + j * THREADS;
-            if (r < d.y) {
-                const int2 ph = sphead[scodes[r]];
-                const DictEnt* pe = spent + ph.x;
-                double o[Epi::NOPS > 0 ? Epi::NOPS : 1];
+        for (int jb = 0; jb < RPT; jb += RB) {
+            int code[RB];
+            bool allhot = HOTN > 0;
 #pragma unroll
-                for (int q = 0; q < Epi::NOPS; ++q) o[q] = sops[q * Cfg::ROWCAP + r];
-                double sum = 0.0;                            // one accumulator, stored order
-                for (int e0 = 0; e0 < ph.y; e0 += JW) {      // (patterns are padded to multiples of 8 entries: no clamp needed)
-                    double xw[JW], vw[JW];
+            for (int j = 0; j < RB; ++j) {
+                const int r = tid + (jb + j) * THREADS;
+                code[j] = r < nrows ? (int)scodes[r] : -2;
+                allhot = allhot && code[j] == W.hot;
+            }
+            if (HOTN > 0 && __all_sync(0xffffffffu, allhot)) {
+                // ---- every row of this warp carries the hot pattern: straight-line body, constants from the parameter bank
+                double xv[RB][HOTN > 0 ? HOTN : 1];
 #pragma unroll
-                    for (int e = 0; e < JW; ++e) { const DictEnt de = pe[e0 + e]; vw[e] = de.val; xw[e] = xs[de.delta + r]; }
+                for (int j = 0; j < RB; ++j) {
+                    const double* xr = xs + tid + (jb + j) * THREADS;
 #pragma unroll
-                    for (int e = 0; e < JW; ++e)
-                        if (e0 + e < ph.y) sum = __dadd_rn(sum, __dmul_rn(vw[e], xw[e]));
+                    for (int e = 0; e < HOTN; ++e) xv[j][e] = xr[W.hs[e]];
                 }
-                if constexpr (NIOPS > 0) epi.store_i(d.x + r, sum, o, reinterpret_cast<const int32_t*>(sops + Epi::NOPS * Cfg::ROWCAP)[r]);
-                else epi.store(d.x + r, sum, o);
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                    const int r = tid + (jb + j) * THREADS;
+                    double o[Epi::NOPS > 0 ? Epi::NOPS : 1];
+                    {
+                        int q = 0;
+#pragma unroll
+                        for (int k = 0; k < Epi::NOPS; ++k) {
+                            if (alias && k == XOP) o[k] = xs[W.vslot + r];
+                            else { o[k] = sops[q * Cfg::ROWCAP + r]; ++q; }
+                        }
+                    }
+                    double sum = 0.0;                        // one accumulator, stored order
+#pragma unroll
+                    for (int e = 0; e < HOTN; ++e) sum = __dadd_rn(sum, __dmul_rn(W.hv[e], xv[j][e]));
+                    if constexpr (NIOPS > 0) epi.store_i(row0 + r, sum, o, reinterpret_cast<const int32_t*>(sops + nops * Cfg::ROWCAP)[r]);
+                    else epi.store(row0 + r, sum, o);
+                }
+            } else {
+                // ---- table path: the row's entries (value, slot) come from the pattern table in shared memory
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                    const int r = tid + (jb + j) * THREADS;
+                    if (code[j] < 0) continue;
+                    double o[Epi::NOPS > 0 ? Epi::NOPS : 1];
+                    {
+                        int q = 0;
+#pragma unroll
+                        for (int k = 0; k < Epi::NOPS; ++k) {
+                            if (alias && k == XOP) o[k] = xs[W.vslot + r];
+                            else { o[k] = sops[q * Cfg::ROWCAP + r]; ++q; }
+                        }
+                    }
+                    const int2 ph = sphead[code[j]];
+                    const DictEnt* pe = spent + ph.x;
+                    const double* xr = xs + r;
+                    double sum = 0.0;                        // one accumulator, stored order
+                    int e = 0;
+                    for (; e + 2 <= ph.y; e += 2) {
+                        const DictEnt d0 = pe[e], d1 = pe[e + 1];
+                        const double x0 = xr[d0.delta], x1 = xr[d1.delta];
+                        sum = __dadd_rn(sum, __dmul_rn(d0.val, x0));
+                        sum = __dadd_rn(sum, __dmul_rn(d1.val, x1));
+                    }
+                    if (e < ph.y) { const DictEnt d0 = pe[e]; sum = __dadd_rn(sum, __dmul_rn(d0.val, xr[d0.delta])); }
+                    if constexpr (NIOPS > 0) epi.store_i(row0 + r, sum, o, reinterpret_cast<const int32_t*>(sops + nops * Cfg::ROWCAP)[r]);
+                    else epi.store(row0 + r, sum, o);
+                }
             }
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(empty + s);
     }
 }
+
+// the most frequent ("hot") row pattern of a pattern-coded operator, found from a sample of the codes at set-up
+struct HotPlan {
+    int hot, hotlen;                     // pattern number and length
+    int hd[WIN_HOT];                     // its column offsets (col - row) ...
+    double hv[WIN_HOT];                  // ... and values
+};
 
 // ---- sub-warp family --------------------------------------------------------------------------------
 // LPR lanes cooperate on one row (LPR = 32: warp per row), partial sums combined with a shuffle tree.

@@ -16,8 +16,9 @@ struct Coded {
     DictEnt* dict = nullptr;         // device, 256 entries (mode 3: npent pattern entries)
     int2* phead = nullptr;           // mode 3: device, 256 x {first entry, length}
     int npent = 0;                   // mode 3: entries in the pattern table (multiple of 8)
-    DictEnt* dict_sx = nullptr;      // mode 3, option "stage_x" (experimental): the pattern table again, with the slot of each entry's x
-    SxGroups sx{};                   // value in the stage's staged-x area instead of (col - row); sx.ng == 0: not available
+    DictEnt* dict_win = nullptr;     // mode 3, row-window kernel (k_rowwin): the pattern table again, every entry's offset expressed as
+    WinPlan win{};                   // (window << WIN_GSHIFT) | (offset - window minimum); win.ng == 0: not available
+    HotPlan hotplan{};               // mode 3: the most frequent pattern (handed to the row-window kernel as kernel parameters)
     int ndict = 0;                   // entries (mode 3: patterns) in use
     int nvals = 0, ndeltas = 0;      // distinct values / distinct (col - row) found
 };
@@ -26,6 +27,7 @@ struct DevCsr {
     int64_t nrows = 0, ncols = 0, nnz = 0;
     Coded cd;
     int ccfg = 0;            // row-stream kernel configuration (code_choice) when cd.mode != 0
+    int wcfg = 0;            // > 0: row-window kernel configuration (win_choice): x staged in shared memory
     int32_t* rowptr = nullptr;
     int32_t* cols = nullptr;
     double* vals = nullptr;
@@ -149,7 +151,10 @@ struct mgb_handle {
     int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
     int compress = 2;              // lossless coding of repetitive operators (mgb_code.cuh): 0 off, 1 per-entry codes, 2 + row patterns
     int code_cfg = 1;              // row-stream kernel configuration for coded operators (code_choice)
-    int stage_x = 0;               // EXPERIMENTAL, unmeasured: x staged in shared memory by TMA for row-pattern-coded operators (k_rowstream_sx)
+    int stage_x = 1;               // row-pattern-coded operators: 1 x staged in shared memory by bulk copies (k_rowwin); 0 bulk-copied codes /
+                                   // operands + x gathered through L1 (k_rowstream)
+    int win_cfg = 1;               // row-window kernel configuration (win_choice)
+    int win_prefetch = 0;          // row-window kernel: tiles (per CTA) whose DRAM streams are prefetched into L2 ahead of the copies
     bool allow_stream = true;      // false while borrowed user pointers are in play (no padding / alignment guarantee)
     int coarsest = 0, finest = 0;
     double* coarse_inv = nullptr;
