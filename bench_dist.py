@@ -1,7 +1,10 @@
-"""bench.py's multi-GPU arm: one process per GPU (torchrun), row-sharded V-cycles, strong scaling.
+"""bench.py's arm for device-generated hierarchies: one process per GPU (torchrun for N > 1), row-sharded V-cycles, strong
+scaling; N = 1 runs the same code on the whole problem (world = 1).
 
 Timing: W warm-up cycles, barrier + synchronize, K cycles bracketed by CUDA events on every rank's engine
-stream, MAX over ranks; value = global smoother DOF-updates of K cycles / that time."""
+stream, MAX over ranks; value = global smoother DOF-updates of K cycles / that time.
+Parity: the residual norms of 3 cycles from a zero guess are compared with the CPU oracle on the same hierarchy (N = 1, unless
+--no-cpu) or with the committed single-GPU values (profiles/expected_resnorms.json); the run exits non-zero beyond 1e-12."""
 from __future__ import annotations
 
 import json
@@ -55,14 +58,16 @@ def run(args):
     else:
         src = ds.StructuredSource(dim, c, lc, lf)
     mg = ds.DistMG(src, device=local_rank, r_mode=args.restriction, smoother=args.smoother, gather_threshold=args.gather_threshold,
-                   options={"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg, "use_graph": args.use_graph,
-                            "overlap_halo": args.overlap, "overlap_waves": args.overlap_waves,
-                            "compress": getattr(args, "compress", 2), "code_cfg": getattr(args, "code_cfg", 1)},
+                   options={**{"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg, "use_graph": args.use_graph,
+                               "overlap_halo": args.overlap, "overlap_waves": args.overlap_waves,
+                               "compress": getattr(args, "compress", 2), "code_cfg": getattr(args, "code_cfg", 1)}, **args.options},
                    device_gen=bool(args.device_gen) and args.restriction == "injection", p2p=bool(args.p2p))
     setup_s = time.perf_counter() - t0
     eng = mg.eng
     stream = eng.torch_stream()
     dofu = mg.dof_updates_per_cycle()
+    mg.load_rhs()
+    hist3 = [float(x) for x in mg.cycles(3, history=True)]        # parity: 3 cycles from a zero guess, ||f - A v||_2 after each
     mg.load_rhs()
     mg.cycles(args.warmup)
     eng.synchronize(); barrier(); torch.cuda.synchronize()
@@ -78,7 +83,6 @@ def run(args):
         ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)      # identical on every rank (the cycles are collective)
         if ms * args.steps < 1000.0:         # ~1 s under load for the clock sampler
             mg.cycles(int(min(2000, max(1, (1000.0 - ms * args.steps) / max(ms, 1e-3))))); torch.cuda.synchronize()
-    hist = mg.cycles(1, history=True)
 
     # dominant kernel on rank 0, event-timed (all ranks run the same cycles: the halo exchanges are collective)
     ncyc = max(3, min(args.steps, 5))
@@ -97,6 +101,21 @@ def run(args):
         eng._ck(lib.mgb_vcycle(h, lf, vp.data_ptr(), fp.data_ptr(), 0, 1, None))
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t1) / e2e_steps)
+    # ---- CPU baseline (N = 1 only, rank 0): the C/OpenMP port on the SAME hierarchy, also the parity reference ----------------
+    cpu, expected, esrc = None, B.expected_from_file(name), f"profiles/expected_resnorms.json ({name}, single-GPU run)"
+    if rank == 0 and not multi and not args.no_cpu and name in B.STRUCTURED:
+        cm, f, dofu_cpu, threads, note = B.cpu_oracle(name)
+        if cm is None:
+            cpu = {"value": None, "unit": B.UNIT, "cores": threads, "kind": "port", "sample": f"not run: {note}"}
+        else:
+            cyc = 2 if name == "cfg5" else 5
+            per = B.time_cpu(cm, f, cyc, 1)
+            _, hist_cpu = cm.vcycle(np.zeros_like(f), f, ncycles=3, history=True)
+            cpu = {"value": dofu_cpu / per, "unit": B.UNIT, "cores": threads, "kind": "port", "ms_per_cycle": per * 1e3,
+                   "sample": f"{cyc} full V-cycles of {name} after one warm-up ({note}), C/OpenMP port of the reference, {threads} threads of {os.cpu_count()} cores"}
+            expected, esrc = [float(x) for x in hist_cpu], "CPU oracle (oracle/mg_oracle.c) on the same hierarchy, 3 cycles from a zero guess"
+            cm.close()
+    parity = B.parity_block(hist3, expected, esrc)
     if rank == 0:
         peak, peak_src = B.measured_peak()
         comp = [r for r in prof if r["kind"] not in ("halo",)]
@@ -109,21 +128,24 @@ def run(args):
                 "config": {"workload": f"{name}: {desc}", "restriction": args.restriction, "smoother": args.smoother, "fine_dofs": n_glob,
                            "levels": lf - lc + 1, "mu1": src.mu1, "mu2": src.mu2, "generated_on_device": bool(mg.device_gen), "compress": getattr(args, "compress", 2),
                            "parallelism": f"row-sharded x{world}, levels <= {mg.gather_level} on rank 0" if multi else "single GPU",
-                           "l2": "per-rank fine-level operators exceed the 126 MB L2" if n_glob / world > 2e6 else "fine level partly L2-resident", "setup_s": setup_s},
-                "fine_dof_cycles_per_s": n_glob / (ms * 1e-3), "resnorm_after": float(hist[0]),
-                "roofline": {"bound": "hbm", "kernel": f"{dom['kind']}@level{dom['level']} (rank 0 shard)", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-                             "frac": dom["gbs"] / peak, "frac_of_8TBs": dom["gbs"] / 8000.0, "traffic": None, "peak_source": peak_src,
-                             "bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms_per_launch"],
-                             "moved_bytes_per_launch": dom["moved_bytes"], "moved_achieved": dom["moved_gbs"], "moved_frac": dom["moved_gbs"] / peak},
+                           "options": args.options,
+                           "l2": ("per-rank working set of one fine-level sweep (codes + 3 vectors, %.0f MB) " % (25.0 * n_glob / world / 1e6)) +
+                                 ("exceeds the 126 MB L2: no flush needed" if 25.0 * n_glob / world > 126e6 else "fits the 126 MB L2 (stated, not flushed)"),
+                           "setup_s": setup_s},
+                "fine_dof_cycles_per_s": n_glob / (ms * 1e-3), "parity": parity,
+                "roofline": B.roofline_block(dom, peak, peak_src, name if not multi else f"{name}-n{world}", prof,
+                                             {"kernel": f"{dom['kind']}@level{dom['level']}" + (" (rank 0 shard)" if multi else "")}),
                 "halo_ms_per_cycle_rank0": halo_ms, "profiled_cycle_ms_rank0": tot_ms,
-                "cpu_baseline": None,
+                "cpu_baseline": cpu,
                 "e2e": {"value": dofu / e2e_s, "unit": B.UNIT, "h2d_bytes_per_step": 16 * n_glob, "d2h_bytes_per_step": 8 * n_glob, "ms_per_step": e2e_s * 1e3,
                         "api": "mgb_vcycle(mem=MGB_MEM_HOST) on every rank's row block, pinned host buffers"},
                 "gpu_launches": int(launches), "clocks": clk.summary(),
-                "kernels": [{"k": f"{r['kind']}@{r['level']}", "ms": round(r["ms_per_launch"], 5), "n": r["launches"], "gbs": round(r["gbs"], 1), "moved_gbs": round(r["moved_gbs"], 1)}
+                "kernels": [{"k": f"{r['kind']}@{r['level']}", "ms": round(r["ms_per_launch"], 5), "n": r["launches"], "gbs": round(r["moved_gbs"], 1), "algorithmic_gbs": round(r["gbs"], 1)}
                             for r in sorted(prof, key=lambda r: -r["total_ms"])[:10]]}
         print(json.dumps(line), flush=True)
     barrier()
     mg.close()
     if multi:
         td.destroy_process_group()
+    if parity["ok"] is False:
+        raise SystemExit(f"parity FAILED: residual norms differ from the expected ones by {parity['rel']:.3e} relative (> {B.PARITY_TOL})")

@@ -213,6 +213,12 @@ int mgb_set_mass_matrix(mgb_handle* h, int level, int64_t n, int64_t nnz, const 
  * v_out (nullable) receives the finest-level solution; resnorm_hist[0..min(cycles, hist_capacity)) the norms. */
 int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, int mem, int* cycles_done,
             double* resnorm_hist, int hist_capacity);
+/* optional nodal vector of the exact solution on the finest level: mgb_fmg then also records, after EVERY finest-level cycle,
+ * the norm of (v - u_exact) in the same norm as the residual -- the reference's error_per_V_cycle_finest list
+ * (err_calculator, multigrid.py:213-218, appended per cycle at multigrid.py:292-293).  mgb_fmg_error_history returns the
+ * list of the last mgb_fmg run (count = number of finest-level cycles, 0 when no exact solution was set). */
+int mgb_set_exact_solution(mgb_handle* h, int level, const double* u_exact, int mem);
+int mgb_fmg_error_history(mgb_handle* h, double* errnorm_hist, int capacity, int* count);
 
 /* ---- per-operator entry points (parity tests, profiling) -------------------------------------- */
 int mgb_spmv(mgb_handle* h, int level, const double* x, double* y, int mem);                       /* A.dot(x), multigrid.py:244 */

@@ -926,7 +926,7 @@ int mgb_destroy(mgb_handle* h)
     drop_graphs(h);
     for (auto& kv : h->levels) {
         Level& L = kv.second;
-        free_csr(L.A); free_csr(L.RJ); free_csr(L.P); free_csr(L.R); free_csr(L.G); free_csr(L.M); cudaFree(L.b);
+        free_csr(L.A); free_csr(L.RJ); free_csr(L.P); free_csr(L.R); free_csr(L.G); free_csr(L.M); cudaFree(L.b); cudaFree(L.uex);
         cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.cmap); cudaFree(L.inj_desc); cudaFree(L.send_idx); cudaFree(L.send_buf); cudaFree(L.p2p_counters);
         for (void* q : L.p2p_opened) cudaIpcCloseMemHandle(q);
         cudaFree(L.p2p_arena); cudaFree(L.v); cudaFree(L.vtmp); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
@@ -1482,7 +1482,9 @@ int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, i
     CU(cudaMemcpyAsync(C0.f, C0.b, sizeof(double) * (size_t)C0.n, cudaMemcpyDeviceToDevice, h->stream));
     TRY(coarse_apply(h, C0, C0.f, C0.v));                                         // multigrid.py:274-277
     int done = 0;
+    h->fmg_err.clear();
     TRY(ensure_hist(h, 2));
+    CU(cudaMemsetAsync(h->d_hist, 0, 2 * sizeof(double), h->stream));
     for (int l = h->coarsest + 1; l <= h->finest; ++l) {
         Level& L = h->levels[l];
         Level& C = h->levels[l - 1];
@@ -1496,20 +1498,31 @@ int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, i
         while (done < max_cycles) {                                               // multigrid.py:288-302 (with a cap)
             TRY(run_cycle(h, l));
             ++done;
+            // norm of L.r into d_hist[slot]: sqrt(r^T M r) with a mass matrix (multigrid.py:203-208), else the l2 norm
+            auto norm_of_r = [&](int slot) -> int {
+                if (L.M.present()) {
+                    EpiStore epi{L.vtmp};
+                    TRY(row_sums(h, MGB_K_SPMV, l, bytes_rowsum(L.M, 2.0 * (double)L.n), L.M, L.r, epi));
+                    return launch(h, MGB_K_NORM, l, 16.0 * (double)L.n, [&] {
+                        k_dot_partial<<<h->norm_blocks, 256, 0, h->stream>>>(L.n, L.r, L.vtmp, h->d_partial);
+                        k_sumsq_final<<<1, 1024, 0, h->stream>>>(h->norm_blocks, h->d_partial, h->d_hist + slot, 1);
+                    });
+                }
+                return norm2_device(h, L.n, L.r, h->d_hist + slot, l);
+            };
             TRY(residual(h, L, L.v, L.f, L.r));                                   // multigrid.py:291
-            if (L.M.present()) {
-                EpiStore epi{L.vtmp};
-                TRY(row_sums(h, MGB_K_SPMV, l, bytes_rowsum(L.M, 2.0 * (double)L.n), L.M, L.r, epi));
-                TRY(launch(h, MGB_K_NORM, l, 16.0 * (double)L.n, [&] {
-                    k_dot_partial<<<h->norm_blocks, 256, 0, h->stream>>>(L.n, L.r, L.vtmp, h->d_partial);
-                    k_sumsq_final<<<1, 1024, 0, h->stream>>>(h->norm_blocks, h->d_partial, h->d_hist, 1);
+            TRY(norm_of_r(0));
+            if (L.uex) {                                                          // multigrid.py:292-293: the error, every cycle
+                TRY(launch(h, MGB_K_NORM, l, 24.0 * (double)L.n, [&] {
+                    k_diff<<<(int)((L.n + 255) / 256), 256, 0, h->stream>>>(L.n, L.v, L.uex, L.r);
                 }));
-            } else {
-                TRY(norm2_device(h, L.n, L.r, h->d_hist, l));
+                TRY(norm_of_r(1));
             }
-            double nrm = 0.0;
-            CU(cudaMemcpyAsync(&nrm, h->d_hist, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            double nrm2[2] = {0.0, 0.0};
+            CU(cudaMemcpyAsync(nrm2, h->d_hist, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             CU(cudaStreamSynchronize(h->stream));
+            const double nrm = nrm2[0];
+            if (L.uex) h->fmg_err.push_back(nrm2[1]);
             if (resnorm_hist && done <= hist_capacity) resnorm_hist[done - 1] = nrm;
             if (nrm <= tol) break;                                                // multigrid.py:296
         }
@@ -1519,6 +1532,25 @@ int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, i
         TRY(copy_out(h, v_out, T->v, T->n, mem));
         if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream));
     }
+    return MGB_OK;
+}
+
+int mgb_set_exact_solution(mgb_handle* h, int level, const double* u_exact, int mem)
+{
+    Level* L = nullptr;
+    TRY(check_ready(h, level, &L));
+    if (!u_exact) { cudaFree(L->uex); L->uex = nullptr; return MGB_OK; }      // (null: forget it)
+    if (!L->uex) TRY(dev_alloc(h, &L->uex, (size_t)L->n + 16));
+    TRY(copy_in(h, L->uex, u_exact, L->n, mem));
+    if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream));
+    return MGB_OK;
+}
+
+int mgb_fmg_error_history(mgb_handle* h, double* errnorm_hist, int capacity, int* count)
+{
+    if (!h || !count) return MGB_ERR_INVALID;
+    *count = (int)h->fmg_err.size();
+    if (errnorm_hist) for (int i = 0; i < *count && i < capacity; ++i) errnorm_hist[i] = h->fmg_err[(size_t)i];
     return MGB_OK;
 }
 

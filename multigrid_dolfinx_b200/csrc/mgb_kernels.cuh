@@ -1121,8 +1121,14 @@ __global__ void k_sumsq_final(int nb, const double* __restrict__ partial, double
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
-        *out = take_root ? sqrt(t) : t;
+        *out = take_root ? sqrt(fmax(t, 0.0)) : t;          // (r^T M r can round below zero for a tiny r: never a NaN norm)
     }
+}
+// d = a - b   (error of the iterate against the exact solution, err_calculator multigrid.py:213-218)
+__global__ void k_diff(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ d)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = __dsub_rn(a[i], b[i]);
 }
 
 // level-scheduled forward Gauss-Seidel: one cooperative launch per sweep, grid-wide barrier between

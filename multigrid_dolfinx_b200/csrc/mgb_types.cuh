@@ -117,6 +117,7 @@ struct Level {
     double *v = nullptr, *vtmp = nullptr, *f = nullptr, *r = nullptr, *g = nullptr;
     double* b = nullptr;             // re-discretised right-hand side b_dict[l] (FMG, multigrid.py:279)
     DevCsr M;                        // optional mass matrix for the L2(Omega) norm of the FMG stopping rule
+    double* uex = nullptr;           // optional exact solution (nodal values): per-cycle error norms of the FMG driver
     // Gauss-Seidel artefacts (host copies are what mgb_get_artifact returns)
     std::vector<int32_t> lev_of_row, lev_order, lev_off, col_of_row, col_order, col_off;
     int32_t* gs_order = nullptr;     // device: execution order actually used by G
@@ -164,6 +165,7 @@ struct mgb_handle {
     int norm_blocks = 0;
     std::map<int, cudaGraphExec_t> graphs;
     std::map<int, int64_t> graph_kernels;
+    std::vector<double> fmg_err;   // error norms of the last mgb_fmg run (one per finest-level cycle)
     bool prof = false;
     std::vector<ProfEvent> prof_events;
     std::map<std::pair<int, int>, mgb_profile_record> prof_records;

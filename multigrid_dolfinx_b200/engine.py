@@ -201,7 +201,9 @@ class MGEngine:
         return a.ctypes.data, a
 
     def _fence_in(self, *xs):
-        """Make the engine stream wait for torch's current stream when device tensors are passed."""
+        """Make the engine stream wait for torch's current stream when device tensors are passed.  Must be called AFTER all
+        torch-side marshalling (clone / contiguous / output allocation): the engine stream is non-blocking, so only work
+        enqueued on torch's stream BEFORE the event is recorded is ordered before the engine's kernels."""
         if any(_is_torch(x) for x in xs if x is not None):
             import torch
             ev = torch.cuda.Event()
@@ -229,7 +231,6 @@ class MGEngine:
         """ncycles x V_cycle_scheme (multigrid.py:231-268).  Inputs are not modified; returns the new
         iterate shaped like ``v`` (and the per-cycle residual norms if ``history``)."""
         n = self.n[level]
-        fence = self._fence_in(v, f)
         if _is_torch(v):
             vv = v.detach().clone().contiguous().view(-1)
             vp, mem, keep = vv.data_ptr(), L.MEM_DEVICE, vv
@@ -242,6 +243,7 @@ class MGEngine:
         if (vv.numel() if _is_torch(v) else vv.size) != n:
             raise ValueError(f"v: expected {n} entries")
         hist = np.zeros(ncycles) if history else None
+        fence = self._fence_in(v, f)
         self._ck(self._lib.mgb_vcycle(self._h, int(level), vp, fp, mem, int(ncycles), hist.ctypes.data if history else None))
         self._fence_out(fence)
         out = self._shape_like(vv, v)
@@ -267,6 +269,23 @@ class MGEngine:
         ip, ix, ax = _as_csr_arrays(M)
         self._ck(self._lib.mgb_set_mass_matrix(self._h, int(level), M.shape[0], len(ax), ip.ctypes.data, ip.dtype.itemsize,
                                                ix.ctypes.data, ax.ctypes.data))
+
+    def set_exact_solution(self, level, u):
+        """Nodal values of the exact solution: ``fmg`` then records the error norm after every finest-level cycle
+        (error_per_V_cycle_finest, multigrid.py:292-293).  ``None`` forgets it."""
+        if u is None:
+            self._ck(self._lib.mgb_set_exact_solution(self._h, int(level), None, L.MEM_HOST))
+            return
+        up, mem, keep = self._in(u, self.n[level], "u_exact")
+        self._ck(self._lib.mgb_set_exact_solution(self._h, int(level), up, mem))
+
+    def fmg_errors(self):
+        """Error norms of the last ``fmg`` run, one per finest-level cycle (empty without an exact solution)."""
+        cnt = C.c_int()
+        self._ck(self._lib.mgb_fmg_error_history(self._h, None, 0, C.byref(cnt)))
+        out = np.zeros(max(cnt.value, 1))
+        self._ck(self._lib.mgb_fmg_error_history(self._h, out.ctypes.data, len(out), C.byref(cnt)))
+        return out[:cnt.value]
 
     def fmg(self, mu0=2, tol=1e-11, max_cycles=10000):
         """-> (finest-level solution (n,), residual norms per finest-level cycle)."""
@@ -295,9 +314,9 @@ class MGEngine:
 
     # -- per-operator entry points ---------------------------------------------------------------------
     def _binary(self, fn, level, n_in, n_out, x, name):
-        fence = self._fence_in(x)
         xp, mem, keep = self._in(x, n_in, name)
         yp, y = self._out_like(x, n_out)
+        fence = self._fence_in(x)
         self._ck(fn(self._h, int(level), xp, yp, mem))
         self._fence_out(fence)
         return y
@@ -307,10 +326,10 @@ class MGEngine:
 
     def residual(self, level, v, f):
         n = self.n[level]
-        fence = self._fence_in(v, f)
         vp, mem, k1 = self._in(v, n, "v")
         fp, mem2, k2 = self._in(f, n, "f")
         rp, r = self._out_like(v, n)
+        fence = self._fence_in(v, f)
         self._ck(self._lib.mgb_residual(self._h, int(level), vp, fp, rp, mem))
         self._fence_out(fence)
         return self._shape_like(r, v)
@@ -318,12 +337,12 @@ class MGEngine:
     def smooth(self, level, v, f, nsweeps):
         """jacobiRelaxation (multigrid.py:223-228) or the selected Gauss-Seidel; inputs not modified."""
         n = self.n[level]
-        fence = self._fence_in(v, f)
         if _is_torch(v):
             vv = v.detach().clone().contiguous().view(-1); vp, mem = vv.data_ptr(), L.MEM_DEVICE
         else:
             vv = np.array(v, dtype=np.float64).reshape(-1).copy(); vp, mem = vv.ctypes.data, L.MEM_HOST
         fp, memf, keep = self._in(f, n, "f")
+        fence = self._fence_in(v, f)
         self._ck(self._lib.mgb_smooth(self._h, int(level), vp, fp, int(nsweeps), mem))
         self._fence_out(fence)
         return self._shape_like(vv, v)
@@ -334,12 +353,12 @@ class MGEngine:
 
     def prolong_add(self, fine_level, e, v):
         n, nc = self.n[fine_level], self.n[fine_level - 1]
-        fence = self._fence_in(e, v)
         if _is_torch(v):
             vv = v.detach().clone().contiguous().view(-1); vp, mem = vv.data_ptr(), L.MEM_DEVICE
         else:
             vv = np.array(v, dtype=np.float64).reshape(-1).copy(); vp, mem = vv.ctypes.data, L.MEM_HOST
         ep, meme, keep = self._in(e, nc, "e")
+        fence = self._fence_in(e, v)
         self._ck(self._lib.mgb_prolong_add(self._h, int(fine_level), ep, vp, mem))
         self._fence_out(fence)
         return self._shape_like(vv, v)
@@ -347,18 +366,18 @@ class MGEngine:
     def coarse_solve(self, f):
         lc = min(self.n)
         n = self.n[lc]
-        fence = self._fence_in(f)
         fp, mem, keep = self._in(f, n, "f")
         up, u = self._out_like(f, n)
+        fence = self._fence_in(f)
         self._ck(self._lib.mgb_coarse_solve(self._h, fp, up, mem))
         self._fence_out(fence)
         return self._shape_like(u, f)
 
     def norm2(self, x):
-        fence = self._fence_in(x)
         n = x.numel() if _is_torch(x) else np.asarray(x).size
         xp, mem, keep = self._in(x, n, "x")
         out = C.c_double()
+        fence = self._fence_in(x)
         self._ck(self._lib.mgb_norm2(self._h, n, xp, mem, C.byref(out)))
         return out.value
 

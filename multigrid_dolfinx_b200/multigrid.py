@@ -292,12 +292,28 @@ def FullMultiGrid(A_h, f_h):
         for l in range(coarsest_level, finest_level):
             eng.set_rhs(l, np.asarray(b_dict[l], dtype=np.float64).reshape(-1))
         eng.set_rhs(finest_level, np.asarray(f_h, dtype=np.float64).reshape(-1))
-        if hasattr(V_fine_dolfx, "dot") and hasattr(V_fine_dolfx, "indptr"):
-            eng.set_mass_matrix(finest_level, V_fine_dolfx)
-        v, hist = eng.fmg(mu0, 1E-11, max_fmg_cycles)
-        residual_per_V_cycle_finest.extend(float(x) for x in hist)
+        # the reference measures both norms with dolfinx (multigrid.py:203-218); here V_fine_dolfx is a CSR mass matrix
+        # (-> sqrt(r^T M r), the same L2(Omega) norm) or None (-> l2 norm), u_exact_fine a nodal vector or None.  Anything
+        # else (a live dolfinx FunctionSpace / Function) is refused BEFORE the solve instead of silently changing the norm
+        # the 1e-11 stopping rule is measured in.
+        if V_fine_dolfx is not None and not (hasattr(V_fine_dolfx, "dot") and hasattr(V_fine_dolfx, "indptr")):
+            raise TypeError("FullMultiGrid: V_fine_dolfx must be a scipy CSR mass matrix (L2(Omega) norm, multigrid.py:203-208) or None "
+                            f"(l2 norm); got {type(V_fine_dolfx).__name__}.  Export the mass matrix of the dolfinx FunctionSpace instead.")
+        u_ex = None
         if u_exact_fine is not None:
-            error_per_V_cycle_finest.append(err_calculator(v, u_exact_fine, V_fine_dolfx))
+            try:
+                u_ex = np.asarray(u_exact_fine, dtype=np.float64).reshape(-1)
+            except (TypeError, ValueError):
+                u_ex = None
+            if u_ex is None or u_ex.size != n:
+                raise TypeError(f"FullMultiGrid: u_exact_fine must be the nodal values of the exact solution ({n} entries) or None; "
+                                f"got {type(u_exact_fine).__name__}.  Pass u_exact.x.array of the dolfinx Function.")
+        if V_fine_dolfx is not None:
+            eng.set_mass_matrix(finest_level, V_fine_dolfx)
+        eng.set_exact_solution(finest_level, u_ex)
+        v, hist = eng.fmg(mu0, 1E-11, max_fmg_cycles)
+        residual_per_V_cycle_finest.extend(float(x) for x in hist)                 # multigrid.py:294-295, one entry per cycle
+        error_per_V_cycle_finest.extend(float(x) for x in eng.fmg_errors())        # multigrid.py:292-293, one entry per cycle
         with open(f'iter_count_for_diff_num_elems_{finest_level - coarsest_level + 1}_levels.csv', mode='a') as file1:
             csv.writer(file1, delimiter=',').writerow([coarsest_level_elements_per_dim * 2 ** finest_level, len(hist)])
         return v.reshape(n, 1)

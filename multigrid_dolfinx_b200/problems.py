@@ -415,8 +415,21 @@ class Hierarchy:
         return self.nodes_per_dim[l] ** self.dim
 
 
+def rcm_permutation(m, dim, seed):
+    """perm[lexicographic node] = dof for a banded-but-not-lexicographic numbering: the reverse Cuthill-McKee ordering
+    (scipy.sparse.csgraph) of a seeded random numbering of the P1 pattern.  The closest synthetic stand-in for the numbering
+    dolfinx itself produces (graph-reordered); neighbouring DOFs are close, whole rows do not repeat."""
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    n = (m + 1) ** dim
+    p = make_permutation(n, seed)
+    order = reverse_cuthill_mckee(stencil_p1(m, dim, p), symmetric_mode=True)      # order[k] = old dof placed at position k
+    inv = np.empty(n, dtype=np.int64)
+    inv[order] = np.arange(n, dtype=np.int64)
+    return inv[p]
+
+
 def build_hierarchy(dim=2, c=8, coarsest_level=0, finest_level=2, perm_seed=None, mu0=2, mu1=2, mu2=2,
-                    omega=2.0 / 3.0, with_dicts=None, with_rhs=True, assemble="stencil"):
+                    omega=2.0 / 3.0, with_dicts=None, with_rhs=True, assemble="stencil", rcm=False):
     """Build the level hierarchy the reference's driver would hand to ``initialize_problem``.
 
     cells per dimension at level l = c * 2**l (Multigrid_prototype.py:63).  ``perm_seed`` not None
@@ -432,6 +445,8 @@ def build_hierarchy(dim=2, c=8, coarsest_level=0, finest_level=2, perm_seed=None
         H.nodes_per_dim[l] = N
         H.element_size[l] = 1 / m
         perm = make_permutation(n, None if perm_seed is None else perm_seed + 1000 * l)
+        if rcm and perm_seed is not None:
+            perm = rcm_permutation(m, dim, perm_seed + 1000 * l)
         H.perms[l] = perm
         if assemble == "stencil":
             A = stencil_p1(m, dim, perm)

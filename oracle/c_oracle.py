@@ -50,6 +50,10 @@ def lib():
         L.orc_mg_finalize.argtypes = [C.c_void_p]; L.orc_mg_finalize.restype = C.c_int
         L.orc_mg_destroy.argtypes = [C.c_void_p]
         L.orc_mg_vcycle.argtypes = [C.c_void_p, C.c_int, f64p, f64p, C.c_int, C.c_void_p]
+        L.orc_set_threads.argtypes = [C.c_int]; L.orc_set_threads.restype = C.c_int
+        L.orc_mg_build_poisson.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]
+        L.orc_mg_build_poisson.restype = C.c_void_p
+        L.orc_mg_level_array.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]; L.orc_mg_level_array.restype = C.c_int64
         _LIB = L
     return _LIB
 
@@ -61,6 +65,59 @@ def _csr(A):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def set_threads(n=0):
+    """OpenMP threads of the C oracle: n > 0 sets them (``torchrun`` exports OMP_NUM_THREADS=1, which would otherwise
+    silently make the "all cores" baseline single-threaded); returns the number in effect."""
+    return int(lib().orc_set_threads(int(n)))
+
+
+class StructuredCOracleMG:
+    """The synthetic P1 Poisson hierarchy (lexicographic DOFs, injection) built INSIDE the C oracle by index arithmetic --
+    the same arrays as problems.stencil_p1 / prolongation / injection + the reference's getJacobiMatrices, but without a
+    scipy matrix ever existing, so that the 513^3 configuration (2.0e9 stored entries, ~50 GB) fits a host run."""
+    _KIND = {0: np.int64, 1: np.int32, 2: np.float64, 3: np.int64, 4: np.int32, 5: np.float64, 6: np.float64,
+             7: np.int64, 8: np.int32, 9: np.float64, 10: np.int32}
+
+    def __init__(self, dim, c, coarsest_level, finest_level, omega=2.0 / 3.0, mu1=2, mu2=2):
+        self.h = lib().orc_mg_build_poisson(int(dim), int(c), int(coarsest_level), int(finest_level), float(omega), int(mu1), int(mu2))
+        if not self.h:
+            raise RuntimeError("orc_mg_build_poisson failed")
+        self.dim, self.c, self.levels = dim, c, list(range(coarsest_level, finest_level + 1))
+        self.n = [(c * 2 ** l + 1) ** dim for l in self.levels]
+        self.mu1, self.mu2 = mu1, mu2
+
+    def array(self, k, what):
+        """Level k (0 = coarsest) array ``what`` (see orc_mg_level_array) as a numpy VIEW."""
+        p = C.c_void_p()
+        cnt = lib().orc_mg_level_array(self.h, int(k), int(what), C.byref(p))
+        if cnt <= 0 or not p.value:
+            return np.zeros(0, dtype=self._KIND[what])
+        dt = np.dtype(self._KIND[what])
+        buf = (C.c_char * (cnt * dt.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt, count=cnt)
+
+    def vcycle(self, v, f, ncycles=1, history=False):
+        v = np.ascontiguousarray(v, dtype=np.float64).ravel().copy()
+        f = np.ascontiguousarray(f, dtype=np.float64).ravel()
+        hist = np.zeros(ncycles) if history else None
+        lib().orc_mg_vcycle(self.h, len(self.n) - 1, v, f, ncycles, _ptr(hist))
+        return (v, hist) if history else v
+
+    def dof_updates_per_cycle(self):
+        return (self.mu1 + self.mu2) * sum(self.n[1:])
+
+    def close(self):
+        if self.h:
+            lib().orc_mg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def csr_matvec(A, x):

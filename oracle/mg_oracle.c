@@ -19,13 +19,16 @@
  * No reference text exists for Gauss-Seidel, level sets and colouring: those follow the
  * definitions in DESIGN.md.
  *
- * Pinning: tests/test_oracle_vs_reference.py + tests/golden/ (vectors produced by the reference
+ * Pinning: tests/test_oracle.py + tests/golden/ (vectors produced by the reference
  * itself in the development container).
  */
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 typedef int64_t i64;
 typedef int32_t i32;
@@ -240,6 +243,7 @@ typedef struct {
 
 typedef struct {
     int nlev;
+    int owns;              /* level arrays were allocated by orc_mg_build_poisson and are freed with the handle */
     orc_level *L;          /* L[0] = coarsest */
     double *lu; i32 *piv;  /* dense LU of coarsest A */
     double omega; int mu1, mu2;
@@ -290,7 +294,15 @@ int orc_mg_finalize(orc_mg *m)
 
 void orc_mg_destroy(orc_mg *m)
 {
-    for (int k = 0; k < m->nlev; ++k) { free(m->L[k].v); free(m->L[k].f); free(m->L[k].r); free(m->L[k].t); }
+    for (int k = 0; k < m->nlev; ++k) {
+        orc_level *L = &m->L[k];
+        free(L->v); free(L->f); free(L->r); free(L->t);
+        if (m->owns) {
+            free((void *)L->a_ip); free((void *)L->a_ix); free((void *)L->a_ax);
+            free((void *)L->r_ip); free((void *)L->r_ix); free((void *)L->r_ax); free((void *)L->dinv);
+            free((void *)L->p_ip); free((void *)L->p_ix); free((void *)L->p_ax); free((void *)L->inj);
+        }
+    }
     free(m->L); free(m->lu); free(m->piv); free(m);
 }
 
@@ -341,4 +353,178 @@ void orc_mg_vcycle(orc_mg *m, int top, double *v, const double *f, int ncycles, 
         }
     }
     memcpy(v, L->v, sizeof(double) * (size_t)L->n);
+}
+
+
+/* ---------------------------------------------------------------- threads (bench.py states how many were used) */
+int orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n; return 1;
+#endif
+}
+
+/* ---------------------------------------------------------------- structured P1 Poisson hierarchy, built in place
+ * The synthetic stand-in for Multigrid_prototype.py:62-118 at sizes no numpy/scipy build can hold (513^3: 2.0e9 stored
+ * entries): the SAME arrays as multigrid_dolfinx_b200/problems.py (stencil_p1, prolongation, injection; lexicographic
+ * DOFs) and as the reference's getJacobiMatrices (multigrid.py:48-56: off-diagonal NON-ZEROS of A scaled by fl(1/a_ii),
+ * rows left in descending column order by scipy's DIA x CSR product), generated row by row with OpenMP.
+ * tests/test_oracle.py compares every array bit for bit with those Python builders at small sizes. */
+typedef struct { int noff; i64 lin[27]; int o[27][3]; double w[27]; } orc_stencil;
+
+static void make_stencil(int dim, i64 N, double unit, orc_stencil *S)
+{
+    /* neighbour offsets of the cell-connectivity pattern ("/" mesh in 2-D, Kuhn mesh in 3-D): all components >= 0 or all <= 0;
+     * weight -unit for axis neighbours, stored 0.0 for the others; sorted by linear displacement */
+    S->noff = 0;
+    int lo[3] = {-1, -1, -1}, hi[3] = {1, 1, 1};
+    if (dim == 2) { lo[2] = hi[2] = 0; }
+    for (int c = lo[2]; c <= hi[2]; ++c)
+        for (int b = -1; b <= 1; ++b)
+            for (int a = -1; a <= 1; ++a) {
+                int allp = a >= 0 && b >= 0 && c >= 0, alln = a <= 0 && b <= 0 && c <= 0;
+                if (!allp && !alln) continue;
+                int nz = (a != 0) + (b != 0) + (c != 0);
+                int k = S->noff++;
+                S->o[k][0] = a; S->o[k][1] = b; S->o[k][2] = c;
+                S->lin[k] = a + N * b + N * N * c;
+                S->w[k] = nz == 1 ? -unit : 0.0;           /* (the centre is handled separately) */
+            }
+    /* the triple loop above already enumerates in ascending linear displacement (x fastest) */
+}
+
+static i64 *alloc_ptr(i64 n) { return (i64 *)malloc(sizeof(i64) * (size_t)(n + 1)); }
+
+static void prefix_counts(i64 n, i64 *ip)      /* ip[i+1] holds the count of row i on entry */
+{
+    ip[0] = 0;
+    for (i64 i = 0; i < n; ++i) ip[i + 1] += ip[i];
+}
+
+orc_mg *orc_mg_create(int nlev);
+void orc_mg_set_params(orc_mg *m, double omega, int mu1, int mu2, int smoother);
+int orc_mg_finalize(orc_mg *m);
+
+orc_mg *orc_mg_build_poisson(int dim, int c, int coarsest_level, int finest_level, double omega, int mu1, int mu2)
+{
+    if ((dim != 2 && dim != 3) || finest_level < coarsest_level) return NULL;
+    const int nlev = finest_level - coarsest_level + 1;
+    orc_mg *m = orc_mg_create(nlev);
+    m->owns = 1;
+    orc_mg_set_params(m, omega, mu1, mu2, 0);
+    for (int k = 0; k < nlev; ++k) {
+        const i64 cells = (i64)c << (coarsest_level + k), N = cells + 1;
+        i64 n = 1; for (int d = 0; d < dim; ++d) n *= N;
+        const double h = 1.0 / (double)cells, unit = dim == 2 ? 1.0 : h, diag_int = (dim == 2 ? 4.0 : 6.0) * unit;
+        orc_stencil S; make_stencil(dim, N, unit, &S);
+        orc_level *L = &m->L[k];
+        L->n = n;
+        /* ---- A (stored zeros kept, identity rows on the boundary) and R_omega, two passes: count, fill */
+        i64 *a_ip = alloc_ptr(n), *r_ip = alloc_ptr(n);
+        double *dinv = (double *)malloc(sizeof(double) * (size_t)n);
+#pragma omp parallel for schedule(static)
+        for (i64 i = 0; i < n; ++i) {
+            i64 t = i; int mi[3] = {0, 0, 0};
+            for (int d = 0; d < dim; ++d) { mi[d] = (int)(t % N); t /= N; }
+            int onb = 0; for (int d = 0; d < dim; ++d) onb |= (mi[d] == 0) | (mi[d] == N - 1);
+            i64 ca = 0, cr = 0;
+            for (int q = 0; q < S.noff; ++q) {
+                int ok = 1, nbb = 0;
+                for (int d = 0; d < dim; ++d) { int cc = mi[d] + S.o[q][d]; ok &= cc >= 0 && cc <= N - 1; nbb |= (cc <= 0) | (cc >= N - 1); }
+                if (!ok) continue;
+                ++ca;
+                if (S.lin[q] != 0 && !(onb || nbb) && S.w[q] != 0.0) ++cr;
+            }
+            a_ip[i + 1] = ca; r_ip[i + 1] = cr;
+        }
+        prefix_counts(n, a_ip); prefix_counts(n, r_ip);
+        i32 *a_ix = (i32 *)malloc(sizeof(i32) * (size_t)(a_ip[n] + 1)); double *a_ax = (double *)malloc(sizeof(double) * (size_t)(a_ip[n] + 1));
+        i32 *r_ix = (i32 *)malloc(sizeof(i32) * (size_t)(r_ip[n] + 1)); double *r_ax = (double *)malloc(sizeof(double) * (size_t)(r_ip[n] + 1));
+#pragma omp parallel for schedule(static)
+        for (i64 i = 0; i < n; ++i) {
+            i64 t = i; int mi[3] = {0, 0, 0};
+            for (int d = 0; d < dim; ++d) { mi[d] = (int)(t % N); t /= N; }
+            int onb = 0; for (int d = 0; d < dim; ++d) onb |= (mi[d] == 0) | (mi[d] == N - 1);
+            const double dii = onb ? 1.0 : diag_int, di = 1 / dii;
+            dinv[i] = di;
+            i64 ka = a_ip[i], kr = r_ip[i + 1];          /* R_omega rows are filled backwards: descending columns */
+            for (int q = 0; q < S.noff; ++q) {
+                int ok = 1, nbb = 0;
+                for (int d = 0; d < dim; ++d) { int cc = mi[d] + S.o[q][d]; ok &= cc >= 0 && cc <= N - 1; nbb |= (cc <= 0) | (cc >= N - 1); }
+                if (!ok) continue;
+                const double val = S.lin[q] == 0 ? dii : ((onb || nbb) ? 0.0 : S.w[q] + 0.0);
+                a_ix[ka] = (i32)(i + S.lin[q]); a_ax[ka] = val; ++ka;
+                if (S.lin[q] != 0 && val != 0.0) { --kr; r_ix[kr] = (i32)(i + S.lin[q]); r_ax[kr] = di * val; }
+            }
+        }
+        L->a_ip = a_ip; L->a_ix = a_ix; L->a_ax = a_ax; L->r_ip = r_ip; L->r_ix = r_ix; L->r_ax = r_ax; L->dinv = dinv;
+        L->v = (double *)malloc(sizeof(double) * (size_t)n); L->f = (double *)malloc(sizeof(double) * (size_t)n);
+        L->r = (double *)malloc(sizeof(double) * (size_t)n); L->t = (double *)malloc(sizeof(double) * (size_t)n);
+        if (k == 0) continue;
+        /* ---- P from level k-1 (multigrid.py:59-120, tensor-product extension in 3-D; entries in the reference's order:
+         * "-" before "+" with x fastest) and the injection list (multigrid.py:123-132) */
+        const i64 Nc = (N + 1) / 2;
+        i64 nc = 1; for (int d = 0; d < dim; ++d) nc *= Nc;
+        i64 *p_ip = alloc_ptr(n);
+#pragma omp parallel for schedule(static)
+        for (i64 i = 0; i < n; ++i) {
+            i64 t = i, cnt = 1;
+            for (int d = 0; d < dim; ++d) { if ((t % N) & 1) cnt *= 2; t /= N; }
+            p_ip[i + 1] = cnt;
+        }
+        prefix_counts(n, p_ip);
+        i32 *p_ix = (i32 *)malloc(sizeof(i32) * (size_t)(p_ip[n] + 1)); double *p_ax = (double *)malloc(sizeof(double) * (size_t)(p_ip[n] + 1));
+#pragma omp parallel for schedule(static)
+        for (i64 i = 0; i < n; ++i) {
+            i64 t = i; int mi[3] = {0, 0, 0};
+            for (int d = 0; d < dim; ++d) { mi[d] = (int)(t % N); t /= N; }
+            i64 kp = p_ip[i];
+            for (int comb = 0; comb < (1 << dim); ++comb) {
+                int valid = 1; double w = 1.0; i64 col = 0, stride = 1;
+                for (int d = 0; d < dim; ++d) {
+                    const int hi = (comb >> d) & 1, odd = mi[d] & 1;
+                    if (hi && !odd) valid = 0;
+                    w *= odd ? 0.5 : 1.0;
+                    col += (i64)(odd ? (mi[d] - 1) / 2 + hi : mi[d] / 2) * stride;
+                    stride *= Nc;
+                }
+                if (valid) { p_ix[kp] = (i32)col; p_ax[kp] = w; ++kp; }
+            }
+        }
+        i32 *inj = (i32 *)malloc(sizeof(i32) * (size_t)nc);
+#pragma omp parallel for schedule(static)
+        for (i64 i = 0; i < nc; ++i) {
+            i64 t = i, f = 0, stride = 1;
+            for (int d = 0; d < dim; ++d) { f += 2 * (t % Nc) * stride; t /= Nc; stride *= N; }
+            inj[i] = (i32)f;
+        }
+        L->p_ip = p_ip; L->p_ix = p_ix; L->p_ax = p_ax; L->inj = inj; L->nc = nc;
+    }
+    if (orc_mg_finalize(m) != 0) { orc_mg_destroy(m); return NULL; }
+    return m;
+}
+
+/* array of a level, for the bit-for-bit comparison with the Python builders: what = 0 A.indptr, 1 A.indices, 2 A.data,
+ * 3 RO.indptr, 4 RO.indices, 5 RO.data, 6 dinv, 7 P.indptr, 8 P.indices, 9 P.data, 10 inj; returns the element count */
+i64 orc_mg_level_array(orc_mg *m, int k, int what, const void **out)
+{
+    if (!m || k < 0 || k >= m->nlev) return -1;
+    orc_level *L = &m->L[k];
+    switch (what) {
+        case 0: *out = L->a_ip; return L->n + 1;
+        case 1: *out = L->a_ix; return L->a_ip[L->n];
+        case 2: *out = L->a_ax; return L->a_ip[L->n];
+        case 3: *out = L->r_ip; return L->n + 1;
+        case 4: *out = L->r_ix; return L->r_ip[L->n];
+        case 5: *out = L->r_ax; return L->r_ip[L->n];
+        case 6: *out = L->dinv; return L->n;
+        case 7: *out = L->p_ip; return L->p_ip ? L->n + 1 : 0;
+        case 8: *out = L->p_ix; return L->p_ip ? L->p_ip[L->n] : 0;
+        case 9: *out = L->p_ax; return L->p_ip ? L->p_ip[L->n] : 0;
+        case 10: *out = L->inj; return L->inj ? L->nc : 0;
+        default: return -1;
+    }
 }

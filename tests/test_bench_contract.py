@@ -74,7 +74,9 @@ def test_gpu_arm_json_assembly_with_a_stub_engine(monkeypatch, capsys):
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
     monkeypatch.setattr(E.MGEngine, "from_hierarchy", classmethod(lambda cls, H, **kw: Eng(H)))
     monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "cfg1", "--steps", "3", "--warmup", "3"])
-    bench.main()
+    import pytest
+    with pytest.raises(SystemExit, match="parity FAILED"):
+        bench.main()
     lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     r = json.loads(lines[0])
@@ -83,13 +85,37 @@ def test_gpu_arm_json_assembly_with_a_stub_engine(monkeypatch, capsys):
         assert k in r, k
     assert r["n_gpus"] == 1 and r["dtype"] == "f64" and r["vs_baseline"] is None and r["data"] == "synthetic" and "workload" in r["config"]
     rf = r["roofline"]
-    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "moved_bytes_per_launch", "moved_achieved", "moved_frac"):
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "bytes_per_launch", "algorithmic_bytes_per_launch", "algorithmic_gbs"):
         assert k in rf, k
+    # frac is a PHYSICAL fraction: bytes the kernel streams / time / measured peak (the CSR-form figure is algorithmic_gbs)
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
-    assert rf["kernel"] == "jacobi@level2" and rf["moved_bytes_per_launch"] == 1e8
+    assert rf["kernel"] == "jacobi@level2" and rf["bytes_per_launch"] == 1e8 and rf["achieved"] == 4e3 and rf["algorithmic_gbs"] == 1.2e4
+    # the stub's residual norms (all ones) cannot match the oracle's: the parity block must say so and the run must fail
     cb = r["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb and cb["unit"] == r["unit"]
     e = r["e2e"]
     n = r["config"]["fine_dofs"]
     assert e["h2d_bytes_per_step"] == 16 * n and e["d2h_bytes_per_step"] == 8 * n and e["unit"] == r["unit"] and e["value"] > 0
     assert r["gpu_launches"] == 37 * 3
+    p = r["parity"]
+    assert p["ok"] is False and p["rel"] > 1e-12 and len(p["resnorm"]) == 3 and len(p["expected"]) == 3 and p["tol"] == 1e-12
+
+
+def test_default_workload_is_config5_at_every_gpu_count():
+    """One workload across the driver's 1 -> 8 scaling run (N = 1 used to run config 2 and N > 1 config 5)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert 'args.workload = "cfg5"' in src and '"cfg2" if' not in src and "else \"cfg2\"" not in src
+    assert bench.WORKLOADS["cfg5"][:4] == (3, 8, 0, 6) and "cfg5" in bench.STRUCTURED
+
+
+def test_reference_arm_sets_the_thread_count_explicitly():
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm must still use the cores it reports."""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    import bench
+    assert r["cpu_baseline"]["cores"] == bench.cpu_threads() and f"omp_set_num_threads({bench.cpu_threads()})" in r["cpu_baseline"]["sample"]

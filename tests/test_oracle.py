@@ -172,3 +172,35 @@ def test_oracle_reproduces_its_committed_fixtures(name):
         col, corder, coff = co.greedy_colouring(A)
         assert np.array_equal(lev, d["level_of_row"]) and np.array_equal(off, d["level_offsets"])
         assert np.array_equal(col, d["colour_of_row"]) and np.array_equal(coff, d["colour_offsets"])
+
+
+@pytest.mark.parametrize("dim,c,lf", [(2, 4, 2), (3, 2, 2), (2, 1, 3)])
+def test_c_structured_builder_bitwise_equal_python_builders(dim, c, lf):
+    """orc_mg_build_poisson (the in-place builder that lets the 513^3 configuration run on a host) produces, array for array
+    and bit for bit, what problems.stencil_p1 / prolongation / injection and the reference's getJacobiMatrices produce."""
+    from multigrid_dolfinx_b200 import problems as pr
+    if c * 2 ** 0 + 1 < 3:
+        lc = 1
+    else:
+        lc = 0
+    S = co.StructuredCOracleMG(dim, c, lc, lf)
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=lc, finest_level=lf, with_dicts=False)
+    for k, l in enumerate(range(lc, lf + 1)):
+        A = H.A_sp_dict[l][0]
+        RO, dinv = rs.jacobi_matrices(A)
+        assert np.array_equal(S.array(k, 0), A.indptr) and np.array_equal(S.array(k, 1), A.indices)
+        assert S.array(k, 2).tobytes() == np.ascontiguousarray(A.data).tobytes()
+        assert np.array_equal(S.array(k, 3), RO.indptr) and np.array_equal(S.array(k, 4), RO.indices)
+        assert S.array(k, 5).tobytes() == np.ascontiguousarray(RO.data).tobytes()
+        assert S.array(k, 6).tobytes() == np.ascontiguousarray(dinv).tobytes()
+        if k > 0:
+            P = H.P[l - 1]
+            assert np.array_equal(S.array(k, 7), P.indptr) and np.array_equal(S.array(k, 8), P.indices)
+            assert S.array(k, 9).tobytes() == np.ascontiguousarray(P.data).tobytes()
+            assert np.array_equal(S.array(k, 10), H.inj[l - 1])
+    # and the cycle on it equals the cycle on the scipy-built hierarchy
+    f = H.b_dict[lf][:, 0]
+    v0 = np.zeros_like(f)
+    assert np.array_equal(S.vcycle(v0, f, ncycles=3), co.from_hierarchy(H).vcycle(v0, f, ncycles=3))
+    assert co.set_threads(0) >= 1
+    S.close()
