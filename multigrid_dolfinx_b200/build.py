@@ -35,7 +35,7 @@ def up_to_date():
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
-    cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    cmd = [nvcc_path(), "-O3", "-std=c++17", "--split-compile", "0", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-Xcompiler", "-fPIC,-fopenmp,-O3", "-shared", "-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")

@@ -151,7 +151,7 @@ k_code_verify(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__
 
 void free_coded(Coded& c)
 {
-    cudaFree(c.codes); cudaFree(c.dict); cudaFree(c.phead); cudaFree(c.dict_win);
+    cudaFree(c.codes); cudaFree(c.dict); cudaFree(c.phead); cudaFree(c.dict_win); cudaFree(c.pmask);
     c = Coded();
 }
 
@@ -230,6 +230,18 @@ k_pat_verify(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ 
         ok = (i + de.delta == cols[a + e]) && __double_as_longlong(de.val) == __double_as_longlong(vals[a + e]);
     }
     if (!ok) *bad = 1;
+}
+
+// occurrences of every row code (grid-stride, per-block histogram in shared memory)
+__global__ void __launch_bounds__(256)
+k_code_hist(int n, const unsigned char* __restrict__ rcodes, unsigned long long* __restrict__ hist)
+{
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&sh[rcodes[i]], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 
 // Row-pattern coding of D (mode 3).  ip: the operator's row pointers on the host.  Leaves D.cd.mode == 0 when it does not apply.
@@ -322,15 +334,21 @@ int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip)
 #undef CUC
     if (hb) { free_coded(D.cd); return MGB_OK; }          // never trust an unverified coding
     D.cd.mode = 3; D.cd.ndict = (int)pats.size(); D.cd.npent = total;
-    {   // the most frequent ("hot") pattern -- mode of 1024 evenly spaced codes -- travels to the row-direct / row-window
-        // kernels as kernel parameters
-        std::vector<unsigned char> smp(1024);
-        const size_t stride = std::max<size_t>(1, (size_t)n / 1024), cnt = std::min<size_t>(1024, (size_t)n / stride);
-        cudaError_t e1 = cudaMemcpy2DAsync(smp.data(), 1, D.cd.codes, stride, 1, cnt, cudaMemcpyDeviceToHost, h->stream);
+    {   // the most frequent ("hot") pattern -- exact histogram of the row codes (a strided sample can fall on boundary rows
+        // only: 513^3 rows sampled 1024 times land on multiples of 513) -- travels to the hot-row / row-window kernels as
+        // kernel parameters
+        unsigned long long* dh = nullptr;
+        unsigned long long hist[256];
+        cudaError_t e1 = cudaMalloc((void**)&dh, 256 * sizeof(unsigned long long));
+        if (e1 == cudaSuccess) e1 = cudaMemsetAsync(dh, 0, 256 * sizeof(unsigned long long), h->stream);
+        if (e1 == cudaSuccess) {
+            k_code_hist<<<std::min(grid, 1024), 256, 0, h->stream>>>(n, D.cd.codes, dh);
+            e1 = cudaGetLastError();
+        }
+        if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(hist, dh, sizeof hist, cudaMemcpyDeviceToHost, h->stream);
         if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(h->stream);
-        if (e1 != cudaSuccess) { free_coded(D.cd); return fail(h, MGB_ERR_CUDA, "sampling the row codes failed: %s", cudaGetErrorString(e1)); }
-        int hist[256] = {0};
-        for (size_t k = 0; k < cnt; ++k) hist[smp[k]]++;
+        cudaFree(dh);
+        if (e1 != cudaSuccess) { free_coded(D.cd); return fail(h, MGB_ERR_CUDA, "histogram of the row codes failed: %s", cudaGetErrorString(e1)); }
         HotPlan& H = D.cd.hotplan;
         H = HotPlan{};
         H.hot = (int)(std::max_element(hist, hist + 256) - hist);
@@ -340,6 +358,43 @@ int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip)
             H.hd[e] = in ? pent[(size_t)(phead[(size_t)H.hot].x + e)].delta : 0;
             H.hv[e] = in ? pent[(size_t)(phead[(size_t)H.hot].x + e)].val : 0.0;
         }
+    }
+    if (D.cd.hotplan.hotlen >= 1 && D.cd.hotplan.hotlen <= WIN_HOT) {
+        // hot-row kernel (k_hotrow): every pattern that is a subsequence of the hot one -- same (col - row, value bits) pairs in
+        // the same order, some missing -- becomes a bit mask over the hot entries; anything else is marked for the table walk
+        const HotPlan& HP = D.cd.hotplan;
+        std::vector<uint32_t> pm(256, 0u);
+        int slow = 0;
+        for (size_t p = 0; p < pats.size(); ++p) {
+            uint32_t m = 0;
+            int at = 0;                                                     // next hot entry that may match
+            bool sub = true;
+            for (int e = 0; e < phead[p].y && sub; ++e) {
+                const DictEnt& d = pent[(size_t)(phead[p].x + e)];
+                unsigned long long vb, hb2;
+                std::memcpy(&vb, &d.val, 8);
+                while (at < HP.hotlen) {
+                    std::memcpy(&hb2, &HP.hv[at], 8);
+                    if (HP.hd[at] == d.delta && hb2 == vb) break;
+                    ++at;
+                }
+                if (at == HP.hotlen) sub = false;
+                else { m |= 1u << at; ++at; }
+            }
+            if (!sub) { m = HOT_SLOW; ++slow; }
+            pm[p] = m;
+        }
+        HotArgs A{};
+        A.dmin = 0; A.dmax = 0;
+        for (int e = 0; e < WIN_HOT; ++e) {
+            A.hd[e] = HP.hd[e]; A.hv[e] = HP.hv[e];
+            if (e < HP.hotlen) { A.dmin = std::min(A.dmin, HP.hd[e]); A.dmax = std::max(A.dmax, HP.hd[e]); }
+        }
+        cudaError_t e1 = cudaMalloc((void**)&D.cd.pmask, 256 * sizeof(uint32_t));
+        if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(D.cd.pmask, pm.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream);
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(h->stream);
+        if (e1 == cudaSuccess) { D.cd.hot = A; D.cd.hot_ok = true; D.cd.hot_slow = slow; }
+        else { cudaFree(D.cd.pmask); D.cd.pmask = nullptr; (void)cudaGetLastError(); }
     }
     if (h->stage_x == 1) {
         // row-window kernel (k_rowwin): merge the distinct offsets into windows and re-express every table entry as

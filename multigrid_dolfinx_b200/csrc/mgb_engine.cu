@@ -115,6 +115,22 @@ WinChoice win_choice(int cfg)
     }
 }
 
+// Hot-row kernel configurations (option "hot_cfg"): threads per CTA, rows per thread (their product = rows per tile).
+// Measured on the 513^3 smoother sweep (tools/ubench/hotrow.cu, profiles/r2_hotrow_ubench_513.jsonl): 256-row tiles win
+// (128-row tiles are bound by the CTA launch rate, 512-row and larger tiles by the gap a retiring CTA leaves), and
+// 128 threads x 2 rows beats 256 x 1 and 64 x 4.
+struct HotChoice { int threads, rpt; };
+HotChoice hot_choice(int cfg)
+{
+    switch (cfg) {
+        case 2: return {256, 1};
+        case 3: return {128, 1};
+        case 4: return {256, 2};
+        default: return {128, 2};
+    }
+}
+bool hot_len_supported(int hotlen) { return hotlen == 4 || hotlen == 6 || hotlen == 7 || hotlen == 15; }
+
 int try_encode(mgb_handle* h, DevCsr& D);
 int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip);
 void free_coded(Coded& c);
@@ -164,8 +180,11 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
             D.ccfg = h->code_cfg;
             const CodeChoice cc = code_choice(D.ccfg);
             int64_t rowcap = (int64_t)cc.threads * cc.rpt;
-            D.wcfg = 0;
-            if (D.cd.mode == 3 && h->stage_x == 1 && D.cd.win.ng > 0 && D.cd.dict_win) {          // row-window kernel: its own tile size
+            D.wcfg = 0; D.hcfg = 0;
+            if (D.cd.mode == 3 && h->stage_x == 3 && D.cd.hot_ok && hot_len_supported(D.cd.hotplan.hotlen)) {   // hot-row kernel: its own tile size
+                D.hcfg = std::max(1, h->hot_cfg);
+                rowcap = (int64_t)hot_choice(D.hcfg).threads * hot_choice(D.hcfg).rpt;
+            } else if (D.cd.mode == 3 && h->stage_x == 1 && D.cd.win.ng > 0 && D.cd.dict_win) {          // row-window kernel: its own tile size
                 D.wcfg = std::max(1, h->win_cfg);
                 rowcap = 256 * (int64_t)win_choice(D.wcfg).rpt;
             }
@@ -450,6 +469,67 @@ void launch_rowwin(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles,
     launch_rowwin_hot<0, Epi>(h, D, desc, ntiles, x, epi, chunked);
 }
 
+// Hot-row kernel (k_hotrow).  Registers per thread are budgeted from what a thread keeps in flight (RPT rows x (HOTN x values +
+// operands)), and the resident CTAs per SM follow from that budget.
+template <int HOTN, int T, int RPT, int NOPS>
+constexpr int hot_minb()
+{
+    int regs = 28 + 2 * RPT * (HOTN + NOPS + 1);
+    regs = (regs + 7) / 8 * 8;
+    int b = 65536 / (T * regs);
+    const int cap = 2048 / T > 16 ? 16 : 2048 / T;
+    return b < 1 ? 1 : (b > cap ? cap : b);
+}
+
+template <int HOTN, int T, int RPT, class Epi>
+void launch_hotrow_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi)
+{
+    constexpr int MINB = hot_minb<HOTN, T, RPT, Epi::NOPS>();
+    constexpr int ROWS = T * RPT;
+    auto kern = k_hotrow<HOTN, T, RPT, MINB, Epi>;
+    const bool linear = desc == D.sdesc && ntiles == D.sntiles;              // all rows: tiles follow from blockIdx, no descriptor is read
+    const int grid = linear ? (int)((D.nrows + ROWS - 1) / ROWS) : ntiles;
+    if (grid <= 0) return;
+    // L2 prefetch distance in tiles; none while borrowed user pointers are in play (bulk prefetches need 16-byte aligned operands)
+    const int pf = h->allow_stream && h->hot_pf > 0 ? std::max(1, h->hot_pf / ROWS) : 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->pdl != 0 ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, (const unsigned char*)D.cd.codes, (const uint32_t*)D.cd.pmask, (const int2*)D.cd.phead, (const DictEnt*)D.cd.dict,
+                       D.cd.hot, linear ? (const int4*)nullptr : desc, grid, 0, (int)D.nrows, (int)D.ncols, pf, x, epi);
+}
+
+template <int HOTN, class Epi>
+void launch_hotrow_len(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi)
+{
+    switch (D.hcfg) {                    // hot_choice()
+        case 2: launch_hotrow_cfg<HOTN, 256, 1, Epi>(h, D, desc, ntiles, x, epi); break;
+        case 3: launch_hotrow_cfg<HOTN, 128, 1, Epi>(h, D, desc, ntiles, x, epi); break;
+        case 4: launch_hotrow_cfg<HOTN, 256, 2, Epi>(h, D, desc, ntiles, x, epi); break;
+        default: launch_hotrow_cfg<HOTN, 128, 2, Epi>(h, D, desc, ntiles, x, epi); break;
+    }
+}
+
+// The hot-row body exists for the pattern lengths of the operators this engine is built for: the smoother matrix of the P1
+// Laplacian (4 couplings per row in 2-D, 6 in 3-D) and the level matrix as exported (7 / 15 stored entries).  false: not
+// instantiated for this epilogue / length -- the caller falls back to the row-stream kernel (same tiles).
+template <class Epi>
+bool launch_hotrow(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi)
+{
+    const int hl = D.cd.hotplan.hotlen;
+    if constexpr (std::is_same<Epi, EpiJacobiRJ>::value || std::is_same<Epi, EpiJacobiRJFirst>::value) {
+        if (hl == 4) { launch_hotrow_len<4, Epi>(h, D, desc, ntiles, x, epi); return true; }
+        if (hl == 6) { launch_hotrow_len<6, Epi>(h, D, desc, ntiles, x, epi); return true; }
+    } else if constexpr (!std::is_same<Epi, EpiProlongAdd>::value) {
+        if (hl == 7) { launch_hotrow_len<7, Epi>(h, D, desc, ntiles, x, epi); return true; }
+        if (hl == 15) { launch_hotrow_len<15, Epi>(h, D, desc, ntiles, x, epi); return true; }
+    }
+    return false;
+}
+
 // MODE: the coding (pair / value codes); JW: gathers issued up front per row (4 when no row is longer, else 8)
 template <int MODE, int JW, class Epi>
 void launch_rowstream(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
@@ -467,6 +547,7 @@ void launch_stream(mgb_handle* h, const DevCsr& D, const double* x, const Epi& e
     if (!desc) { desc = D.sdesc; ntiles = D.sntiles; }
     if (ntiles <= 0) return;
     if constexpr (Epi::CONTIG) {
+        if (D.cd.mode == 3 && D.hcfg > 0 && launch_hotrow<Epi>(h, D, desc, ntiles, x, epi)) return;
         if (D.cd.mode == 3 && D.wcfg > 0) {              // x staged in shared memory (tiles were cut for this configuration)
             return launch_rowwin<Epi>(h, D, desc, ntiles, x, epi, chunked);
         }
@@ -660,6 +741,28 @@ int residual_injected(mgb_handle* h, Level& L, const double* v, const double* f,
 {
     const int64_t nc = L.n_coarse;
     const double avg = L.A.nrows ? (double)L.A.nnz / (double)L.A.nrows : 0.0;
+    const int hl = L.A.cd.hotplan.hotlen;
+    if (L.A.cd.mode == 3 && L.A.hcfg > 0 && (hl == 7 || hl == 15) && L.inj && nc > 0 && h->hot_inj && h->stream_cfg > 0 && h->allow_stream) {
+        // thread per coarse row on the pattern-coded level matrix (k_hotinj): only the injected rows are summed
+        TRY(exchange(h, L, const_cast<double*>(v)));
+        const double nb = (12.0 * avg + 4.0 + 8.0 + 4.0 + 8.0 + 8.0) * (double)nc + 8.0 * (double)L.n;
+        const double moved = 8.0 * (double)L.n + 21.0 * (double)nc;      // all of v (every line is touched), inj + code + f + result per coarse row
+        return launch(h, MGB_K_RESIDUAL, L.level, nb, [&] {
+            constexpr int T = 128;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)((nc + T - 1) / T)); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = h->pdl != 0 ? 1 : 0;
+            const DevCsr& A = L.A;
+            const int pf = h->hot_pf > 0 ? std::max(1, h->hot_pf / 8 / T) : 0;
+            if (hl == 7) cudaLaunchKernelEx(&cfg, k_hotinj<7, T, 10>, (const unsigned char*)A.cd.codes, (const uint32_t*)A.cd.pmask, (const int2*)A.cd.phead,
+                                            (const DictEnt*)A.cd.dict, A.cd.hot, (const int32_t*)L.inj, (int)nc, (int)A.ncols, pf, v, f, f_coarse);
+            else cudaLaunchKernelEx(&cfg, k_hotinj<15, T, 8>, (const unsigned char*)A.cd.codes, (const uint32_t*)A.cd.pmask, (const int2*)A.cd.phead,
+                                    (const DictEnt*)A.cd.dict, A.cd.hot, (const int32_t*)L.inj, (int)nc, (int)A.ncols, pf, v, f, f_coarse);
+        }, moved);
+    }
     if (L.inj_desc && (L.inj_fraction < 0.8 || L.A.cd.mode) && h->stream_cfg > 0 && h->allow_stream) {
         // stream only the tiles of A that hold injected rows; every row of such a tile is summed, injected ones are stored
         const double nb = L.inj_fraction * (12.0 * (double)L.A.nnz + (4.0 + 8.0 + 4.0) * (double)L.n) + 8.0 * (double)L.n + 8.0 * (double)nc;
@@ -720,7 +823,9 @@ int norm2_device(mgb_handle* h, int64_t n, const double* x, double* out_dev, int
 // ---- one V-cycle, enqueued on the stream (multigrid.py:231-268 unrolled into a down and an up sweep) ----
 // v and f of the top level live in levels[top].v / .f.  dbg: copy the test=True outputs into L.r (err_h);
 // f2h / v2h are left in the coarse level's f / v buffers.
-int enqueue_cycle(mgb_handle* h, int top, bool debug, double** v2h_ptr)
+// top_g_valid: levels[top].g already holds w*(dinv*f) for the f in place (a previous cycle of the same call formed it: the
+// product is the same every cycle, multigrid.py:226), so the top level's first sweep need not form and store it again.
+int enqueue_cycle(mgb_handle* h, int top, bool debug, double** v2h_ptr, bool top_g_valid = false)
 {
     if (top == h->coarsest) {          // multigrid.py:238-241
         Level& C = h->levels[top];
@@ -739,7 +844,7 @@ int enqueue_cycle(mgb_handle* h, int top, bool debug, double** v2h_ptr)
         Level& L = h->levels[l];
         Level& C = h->levels[l - 1];
         double* v = L.v; double* o = L.vtmp;
-        bool g_valid = false;
+        bool g_valid = l == top && top_g_valid && h->smoother == MGB_SM_JACOBI_RJ;
         int sweeps = h->mu1;
         if (l != top) {                                 // zero initial guess (multigrid.py:253)
             if (jacobi && h->mu1 > 0) {
@@ -796,16 +901,18 @@ void drop_graphs(mgb_handle* h)
     h->graph_kernels.clear();
 }
 
-int run_cycle(mgb_handle* h, int top)
+int run_cycle(mgb_handle* h, int top, bool top_g_valid = false)
 {
     const bool graphable = h->use_graph && !h->prof && h->smoother != MGB_SM_GS_LEVEL;
-    if (!graphable) return enqueue_cycle(h, top, false, nullptr);
-    auto it = h->graphs.find(top);
+    if (h->smoother != MGB_SM_JACOBI_RJ || !h->reuse_g) top_g_valid = false;
+    if (!graphable) return enqueue_cycle(h, top, false, nullptr, top_g_valid);
+    const int key = top * 2 + (top_g_valid ? 1 : 0);          // two graphs per top level: first cycle of a call / the following ones
+    auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
         cudaGraph_t graph = nullptr;
         const int64_t before = h->launches;
         CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
-        int rc = enqueue_cycle(h, top, false, nullptr);
+        int rc = enqueue_cycle(h, top, false, nullptr, top_g_valid);
         cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
         const int64_t captured = h->launches - before;
         h->launches = before;
@@ -815,12 +922,12 @@ int run_cycle(mgb_handle* h, int top)
         e = cudaGraphInstantiate(&exec, graph, h->dist ? cudaGraphInstantiateFlagUseNodePriority : 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return fail(h, MGB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
-        h->graphs[top] = exec;
-        h->graph_kernels[top] = captured;
-        it = h->graphs.find(top);
+        h->graphs[key] = exec;
+        h->graph_kernels[key] = captured;
+        it = h->graphs.find(key);
     }
     CU(cudaGraphLaunch(it->second, h->stream));
-    h->launches += h->graph_kernels[top];
+    h->launches += h->graph_kernels[key];
     return MGB_OK;
 }
 
@@ -868,7 +975,7 @@ int cycles_on_buffers(mgb_handle* h, int top, int ncycles, double* resnorm_hist)
     Level& T = h->levels[top];
     if (resnorm_hist) TRY(ensure_hist(h, ncycles));
     for (int c = 0; c < ncycles; ++c) {
-        TRY(run_cycle(h, top));
+        TRY(run_cycle(h, top, c > 0));          // (f is untouched between the cycles of one call)
         if (resnorm_hist) {                    // the residual the reference's driver forms after each cycle (multigrid.py:291)
             TRY(residual(h, T, T.v, T.f, T.r));
             TRY(norm2_device(h, T.n, T.r, h->d_hist + c, top));
@@ -1249,6 +1356,10 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "code_cfg" && pre) h->code_cfg = iv;
     else if (k == "stage_x" && pre) h->stage_x = iv;
     else if (k == "win_cfg" && pre) h->win_cfg = iv;
+    else if (k == "hot_cfg" && pre) h->hot_cfg = iv;
+    else if (k == "reuse_g") { h->reuse_g = iv; drop_graphs(h); }
+    else if (k == "hot_inj") { h->hot_inj = iv; drop_graphs(h); }
+    else if (k == "hot_pf") { h->hot_pf = iv; drop_graphs(h); }
     else if (k == "win_prefetch") { h->win_prefetch = iv; drop_graphs(h); }
     else if (k == "gs_cluster") h->gs_cluster = iv;
     else if (k == "pdl") { h->pdl = iv; drop_graphs(h); }
@@ -1492,11 +1603,11 @@ int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, i
         TRY(prolong_add(h, L, C.v, L.v, nullptr));                                // v_h = Interpolation(v_2h), multigrid.py:283-284
         CU(cudaMemcpyAsync(L.f, L.b, sizeof(double) * (size_t)L.n, cudaMemcpyDeviceToDevice, h->stream));
         if (l < h->finest) {
-            for (int c = 0; c < mu0; ++c) TRY(run_cycle(h, l));                   // multigrid.py:305-306
+            for (int c = 0; c < mu0; ++c) TRY(run_cycle(h, l, c > 0));            // multigrid.py:305-306
             continue;
         }
         while (done < max_cycles) {                                               // multigrid.py:288-302 (with a cap)
-            TRY(run_cycle(h, l));
+            TRY(run_cycle(h, l, done > 0));
             ++done;
             // norm of L.r into d_hist[slot]: sqrt(r^T M r) with a mass matrix (multigrid.py:203-208), else the l2 norm
             auto norm_of_r = [&](int slot) -> int {
@@ -1844,10 +1955,11 @@ int mgb_describe(mgb_handle* h, char* out, int64_t capacity)
 {
     if (!h || !out || capacity <= 0) return MGB_ERR_INVALID;
     std::string s;
-    char buf[256];
+    char buf[384];
     auto one = [&](const char* name, const DevCsr& D) {
         if (!D.present()) return;
-        if (D.family == 1 && D.sdesc && D.cd.mode == 3 && D.wcfg > 0) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowwin(coded mode=3: %d row patterns, %d table entries, %d x-windows, hot pattern %d; cfg=%d, 256 x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.cd.win.ng, D.cd.win.hot, D.wcfg, win_choice(D.wcfg).rpt, win_choice(D.wcfg).stages, D.sntiles);
+        if (D.family == 1 && D.sdesc && D.cd.mode == 3 && D.hcfg > 0) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d hotrow(coded mode=3: %d row patterns, %d table entries, hot pattern %d of %d entries, %d patterns take the table walk; cfg=%d, %d x %d rows) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.cd.hotplan.hot, D.cd.hotplan.hotlen, D.cd.hot_slow, D.hcfg, hot_choice(D.hcfg).threads, hot_choice(D.hcfg).rpt, D.sntiles);
+        else if (D.family == 1 && D.sdesc && D.cd.mode == 3 && D.wcfg > 0) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowwin(coded mode=3: %d row patterns, %d table entries, %d x-windows, hot pattern %d; cfg=%d, 256 x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.cd.win.ng, D.cd.win.hot, D.wcfg, win_choice(D.wcfg).rpt, win_choice(D.wcfg).stages, D.sntiles);
         else if (D.family == 1 && D.sdesc && D.cd.mode == 3) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowstream(coded mode=3: %d row patterns, %d table entries; cfg=%d, %d x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.ccfg, code_choice(D.ccfg).threads, code_choice(D.ccfg).rpt, code_choice(D.ccfg).stages, D.sntiles);
         else if (D.family == 1 && D.sdesc && D.cd.mode) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowstream(coded mode=%d: %d dictionary entries, %d values, %d offsets; cfg=%d, %d x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.mode, D.cd.ndict, D.cd.nvals, D.cd.ndeltas, D.ccfg, code_choice(D.ccfg).threads, code_choice(D.ccfg).rpt, code_choice(D.ccfg).stages, D.sntiles);
         else if (D.family == 1 && D.sdesc) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d stream(cfg=%d, %d x %d entries, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.scfg, stream_choice(D.scfg).threads, stream_choice(D.scfg).ept, stream_choice(D.scfg).stages, D.sntiles);

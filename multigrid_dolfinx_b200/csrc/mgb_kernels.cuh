@@ -954,6 +954,169 @@ struct HotPlan {
     double hv[WIN_HOT];                  // ... and values
 };
 
+// ---- hot-row family: row patterns, speculative loads at the hot pattern's offsets ------------------------------
+// ncu on k_rowstream / k_rowwin (profiles/r2_ncu_*): half of the issued instructions were consumers spinning on a
+// stage that had not landed, and a thread-per-row kernel that first loads its code and only then its x values pays two
+// DRAM latencies per row.  This family removes the dependency instead of hiding it:
+//   * every pattern that is a SUBSEQUENCE of the most frequent ("hot") pattern -- same (col - row, value) pairs, same
+//     order, some missing: the rows next to a Dirichlet boundary -- is described by a bit mask over the hot entries
+//     (pmask[code]); any other pattern carries HOT_SLOW and takes the table walk;
+//   * a thread issues, back to back and before anything has arrived, its code byte, ALL x values at the hot offsets
+//     (speculatively: a masked-off value is loaded and ignored; in the first / last tiles the index is clamped into x)
+//     and the epilogue operands.  One memory latency per row, no shared memory, no barrier, no descriptor;
+//   * a CTA prefetches into L2 (cp.async.bulk.prefetch.L2) what the tile `pf` tiles ahead will read from DRAM for the
+//     first time (codes, operand slices, the leading x slice), so the demand loads of that tile find L2, not DRAM.
+// The row sum is formed as everywhere else: one accumulator, stored order, separately rounded multiply and add; a masked
+// entry is skipped by predication (never multiplied by zero), so results are bit-identical to the CSR kernels.
+constexpr uint32_t HOT_SLOW = 0x80000000u;
+struct HotArgs {
+    int dmin, dmax;                      // smallest / largest hot offset (tiles that may leave [0, xlen) take the clamped body)
+    int hd[WIN_HOT];                     // hot pattern: col - row of every entry ...
+    double hv[WIN_HOT];                  // ... and its value
+};
+
+__device__ __forceinline__ int ld_stream_u8(const unsigned char* p)
+{
+    unsigned short v;
+    asm("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=h"(v) : "l"(p));
+    return (int)v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double* p)
+{
+    double v;      // volatile: stays behind griddepcontrol.wait (the predecessor kernel may have written the operand)
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// Tiles: with desc == nullptr the rows [rb, re) are cut into tiles of T = THREADS * RPT consecutive rows (no descriptor is
+// read: the tile's rows follow from blockIdx); with a descriptor list, tile t holds the rows [desc[t].x, desc[t].x + desc[t].y),
+// desc[t].y <= T (tile subsets: the interior / boundary split of a sharded operator, the tiles holding injected rows).
+// Thread t owns rows t, t + THREADS, ... of its tile.
+template <int HOTN, int THREADS, int RPT, int MINB, class Epi>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ pmask, const int2* __restrict__ phead,
+         const DictEnt* __restrict__ pent, const __grid_constant__ HotArgs H, const int4* __restrict__ desc, int ntiles,
+         int rb, int re, int xlen, int pf, const double* x, Epi epi)
+{
+    static_assert(Epi::CONTIG, "hot-row kernel needs contiguous epilogue operands");
+    static_assert(HOTN >= 1 && HOTN <= WIN_HOT, "hot pattern length");
+    constexpr int T = THREADS * RPT;
+    constexpr int NOPS = Epi::NOPS, NIOPS = EpiNI<Epi>::value, XOP = EpiXop<Epi>::value;
+    const int tid = threadIdx.x;
+    bool alias = false;                                      // the operand that is x itself (old iterate of a Jacobi sweep)
+    if constexpr (XOP >= 0) alias = epi.operand(XOP) == x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    int row0 = rb + (int)blockIdx.x * T, rend = re;          // this tile: rows [row0, min(row0 + T, rend))
+    if (desc) { const int4 d = __ldg(desc + blockIdx.x); row0 = d.x; rend = d.x + d.y; }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    int code[RPT];
+    double xv[RPT][HOTN];
+    double o[RPT][NOPS > 0 ? NOPS : 1];
+    int io[RPT];
+    const bool fast = row0 + H.dmin >= 0 && (long long)row0 + T + H.dmax <= (long long)xlen && row0 + T <= rend;   // CTA-uniform
+    if (fast) {
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int r = row0 + tid + j * THREADS;
+            code[j] = ld_stream_u8(rcodes + r);
+            const double* xr = x + r;
+#pragma unroll
+            for (int e = 0; e < HOTN; ++e) xv[j][e] = __ldg(xr + H.hd[e]);
+#pragma unroll
+            for (int k = 0; k < NOPS; ++k) o[j][k] = (alias && k == XOP) ? __ldg(xr) : ld_stream_f64(epi.operand(k) + r);
+            if constexpr (NIOPS > 0) io[j] = __ldg(epi.ioperand() + r);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int r = min(row0 + tid + j * THREADS, rend - 1);        // threads past the end redo the last row (and do not store)
+            code[j] = ld_stream_u8(rcodes + r);
+#pragma unroll
+            for (int e = 0; e < HOTN; ++e) xv[j][e] = __ldg(x + min(max(r + H.hd[e], 0), xlen - 1));
+#pragma unroll
+            for (int k = 0; k < NOPS; ++k) o[j][k] = epi.operand(k)[r];
+            if constexpr (NIOPS > 0) io[j] = epi.ioperand()[r];
+        }
+    }
+    if (pf > 0 && tid < 32 && (int)blockIdx.x + pf < ntiles) {   // L2 prefetch for the tile pf tiles ahead (whole 16-byte groups, in bounds)
+        long long p0 = (long long)row0 + (long long)pf * T;
+        int pn = T;
+        if (desc) { const int4 d = __ldg(desc + blockIdx.x + pf); p0 = d.x; pn = (d.y + 15) & ~15; }
+        if (p0 + pn <= (long long)re) {
+            if (tid == 0) bulk_prefetch_l2(rcodes + (p0 & ~15LL), pn);
+            if (tid == 1) { const long long q = (p0 + H.dmax) & ~1LL; if (q >= 0 && q + pn <= (long long)xlen) bulk_prefetch_l2(x + q, pn * 8); }
+            if (tid >= 2 && tid < 2 + NOPS) { const int k = tid - 2; if (!(alias && k == XOP)) bulk_prefetch_l2(epi.operand(k) + (p0 & ~1LL), pn * 8); }
+            if constexpr (NIOPS > 0) if (tid == 2 + NOPS) bulk_prefetch_l2(epi.ioperand() + (p0 & ~3LL), pn * 4);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int r = row0 + tid + j * THREADS;
+        const uint32_t m = __ldg(pmask + code[j]);
+        double sum = 0.0;                                    // one accumulator, stored order
+        if (!(m & HOT_SLOW)) {
+#pragma unroll
+            for (int e = 0; e < HOTN; ++e)
+                if ((m >> e) & 1u) sum = __dadd_rn(sum, __dmul_rn(H.hv[e], xv[j][e]));
+        } else if (r < rend) {                               // any other pattern: walk its entry list
+            const int2 ph = __ldg(phead + code[j]);
+            for (int e = 0; e < ph.y; ++e) {
+                const double val = __ldg(&pent[ph.x + e].val);
+                const int dl = __ldg(&pent[ph.x + e].delta);
+                sum = __dadd_rn(sum, __dmul_rn(val, __ldg(x + r + dl)));
+            }
+        }
+        if (fast || r < rend) {
+            if constexpr (NIOPS > 0) epi.store_i(r, sum, o[j], io[j]);
+            else epi.store(r, sum, o[j]);
+        }
+    }
+}
+
+// Fused residual + injection on a row-pattern-coded operator, one thread per COARSE row i: out[i] = f[g_i] - (A v)[g_i],
+// g_i = inj[i] the fine row with the same coordinate (multigrid.py:244 restricted to the rows Restriction2D_direct keeps,
+// multigrid.py:128-131).  Only the injected rows are summed -- 1/4 (2-D) or 1/8 (3-D) of the fine rows -- with the same
+// speculative loads as k_hotrow (every index clamped into x: the rows are scattered, there is no tile-wide range test).
+// The inj slice of the tile pf tiles ahead is prefetched into L2.
+// x, f and out are deliberately NOT __restrict__: a const __restrict__ pointer turns its loads into invariant loads, which the
+// compiler may hoist above griddepcontrol.wait -- i.e. read the iterate before the predecessor kernel has written it (found
+// the hard way; tools/check_pdl_order.py lists the loads scheduled before the wait).
+template <int HOTN, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_hotinj(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ pmask, const int2* __restrict__ phead,
+         const DictEnt* __restrict__ pent, const __grid_constant__ HotArgs H, const int32_t* __restrict__ inj, int nc, int xlen, int pf,
+         const double* x, const double* f, double* out)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int i = (int)blockIdx.x * THREADS + (int)threadIdx.x;
+    const int r = __ldg(inj + min(i, nc - 1));               // (static data: may be read before the predecessor has finished)
+    if (pf > 0 && threadIdx.x == 0) {
+        const long long p0 = ((long long)blockIdx.x + pf) * THREADS;
+        if (p0 + THREADS <= (long long)nc) bulk_prefetch_l2(inj + p0, THREADS * 4);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int code = ld_stream_u8(rcodes + r);
+    double xv[HOTN];
+#pragma unroll
+    for (int e = 0; e < HOTN; ++e) xv[e] = ld_x<true>(x, min(max(r + H.hd[e], 0), xlen - 1));
+    const double fr = ld_x<true>(f, r);
+    const uint32_t m = __ldg(pmask + code);
+    double sum = 0.0;                                        // one accumulator, stored order
+    if (!(m & HOT_SLOW)) {
+#pragma unroll
+        for (int e = 0; e < HOTN; ++e)
+            if ((m >> e) & 1u) sum = __dadd_rn(sum, __dmul_rn(H.hv[e], xv[e]));
+    } else {
+        const int2 ph = __ldg(phead + code);
+        for (int e = 0; e < ph.y; ++e) {
+            const double val = __ldg(&pent[ph.x + e].val);
+            const int dl = __ldg(&pent[ph.x + e].delta);
+            sum = __dadd_rn(sum, __dmul_rn(val, ld_x<true>(x, r + dl)));
+        }
+    }
+    if (i < nc) out[i] = __dsub_rn(fr, sum);
+}
+
 // ---- sub-warp family --------------------------------------------------------------------------------
 // LPR lanes cooperate on one row (LPR = 32: warp per row), partial sums combined with a shuffle tree.
 template <int LPR, bool NCX, class Epi>

@@ -19,6 +19,10 @@ struct Coded {
     DictEnt* dict_win = nullptr;     // mode 3, row-window kernel (k_rowwin): the pattern table again, every entry's offset expressed as
     WinPlan win{};                   // (window << WIN_GSHIFT) | (offset - window minimum); win.ng == 0: not available
     HotPlan hotplan{};               // mode 3: the most frequent pattern (handed to the row-window kernel as kernel parameters)
+    uint32_t* pmask = nullptr;       // mode 3, hot-row kernel (k_hotrow): device, 256 x (bit mask over the hot pattern's entries | HOT_SLOW)
+    HotArgs hot{};                   // ... and the hot pattern as kernel parameters; hot_ok: the kernel applies
+    bool hot_ok = false;
+    int hot_slow = 0;                // patterns that are not sub-patterns of the hot one (table walk)
     int ndict = 0;                   // entries (mode 3: patterns) in use
     int nvals = 0, ndeltas = 0;      // distinct values / distinct (col - row) found
 };
@@ -28,6 +32,7 @@ struct DevCsr {
     Coded cd;
     int ccfg = 0;            // row-stream kernel configuration (code_choice) when cd.mode != 0
     int wcfg = 0;            // > 0: row-window kernel configuration (win_choice): x staged in shared memory
+    int hcfg = 0;            // > 0: hot-row kernel configuration (hot_choice): speculative loads at the hot pattern's offsets
     int32_t* rowptr = nullptr;
     int32_t* cols = nullptr;
     double* vals = nullptr;
@@ -152,8 +157,13 @@ struct mgb_handle {
     int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
     int compress = 2;              // lossless coding of repetitive operators (mgb_code.cuh): 0 off, 1 per-entry codes, 2 + row patterns
     int code_cfg = 1;              // row-stream kernel configuration for coded operators (code_choice)
-    int stage_x = 1;               // row-pattern-coded operators: 1 x staged in shared memory by bulk copies (k_rowwin); 0 bulk-copied codes /
-                                   // operands + x gathered through L1 (k_rowstream)
+    int stage_x = 3;               // row-pattern-coded operators: 3 speculative loads at the hot pattern's offsets (k_hotrow, the default);
+                                   // 1 x staged in shared memory by bulk copies (k_rowwin); 0 bulk-copied codes / operands + x gathered
+                                   // through L1 (k_rowstream)
+    int reuse_g = 1;               // cycles after the first of one call reuse the top level's w*(dinv*f) instead of forming it again
+    int hot_inj = 1;               // fused residual + injection: thread per coarse row on a pattern-coded level matrix (k_hotinj)
+    int hot_cfg = 1;               // hot-row kernel configuration (hot_choice)
+    int hot_pf = 262144;           // hot-row kernel: L2 prefetch distance in rows (0: none)
     int win_cfg = 1;               // row-window kernel configuration (win_choice)
     int win_prefetch = 0;          // row-window kernel: tiles (per CTA) whose DRAM streams are prefetched into L2 ahead of the copies
     bool allow_stream = true;      // false while borrowed user pointers are in play (no padding / alignment guarantee)

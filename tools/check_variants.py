@@ -18,6 +18,15 @@ from multigrid_dolfinx_b200 import dist as ds  # noqa: E402
 VARIANTS = {
     "csr": {"compress": 0},
     "gather": {"stage_x": 0},                      # round-1 default: row patterns, x gathered through L1/L2
+    "hot1": {"stage_x": 3, "hot_cfg": 1},           # round-2 default: speculative loads at the hot pattern's offsets
+    "hot2": {"stage_x": 3, "hot_cfg": 2},
+    "hot3": {"stage_x": 3, "hot_cfg": 3},
+    "hot4": {"stage_x": 3, "hot_cfg": 4},
+    "hot1noinj": {"stage_x": 3, "hot_cfg": 1, "hot_inj": 0, "reuse_g": 0},
+    "hot1pf0": {"stage_x": 3, "hot_cfg": 1, "hot_pf": 0},
+    "hot1pf128k": {"stage_x": 3, "hot_cfg": 1, "hot_pf": 131072},
+    "hot1pf384k": {"stage_x": 3, "hot_cfg": 1, "hot_pf": 393216},
+    "hot1pf512k": {"stage_x": 3, "hot_cfg": 1, "hot_pf": 524288},
     "win1": {"stage_x": 1, "win_cfg": 1},
     "win2": {"stage_x": 1, "win_cfg": 2},
     "win3": {"stage_x": 1, "win_cfg": 3},

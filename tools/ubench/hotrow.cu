@@ -1,0 +1,181 @@
+// Micro-benchmark + bit-exactness check of the hot-row kernel (k_hotrow, mgb_kernels.cuh) on the weighted-Jacobi sweep of
+// the 3-D 7-point smoother matrix (N^3 nodes, lexicographic numbering, Dirichlet boundary rows empty, rows next to the
+// boundary carrying sub-patterns) -- the dominant kernel of BASELINE config 5 -- against a plain table-walk kernel.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/ubench/hotrow tools/ubench/hotrow.cu
+//   tools/ubench/hotrow [N] > gpurun_out/r2_hotrow.jsonl
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
+#include "../../multigrid_dolfinx_b200/csrc/mgb_kernels.cuh"
+
+using namespace mgb;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s (line %d)\n", #x, cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
+
+// code of row (z, y, x): 64 = Dirichlet row (empty); else 6 bits, bit e set when neighbour e (stored order -N^2, -N, -1, +1, +N, +N^2)
+// is an interior node; code 65: an artificial pattern that is NOT a sub-pattern of the hot one (exercises the table walk)
+__global__ void k_make_codes(int N, unsigned char* codes)
+{
+    const long long n = (long long)N * N * N;
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int x = (int)(r % N), y = (int)((r / N) % N), z = (int)(r / ((long long)N * N));
+    auto bnd = [&](int a) { return a == 0 || a == N - 1; };
+    if (bnd(x) || bnd(y) || bnd(z)) { codes[r] = 64; return; }
+    int m = 0;
+    if (!bnd(z - 1)) m |= 1;
+    if (!bnd(y - 1)) m |= 2;
+    if (!bnd(x - 1)) m |= 4;
+    if (!bnd(x + 1)) m |= 8;
+    if (!bnd(y + 1)) m |= 16;
+    if (!bnd(z + 1)) m |= 32;
+    if (z == N / 2 && y == N / 3 && (x % 7) == 3) { codes[r] = 65; return; }
+    codes[r] = (unsigned char)m;
+}
+
+__global__ void k_fill(long long n, double* a, unsigned seed)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long h = (unsigned long long)i * 0x9E3779B97F4A7C15ULL + seed;
+    h ^= h >> 31; h *= 0xff51afd7ed558ccdULL; h ^= h >> 29;
+    a[i] = (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+// reference: thread per row, table walk, same numerics contract
+template <class Epi>
+__global__ void k_ref(long long n, const unsigned char* codes, const int2* phead, const DictEnt* pent, const double* x, Epi epi)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int2 ph = phead[codes[r]];
+    double sum = 0.0;
+    for (int e = 0; e < ph.y; ++e) sum = __dadd_rn(sum, __dmul_rn(pent[ph.x + e].val, x[r + pent[ph.x + e].delta]));
+    double o[Epi::NOPS];
+    for (int k = 0; k < Epi::NOPS; ++k) o[k] = epi.operand(k)[r];
+    epi.store((int)r, sum, o);
+}
+
+__global__ void k_cmp(long long n, const double* a, const double* b, unsigned long long* bad)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && __double_as_longlong(a[i]) != __double_as_longlong(b[i])) atomicAdd(bad, 1ULL);
+}
+
+struct Problem {
+    int N; long long n; int xlen;
+    unsigned char* codes; uint32_t* pmask; int2* phead; DictEnt* pent; HotArgs H;
+    double *x, *g, *out, *ref;
+    unsigned long long* bad;
+};
+
+template <int THREADS, int RPT, int MINB, bool PERSIST = false>
+void run_variant(Problem& P, int pf_rows, const char* name, int reps)
+{
+    constexpr int T = THREADS * RPT;
+    int pf = pf_rows / T;                              // prefetch distance in tiles
+    auto kern = k_hotrow<6, THREADS, RPT, MINB, PERSIST, EpiJacobiRJ>;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0);
+    const int ntiles = (int)((P.n + T - 1) / T);
+    const int grid = PERSIST ? std::min(ntiles, 148 * occ) : ntiles;
+    if (PERSIST) pf = pf_rows / T / grid * 1;               // persistent: distance in tiles = whole passes of the grid
+    if (PERSIST && pf_rows > 0) pf = std::max(1, (pf_rows + T * grid / 2) / (T * grid)) * grid;
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
+    auto launch = [&](const double* in, double* out) {
+        EpiJacobiRJ epi{in, P.g, out, 1.0 - 2.0 / 3.0, 2.0 / 3.0};
+        kern<<<grid, THREADS>>>(P.codes, P.pmask, P.phead, P.pent, P.H, 0, (int)P.n, P.xlen, pf, in, epi);
+    };
+    // correctness: one sweep x -> out against the reference
+    CK(cudaMemset(P.out, 0xFF, sizeof(double) * P.n));
+    launch(P.x, P.out);
+    CK(cudaMemset(P.bad, 0, 8));
+    k_cmp<<<(int)((P.n + 255) / 256), 256>>>(P.n, P.out, P.ref, P.bad);
+    unsigned long long bad = 0;
+    CK(cudaMemcpy(&bad, P.bad, 8, cudaMemcpyDeviceToHost));
+    // timing: ping-pong sweeps (values drift but stay finite: |R_omega row sum| <= 1)
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int i = 0; i < 2; ++i) { launch(P.x, P.out); launch(P.out, P.x); }
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(a);
+    for (int i = 0; i < reps; ++i) { launch(P.x, P.out); launch(P.out, P.x); }
+    cudaEventRecord(b);
+    CK(cudaEventSynchronize(b));
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    const double us = ms * 1e3 / (2.0 * reps);
+    printf("{\"variant\": \"%s\", \"N\": %d, \"threads\": %d, \"rpt\": %d, \"minb\": %d, \"pf_rows\": %d, \"pf_tiles\": %d, \"regs\": %d, \"occ\": %d, \"us\": %.2f, \"GBs\": %.1f, \"mismatches\": %llu}\n",
+           name, P.N, THREADS, RPT, MINB, pf_rows, pf, fa.numRegs, occ, us, 25.0 * (double)P.n / us / 1e3, bad);
+    fflush(stdout);
+    // restore x for the next variant's correctness check
+    k_fill<<<(int)((P.n + 255) / 256), 256>>>(P.n, P.x, 1u);
+    CK(cudaDeviceSynchronize());
+}
+
+int main(int argc, char** argv)
+{
+    Problem P{};
+    P.N = argc > 1 ? atoi(argv[1]) : 513;
+    const int N = P.N;
+    P.n = (long long)N * N * N;
+    P.xlen = (int)(P.n + 16);
+    CK(cudaMalloc(&P.codes, P.n + 4096));
+    CK(cudaMalloc(&P.x, sizeof(double) * (P.n + 16))); CK(cudaMalloc(&P.g, sizeof(double) * (P.n + 16)));
+    CK(cudaMalloc(&P.out, sizeof(double) * (P.n + 16))); CK(cudaMalloc(&P.ref, sizeof(double) * (P.n + 16)));
+    CK(cudaMalloc(&P.bad, 8));
+    CK(cudaMemset(P.codes, 64, P.n + 4096));
+    CK(cudaMemset(P.x, 0, sizeof(double) * (P.n + 16))); CK(cudaMemset(P.out, 0, sizeof(double) * (P.n + 16)));
+    const int gridn = (int)((P.n + 255) / 256);
+    k_make_codes<<<gridn, 256>>>(N, P.codes);
+    k_fill<<<gridn, 256>>>(P.n, P.x, 1u);
+    k_fill<<<gridn, 256>>>(P.n, P.g, 2u);
+    // pattern table: codes 0..63 sub-patterns, 64 empty, 65 foreign
+    const int hd[6] = {-N * N, -N, -1, 1, N, N * N};
+    const double w = (1.0 / 6.0) * -1.0;
+    std::vector<int2> phead(256, make_int2(0, 0));
+    std::vector<DictEnt> pent;
+    std::vector<uint32_t> pmask(256, 0);
+    for (int c = 0; c < 64; ++c) {
+        phead[c].x = (int)pent.size();
+        int len = 0;
+        for (int e = 0; e < 6; ++e) if ((c >> e) & 1) { pent.push_back(DictEnt{w, hd[e], 0}); ++len; }
+        phead[c].y = len;
+        pmask[c] = (uint32_t)c;
+    }
+    phead[65] = make_int2((int)pent.size(), 3);
+    pent.push_back(DictEnt{0.25, -2, 0}); pent.push_back(DictEnt{-0.125, 0, 0}); pent.push_back(DictEnt{0.5, 2 * N, 0});
+    pmask[65] = HOT_SLOW;
+    CK(cudaMalloc(&P.phead, 256 * sizeof(int2))); CK(cudaMemcpy(P.phead, phead.data(), 256 * sizeof(int2), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&P.pent, pent.size() * sizeof(DictEnt))); CK(cudaMemcpy(P.pent, pent.data(), pent.size() * sizeof(DictEnt), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&P.pmask, 256 * 4)); CK(cudaMemcpy(P.pmask, pmask.data(), 256 * 4, cudaMemcpyHostToDevice));
+    P.H.dmin = hd[0]; P.H.dmax = hd[5];
+    for (int e = 0; e < WIN_HOT; ++e) { P.H.hd[e] = e < 6 ? hd[e] : 0; P.H.hv[e] = e < 6 ? w : 0.0; }
+    {
+        EpiJacobiRJ epi{P.x, P.g, P.ref, 1.0 - 2.0 / 3.0, 2.0 / 3.0};
+        k_ref<EpiJacobiRJ><<<gridn, 256>>>(P.n, P.codes, P.phead, P.pent, P.x, epi);
+        CK(cudaDeviceSynchronize());
+    }
+    const int reps = N >= 400 ? 10 : 40;
+    const int set = argc > 2 ? atoi(argv[2]) : 0;
+    for (int pf : {0, 1 << 18, 1 << 19}) {
+        if (set == 0) {
+            run_variant<64, 1, 16>(P, pf, "t64r1", reps);
+            run_variant<64, 2, 16>(P, pf, "t64r2", reps);
+            run_variant<64, 4, 8>(P, pf, "t64r4", reps);
+            run_variant<128, 1, 16>(P, pf, "t128r1", reps);
+            run_variant<128, 2, 8>(P, pf, "t128r2", reps);
+            run_variant<128, 3, 6>(P, pf, "t128r3", reps);
+            run_variant<256, 1, 8>(P, pf, "t256r1", reps);
+        } else {
+            run_variant<256, 1, 8, true>(P, pf, "p256r1", reps);
+            run_variant<128, 1, 16, true>(P, pf, "p128r1", reps);
+            run_variant<128, 2, 8, true>(P, pf, "p128r2", reps);
+            run_variant<256, 2, 4, true>(P, pf, "p256r2", reps);
+            run_variant<64, 2, 16, true>(P, pf, "p64r2", reps);
+            run_variant<128, 3, 6, true>(P, pf, "p128r3", reps);
+            run_variant<1024, 1, 2, true>(P, pf, "p1024r1", reps);
+        }
+    }
+    printf("{\"err\": \"%s\"}\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
