@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--smoother", default="jacobi", choices=["jacobi", "jacobi_a", "gs", "gs_color"])
     ap.add_argument("--fuse-restrict", type=int, default=1)
     ap.add_argument("--stream-cfg", type=int, default=3)
-    ap.add_argument("--compress", type=int, default=2, help="lossless operator coding: 0 CSR stream kernels only, 1 one byte per entry, 2 + row patterns")
+    ap.add_argument("--compress", type=int, default=3, help="lossless operator coding: 0 CSR stream kernels only, 1 one byte per entry, 2 + row patterns, 3 + anchored row patterns (P)")
     ap.add_argument("--code-cfg", type=int, default=1)
     ap.add_argument("--options", default="", help="further engine options, k=v,k=v (mgb_set_option)")
     ap.add_argument("--no-cpu", action="store_true")

@@ -60,7 +60,7 @@ def run(args):
     mg = ds.DistMG(src, device=local_rank, r_mode=args.restriction, smoother=args.smoother, gather_threshold=args.gather_threshold,
                    options={**{"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg, "use_graph": args.use_graph,
                                "overlap_halo": args.overlap, "overlap_waves": args.overlap_waves,
-                               "compress": getattr(args, "compress", 2), "code_cfg": getattr(args, "code_cfg", 1)}, **args.options},
+                               "compress": getattr(args, "compress", 3), "code_cfg": getattr(args, "code_cfg", 1)}, **args.options},
                    device_gen=bool(args.device_gen) and args.restriction == "injection", p2p=bool(args.p2p))
     setup_s = time.perf_counter() - t0
     eng = mg.eng
@@ -126,7 +126,7 @@ def run(args):
         line = {"metric": B.METRIC, "value": dofu / (ms * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{name}: {desc}", "restriction": args.restriction, "smoother": args.smoother, "fine_dofs": n_glob,
-                           "levels": lf - lc + 1, "mu1": src.mu1, "mu2": src.mu2, "generated_on_device": bool(mg.device_gen), "compress": getattr(args, "compress", 2),
+                           "levels": lf - lc + 1, "mu1": src.mu1, "mu2": src.mu2, "generated_on_device": bool(mg.device_gen), "compress": getattr(args, "compress", 3),
                            "parallelism": f"row-sharded x{world}, levels <= {mg.gather_level} on rank 0" if multi else "single GPU",
                            "options": args.options,
                            "l2": ("per-rank working set of one fine-level sweep (codes + 3 vectors, %.0f MB) " % (25.0 * n_glob / world / 1e6)) +

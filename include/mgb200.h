@@ -85,9 +85,12 @@ enum {
 /* The lossless coding mgb_finalize built for an operator of the level (compare with mgb_host_code_operator):
  * kind = MGB_ART_CODE(op, part), op: 0 A, 1 R_omega, 2 P, 3 R;
  * part 0: int32[4] {mode, dictionary entries / patterns in use, table entries, number of codes};
- * part 1: uint8 codes (per row in mode 3, per stored entry in modes 1 and 2); part 2: table, 16-byte entries
- * {double value; int32 col_minus_row; int32 0}; part 3 (mode 3): int32 {first entry, length} x 256. */
+ * part 1: uint8 codes (per row in modes 3 and 4, per stored entry in modes 1 and 2); part 2: table, 16-byte entries
+ * {double value; int32 col_minus_row (mode 4: col minus the row's anchor column); int32 0}; part 3 (modes 3, 4): int32
+ * {first entry, length} x 256.  MGB_ART_CODE_ANCHOR(op) (mode 4): int32[nrows], every row's anchor = its first stored column
+ * (0 for an empty row). */
 #define MGB_ART_CODE(op, part) (32 + 4 * (op) + (part))
+#define MGB_ART_CODE_ANCHOR(op) (48 + (op))
 
 /* per-level device buffers (mgb_level_buffer) */
 enum { MGB_BUF_V = 0, MGB_BUF_F = 1, MGB_BUF_R = 2 };
@@ -263,10 +266,12 @@ int mgb_host_dense_inverse(int64_t n, const int64_t* indptr, const int32_t* indi
 int mgb_host_make_tiles(int64_t n, const int64_t* indptr, int64_t cap, int64_t row_cap, int nbreaks, const int32_t* breaks,
                         int64_t row_align, int32_t* tiles, int64_t tiles_capacity, int64_t* ntiles, int32_t* break_tile);
 /* The lossless operator coding of DESIGN.md 4.1 as a host routine: the definition of what mgb_finalize builds (and verifies
- * entry by entry) on the device.  *mode_out: 0 none, 1 pair codes, 2 value codes, 3 row patterns (tried only if allow_patterns).
- * codes: uint8[nrows] (mode 3) or uint8[nnz] (modes 1, 2).  table: 16-byte entries {double value; int32 col_minus_row; int32 0},
- * 256 of them (modes 1, 2) or *table_entries <= 2048 (mode 3: every pattern padded to a multiple of 8 entries).
- * pattern_head (mode 3): int32 {first entry, length} x 256.  *ndict_out: dictionary entries / patterns in use.
+ * entry by entry) on the device.  *mode_out: 0 none, 1 pair codes, 2 value codes, 3 row patterns (tried only if allow_patterns
+ * >= 1), 4 anchored row patterns -- columns measured from each row's first stored column (tried after mode 3 if allow_patterns
+ * >= 2; the anchors themselves are indices[indptr[i]], 0 for an empty row).
+ * codes: uint8[nrows] (modes 3, 4) or uint8[nnz] (modes 1, 2).  table: 16-byte entries {double value; int32 col_minus_row (mode 4:
+ * col minus anchor); int32 0}, 256 of them (modes 1, 2) or *table_entries <= 2048 (modes 3, 4: every pattern padded to a multiple
+ * of 8 entries).  pattern_head (modes 3, 4): int32 {first entry, length} x 256.  *ndict_out: dictionary entries / patterns in use.
  * codes, table, pattern_head may be NULL to query the mode and the counts only. */
 int mgb_host_code_operator(int64_t nrows, int64_t ncols, const int64_t* indptr, const int32_t* indices, const double* values,
                            int allow_patterns, int* mode_out, int* ndict_out, uint8_t* codes, void* table, int* table_entries,

@@ -151,7 +151,7 @@ k_code_verify(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__
 
 void free_coded(Coded& c)
 {
-    cudaFree(c.codes); cudaFree(c.dict); cudaFree(c.phead); cudaFree(c.dict_win); cudaFree(c.pmask);
+    cudaFree(c.codes); cudaFree(c.dict); cudaFree(c.phead); cudaFree(c.dict_win); cudaFree(c.pmask); cudaFree(c.anchor);
     c = Coded();
 }
 
@@ -159,13 +159,21 @@ void free_coded(Coded& c)
 constexpr int PAT_MAX_ENTRIES = 2048;                // pattern-table entries the kernel keeps in shared memory (32 KB)
 constexpr int PAT_REP_EMPTY = 0x7F7F7F7F;
 
-__device__ __forceinline__ unsigned long long pat_row_hash(int i, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols,
+// base: what a row's columns are measured from -- the row index (square operators, mode 3) or the row's first stored column
+// (anchored patterns, mode 4: rectangular operators such as the prolongation, whose columns do not follow the row index)
+__device__ __forceinline__ int pat_base(int i, bool anchored, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols)
+{
+    if (!anchored) return i;
+    return rp[i + 1] > rp[i] ? cols[rp[i]] : 0;
+}
+__device__ __forceinline__ unsigned long long pat_row_hash(int i, bool anchored, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols,
                                                            const double* __restrict__ vals)
 {
     const int a = rp[i], b = rp[i + 1];
+    const int base = pat_base(i, anchored, rp, cols);
     unsigned long long h = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)(unsigned)(b - a);
     for (int k = a; k < b; ++k) {
-        h ^= (unsigned long long)(unsigned)(cols[k] - i);
+        h ^= (unsigned long long)(unsigned)(cols[k] - base);
         h *= 0xff51afd7ed558ccdULL; h ^= h >> 32;
         h ^= (unsigned long long)__double_as_longlong(vals[k]);
         h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 29;
@@ -175,13 +183,13 @@ __device__ __forceinline__ unsigned long long pat_row_hash(int i, const int32_t*
 
 // flags: [0] abandoned (more than 256 distinct hashes), [2] distinct hashes
 __global__ void __launch_bounds__(256)
-k_pat_collect(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, const double* __restrict__ vals,
+k_pat_collect(int n, bool anchored, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, const double* __restrict__ vals,
               unsigned long long* htbl, int* rep, int* flags)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (((volatile int*)flags)[0]) return;
-    const unsigned long long key = pat_row_hash(i, rp, cols, vals);
+    const unsigned long long key = pat_row_hash(i, anchored, rp, cols, vals);
     unsigned s = code_hash(key) & (CODE_SLOTS - 1);
     for (int p = 0; p < CODE_SLOTS; ++p) {
         unsigned long long cur = htbl[s];
@@ -201,8 +209,8 @@ k_pat_collect(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__
 struct PatDicts { unsigned long long h[256]; int id[256]; int n; };      // hashes ascending -> pattern number
 
 __global__ void __launch_bounds__(256)
-k_pat_encode(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, const double* __restrict__ vals,
-             const PatDicts* __restrict__ pd, unsigned char* __restrict__ rcodes)
+k_pat_encode(int n, bool anchored, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, const double* __restrict__ vals,
+             const PatDicts* __restrict__ pd, unsigned char* __restrict__ rcodes, int32_t* __restrict__ anchor)
 {
     __shared__ unsigned long long sh[256];
     __shared__ int sid[256];
@@ -212,22 +220,24 @@ k_pat_encode(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ 
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int pos = code_find_value(sh, np, pat_row_hash(i, rp, cols, vals)) & 255;
+    const int pos = code_find_value(sh, np, pat_row_hash(i, anchored, rp, cols, vals)) & 255;
     rcodes[i] = (unsigned char)sid[pos];
+    if (anchored) anchor[i] = pat_base(i, true, rp, cols);
 }
 
 __global__ void __launch_bounds__(256)
-k_pat_verify(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, const double* __restrict__ vals,
+k_pat_verify(int n, const int32_t* __restrict__ anchor, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, const double* __restrict__ vals,
              const unsigned char* __restrict__ rcodes, const int2* __restrict__ phead, const DictEnt* __restrict__ pent, int* __restrict__ bad)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int2 ph = phead[rcodes[i]];
     const int a = rp[i], len = rp[i + 1] - a;
+    const int base = anchor ? anchor[i] : i;                 // (decoded exactly as the kernels decode it: from the stored anchor)
     bool ok = ph.y == len;
     for (int e = 0; ok && e < len; ++e) {
         const DictEnt de = pent[ph.x + e];
-        ok = (i + de.delta == cols[a + e]) && __double_as_longlong(de.val) == __double_as_longlong(vals[a + e]);
+        ok = (base + de.delta == cols[a + e]) && __double_as_longlong(de.val) == __double_as_longlong(vals[a + e]);
     }
     if (!ok) *bad = 1;
 }
@@ -245,11 +255,13 @@ k_code_hist(int n, const unsigned char* __restrict__ rcodes, unsigned long long*
 }
 
 // Row-pattern coding of D (mode 3).  ip: the operator's row pointers on the host.  Leaves D.cd.mode == 0 when it does not apply.
-int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip)
+// anchored: columns measured from each row's first stored column (mode 4) instead of from the row index (mode 3).
+int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, bool anchored)
 {
     free_coded(D.cd);
-    if (h->compress < 2 || D.nrows <= 0 || D.nnz <= 0 || D.ncols < D.nrows) return MGB_OK;
-    if ((double)D.nnz / (double)D.nrows > 24.0) return MGB_OK;
+    if (h->compress < 2 || D.nrows <= 0 || D.nnz <= 0 || (!anchored && D.ncols < D.nrows)) return MGB_OK;
+    if (anchored && h->compress < 3) return MGB_OK;
+    if ((double)D.nnz / (double)D.nrows > (anchored ? 32.0 : 24.0)) return MGB_OK;
     const int n = (int)D.nrows;
     const int grid = (n + 255) / 256;
     unsigned long long* htbl = nullptr; int* rep = nullptr; int* flags = nullptr; PatDicts* dpd = nullptr; int* bad = nullptr;
@@ -265,7 +277,7 @@ int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip)
     CUC(cudaMemsetAsync(htbl, 0xFF, CODE_SLOTS * sizeof(unsigned long long), h->stream));
     CUC(cudaMemsetAsync(rep, 0x7F, CODE_SLOTS * sizeof(int), h->stream));
     CUC(cudaMemsetAsync(flags, 0, 4 * sizeof(int), h->stream));
-    k_pat_collect<<<grid, 256, 0, h->stream>>>(n, D.rowptr, D.cols, D.vals, htbl, rep, flags);
+    k_pat_collect<<<grid, 256, 0, h->stream>>>(n, anchored, D.rowptr, D.cols, D.vals, htbl, rep, flags);
     CUC(cudaGetLastError());
     std::vector<unsigned long long> hh(CODE_SLOTS);
     std::vector<int> hr(CODE_SLOTS);
@@ -299,7 +311,8 @@ int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip)
             CUC(cudaMemcpyAsync(rv.data(), D.vals + ip[(size_t)r], sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, h->stream));
             CUC(cudaStreamSynchronize(h->stream));
         }
-        for (int e = 0; e < len; ++e) pent[(size_t)(off + e)] = DictEnt{rv[(size_t)e], rc[(size_t)e] - r, 0};
+        const int base = anchored ? (len > 0 ? rc[0] : 0) : r;
+        for (int e = 0; e < len; ++e) pent[(size_t)(off + e)] = DictEnt{rv[(size_t)e], rc[(size_t)e] - base, 0};
         const int padded = std::max(8, (len + 7) / 8 * 8);
         for (int e = len; e < padded; ++e)                                // copies of the last entry; (0, 0.0) for an empty row
             pent[(size_t)(off + e)] = len > 0 ? pent[(size_t)(off + len - 1)] : DictEnt{0.0, 0, 0};
@@ -321,11 +334,13 @@ int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip)
     const size_t cbytes = ((size_t)n + 15) / 16 * 16 + 64;
     CUC(cudaMalloc((void**)&D.cd.codes, cbytes));
     CUC(cudaMemsetAsync(D.cd.codes, 0, cbytes, h->stream));
-    k_pat_encode<<<grid, 256, 0, h->stream>>>(n, D.rowptr, D.cols, D.vals, dpd, D.cd.codes);
+    if (anchored) CUC(cudaMalloc((void**)&D.cd.anchor, ((size_t)n + 64) * sizeof(int32_t)));
+    if (anchored) CUC(cudaMemsetAsync(D.cd.anchor, 0, ((size_t)n + 64) * sizeof(int32_t), h->stream));
+    k_pat_encode<<<grid, 256, 0, h->stream>>>(n, anchored, D.rowptr, D.cols, D.vals, dpd, D.cd.codes, D.cd.anchor);
     CUC(cudaGetLastError());
     CUC(cudaMalloc((void**)&bad, sizeof(int)));
     CUC(cudaMemsetAsync(bad, 0, sizeof(int), h->stream));
-    k_pat_verify<<<grid, 256, 0, h->stream>>>(n, D.rowptr, D.cols, D.vals, D.cd.codes, D.cd.phead, D.cd.dict, bad);
+    k_pat_verify<<<grid, 256, 0, h->stream>>>(n, (const int32_t*)D.cd.anchor, D.rowptr, D.cols, D.vals, D.cd.codes, D.cd.phead, D.cd.dict, bad);
     CUC(cudaGetLastError());
     int hb = 0;
     CUC(cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -333,7 +348,8 @@ int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip)
     cleanup();
 #undef CUC
     if (hb) { free_coded(D.cd); return MGB_OK; }          // never trust an unverified coding
-    D.cd.mode = 3; D.cd.ndict = (int)pats.size(); D.cd.npent = total;
+    D.cd.mode = anchored ? 4 : 3; D.cd.ndict = (int)pats.size(); D.cd.npent = total;
+    if (anchored) return MGB_OK;
     {   // the most frequent ("hot") pattern -- exact histogram of the row codes (a strided sample can fall on boundary rows
         // only: 513^3 rows sampled 1024 times land on multiples of 513) -- travels to the hot-row / row-window kernels as
         // kernel parameters

@@ -132,7 +132,7 @@ HotChoice hot_choice(int cfg)
 bool hot_len_supported(int hotlen) { return hotlen == 4 || hotlen == 6 || hotlen == 7 || hotlen == 15; }
 
 int try_encode(mgb_handle* h, DevCsr& D);
-int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip);
+int try_patterns(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, bool anchored);
 void free_coded(Coded& c);
 
 // Kernel family, row tiles and stream descriptors of an operator whose arrays are already on the device.
@@ -174,8 +174,9 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
         // entries counted from a 16-entry aligned start (16-byte bulk copies of one-byte codes)
         bool tiled = false;
         int64_t align_mask = 7;
-        TRY(try_patterns(h, D, ip));             // whole rows repeat (uniform mesh, banded numbering): one byte per ROW
-        if (!D.cd.mode) TRY(try_encode(h, D));   // else one byte per stored entry
+        TRY(try_patterns(h, D, ip, false));                  // whole rows repeat (uniform mesh, banded numbering): one byte per ROW
+        if (!D.cd.mode) TRY(try_patterns(h, D, ip, true));   // ... or repeat when measured from their first column (P): 4 + 1 bytes per row
+        if (!D.cd.mode) TRY(try_encode(h, D));               // else one byte per stored entry
         if (D.cd.mode) {
             D.ccfg = h->code_cfg;
             const CodeChoice cc = code_choice(D.ccfg);
@@ -184,11 +185,14 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
             if (D.cd.mode == 3 && h->stage_x == 3 && D.cd.hot_ok && hot_len_supported(D.cd.hotplan.hotlen)) {   // hot-row kernel: its own tile size
                 D.hcfg = std::max(1, h->hot_cfg);
                 rowcap = (int64_t)hot_choice(D.hcfg).threads * hot_choice(D.hcfg).rpt;
+            } else if (D.cd.mode == 4) {                                                                 // anchored patterns: their own tile size
+                D.hcfg = 1;
+                rowcap = (h->anch_cfg == 1 || h->anch_cfg == 0) ? 512 : 256;
             } else if (D.cd.mode == 3 && h->stage_x == 1 && D.cd.win.ng > 0 && D.cd.dict_win) {          // row-window kernel: its own tile size
                 D.wcfg = std::max(1, h->win_cfg);
                 rowcap = 256 * (int64_t)win_choice(D.wcfg).rpt;
             }
-            if (D.cd.mode == 3) tiled = make_tiles(ip, (int64_t)1 << 40, rowcap, sbreaks, st, &sbt, 16);    // rows only; 16-byte aligned code slices
+            if (D.cd.mode >= 3) tiled = make_tiles(ip, (int64_t)1 << 40, rowcap, sbreaks, st, &sbt, 16);    // rows only; 16-byte aligned code slices
             else tiled = make_tiles(ip, rowcap * cc.epr - 8, rowcap, sbreaks, st, &sbt, 4);
             if (tiled) align_mask = 15; else free_coded(D.cd);
         }
@@ -202,7 +206,7 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
             for (size_t t = 0; t + 1 < st.size(); ++t) {
                 const int64_t r0 = st[t], r1 = st[t + 1];
                 const int64_t z0 = ip[r0] & ~align_mask, z1 = ip[r1];
-                if (D.cd.mode == 3) desc[t] = make_int4((int)r0, (int)(r1 - r0), 0, (int)(ip[r1] - ip[r0]));   // (entry count: accounting only)
+                if (D.cd.mode >= 3) desc[t] = make_int4((int)r0, (int)(r1 - r0), 0, (int)(ip[r1] - ip[r0]));   // (entry count: accounting only)
                 else desc[t] = make_int4((int)r0, (int)(r1 - r0), (int)z0, (int)((z1 - z0 + align_mask) & ~align_mask));
             }
             D.sntiles = (int)desc.size();
@@ -530,6 +534,51 @@ bool launch_hotrow(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles,
     return false;
 }
 
+// Anchored row patterns (k_anchrow).  Configurations (option "anch_cfg"): threads x rows per thread.
+template <int T, int RPT, int JW, int MINB, class Epi>
+void launch_anchrow_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi)
+{
+    constexpr int ROWS = T * RPT;
+    auto kern = k_anchrow<T, RPT, JW, MINB, Epi>;
+    const bool linear = desc == D.sdesc && ntiles == D.sntiles;
+    const int grid = linear ? (int)((D.nrows + ROWS - 1) / ROWS) : ntiles;
+    if (grid <= 0) return;
+    const int pf = h->allow_stream && h->hot_pf > 0 ? std::max(1, h->hot_pf / ROWS) : 0;
+    const int smem = D.cd.npent * 12 + 256 * 8;
+    if (smem > 48 * 1024) {
+        static std::mutex mu;
+        static std::map<int, int> attr;
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > attr[h->device]) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr[h->device] = smem; }
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->pdl != 0 ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, (const unsigned char*)D.cd.codes, (const int32_t*)D.cd.anchor, (const int2*)D.cd.phead, (const DictEnt*)D.cd.dict,
+                       D.cd.ndict, D.cd.npent, linear ? (const int4*)nullptr : desc, grid, 0, (int)D.nrows, pf, x, epi);
+}
+
+template <class Epi>
+void launch_anchrow(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi)
+{
+    if (D.max_row <= 4) {
+        switch (h->anch_cfg) {
+            case 2: return launch_anchrow_cfg<128, 2, 4, 8, Epi>(h, D, desc, ntiles, x, epi);
+            case 3: return launch_anchrow_cfg<64, 4, 4, 16, Epi>(h, D, desc, ntiles, x, epi);
+            default: return launch_anchrow_cfg<128, 4, 4, 8, Epi>(h, D, desc, ntiles, x, epi);
+        }
+    }
+    switch (h->anch_cfg) {
+        case 2: return launch_anchrow_cfg<128, 2, 8, 5, Epi>(h, D, desc, ntiles, x, epi);
+        case 3: return launch_anchrow_cfg<64, 4, 8, 10, Epi>(h, D, desc, ntiles, x, epi);
+        case 4: return launch_anchrow_cfg<256, 1, 8, 5, Epi>(h, D, desc, ntiles, x, epi);
+        default: return launch_anchrow_cfg<128, 4, 8, 5, Epi>(h, D, desc, ntiles, x, epi);
+    }
+}
+
 // MODE: the coding (pair / value codes); JW: gathers issued up front per row (4 when no row is longer, else 8)
 template <int MODE, int JW, class Epi>
 void launch_rowstream(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi, bool chunked)
@@ -547,6 +596,7 @@ void launch_stream(mgb_handle* h, const DevCsr& D, const double* x, const Epi& e
     if (!desc) { desc = D.sdesc; ntiles = D.sntiles; }
     if (ntiles <= 0) return;
     if constexpr (Epi::CONTIG) {
+        if (D.cd.mode == 4) return launch_anchrow<Epi>(h, D, desc, ntiles, x, epi);
         if (D.cd.mode == 3 && D.hcfg > 0 && launch_hotrow<Epi>(h, D, desc, ntiles, x, epi)) return;
         if (D.cd.mode == 3 && D.wcfg > 0) {              // x staged in shared memory (tiles were cut for this configuration)
             return launch_rowwin<Epi>(h, D, desc, ntiles, x, epi, chunked);
@@ -594,6 +644,7 @@ double coded_saving(const DevCsr& D)
         case 1: return 11.0 * (double)D.nnz;
         case 2: return 7.0 * (double)D.nnz;
         case 3: return 12.0 * (double)D.nnz + 3.0 * (double)D.nrows;
+        case 4: return 12.0 * (double)D.nnz - 1.0 * (double)D.nrows;      // anchor (4) + code (1) instead of the entries and the row pointer (4)
         default: return 0.0;
     }
 }
@@ -1053,6 +1104,10 @@ int mgb_set_level(mgb_handle* h, int level, int64_t n, int64_t nnz, const void* 
 {
     if (!h) return MGB_ERR_INVALID;
     if (h->finalized) return fail(h, MGB_ERR_STATE, "hierarchy already finalized");
+    // refused before a single entry is read: one device shard addresses its entries with int32 row pointers
+    if (n >= (int64_t)2147483000 || nnz >= (int64_t)2147483000)
+        return fail(h, MGB_ERR_UNSUPPORTED, "level %d: %lld rows / %lld entries exceed the int32 row-pointer range of one device shard (row-shard it: mgb_set_level_local)",
+                    level, (long long)n, (long long)nnz);
     Level& L = h->levels[level];
     L.level = level; L.n = n;
     std::string e = import_csr(L.A_host, n, n, nnz, indptr, indptr_bytes, indices, values);
@@ -1357,6 +1412,7 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "stage_x" && pre) h->stage_x = iv;
     else if (k == "win_cfg" && pre) h->win_cfg = iv;
     else if (k == "hot_cfg" && pre) h->hot_cfg = iv;
+    else if (k == "anch_cfg" && pre) h->anch_cfg = iv;
     else if (k == "reuse_g") { h->reuse_g = iv; drop_graphs(h); }
     else if (k == "hot_inj") { h->hot_inj = iv; drop_graphs(h); }
     else if (k == "hot_pf") { h->hot_pf = iv; drop_graphs(h); }
@@ -1821,17 +1877,23 @@ int mgb_get_artifact(mgb_handle* h, int level, int kind, void* out, int64_t capa
         case MGB_ART_COARSE_INVERSE:
             src = h->coarse_inv_host.data(); bytes = (int64_t)h->coarse_inv_host.size() * 8; on_device = false; break;
         default: {
+            if (kind >= MGB_ART_CODE_ANCHOR(0) && kind <= MGB_ART_CODE_ANCHOR(3)) {         // mode 4: every row's anchor column
+                const int op = kind - MGB_ART_CODE_ANCHOR(0);
+                const DevCsr& D = op == 0 ? L->A : (op == 1 ? L->RJ : (op == 2 ? L->P : L->R));
+                src = D.cd.anchor; bytes = D.cd.mode == 4 ? D.nrows * 4 : 0;
+                break;
+            }
             if (kind < MGB_ART_CODE(0, 0) || kind > MGB_ART_CODE(3, 3)) return fail(h, MGB_ERR_INVALID, "unknown artefact kind %d", kind);
             const int op = (kind - MGB_ART_CODE(0, 0)) / 4, part = (kind - MGB_ART_CODE(0, 0)) % 4;
             const DevCsr& D = op == 0 ? L->A : (op == 1 ? L->RJ : (op == 2 ? L->P : L->R));
             const Coded& cd = D.cd;
-            const int64_t ncodes = cd.mode == 3 ? D.nrows : (cd.mode ? D.nnz : 0);
-            const int64_t tab = cd.mode == 3 ? cd.npent : (cd.mode ? 256 : 0);
+            const int64_t ncodes = cd.mode >= 3 ? D.nrows : (cd.mode ? D.nnz : 0);
+            const int64_t tab = cd.mode >= 3 ? cd.npent : (cd.mode ? 256 : 0);
             code_info[0] = cd.mode; code_info[1] = cd.ndict; code_info[2] = (int32_t)tab; code_info[3] = (int32_t)ncodes;
             if (part == 0) { src = code_info; bytes = sizeof code_info; on_device = false; }
             else if (part == 1) { src = cd.codes; bytes = ncodes; }
             else if (part == 2) { src = cd.dict; bytes = tab * (int64_t)sizeof(DictEnt); }
-            else { src = cd.phead; bytes = cd.mode == 3 ? 256 * (int64_t)sizeof(int2) : 0; }
+            else { src = cd.phead; bytes = cd.mode >= 3 ? 256 * (int64_t)sizeof(int2) : 0; }
             break;
         }
     }
@@ -1958,7 +2020,8 @@ int mgb_describe(mgb_handle* h, char* out, int64_t capacity)
     char buf[384];
     auto one = [&](const char* name, const DevCsr& D) {
         if (!D.present()) return;
-        if (D.family == 1 && D.sdesc && D.cd.mode == 3 && D.hcfg > 0) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d hotrow(coded mode=3: %d row patterns, %d table entries, hot pattern %d of %d entries, %d patterns take the table walk; cfg=%d, %d x %d rows) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.cd.hotplan.hot, D.cd.hotplan.hotlen, D.cd.hot_slow, D.hcfg, hot_choice(D.hcfg).threads, hot_choice(D.hcfg).rpt, D.sntiles);
+        if (D.family == 1 && D.sdesc && D.cd.mode == 4) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d anchrow(coded mode=4: first column + one of %d row patterns, %d table entries; 256-row tiles) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.sntiles);
+        else if (D.family == 1 && D.sdesc && D.cd.mode == 3 && D.hcfg > 0) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d hotrow(coded mode=3: %d row patterns, %d table entries, hot pattern %d of %d entries, %d patterns take the table walk; cfg=%d, %d x %d rows) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.cd.hotplan.hot, D.cd.hotplan.hotlen, D.cd.hot_slow, D.hcfg, hot_choice(D.hcfg).threads, hot_choice(D.hcfg).rpt, D.sntiles);
         else if (D.family == 1 && D.sdesc && D.cd.mode == 3 && D.wcfg > 0) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowwin(coded mode=3: %d row patterns, %d table entries, %d x-windows, hot pattern %d; cfg=%d, 256 x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.cd.win.ng, D.cd.win.hot, D.wcfg, win_choice(D.wcfg).rpt, win_choice(D.wcfg).stages, D.sntiles);
         else if (D.family == 1 && D.sdesc && D.cd.mode == 3) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowstream(coded mode=3: %d row patterns, %d table entries; cfg=%d, %d x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.ndict, D.cd.npent, D.ccfg, code_choice(D.ccfg).threads, code_choice(D.ccfg).rpt, code_choice(D.ccfg).stages, D.sntiles);
         else if (D.family == 1 && D.sdesc && D.cd.mode) snprintf(buf, sizeof buf, "  %-3s rows=%lld nnz=%lld max_row=%d rowstream(coded mode=%d: %d dictionary entries, %d values, %d offsets; cfg=%d, %d x %d rows, %d stages) tiles=%d\n", name, (long long)D.nrows, (long long)D.nnz, D.max_row, D.cd.mode, D.cd.ndict, D.cd.nvals, D.cd.ndeltas, D.ccfg, code_choice(D.ccfg).threads, code_choice(D.ccfg).rpt, code_choice(D.ccfg).stages, D.sntiles);

@@ -160,13 +160,15 @@ struct TileCfg {
 
 __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
 
-// NCX: x is read-only for the whole launch -> gather it through the non-coherent path (__ldg).
-// NCX = false is used when the epilogue writes into x itself (in-place Gauss-Seidel colours).
+// x is gathered with ordinary (coherent, L1-cached) loads, never through the non-coherent path (__ldg / ld.global.nc): under
+// programmatic dependent launch a kernel is resident while its predecessors still run, and .nc requires the location to be
+// read-only for the kernel's whole lifetime -- x is what the predecessor writes.  With ping-pong iterates a stale line left
+// in L1 by the sweep before the predecessor was actually observed (k_hotinj on small levels, three kernels co-resident).
+// NCX = false additionally marks launches whose epilogue writes into x itself (in-place Gauss-Seidel colours).
 template <bool NCX>
 __device__ __forceinline__ double ld_x(const double* x, int c)
 {
-    if constexpr (NCX) return __ldg(x + c);
-    else return x[c];
+    return x[c];
 }
 
 template <int ITER, int THREADS, bool NCX, class Epi>
@@ -984,7 +986,7 @@ __device__ __forceinline__ int ld_stream_u8(const unsigned char* p)
 __device__ __forceinline__ double ld_stream_f64(const double* p)
 {
     double v;      // volatile: stays behind griddepcontrol.wait (the predecessor kernel may have written the operand)
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));      // (not .nc: an epilogue may update the operand in place)
     return v;
 }
 
@@ -1021,9 +1023,9 @@ k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
             code[j] = ld_stream_u8(rcodes + r);
             const double* xr = x + r;
 #pragma unroll
-            for (int e = 0; e < HOTN; ++e) xv[j][e] = __ldg(xr + H.hd[e]);
+            for (int e = 0; e < HOTN; ++e) xv[j][e] = xr[H.hd[e]];             // (coherent loads: see ld_x)
 #pragma unroll
-            for (int k = 0; k < NOPS; ++k) o[j][k] = (alias && k == XOP) ? __ldg(xr) : ld_stream_f64(epi.operand(k) + r);
+            for (int k = 0; k < NOPS; ++k) o[j][k] = (alias && k == XOP) ? xr[0] : ld_stream_f64(epi.operand(k) + r);
             if constexpr (NIOPS > 0) io[j] = __ldg(epi.ioperand() + r);
         }
     } else {
@@ -1032,7 +1034,7 @@ k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
             const int r = min(row0 + tid + j * THREADS, rend - 1);        // threads past the end redo the last row (and do not store)
             code[j] = ld_stream_u8(rcodes + r);
 #pragma unroll
-            for (int e = 0; e < HOTN; ++e) xv[j][e] = __ldg(x + min(max(r + H.hd[e], 0), xlen - 1));
+            for (int e = 0; e < HOTN; ++e) xv[j][e] = x[min(max(r + H.hd[e], 0), xlen - 1)];
 #pragma unroll
             for (int k = 0; k < NOPS; ++k) o[j][k] = epi.operand(k)[r];
             if constexpr (NIOPS > 0) io[j] = epi.ioperand()[r];
@@ -1054,7 +1056,12 @@ k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
         const int r = row0 + tid + j * THREADS;
         const uint32_t m = __ldg(pmask + code[j]);
         double sum = 0.0;                                    // one accumulator, stored order
-        if (!(m & HOT_SLOW)) {
+        if (__all_sync(0xffffffffu, m == (1u << HOTN) - 1u)) {
+            // every row of the warp carries the complete hot pattern (the common case away from the boundary): straight-line body,
+            // no predicate, no select
+#pragma unroll
+            for (int e = 0; e < HOTN; ++e) sum = __dadd_rn(sum, __dmul_rn(H.hv[e], xv[j][e]));
+        } else if (!(m & HOT_SLOW)) {
 #pragma unroll
             for (int e = 0; e < HOTN; ++e)
                 if ((m >> e) & 1u) sum = __dadd_rn(sum, __dmul_rn(H.hv[e], xv[j][e]));
@@ -1063,7 +1070,7 @@ k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
             for (int e = 0; e < ph.y; ++e) {
                 const double val = __ldg(&pent[ph.x + e].val);
                 const int dl = __ldg(&pent[ph.x + e].delta);
-                sum = __dadd_rn(sum, __dmul_rn(val, __ldg(x + r + dl)));
+                sum = __dadd_rn(sum, __dmul_rn(val, x[r + dl]));
             }
         }
         if (fast || r < rend) {
@@ -1115,6 +1122,109 @@ k_hotinj(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
         }
     }
     if (i < nc) out[i] = __dsub_rn(fr, sum);
+}
+
+// ---- anchored row patterns (mode 4): rectangular operators ------------------------------------------------------
+// The prolongation of a uniform mesh repeats too, but its columns do not follow the row index: row i of P touches coarse
+// nodes around (roughly) i / 2^d.  Measured from the row's FIRST stored column, however, the list of (col - first, value) is one
+// of a handful (8 parity classes for the trilinear P).  Such an operator is kept as 4 + 1 bytes per ROW -- the anchor column
+// and the pattern number -- instead of 12 bytes per entry plus a row pointer; the coding is found and verified on the device
+// (try_patterns, anchored).  Thread per row, RPT rows per thread: (anchor, code, operands) are loaded for all rows first, then
+// the pattern entries (a table of <= 2048 entries, L1-resident) and the x values, then the sums -- one accumulator, stored
+// order, separately rounded multiply and add, as everywhere.  Patterns are padded to a multiple of 8 entries with copies of
+// their last entry, so the JW loads of a chunk are issued without a bounds test.  Tiles as in k_hotrow.
+__device__ __forceinline__ int ld_stream_i32(const int32_t* p)
+{
+    int v;
+    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// What bounds this kernel is the dependent chain (anchor, code) -> pattern entry -> x value: three memory latencies per row.
+// So (1) anchors and codes are static data and are requested BEFORE griddepcontrol.wait, overlapping the predecessor's tail;
+// (2) the pattern table sits in shared memory (copied by the CTA while those requests are in flight), which turns two of the
+// three latencies into shared-memory look-ups; (3) a thread keeps RPT rows in flight, holding only their x values in registers
+// (the entry values are looked up again when the row is summed).
+template <int THREADS, int RPT, int JW, int MINB, class Epi>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ anchor, const int2* __restrict__ phead,
+          const DictEnt* __restrict__ pent, int ndict, int npent, const int4* __restrict__ desc, int ntiles, int rb, int re, int pf,
+          const double* x, Epi epi)
+{
+    static_assert(Epi::CONTIG, "anchored-pattern kernel needs contiguous epilogue operands");
+    static_assert(JW == 4 || JW == 8, "chunk width");
+    constexpr int T = THREADS * RPT;
+    constexpr int NOPS = Epi::NOPS, NIOPS = EpiNI<Epi>::value;
+    extern __shared__ __align__(16) unsigned char smem_anch[];
+    double* sval = reinterpret_cast<double*>(smem_anch);                       // [npent]
+    int2* sphead = reinterpret_cast<int2*>(smem_anch + (size_t)npent * 8);      // [256]
+    int* sdelta = reinterpret_cast<int*>(smem_anch + (size_t)npent * 8 + 256 * 8);   // [npent]
+    const int tid = threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    int row0 = rb + (int)blockIdx.x * T, rend = re;
+    if (desc) { const int4 d = __ldg(desc + blockIdx.x); row0 = d.x; rend = d.x + d.y; }
+    int code[RPT], anc[RPT];
+    const bool full = row0 + T <= rend;                      // CTA-uniform
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {                          // static data: requested before the predecessor has finished
+        const int r = full ? row0 + tid + j * THREADS : min(row0 + tid + j * THREADS, rend - 1);
+        code[j] = ld_stream_u8(rcodes + r);
+        anc[j] = ld_stream_i32(anchor + r);
+    }
+    for (int k = tid; k < npent; k += THREADS) { const DictEnt d = pent[k]; sval[k] = d.val; sdelta[k] = d.delta; }
+    for (int k = tid; k < ndict; k += THREADS) sphead[k] = phead[k];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    double o[RPT][NOPS > 0 ? NOPS : 1];
+    int io[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int r = full ? row0 + tid + j * THREADS : min(row0 + tid + j * THREADS, rend - 1);
+#pragma unroll
+        for (int k = 0; k < NOPS; ++k) o[j][k] = ld_stream_f64(epi.operand(k) + r);
+        if constexpr (NIOPS > 0) io[j] = epi.ioperand()[r];
+    }
+    if (pf > 0 && tid < 32 && (int)blockIdx.x + pf < ntiles) {   // L2 prefetch for the tile pf tiles ahead
+        long long p0 = (long long)row0 + (long long)pf * T;
+        int pn = T;
+        if (desc) { const int4 d = __ldg(desc + blockIdx.x + pf); p0 = d.x; pn = (d.y + 15) & ~15; }
+        if (p0 + pn <= (long long)re) {
+            if (tid == 0) bulk_prefetch_l2(rcodes + (p0 & ~15LL), pn);
+            if (tid == 1) bulk_prefetch_l2(anchor + (p0 & ~3LL), pn * 4);
+            if (tid >= 2 && tid < 2 + NOPS) bulk_prefetch_l2(epi.operand(tid - 2) + (p0 & ~1LL), pn * 8);
+            if constexpr (NIOPS > 0) if (tid == 2 + NOPS) bulk_prefetch_l2(epi.ioperand() + (p0 & ~3LL), pn * 4);
+        }
+    }
+    __syncthreads();                                         // the table is in shared memory
+    int2 ph[RPT];
+    double xv[RPT][JW];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        ph[j] = sphead[code[j]];
+        const int* sd = sdelta + ph[j].x;
+#pragma unroll
+        for (int e = 0; e < JW; ++e) xv[j][e] = x[anc[j] + sd[e]];            // (coherent load: see ld_x; padded entries repeat the last one)
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int r = row0 + tid + j * THREADS;
+        double sum = 0.0;                                    // one accumulator, stored order
+        const double* sv = sval + ph[j].x;
+#pragma unroll
+        for (int e = 0; e < JW; ++e)
+            if (e < ph[j].y) sum = __dadd_rn(sum, __dmul_rn(sv[e], xv[j][e]));
+        for (int e0 = JW; e0 < ph[j].y; e0 += JW) {          // rows longer than JW entries
+            double xw[JW];
+#pragma unroll
+            for (int e = 0; e < JW; ++e) xw[e] = x[anc[j] + sdelta[ph[j].x + e0 + e]];
+#pragma unroll
+            for (int e = 0; e < JW; ++e)
+                if (e0 + e < ph[j].y) sum = __dadd_rn(sum, __dmul_rn(sval[ph[j].x + e0 + e], xw[e]));
+        }
+        if (full || r < rend) {
+            if constexpr (NIOPS > 0) epi.store_i(r, sum, o[j], io[j]);
+            else epi.store(r, sum, o[j]);
+        }
+    }
 }
 
 // ---- sub-warp family --------------------------------------------------------------------------------

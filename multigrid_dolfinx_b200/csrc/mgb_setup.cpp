@@ -382,17 +382,23 @@ extern "C" int mgb_host_code_operator(int64_t nrows, int64_t ncols, const int64_
     *mode_out = 0;
     if (ndict_out) *ndict_out = 0;
     if (table_entries) *table_entries = 0;
-    if (nrows == 0 || nnz == 0 || (double)nnz / (double)nrows > 24.0) return MGB_OK;
+    if (nrows == 0 || nnz == 0) return MGB_OK;
+    const double avg = (double)nnz / (double)nrows;
     HostDictEnt* tab = (HostDictEnt*)table;
-    // ---- row patterns
-    if (allow_patterns && ncols >= nrows) {
+    // ---- row patterns: columns measured from the row index (mode 3), then from the row's first stored column (mode 4)
+    for (int anchored = 0; anchored <= 1; ++anchored) {
+        if (anchored ? (allow_patterns < 2 || avg > 32.0) : (allow_patterns < 1 || ncols < nrows || avg > 24.0)) continue;
         typedef std::vector<std::pair<int32_t, uint64_t>> Row;
         std::map<Row, int64_t> first;                       // pattern -> first row showing it
         bool ok = true;
         Row key;
-        for (int64_t i = 0; i < nrows && ok; ++i) {
+        auto row_key = [&](int64_t i) {
             key.clear();
-            for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) key.push_back({(int32_t)(indices[k] - i), bits_of(values[k])});
+            const int64_t base = anchored ? (indptr[i + 1] > indptr[i] ? (int64_t)indices[indptr[i]] : 0) : i;
+            for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) key.push_back({(int32_t)(indices[k] - base), bits_of(values[k])});
+        };
+        for (int64_t i = 0; i < nrows && ok; ++i) {
+            row_key(i);
             first.emplace(key, i);                          // rows ascend: the first insertion is the smallest row
             ok = first.size() <= 256;
         }
@@ -420,18 +426,18 @@ extern "C" int mgb_host_code_operator(int64_t nrows, int64_t ncols, const int64_
                         id[r] = (int)p;
                     }
                     for (int64_t i = 0; i < nrows; ++i) {
-                        key.clear();
-                        for (int64_t k = indptr[i]; k < indptr[i + 1]; ++k) key.push_back({(int32_t)(indices[k] - i), bits_of(values[k])});
+                        row_key(i);
                         codes[i] = (uint8_t)id[key];
                     }
                 }
-                *mode_out = 3;
+                *mode_out = anchored ? 4 : 3;
                 if (ndict_out) *ndict_out = (int)order.size();
                 if (table_entries) *table_entries = total;
                 return MGB_OK;
             }
         }
     }
+    if (avg > 24.0) return MGB_OK;
     // ---- per-entry codes
     std::set<uint64_t> vs;
     std::set<int32_t> dset;

@@ -11,7 +11,9 @@ thread_local std::string g_create_error;
 // device (artefacts, fallback kernels); the coded copy is what the row-stream kernel moves through HBM.
 struct Coded {
     int mode = 0;                    // 0 none, 1 pair codes: entry -> (col - row, value), 2 value codes (+ the int32 columns),
-                                     // 3 row-pattern codes: row -> its whole list of (col - row, value)
+                                     // 3 row-pattern codes: row -> its whole list of (col - row, value),
+                                     // 4 anchored row patterns: row -> (first column, its list of (col - first column, value))
+    int32_t* anchor = nullptr;       // mode 4: device, i32[nrows + pad]: every row's first stored column
     unsigned char* codes = nullptr;  // u8[nnz + pad]: index into dict (mode 3: u8[nrows + pad]: index into phead)
     DictEnt* dict = nullptr;         // device, 256 entries (mode 3: npent pattern entries)
     int2* phead = nullptr;           // mode 3: device, 256 x {first entry, length}
@@ -155,13 +157,15 @@ struct mgb_handle {
     int stream_auto = 0;           // pick the stream configuration per operator from its average row length (measured: no gain)
     int gs_cluster = 2;            // level-scheduled Gauss-Seidel: 0 grid barrier, 1 one cluster, 2 one cluster + ELL prefetch pipeline
     int stream_cfg = 3;            // 0: register-staged tile kernel; 1..6: TMA stream kernel configuration (stream_choice)
-    int compress = 2;              // lossless coding of repetitive operators (mgb_code.cuh): 0 off, 1 per-entry codes, 2 + row patterns
+    int compress = 3;              // lossless coding of repetitive operators (mgb_code.cuh): 0 off, 1 per-entry codes, 2 + row patterns,
+                                   // 3 + anchored row patterns for rectangular operators
     int code_cfg = 1;              // row-stream kernel configuration for coded operators (code_choice)
     int stage_x = 3;               // row-pattern-coded operators: 3 speculative loads at the hot pattern's offsets (k_hotrow, the default);
                                    // 1 x staged in shared memory by bulk copies (k_rowwin); 0 bulk-copied codes / operands + x gathered
                                    // through L1 (k_rowstream)
     int reuse_g = 1;               // cycles after the first of one call reuse the top level's w*(dinv*f) instead of forming it again
     int hot_inj = 1;               // fused residual + injection: thread per coarse row on a pattern-coded level matrix (k_hotinj)
+    int anch_cfg = 1;              // anchored-pattern kernel: 1 128 threads x 4 rows, 2 128 x 2, 3 64 x 4, 4 256 x 1 (rows of > 4 entries)
     int hot_cfg = 1;               // hot-row kernel configuration (hot_choice)
     int hot_pf = 262144;           // hot-row kernel: L2 prefetch distance in rows (0: none)
     int win_cfg = 1;               // row-window kernel configuration (win_choice)

@@ -405,8 +405,17 @@ class MGEngine:
             return out
         info = fetch(0, np.int32)
         mode = int(info[0])
-        return {"mode": mode, "ndict": int(info[1]), "codes": fetch(1, np.uint8), "table": fetch(2, CODE_TABLE_DTYPE),
-                "head": fetch(3, np.int32).reshape(-1, 2) if mode == 3 else None}
+        out = {"mode": mode, "ndict": int(info[1]), "codes": fetch(1, np.uint8), "table": fetch(2, CODE_TABLE_DTYPE),
+               "head": fetch(3, np.int32).reshape(-1, 2) if mode in (3, 4) else None}
+        if mode == 4:                        # anchored row patterns: every row's first stored column
+            base = 48 + {"A": 0, "RJ": 1, "P": 2, "R": 3}[op] - 0
+            size = C.c_int64()
+            self._ck(self._lib.mgb_get_artifact(self._h, int(level), base, None, 0, C.byref(size)))
+            anc = np.zeros(size.value // 4, dtype=np.int32)
+            if size.value:
+                self._ck(self._lib.mgb_get_artifact(self._h, int(level), base, anc.ctypes.data, size.value, None))
+            out["anchor"] = anc
+        return out
 
     def rj_matrix(self, level):
         """R_omega of ``level`` as scipy CSR + D^-1 (what getJacobiMatrices returns, multigrid.py:56)."""
@@ -510,7 +519,7 @@ def host_dense_inverse(A):
 CODE_TABLE_DTYPE = np.dtype([("val", "<f8"), ("delta", "<i4"), ("pad", "<i4")])
 
 
-def host_code_operator(A, allow_patterns=True):
+def host_code_operator(A, allow_patterns=2):
     """The lossless operator coding of DESIGN.md 4.1, computed by the library's host routine (the definition of what
     ``mgb_finalize`` builds on the device).  -> dict(mode, ndict, codes, table, head): ``codes`` uint8 per row (mode 3) or per
     stored entry (modes 1, 2); ``table`` structured array {val, delta}; ``head`` (mode 3) int32 (256, 2) {first entry, length}."""
@@ -522,10 +531,17 @@ def host_code_operator(A, allow_patterns=True):
     codes = np.zeros(max(n, len(ax), 1), dtype=np.uint8)
     table = np.zeros(2048, dtype=CODE_TABLE_DTYPE)
     head = np.zeros((256, 2), dtype=np.int32)
-    rc = lib.mgb_host_code_operator(n, m, ip.ctypes.data, ix.ctypes.data, ax.ctypes.data, int(bool(allow_patterns)), C.byref(mode), C.byref(ndict),
+    allow = 2 if allow_patterns is True else int(allow_patterns)          # 0 per-entry codes, 1 + row patterns, 2 + anchored row patterns
+    rc = lib.mgb_host_code_operator(n, m, ip.ctypes.data, ix.ctypes.data, ax.ctypes.data, allow, C.byref(mode), C.byref(ndict),
                                     codes.ctypes.data, table.ctypes.data, C.byref(nent), head.ctypes.data)
     if rc != L.OK:
         raise L.MGBError(rc, "mgb_host_code_operator failed")
-    ncodes = {0: 0, 3: n}.get(mode.value, len(ax))
-    return {"mode": mode.value, "ndict": ndict.value, "codes": codes[:ncodes].copy(), "table": table[:nent.value].copy(),
-            "head": head if mode.value == 3 else None}
+    ncodes = {0: 0, 3: n, 4: n}.get(mode.value, len(ax))
+    out = {"mode": mode.value, "ndict": ndict.value, "codes": codes[:ncodes].copy(), "table": table[:nent.value].copy(),
+           "head": head if mode.value in (3, 4) else None}
+    if mode.value == 4:                      # the anchors are, by definition, the first stored column of every row (0: empty row)
+        anc = np.zeros(n, dtype=np.int32)
+        ne = ip[1:] > ip[:-1]
+        anc[ne] = ix[ip[:-1][ne]]
+        out["anchor"] = anc
+    return out

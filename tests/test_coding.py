@@ -21,7 +21,7 @@ def _same(h, o):
     k = len(tv)
     assert np.array_equal(h["table"]["val"][:k].view(np.uint64), tv) and np.array_equal(h["table"]["delta"][:k], td)
     assert not h["table"]["val"][k:].view(np.uint64).any() and not h["table"]["delta"][k:].any()
-    if h["mode"] == 3:
+    if h["mode"] in (3, 4):
         assert np.array_equal(h["head"], o["head"])
 
 
@@ -29,6 +29,9 @@ def _lossless(A, h):
     if h["mode"] == 0:
         return
     coded = {"mode": h["mode"], "codes": h["codes"], "table": list(zip(h["table"]["val"], h["table"]["delta"])), "head": h["head"]}
+    if h["mode"] == 4:
+        assert np.array_equal(h["anchor"], oc.anchors(A))
+        coded["anchor"] = h["anchor"]
     cols, bits = oc.decode(A.shape, A.indptr, A.indices, coded)
     assert np.array_equal(cols, A.indices.astype(np.int64)) and np.array_equal(bits, A.data.view(np.uint64))
 
@@ -49,15 +52,21 @@ def test_hierarchy_operators_host_routine_equals_numpy_definition(dim, c, lf, se
     A = H.A_sp_dict[lf][0].tocsr()
     RO, _ = rs.jacobi_matrices(A)
     P = H.P[lf - 1].tocsr()
-    for M, want in ((A, 3 if seed is None else None), (RO.tocsr(), 3 if seed is None else None), (P, 2)):
-        for allow in (True, False):
+    # P: its rows repeat only when measured from their first column -> anchored row patterns (mode 4) on a lexicographic numbering
+    for M, want in ((A, 3 if seed is None else None), (RO.tocsr(), 3 if seed is None else None), (P, 4 if seed is None else 2)):
+        for allow in (2, 1, 0):
             h, o = host_code_operator(M, allow), oc.code_operator(M, allow)
             _same(h, o)
             _lossless(M, h)
-            if want is not None and M.shape[0] > 300 and (allow or want != 3):
+            if want is not None and M.shape[0] > 300 and allow == 2:
                 assert h["mode"] == want, (h["mode"], want)
-            if not allow:
-                assert h["mode"] != 3
+            if allow < 2:
+                assert h["mode"] != 4
+            if allow < 1:
+                assert h["mode"] not in (3, 4)
+    if seed is None:
+        assert host_code_operator(P)["ndict"] == {2: 4, 3: 8}[dim]      # one pattern per parity class of the fine node
+        assert host_code_operator(P, 1)["mode"] == 2
     if seed is None:                                            # lexicographic numbering: few row patterns
         assert host_code_operator(RO.tocsr())["ndict"] == {2: 10, 3: 28}[dim]
         assert host_code_operator(A)["ndict"] == {2: 17, 3: 53}[dim]

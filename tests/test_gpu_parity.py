@@ -397,15 +397,21 @@ def test_ragged_operators_bit_exact(nf, nc, max_len, seed, opts):
 
 
 def test_shard_size_limit_is_refused_not_truncated():
-    """An operator beyond the int32 row-pointer range of one device must be rejected with MGB_ERR_UNSUPPORTED
-    (checked on the row-pointer values alone: no 2^31-entry array is ever allocated here)."""
+    """An operator beyond the int32 row-pointer range of one device must be rejected with MGB_ERR_UNSUPPORTED -- on the sizes
+    alone, before any entry is read: the arrays handed over here are real but tiny, only indptr[-1] / nnz claim 2^31 + 5 entries."""
     import ctypes as C
     lib = L.load()
     h = C.c_void_p()
     assert lib.mgb_create(C.byref(h), 0) == 0
     ip = np.array([0, 2 ** 31 + 5], dtype=np.int64)
-    rc = lib.mgb_set_level(h, 0, 1, 2 ** 31 + 5, ip.ctypes.data, 8, None, None)
-    assert rc == L.ERR_INVALID                      # null index arrays with nnz > 0 are refused before anything is read
+    ix = np.zeros(4, dtype=np.int32); ax = np.ones(4)
+    rc = lib.mgb_set_level(h, 0, 1, 2 ** 31 + 5, ip.ctypes.data, 8, ix.ctypes.data, ax.ctypes.data)
+    assert rc == L.ERR_UNSUPPORTED
+    assert b"int32 row-pointer range" in lib.mgb_last_error(h)
+    rc = lib.mgb_set_level(h, 0, 2 ** 31 + 5, 4, ip.ctypes.data, 8, ix.ctypes.data, ax.ctypes.data)      # too many rows
+    assert rc == L.ERR_UNSUPPORTED
+    rc = lib.mgb_set_level(h, 0, 1, 4, ip.ctypes.data, 8, None, None)                                     # null arrays with nnz > 0
+    assert rc == L.ERR_INVALID
     lib.mgb_destroy(h)
 
 
@@ -491,17 +497,24 @@ def test_coded_operators_bit_identical_to_uncoded(dim, c, lf, seed, r_mode):
     x, f, e = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(nc)
     A = H.A_sp_dict[lf][0]
     outs = []
-    for opts in [{"compress": 0}, {"stream_cfg": 0}, {"compress": 1}, {"compress": 2}, {"code_cfg": 3}, {"compress": 1, "code_cfg": 3}]:
+    # (the default is compress = 3, hot-row kernels (stage_x = 3), fused thread-per-coarse-row residual, g reused across cycles)
+    for opts in [{"compress": 0}, {"stream_cfg": 0}, {"compress": 1}, {"compress": 2}, {"code_cfg": 3}, {"compress": 1, "code_cfg": 3},
+                 {"compress": 3}, {"anch_cfg": 2}, {"stage_x": 0}, {"stage_x": 1}, {"hot_cfg": 2}, {"hot_cfg": 3}, {"hot_cfg": 4},
+                 {"hot_inj": 0}, {"hot_pf": 0}, {"reuse_g": 0}, {"compress": 2, "stage_x": 0, "hot_inj": 0, "reuse_g": 0}]:
         eng = MGEngine.from_hierarchy(H, r_mode=r_mode, options=opts)
         desc = eng.describe()
         coded = "coded" in desc
-        assert coded == (opts.get("compress", 2) >= 1 and opts.get("stream_cfg", 3) != 0), desc
-        if coded and seed is None:              # lexicographic numbering: whole rows repeat -> row patterns (compress = 2, the
-            want = "coded mode=3" if opts.get("compress", 2) == 2 else "coded mode=1"      # default), else pair codes per entry
+        level = opts.get("compress", 3)
+        assert coded == (level >= 1 and opts.get("stream_cfg", 3) != 0), desc
+        if coded and seed is None:              # lexicographic numbering: whole rows repeat -> row patterns (compress >= 2, the
+            want = "coded mode=3" if level >= 2 else "coded mode=1"                        # default), else pair codes per entry
             assert "A   " in desc and all(want in ln for ln in desc.splitlines() if ln.strip().startswith(("A ", "RJ ")) and f"rows={n} " in ln), desc
-        if coded:                               # transfers: value codes (+ columns); tiny ones may still fit the pair dictionary
-            assert all("coded" in ln for ln in desc.splitlines() if ln.strip().startswith("P ")), desc
-            assert all("coded mode=2" in ln for ln in desc.splitlines() if ln.strip().startswith("P ") and f"rows={n} " in ln), desc
+            if level >= 2 and opts.get("stage_x", 3) == 3:
+                assert all("hotrow(" in ln for ln in desc.splitlines() if ln.strip().startswith(("A ", "RJ ")) and f"rows={n} " in ln), desc
+        if coded:                               # transfers: anchored row patterns on a lexicographic numbering (compress = 3), else value
+            assert all("coded" in ln for ln in desc.splitlines() if ln.strip().startswith("P ")), desc      # codes (+ columns)
+            wantp = "coded mode=4" if level >= 3 and seed is None else "coded mode=2"
+            assert all(wantp in ln for ln in desc.splitlines() if ln.strip().startswith("P ") and f"rows={n} " in ln), desc
         b = H.b_dict[lf][:, 0]
         v, hist = eng.vcycle(lf, np.zeros_like(b), b, ncycles=3, history=True)
         outs.append((eng.spmv(lf, x), eng.residual(lf, x, f), eng.smooth(lf, x, f, 3), eng.prolong_add(lf, e, x), eng.restrict(lf, x), v, hist))
@@ -605,9 +618,9 @@ def test_row_pattern_coding_long_and_empty_rows():
     for tag, rows_ in (("A ", nf), ("RJ ", nf)):
         ln = [l for l in desc.splitlines() if l.strip().startswith(tag) and f"rows={rows_} " in l][0]
         assert "coded mode=3" in ln, desc
-    # R's rows are not translates of each other in (col - row) terms (columns advance by 4 per row): no pattern coding, but
-    # its four values still give the value dictionary
-    assert "coded mode=2" in [l for l in desc.splitlines() if l.strip().startswith("R ")][0], desc
+    # R's rows are not translates of each other in (col - row) terms (columns advance by 4 per row), but they are when measured
+    # from each row's first column: anchored row patterns
+    assert "coded mode=4" in [l for l in desc.splitlines() if l.strip().startswith("R ")][0], desc
     x, f = rng.standard_normal(nf), rng.standard_normal(nf)
     assert np.array_equal(eng.spmv(1, x), Af.dot(x))
     assert np.array_equal(eng.residual(1, x, f), f - Af.dot(x))
@@ -641,9 +654,8 @@ def test_row_pattern_coding_long_and_empty_rows():
 @pytest.mark.parametrize("dim,c,lf,seed", [(2, 8, 3, None), (3, 2, 3, None), (2, 8, 3, 5)])
 def test_device_built_coding_against_host_definition(dim, c, lf, seed):
     """The coding artefact: what mgb_finalize built on the device vs mgb_host_code_operator (the definition, itself pinned to the
-    numpy restatement by tests/test_coding.py).  Mode and dictionary / pattern counts are asserted; the entry-by-entry equality of
-    codes and tables is RECORDED in gpurun_out/parity_report.jsonl (first hardware run of this comparison) and will be asserted
-    once seen green."""
+    numpy restatement by tests/test_coding.py): mode, counts, every code, every table entry (value BITS and offset), the pattern
+    heads and -- for anchored patterns -- every anchor."""
     from multigrid_dolfinx_b200.engine import host_code_operator
     H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=seed, with_dicts=False)
     eng = MGEngine.from_hierarchy(H)
@@ -652,11 +664,15 @@ def test_device_built_coding_against_host_definition(dim, c, lf, seed):
     for op, M in (("A", A), ("RJ", RO.tocsr()), ("P", H.P[lf - 1].tocsr())):
         dev, host = eng.code_artifact(lf, op), host_code_operator(M)
         assert dev["mode"] == host["mode"] and dev["ndict"] == host["ndict"], (op, dev["mode"], host["mode"], dev["ndict"], host["ndict"])
+        if seed is None:
+            assert dev["mode"] == (4 if op == "P" else 3), (op, dev["mode"])
         same_codes = bool(np.array_equal(dev["codes"], host["codes"]))
         k = min(len(dev["table"]), len(host["table"]))
         same_table = bool(len(dev["table"]) == len(host["table"]) and np.array_equal(dev["table"]["val"][:k].view(np.uint64), host["table"]["val"][:k].view(np.uint64))
                           and np.array_equal(dev["table"]["delta"][:k], host["table"]["delta"][:k]))
-        same_head = bool(dev["mode"] != 3 or np.array_equal(dev["head"], host["head"]))
+        same_head = bool(dev["mode"] not in (3, 4) or np.array_equal(dev["head"], host["head"]))
+        same_anchor = bool(dev["mode"] != 4 or np.array_equal(dev["anchor"], host["anchor"]))
         _report("coding_artefact", dim=dim, seed=seed, op=op, mode=dev["mode"], ndict=dev["ndict"], codes_equal=same_codes,
-                table_equal=same_table, head_equal=same_head)
+                table_equal=same_table, head_equal=same_head, anchor_equal=same_anchor)
+        assert same_codes and same_table and same_head and same_anchor, (op, same_codes, same_table, same_head, same_anchor)
     eng.close()

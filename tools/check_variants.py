@@ -22,6 +22,10 @@ VARIANTS = {
     "hot2": {"stage_x": 3, "hot_cfg": 2},
     "hot3": {"stage_x": 3, "hot_cfg": 3},
     "hot4": {"stage_x": 3, "hot_cfg": 4},
+    "hot1c2": {"stage_x": 3, "hot_cfg": 1, "compress": 2},      # without the anchored patterns of P
+    "hot1a2": {"stage_x": 3, "hot_cfg": 1, "anch_cfg": 2},
+    "hot1a3": {"stage_x": 3, "hot_cfg": 1, "anch_cfg": 3},
+    "hot1a4": {"stage_x": 3, "hot_cfg": 1, "anch_cfg": 4},
     "hot1noinj": {"stage_x": 3, "hot_cfg": 1, "hot_inj": 0, "reuse_g": 0},
     "hot1pf0": {"stage_x": 3, "hot_cfg": 1, "hot_pf": 0},
     "hot1pf128k": {"stage_x": 3, "hot_cfg": 1, "hot_pf": 131072},
