@@ -109,7 +109,8 @@ k_p2p_pull(P2PPlan pl, double* __restrict__ vec, int n_owned)
         const unsigned long long want = pl.counters[16 + p] + 1;
         const long long t0 = clock64();
         while (ld_flag(pl.flags + pl.peer_rank[p]) < want)
-            if (clock64() - t0 > 4000000000LL) __trap();          // a lost neighbour must fault, never hang the GPU
+            if (clock64() - t0 > 60000000000LL) __trap();         // ~30 s (ranks may enter a cycle seconds apart: rank 0 alone sets up the
+                                                                  // coarse levels): a lost neighbour must fault, never hang the GPU
     }
     __syncthreads();
     const int par = (int)((pl.counters[16] + 1) & 1);
@@ -178,10 +179,25 @@ int exchange(mgb_handle* h, Level& L, double* vec)
 
 // Row sums of a sharded operator whose input vector x lives on level XL: exchange XL's ghosts, overlapped with the
 // interior tiles when the operator has an interior / boundary split.
+// OL / out: when the kernel writes an iterate of level OL into buffer out, and OL's exchange is fused, the rows OL's neighbours
+// hold as ghosts are stored into their copies by the kernel itself (HaloFuse).
 template <class Epi>
 int row_sums_halo(mgb_handle* h, int kind, int level, double bytes, const DevCsr& D, Level& XL, double* x, const Epi& epi,
-                  const int4* sub_desc = nullptr, int sub_int = 0, int sub_bnd = 0, double sub_moved = -1.0)
+                  const int4* sub_desc = nullptr, int sub_int = 0, int sub_bnd = 0, double sub_moved = -1.0,
+                  Level* OL = nullptr, const double* out = nullptr)
 {
+    // (only an ITERATE of XL has its ghosts kept valid by the kernels: any other vector, e.g. a residual about to be restricted,
+    // still needs the ordinary exchange)
+    const bool xf = XL.fuse_ok && (x == XL.v || x == XL.vtmp);
+    if (h->in_cycle && !sub_desc && kernel_takes_hf<Epi>(D) && D.sdesc && h->stream_cfg > 0 && h->allow_stream && (xf || (OL && OL->fuse_ok))) {
+        // fused exchange: the kernel waits for the ghosts of x itself and / or sends its boundary rows itself
+        if (h->dist && !XL.peers.empty() && !xf) TRY(exchange(h, XL, x));
+        h->hf_cur = make_hf(h, xf ? &XL : nullptr, &D, OL, out);
+        const int rc = row_sums(h, kind, level, bytes, D, x, epi);
+        h->hf_cur = no_hf();
+        return rc;
+    }
+    if (OL && OL->fuse_ok && h->in_cycle) return fail(h, MGB_ERR_STATE, "level %d: fused exchange, but this kernel cannot send its boundary rows", OL->level);
     // bytes actually streamed (profile records): the tile subset's own figure, else CSR bytes minus the coding's saving
     const bool streamable = Epi::CONTIG && D.family == 1 && D.sdesc && h->stream_cfg > 0 && h->allow_stream;
     const double moved = sub_desc ? sub_moved : (streamable ? bytes - coded_saving(D) : -1.0);

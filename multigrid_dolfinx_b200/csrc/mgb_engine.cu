@@ -213,6 +213,7 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
             if (D.sntiles > 0) TRY(dev_upload(h, &D.sdesc, desc.data(), desc.size()));
             if (interior) {
                 D.split = true;
+                D.int_r0 = interior[0]; D.int_r1 = interior[1];
                 D.t_int0 = sbreaks.empty() ? 0 : sbt[0];
                 D.t_int1 = sbreaks.empty() ? 0 : sbt[1];
                 std::vector<int4> bnd(desc.begin(), desc.begin() + D.t_int0);
@@ -237,6 +238,12 @@ int finish_csr(mgb_handle* h, DevCsr& D, const std::vector<int64_t>& ip, const s
         D.break_tile.assign(breaks.begin(), breaks.end());
     }
     return MGB_OK;
+}
+
+__global__ void k_not_ascending(int n, const int32_t* __restrict__ a, int* __restrict__ bad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 < n && a[i + 1] <= a[i]) *bad = 1;
 }
 
 __global__ void k_row_refs_ghost(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols, int n_owned_cols,
@@ -473,6 +480,74 @@ void launch_rowwin(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles,
     launch_rowwin_hot<0, Epi>(h, D, desc, ntiles, x, epi, chunked);
 }
 
+// ---- fused halo exchange (HaloFuse, mgb_kernels.cuh): plan of one launch ---------------------------------------------
+// which epilogue / pattern-length combinations the hot-row kernel is instantiated for (launch_hotrow)
+template <class Epi>
+bool hot_len_ok(int hl)
+{
+    if constexpr (std::is_same<Epi, EpiJacobiRJ>::value || std::is_same<Epi, EpiJacobiRJFirst>::value) return hl == 4 || hl == 6;
+    else if constexpr (std::is_same<Epi, EpiProlongAdd>::value) return false;
+    else return hl == 7 || hl == 15;
+}
+// true when the kernel launch_stream will pick for (D, Epi) takes a HaloFuse (hot-row and anchored-pattern kernels)
+template <class Epi>
+bool kernel_takes_hf(const DevCsr& D)
+{
+    if constexpr (!Epi::CONTIG) return false;
+    return D.cd.mode == 4 || (D.cd.mode == 3 && D.hcfg > 0 && hot_len_ok<Epi>(D.cd.hotplan.hotlen));
+}
+// XL: level whose vector the kernel reads through operator D (its ghost entries must have arrived); OL / out: level and buffer
+// the kernel writes an iterate to (its boundary rows go to the neighbours).  Either may be null.  Outside a cycle, or on a level
+// whose exchange is not fused, the corresponding half stays empty (and the caller uses the push / pull kernels).
+HaloFuse no_hf()
+{
+    HaloFuse hf{};
+    hf.int_b0 = 0; hf.int_b1 = INT_MAX;
+    return hf;
+}
+HaloFuse make_hf(mgb_handle* h, const Level* XL, const DevCsr* D, const Level* OL, const double* out)
+{
+    HaloFuse hf{};
+    hf.int_b0 = 0; hf.int_b1 = INT_MAX;
+    if (!h->in_cycle) return hf;
+    if (XL && XL->fuse_ok) {
+        const P2PPlan& pl = XL->p2p;
+        hf.wait_n = pl.npeers;
+        for (int p = 0; p < pl.npeers && p < 2; ++p) hf.wflag[p] = pl.flags2 + pl.peer_rank[p];
+        hf.wepoch = XL->fuse_counters;
+        if (D && D->split) { hf.int_b0 = (int)D->int_r0; hf.int_b1 = (int)D->int_r1; }
+        else { hf.int_b0 = 0; hf.int_b1 = 0; }              // (no row classification: every CTA waits)
+    }
+    if (OL && OL->fuse_ok && (out == OL->v || out == OL->vtmp)) {
+        const P2PPlan& pl = OL->p2p;
+        const int which = out == OL->v ? 0 : 1;
+        hf.send_n = pl.npeers;
+        for (int p = 0; p < pl.npeers && p < 2; ++p) {
+            hf.send_a[p] = OL->send_a[p]; hf.send_cnt[p] = OL->send_cnt[(size_t)p];
+            hf.dst[p] = pl.rvec[p][which]; hf.rflag[p] = pl.rflag2[p];
+        }
+        hf.sepoch = OL->fuse_counters;
+    }
+    return hf;
+}
+// per-launch part: CTAs per send range and the boundary-first tile order, for tiles of `rows` rows over n rows
+void finish_hf(HaloFuse& hf, int rows, int64_t n)
+{
+    const int64_t ntiles = (n + rows - 1) / rows;
+    int64_t lo_end = 0, hi_start = n;
+    if (hf.wait_n) { lo_end = std::max<int64_t>(lo_end, std::min<int64_t>(hf.int_b0, n)); hi_start = std::min<int64_t>(hi_start, std::max<int64_t>(hf.int_b1, 0)); }
+    for (int p = 0; p < hf.send_n; ++p) {
+        const int64_t a = hf.send_a[p], b = a + hf.send_cnt[p];
+        hf.send_ctas[p] = (int)((b - 1) / rows - a / rows + 1);
+        if (a < n / 2) lo_end = std::max(lo_end, b); else hi_start = std::min(hi_start, a);
+    }
+    hf.nlo = hf.nhi = 0;
+    if (hf.wait_n || hf.send_n) {
+        const int64_t nlo = (lo_end + rows - 1) / rows, nhi = hi_start >= n ? 0 : ntiles - hi_start / rows;
+        if (nlo + nhi <= ntiles) { hf.nlo = (int)nlo; hf.nhi = (int)nhi; }
+    }
+}
+
 // Hot-row kernel (k_hotrow).  Registers per thread are budgeted from what a thread keeps in flight (RPT rows x (HOTN x values +
 // operands)), and the resident CTAs per SM follow from that budget.
 template <int HOTN, int T, int RPT, int NOPS>
@@ -502,8 +577,10 @@ void launch_hotrow_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nti
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = h->pdl != 0 ? 1 : 0;
+    HaloFuse hf = linear ? h->hf_cur : no_hf();    // (tile subsets never run inside a fused exchange)
+    finish_hf(hf, ROWS, D.nrows);
     cudaLaunchKernelEx(&cfg, kern, (const unsigned char*)D.cd.codes, (const uint32_t*)D.cd.pmask, (const int2*)D.cd.phead, (const DictEnt*)D.cd.dict,
-                       D.cd.hot, linear ? (const int4*)nullptr : desc, grid, 0, (int)D.nrows, (int)D.ncols, pf, x, epi);
+                       D.cd.hot, hf, linear ? (const int4*)nullptr : desc, grid, 0, (int)D.nrows, (int)D.ncols, pf, x, epi);
 }
 
 template <int HOTN, class Epi>
@@ -557,8 +634,10 @@ void launch_anchrow_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nt
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = h->pdl != 0 ? 1 : 0;
+    HaloFuse hf = linear ? h->hf_cur : no_hf();
+    finish_hf(hf, ROWS, D.nrows);
     cudaLaunchKernelEx(&cfg, kern, (const unsigned char*)D.cd.codes, (const int32_t*)D.cd.anchor, (const int2*)D.cd.phead, (const DictEnt*)D.cd.dict,
-                       D.cd.ndict, D.cd.npent, linear ? (const int4*)nullptr : desc, grid, 0, (int)D.nrows, pf, x, epi);
+                       D.cd.ndict, D.cd.npent, hf, linear ? (const int4*)nullptr : desc, grid, 0, (int)D.nrows, pf, x, epi);
 }
 
 template <class Epi>
@@ -750,11 +829,11 @@ int smooth(mgb_handle* h, Level& L, double*& v, double*& o, const double* f, int
         if (h->smoother == MGB_SM_JACOBI_RJ) {     // (the ghost entries of the iterate are exchanged inside row_sums_halo)
             if (!g_valid) {
                 EpiJacobiRJFirst epi{v, L.dinv, f, L.g, o, 1 - h->omega, h->omega};
-                TRY(row_sums_halo(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.RJ, 5 * n), L.RJ, L, v, epi));
+                TRY(row_sums_halo(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.RJ, 5 * n), L.RJ, L, v, epi, nullptr, 0, 0, -1.0, &L, o));
                 g_valid = true;
             } else {
                 EpiJacobiRJ epi{v, L.g, o, 1 - h->omega, h->omega};
-                TRY(row_sums_halo(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.RJ, 3 * n), L.RJ, L, v, epi));
+                TRY(row_sums_halo(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.RJ, 3 * n), L.RJ, L, v, epi, nullptr, 0, 0, -1.0, &L, o));
             }
             std::swap(v, o);
         } else if (h->smoother == MGB_SM_JACOBI_A) {
@@ -795,7 +874,9 @@ int residual_injected(mgb_handle* h, Level& L, const double* v, const double* f,
     const int hl = L.A.cd.hotplan.hotlen;
     if (L.A.cd.mode == 3 && L.A.hcfg > 0 && (hl == 7 || hl == 15) && L.inj && nc > 0 && h->hot_inj && h->stream_cfg > 0 && h->allow_stream) {
         // thread per coarse row on the pattern-coded level matrix (k_hotinj): only the injected rows are summed
-        TRY(exchange(h, L, const_cast<double*>(v)));
+        const bool fused = h->in_cycle && L.fuse_ok && (v == L.v || v == L.vtmp);    // ghosts of an iterate are kept valid by the kernels that wrote it
+        if (!fused) TRY(exchange(h, L, const_cast<double*>(v)));
+        const HaloFuse hf = fused ? make_hf(h, &L, &L.A, nullptr, nullptr) : no_hf();
         const double nb = (12.0 * avg + 4.0 + 8.0 + 4.0 + 8.0 + 8.0) * (double)nc + 8.0 * (double)L.n;
         const double moved = 8.0 * (double)L.n + 21.0 * (double)nc;      // all of v (every line is touched), inj + code + f + result per coarse row
         return launch(h, MGB_K_RESIDUAL, L.level, nb, [&] {
@@ -809,9 +890,9 @@ int residual_injected(mgb_handle* h, Level& L, const double* v, const double* f,
             const DevCsr& A = L.A;
             const int pf = h->hot_pf > 0 ? std::max(1, h->hot_pf / 8 / T) : 0;
             if (hl == 7) cudaLaunchKernelEx(&cfg, k_hotinj<7, T, 10>, (const unsigned char*)A.cd.codes, (const uint32_t*)A.cd.pmask, (const int2*)A.cd.phead,
-                                            (const DictEnt*)A.cd.dict, A.cd.hot, (const int32_t*)L.inj, (int)nc, (int)A.ncols, pf, v, f, f_coarse);
+                                            (const DictEnt*)A.cd.dict, A.cd.hot, hf, (const int32_t*)L.inj, L.inj_mono ? 1 : 0, (int)nc, (int)A.ncols, pf, v, f, f_coarse);
             else cudaLaunchKernelEx(&cfg, k_hotinj<15, T, 8>, (const unsigned char*)A.cd.codes, (const uint32_t*)A.cd.pmask, (const int2*)A.cd.phead,
-                                    (const DictEnt*)A.cd.dict, A.cd.hot, (const int32_t*)L.inj, (int)nc, (int)A.ncols, pf, v, f, f_coarse);
+                                    (const DictEnt*)A.cd.dict, A.cd.hot, hf, (const int32_t*)L.inj, L.inj_mono ? 1 : 0, (int)nc, (int)A.ncols, pf, v, f, f_coarse);
         }, moved);
     }
     if (L.inj_desc && (L.inj_fraction < 0.8 || L.A.cd.mode) && h->stream_cfg > 0 && h->allow_stream) {
@@ -835,8 +916,14 @@ int prolong_add(mgb_handle* h, Level& L, const double* e_coarse, double* v_fine,
     EpiProlongAdd epi{v_fine, err};
     const double nb = bytes_rowsum(L.P, (double)L.n_coarse + 2.0 * (double)L.n);
     if (C && !C->gathered && !C->stub)          // (gathered level: everybody already has all of e)
-        return row_sums_halo(h, MGB_K_PROLONG_ADD, L.level, nb, L.P, *C, const_cast<double*>(e_coarse), epi);
-    return row_sums(h, MGB_K_PROLONG_ADD, L.level, nb, L.P, e_coarse, epi);
+        return row_sums_halo(h, MGB_K_PROLONG_ADD, L.level, nb, L.P, *C, const_cast<double*>(e_coarse), epi, nullptr, 0, 0, -1.0, &L, v_fine);
+    // the corrected iterate's boundary rows still go to the neighbours when this level's exchange is fused
+    h->hf_cur = kernel_takes_hf<EpiProlongAdd>(L.P) ? make_hf(h, nullptr, nullptr, &L, v_fine) : no_hf();
+    const bool pushed = h->hf_cur.send_n > 0;
+    int rc = row_sums(h, MGB_K_PROLONG_ADD, L.level, nb, L.P, e_coarse, epi);
+    h->hf_cur = no_hf();
+    if (rc == MGB_OK && !pushed && h->in_cycle && L.fuse_ok) rc = fail(h, MGB_ERR_STATE, "level %d: fused exchange without a fused prolongation", L.level);
+    return rc;
 }
 
 int coarse_apply(mgb_handle* h, Level& C, const double* f, double* u)
@@ -899,8 +986,10 @@ int enqueue_cycle(mgb_handle* h, int top, bool debug, double** v2h_ptr, bool top
         int sweeps = h->mu1;
         if (l != top) {                                 // zero initial guess (multigrid.py:253)
             if (jacobi && h->mu1 > 0) {
+                HaloFuse hf = make_hf(h, nullptr, nullptr, &L, v);         // sharded: the neighbours' ghosts of v are filled as well
+                finish_hf(hf, 256, L.n);
                 TRY(launch(h, MGB_K_INIT_GUESS, l, 32.0 * (double)L.n, [&] {
-                    k_init_guess<<<(int)((L.n + 255) / 256), 256, 0, h->stream>>>((int)L.n, L.dinv, L.f, h->omega, L.g, v);
+                    k_init_guess<<<(int)((L.n + 255) / 256), 256, 0, h->stream>>>((int)L.n, L.dinv, L.f, h->omega, L.g, v, hf);
                 }));
                 g_valid = (h->smoother == MGB_SM_JACOBI_RJ);
                 sweeps = h->mu1 - 1;
@@ -939,8 +1028,8 @@ int enqueue_cycle(mgb_handle* h, int top, bool debug, double** v2h_ptr, bool top
         cur[l] = v;
     }
     Level& T = h->levels[top];
-    if (cur[top] != T.v)
-        CU(cudaMemcpyAsync(T.v, cur[top], sizeof(double) * (size_t)T.n, cudaMemcpyDeviceToDevice, h->stream));
+    if (cur[top] != T.v)                                  // (with the ghost section: it is valid in cur[top] when the exchange is fused)
+        CU(cudaMemcpyAsync(T.v, cur[top], sizeof(double) * (size_t)(T.n + T.n_ghost), cudaMemcpyDeviceToDevice, h->stream));
     if (v2h_ptr) *v2h_ptr = cur[top - 1];
     return MGB_OK;
 }
@@ -1025,6 +1114,11 @@ int cycles_on_buffers(mgb_handle* h, int top, int ncycles, double* resnorm_hist)
 {
     Level& T = h->levels[top];
     if (resnorm_hist) TRY(ensure_hist(h, ncycles));
+    // fused halo exchange: from here on every kernel that writes an iterate also fills the neighbours' ghosts of it; the iterate
+    // the caller handed over gets its ghosts from one explicit exchange
+    if (T.fuse_ok) TRY(exchange(h, T, T.v));
+    struct InCycle { mgb_handle* h; ~InCycle() { h->in_cycle = false; h->hf_cur = no_hf(); } } guard{h};
+    h->in_cycle = true;
     for (int c = 0; c < ncycles; ++c) {
         TRY(run_cycle(h, top, c > 0));          // (f is untouched between the cycles of one call)
         if (resnorm_hist) {                    // the residual the reference's driver forms after each cycle (multigrid.py:291)
@@ -1087,7 +1181,8 @@ int mgb_destroy(mgb_handle* h)
         free_csr(L.A); free_csr(L.RJ); free_csr(L.P); free_csr(L.R); free_csr(L.G); free_csr(L.M); cudaFree(L.b); cudaFree(L.uex);
         cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.cmap); cudaFree(L.inj_desc); cudaFree(L.send_idx); cudaFree(L.send_buf); cudaFree(L.p2p_counters);
         for (void* q : L.p2p_opened) cudaIpcCloseMemHandle(q);
-        cudaFree(L.p2p_arena); cudaFree(L.v); cudaFree(L.vtmp); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
+        if (!L.vec_in_arena) { cudaFree(L.v); cudaFree(L.vtmp); }
+        cudaFree(L.p2p_arena); cudaFree(L.fuse_counters); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
         cudaFree(L.gs_order); cudaFree(L.gs_off); cudaFree(L.gs_diag); cudaFree(L.gs_ecols); cudaFree(L.gs_evals);
     }
     cudaFree(h->coarse_inv); cudaFree(h->d_partial); cudaFree(h->d_hist);
@@ -1250,6 +1345,16 @@ int mgb_set_halo(mgb_handle* h, int level, int npeers, const int32_t* peer_ranks
     for (int64_t k = 0; k < st; ++k)
         if (send_indices[k] < 0 || send_indices[k] >= L->n) return fail(h, MGB_ERR_INVALID, "send index out of the owned range");
     L->send_total = st;
+    L->send_a[0] = L->send_a[1] = -1;                       // fused exchange: the send list of a neighbour must be one run of rows
+    if (npeers <= 2) {
+        int64_t off = 0;
+        for (int p = 0; p < npeers; ++p) {
+            bool run = send_counts[p] > 0;
+            for (int k = 1; k < send_counts[p] && run; ++k) run = send_indices[off + k] == send_indices[off] + k;
+            if (run) L->send_a[p] = send_indices[off];
+            off += send_counts[p];
+        }
+    }
     cudaFree(L->send_idx); cudaFree(L->send_buf);
     TRY(dev_upload(h, &L->send_idx, send_indices, (size_t)st));
     TRY(dev_alloc(h, &L->send_buf, (size_t)st));
@@ -1266,16 +1371,29 @@ int mgb_p2p_export(mgb_handle* h, int level, void* blob, int capacity, int* size
     if (!L || !h->dist) return fail(h, MGB_ERR_STATE, "level %d has no halo plan", level);
     if ((int)L->peers.size() > P2P_MAX_PEERS || h->world > P2P_FLAG_SLOTS) return fail(h, MGB_ERR_UNSUPPORTED, "too many neighbours for the peer-memory exchange");
     CU(cudaSetDevice(h->device));
+    // arena: [flags][fused flags][stage 0][stage 1][pad to 256 B][v][vtmp] -- the iterate buffers live here so that the
+    // neighbours can store their boundary rows straight into this rank's ghost sections (HaloFuse)
+    const size_t np = (size_t)L->n + (size_t)L->n_ghost + 16;
+    const size_t off_stage = 2 * P2P_FLAG_SLOTS * sizeof(unsigned long long);
+    const size_t off_v0 = (off_stage + 2 * ((size_t)L->n_ghost + 2) * sizeof(double) + 255) / 256 * 256;
+    const size_t off_v1 = off_v0 + (np * sizeof(double) + 255) / 256 * 256;
     if (!L->p2p_arena) {
-        const size_t bytes = P2P_FLAG_SLOTS * sizeof(unsigned long long) + 2 * ((size_t)L->n_ghost + 2) * sizeof(double);
+        const size_t bytes = off_v1 + np * sizeof(double);
         CU(cudaMalloc(&L->p2p_arena, bytes));
         CU(cudaMemset(L->p2p_arena, 0, bytes));
         TRY(dev_alloc(h, &L->p2p_counters, 64));
         CU(cudaMemset(L->p2p_counters, 0, 64 * sizeof(unsigned long long)));
+        TRY(dev_alloc(h, &L->fuse_counters, 16));
+        CU(cudaMemset(L->fuse_counters, 0, 16 * sizeof(unsigned long long)));
+        L->v = (double*)((char*)L->p2p_arena + off_v0);
+        L->vtmp = (double*)((char*)L->p2p_arena + off_v1);
+        L->vec_in_arena = true;
     }
     P2PBlob b{};
     CU(cudaIpcGetMemHandle(&b.handle, L->p2p_arena));
     b.n_ghost = L->n_ghost;
+    b.n_owned = L->n;
+    b.off_vec[0] = (long long)off_v0; b.off_vec[1] = (long long)off_v1;
     b.npeers = (int)L->peers.size();
     int ro = 0;
     for (int p = 0; p < b.npeers; ++p) { b.peer_rank[p] = L->peers[p]; b.recv_off[p] = ro; ro += L->recv_cnt[p]; }
@@ -1302,8 +1420,10 @@ int mgb_p2p_import(mgb_handle* h, int level, int peer_rank, const void* blob, in
     CU(cudaIpcOpenMemHandle(&base, b.handle, cudaIpcMemLazyEnablePeerAccess));
     L->p2p_opened.push_back(base);
     unsigned long long* rflags = (unsigned long long*)base;
-    double* rstage = (double*)((char*)base + P2P_FLAG_SLOTS * sizeof(unsigned long long));
+    double* rstage = (double*)((char*)base + 2 * P2P_FLAG_SLOTS * sizeof(unsigned long long));
     L->p2p.rflag[p] = rflags + h->rank;
+    L->p2p.rflag2[p] = rflags + P2P_FLAG_SLOTS + h->rank;
+    for (int q = 0; q < 2; ++q) L->p2p.rvec[p][q] = (double*)((char*)base + b.off_vec[q]) + b.n_owned + b.recv_off[mine];
     L->p2p.rstage[p][0] = rstage + b.recv_off[mine];
     L->p2p.rstage[p][1] = rstage + (size_t)b.n_ghost + b.recv_off[mine];
     L->p2p.peer_rank[p] = peer_rank;
@@ -1315,7 +1435,8 @@ int mgb_p2p_import(mgb_handle* h, int level, int peer_rank, const void* blob, in
         pl.send_off[pl.npeers] = so; pl.recv_off[pl.npeers] = ro;
         pl.counters = L->p2p_counters;
         pl.flags = (unsigned long long*)L->p2p_arena;
-        pl.stage = (double*)((char*)L->p2p_arena + P2P_FLAG_SLOTS * sizeof(unsigned long long));
+        pl.flags2 = (unsigned long long*)L->p2p_arena + P2P_FLAG_SLOTS;
+        pl.stage = (double*)((char*)L->p2p_arena + 2 * P2P_FLAG_SLOTS * sizeof(unsigned long long));
         pl.n_ghost = (int)L->n_ghost;
         L->p2p_ready = true;
     }
@@ -1415,6 +1536,7 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "anch_cfg" && pre) h->anch_cfg = iv;
     else if (k == "reuse_g") { h->reuse_g = iv; drop_graphs(h); }
     else if (k == "hot_inj") { h->hot_inj = iv; drop_graphs(h); }
+    else if (k == "fuse_halo" && pre) h->fuse_halo = iv;
     else if (k == "hot_pf") { h->hot_pf = iv; drop_graphs(h); }
     else if (k == "win_prefetch") { h->win_prefetch = iv; drop_graphs(h); }
     else if (k == "gs_cluster") h->gs_cluster = iv;
@@ -1538,6 +1660,18 @@ int mgb_finalize(mgb_handle* h)
             }
             if (L.r_mode == MGB_R_INJECTION) {
                 if (!L.device_born) TRY(dev_upload(h, &L.inj, L.inj_host.data(), L.inj_host.size()));
+                L.inj_mono = false;
+                if (L.inj && L.n_coarse > 0) {                // ascending injection list: a CTA of k_hotinj knows the row range it touches
+                    int* bad = nullptr;
+                    TRY(dev_alloc(h, &bad, 1));
+                    CU(cudaMemsetAsync(bad, 0, sizeof(int), h->stream));
+                    k_not_ascending<<<(int)((L.n_coarse + 255) / 256), 256, 0, h->stream>>>((int)L.n_coarse, L.inj, bad);
+                    int hb = 1;
+                    CU(cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+                    CU(cudaStreamSynchronize(h->stream));
+                    cudaFree(bad);
+                    L.inj_mono = hb == 0;
+                }
                 if (!L.A.sdesc_host.empty()) {
                     std::vector<int32_t> cmap(n + 16, -1);
                     for (size_t c = 0; c < L.inj_host.size(); ++c) cmap[(size_t)L.inj_host[c]] = (int32_t)c;
@@ -1566,7 +1700,8 @@ int mgb_finalize(mgb_handle* h)
             }
         }
         const size_t np = n + (size_t)L.n_ghost + 16;   // [owned | ghost | tail padding for 16-byte bulk copies]
-        TRY(dev_alloc(h, &L.v, np)); TRY(dev_alloc(h, &L.vtmp, np)); TRY(dev_alloc(h, &L.f, np));
+        if (!L.vec_in_arena) { TRY(dev_alloc(h, &L.v, np)); TRY(dev_alloc(h, &L.vtmp, np)); }     // (else: inside the exported arena)
+        TRY(dev_alloc(h, &L.f, np));
         TRY(dev_alloc(h, &L.r, np)); TRY(dev_alloc(h, &L.g, np));
         for (double* p : {L.v, L.vtmp, L.f, L.r, L.g}) CU(cudaMemsetAsync(p, 0, np * sizeof(double), h->stream));
     }
@@ -1581,6 +1716,21 @@ int mgb_finalize(mgb_handle* h)
         Level& L = kv.second;
         L.A_host = HostCsr(); L.P_host = HostCsr(); L.R_host = HostCsr();
         std::vector<int32_t>().swap(L.inj_host);
+    }
+    // levels whose halo exchange is fused into the kernels (HaloFuse): slab-like partitions (<= 2 neighbours, each send list one
+    // run of rows), peer memory mapped, and every kernel that writes an iterate on the level able to send (hot-row smoother,
+    // anchored-pattern prolongation, the zero-guess sweep)
+    for (auto& kv : h->levels) {
+        Level& L = kv.second;
+        L.fuse_ok = false;
+        if (!h->fuse_halo || !h->dist || L.stub || L.gathered || L.peers.empty() || L.peers.size() > 2) continue;
+        if (!L.p2p_ready || !h->p2p_enable || !L.vec_in_arena || !L.fuse_counters) continue;
+        if (h->smoother != MGB_SM_JACOBI_RJ || h->mu1 < 1 || h->stream_cfg <= 0) continue;
+        bool ok = true;
+        for (size_t p = 0; p < L.peers.size(); ++p) ok = ok && L.send_a[p] >= 0 && L.send_cnt[p] > 0;
+        ok = ok && kernel_takes_hf<EpiJacobiRJ>(L.RJ) && kernel_takes_hf<EpiResidual>(L.A);
+        if (L.has_transfer) ok = ok && L.P.cd.mode == 4;
+        L.fuse_ok = ok;
     }
     h->finalized = true;
     {   // one eager cycle on zero data: sets kernel attributes outside any graph capture and faults early if a kernel is broken
@@ -2032,7 +2182,7 @@ int mgb_describe(mgb_handle* h, char* out, int64_t capacity)
         s += buf;
     };
     for (auto& kv : h->levels) {
-        snprintf(buf, sizeof buf, "level %d n=%lld\n", kv.first, (long long)kv.second.n);
+        snprintf(buf, sizeof buf, "level %d n=%lld%s\n", kv.first, (long long)kv.second.n, kv.second.fuse_ok ? " (halo exchange fused into the kernels)" : "");
         s += buf;
         one("A", kv.second.A); one("RJ", kv.second.RJ); one("P", kv.second.P); one("R", kv.second.R); one("G", kv.second.G);
     }

@@ -43,23 +43,25 @@ struct EpiStore {
     static constexpr int NOPS = 0; static constexpr bool CONTIG = true;
     double* y;
     __host__ __device__ __forceinline__ const double* operand(int) const { return nullptr; }
-    __device__ __forceinline__ void store(int i, double s, const double*) const { y[i] = s; }
+    __device__ __forceinline__ double store(int i, double s, const double*) const { y[i] = s; return s; }
 };
 // r = f - A v                                               (multigrid.py:244)
 struct EpiResidual {
     static constexpr int NOPS = 1; static constexpr bool CONTIG = true;
     const double* f; double* r;
     __host__ __device__ __forceinline__ const double* operand(int) const { return f; }
-    __device__ __forceinline__ void store(int i, double s, const double* o) const { r[i] = __dsub_rn(o[0], s); }
+    __device__ __forceinline__ double store(int i, double s, const double* o) const { const double t = __dsub_rn(o[0], s); r[i] = t; return t; }
 };
 // weighted Jacobi, reference form (multigrid.py:226): out = ((1-w)*v + g) - w*s, g = w*(dinv*f)
 struct EpiJacobiRJ {
     static constexpr int NOPS = 2; static constexpr bool CONTIG = true; static constexpr int XOP = 0;
     const double* v; const double* g; double* out; double om1, om;
     __host__ __device__ __forceinline__ const double* operand(int j) const { return j == 0 ? v : g; }
-    __device__ __forceinline__ void store(int i, double s, const double* o) const
+    __device__ __forceinline__ double store(int i, double s, const double* o) const
     {
-        out[i] = __dsub_rn(__dadd_rn(__dmul_rn(om1, o[0]), o[1]), __dmul_rn(om, s));
+        const double t = __dsub_rn(__dadd_rn(__dmul_rn(om1, o[0]), o[1]), __dmul_rn(om, s));
+        out[i] = t;
+        return t;
     }
 };
 // same, first sweep of a relaxation call: also produces g (multigrid.py:226 recomputes w*(Dinv f) per sweep;
@@ -68,11 +70,13 @@ struct EpiJacobiRJFirst {
     static constexpr int NOPS = 3; static constexpr bool CONTIG = true; static constexpr int XOP = 0;
     const double* v; const double* dinv; const double* f; double* g; double* out; double om1, om;
     __host__ __device__ __forceinline__ const double* operand(int j) const { return j == 0 ? v : (j == 1 ? dinv : f); }
-    __device__ __forceinline__ void store(int i, double s, const double* o) const
+    __device__ __forceinline__ double store(int i, double s, const double* o) const
     {
         const double gi = __dmul_rn(om, __dmul_rn(o[1], o[2]));
         g[i] = gi;
-        out[i] = __dsub_rn(__dadd_rn(__dmul_rn(om1, o[0]), gi), __dmul_rn(om, s));
+        const double t = __dsub_rn(__dadd_rn(__dmul_rn(om1, o[0]), gi), __dmul_rn(om, s));
+        out[i] = t;
+        return t;
     }
 };
 // single-matrix Jacobi: out = v + w*(dinv*(f - s)), s = (A v)_i
@@ -80,9 +84,11 @@ struct EpiJacobiA {
     static constexpr int NOPS = 3; static constexpr bool CONTIG = true; static constexpr int XOP = 0;
     const double* v; const double* dinv; const double* f; double* out; double om;
     __host__ __device__ __forceinline__ const double* operand(int j) const { return j == 0 ? v : (j == 1 ? dinv : f); }
-    __device__ __forceinline__ void store(int i, double s, const double* o) const
+    __device__ __forceinline__ double store(int i, double s, const double* o) const
     {
-        out[i] = __dadd_rn(o[0], __dmul_rn(om, __dmul_rn(o[1], __dsub_rn(o[2], s))));
+        const double t = __dadd_rn(o[0], __dmul_rn(om, __dmul_rn(o[1], __dsub_rn(o[2], s))));
+        out[i] = t;
+        return t;
     }
 };
 // v = v + P e   (multigrid.py:258-260); err (nullable) receives P e (the test=True output, multigrid.py:265)
@@ -90,10 +96,12 @@ struct EpiProlongAdd {
     static constexpr int NOPS = 1; static constexpr bool CONTIG = true;
     double* v; double* err;
     __host__ __device__ __forceinline__ const double* operand(int) const { return v; }
-    __device__ __forceinline__ void store(int i, double s, const double* o) const
+    __device__ __forceinline__ double store(int i, double s, const double* o) const
     {
         if (err) err[i] = s;
-        v[i] = __dadd_rn(o[0], s);
+        const double t = __dadd_rn(o[0], s);
+        v[i] = t;
+        return t;
     }
 };
 // Gauss-Seidel row update on a row-permuted off-diagonal operator: v[order[p]] = (f - s) / d
@@ -112,7 +120,7 @@ struct EpiResidualInject {
     const double* f; const int32_t* cmap; double* out;
     __host__ __device__ __forceinline__ const double* operand(int) const { return f; }
     __device__ __forceinline__ const int32_t* ioperand() const { return cmap; }
-    __device__ __forceinline__ void store_i(int, double s, const double* o, int c) const { if (c >= 0) out[c] = __dsub_rn(o[0], s); }
+    __device__ __forceinline__ double store_i(int, double s, const double* o, int c) const { const double t = __dsub_rn(o[0], s); if (c >= 0) out[c] = t; return t; }
 };
 
 template <class Epi, class = void> struct EpiNI { static constexpr int value = 0; };
@@ -956,6 +964,107 @@ struct HotPlan {
     double hv[WIN_HOT];                  // ... and values
 };
 
+// ---- halo exchange fused into the kernels that write / read an iterate (row-sharded hierarchies) ---------------
+// Every kernel that writes an iterate (Jacobi sweep, prolongation + correction, zero-guess sweep) also stores the rows its
+// neighbours hold as ghosts straight into the neighbours' copy of that vector (peer memory over NVLink), and the last CTA to
+// finish such rows publishes a new epoch in the neighbour's arrival flag.  Every kernel that reads ghost entries makes the CTAs
+// whose rows reference them wait until the neighbours' flags have reached this rank's own epoch count (all ranks run the same
+// kernel sequence, so the counts agree).  No pack / push / pull launch remains.  Boundary tiles run FIRST in every kernel, so a
+// flag is published a whole sweep before the neighbour's next kernel asks for it: the wait is over before it starts.
+// Safety of writing into the neighbour's vector directly: iterates ping-pong between two buffers; this rank writes buffer Y of
+// the neighbour during sweep s, the neighbour last read Y's ghosts in sweep s-1, and this rank can only be in sweep s after it
+// has seen the neighbour's flag for the END of the neighbour's boundary rows of sweep s-1.
+struct HaloFuse {
+    int wait_n;                               // consumer: neighbours whose flag must have reached wepoch[p] (0: no ghost is read)
+    const unsigned long long* wflag[2];       //   this rank's arrival flags, written by the neighbours
+    const unsigned long long* wepoch;         //   device: [p] = pushes exchanged with neighbour p so far (level of x)
+    int int_b0, int_b1;                       //   rows [int_b0, int_b1) reference no ghost entry
+    int send_n;                               // producer: neighbours that hold some of this rank's rows as ghosts
+    int send_a[2], send_cnt[2];               //   owned rows [a, a + cnt) are neighbour p's ghosts ...
+    double* dst[2];                           //   ... at dst[p][row - a] in the neighbour's copy of the vector this kernel writes
+    unsigned long long* rflag[2];             //   the neighbour's arrival flag for this rank
+    unsigned long long* sepoch;               //   device: [p] pushes so far (level of the output), [8 + p] CTA arrival counters
+    int send_ctas[2];                         //   CTAs whose tile intersects the range: the last one to arrive publishes
+    int nlo, nhi;                             // tiles at the low / high end that wait or send: they run first
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// tile this CTA works on: boundary tiles (nlo at the low end, nhi at the high end) first, then the interior in order
+__device__ __forceinline__ int halo_tile(const HaloFuse& hf, int b, int ntiles)
+{
+    if (hf.nlo + hf.nhi == 0 || b < hf.nlo) return b;
+    if (b < hf.nlo + hf.nhi) return ntiles - hf.nhi + (b - hf.nlo);
+    return b - hf.nhi;
+}
+// CTA-uniform: rows [row0, rend) read a ghost entry of x -> wait for the neighbours (one polling thread per neighbour; its
+// acquire also drops stale L1 lines of this SM), then release the CTA
+__device__ __forceinline__ void halo_wait(const HaloFuse& hf, int row0, int rend)
+{
+    if (hf.wait_n == 0 || (row0 >= hf.int_b0 && rend <= hf.int_b1)) return;
+    if ((int)threadIdx.x < hf.wait_n) {
+        const int p = threadIdx.x;
+        const unsigned long long want = ld_relaxed_gpu(hf.wepoch + p);
+        const long long t0 = clock64();
+        unsigned long long got;
+        do {                                                 // relaxed polls, one acquire fence at the end (an acquire drops the SM's L1 lines)
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(hf.wflag[p]) : "memory");
+            if (got < want && clock64() - t0 > 60000000000LL) __trap();   // ~30 s: a lost neighbour must fault, never hang the GPU
+        } while (got < want);
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+    }
+    __syncthreads();
+}
+// CTA-uniform: bit p set when rows [row0, rend) intersect the rows neighbour p holds as ghosts (0 for almost every CTA, which
+// then skips all per-row work of the exchange)
+__device__ __forceinline__ int halo_sends(const HaloFuse& hf, int row0, int rend)
+{
+    int m = 0;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+        if (p < hf.send_n && row0 < hf.send_a[p] + hf.send_cnt[p] && rend > hf.send_a[p]) m |= 1 << p;
+    return m;
+}
+// the value just written to row r of the iterate also goes to the neighbours that hold row r as a ghost
+__device__ __forceinline__ void halo_send(const HaloFuse& hf, int r, double val)
+{
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+        if (p < hf.send_n && r >= hf.send_a[p] && r < hf.send_a[p] + hf.send_cnt[p]) hf.dst[p][r - hf.send_a[p]] = val;
+}
+// CTA-uniform, after the CTA's rows [row0, rend) have been stored: if they intersect a send range, fence, count this CTA in,
+// and -- last CTA of the range -- publish the next epoch in the neighbour's flag
+__device__ __forceinline__ void halo_publish(const HaloFuse& hf, int row0, int rend)
+{
+    if (!halo_sends(hf, row0, rend)) return;
+    __syncthreads();                                         // every thread's peer stores are ordered before thread 0's fence (cumulativity)
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            if (!(p < hf.send_n && row0 < hf.send_a[p] + hf.send_cnt[p] && rend > hf.send_a[p])) continue;
+            const unsigned long long prev = atomicAdd(hf.sepoch + 8 + p, 1ULL);
+            if (prev == (unsigned long long)(hf.send_ctas[p] - 1)) {
+                hf.sepoch[8 + p] = 0;
+                const unsigned long long e = ld_relaxed_gpu(hf.sepoch + p) + 1;
+                hf.sepoch[p] = e;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(hf.rflag[p]), "l"(e) : "memory");
+            }
+        }
+    }
+}
+
 // ---- hot-row family: row patterns, speculative loads at the hot pattern's offsets ------------------------------
 // ncu on k_rowstream / k_rowwin (profiles/r2_ncu_*): half of the issued instructions were consumers spinning on a
 // stage that had not landed, and a thread-per-row kernel that first loads its code and only then its x values pays two
@@ -997,8 +1106,8 @@ __device__ __forceinline__ double ld_stream_f64(const double* p)
 template <int HOTN, int THREADS, int RPT, int MINB, class Epi>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ pmask, const int2* __restrict__ phead,
-         const DictEnt* __restrict__ pent, const __grid_constant__ HotArgs H, const int4* __restrict__ desc, int ntiles,
-         int rb, int re, int xlen, int pf, const double* x, Epi epi)
+         const DictEnt* __restrict__ pent, const __grid_constant__ HotArgs H, const __grid_constant__ HaloFuse hf,
+         const int4* __restrict__ desc, int ntiles, int rb, int re, int xlen, int pf, const double* x, Epi epi)
 {
     static_assert(Epi::CONTIG, "hot-row kernel needs contiguous epilogue operands");
     static_assert(HOTN >= 1 && HOTN <= WIN_HOT, "hot pattern length");
@@ -1008,9 +1117,12 @@ k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
     bool alias = false;                                      // the operand that is x itself (old iterate of a Jacobi sweep)
     if constexpr (XOP >= 0) alias = epi.operand(XOP) == x;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    int row0 = rb + (int)blockIdx.x * T, rend = re;          // this tile: rows [row0, min(row0 + T, rend))
+    const int tile = desc ? (int)blockIdx.x : halo_tile(hf, (int)blockIdx.x, ntiles);       // (sharded: boundary tiles first)
+    int row0 = rb + tile * T, rend = re;                     // this tile: rows [row0, min(row0 + T, rend))
     if (desc) { const int4 d = __ldg(desc + blockIdx.x); row0 = d.x; rend = d.x + d.y; }
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    halo_wait(hf, row0, min(row0 + T, rend));                // rows that read ghost entries: the neighbours' rows have arrived
+    const int sends = halo_sends(hf, row0, min(row0 + T, rend));
     int code[RPT];
     double xv[RPT][HOTN];
     double o[RPT][NOPS > 0 ? NOPS : 1];
@@ -1040,7 +1152,7 @@ k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
             if constexpr (NIOPS > 0) io[j] = epi.ioperand()[r];
         }
     }
-    if (pf > 0 && tid < 32 && (int)blockIdx.x + pf < ntiles) {   // L2 prefetch for the tile pf tiles ahead (whole 16-byte groups, in bounds)
+    if (pf > 0 && tid < 32 && tile + pf < ntiles) {          // L2 prefetch for the tile pf tiles ahead (whole 16-byte groups, in bounds)
         long long p0 = (long long)row0 + (long long)pf * T;
         int pn = T;
         if (desc) { const int4 d = __ldg(desc + blockIdx.x + pf); p0 = d.x; pn = (d.y + 15) & ~15; }
@@ -1074,10 +1186,13 @@ k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
             }
         }
         if (fast || r < rend) {
-            if constexpr (NIOPS > 0) epi.store_i(r, sum, o[j], io[j]);
-            else epi.store(r, sum, o[j]);
+            double t;
+            if constexpr (NIOPS > 0) t = epi.store_i(r, sum, o[j], io[j]);
+            else t = epi.store(r, sum, o[j]);
+            if (sends) halo_send(hf, r, t);
         }
     }
+    if (sends) halo_publish(hf, row0, min(row0 + T, rend));
 }
 
 // Fused residual + injection on a row-pattern-coded operator, one thread per COARSE row i: out[i] = f[g_i] - (A v)[g_i],
@@ -1091,8 +1206,8 @@ k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
 template <int HOTN, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_hotinj(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ pmask, const int2* __restrict__ phead,
-         const DictEnt* __restrict__ pent, const __grid_constant__ HotArgs H, const int32_t* __restrict__ inj, int nc, int xlen, int pf,
-         const double* x, const double* f, double* out)
+         const DictEnt* __restrict__ pent, const __grid_constant__ HotArgs H, const __grid_constant__ HaloFuse hf,
+         const int32_t* __restrict__ inj, int mono, int nc, int xlen, int pf, const double* x, const double* f, double* out)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int i = (int)blockIdx.x * THREADS + (int)threadIdx.x;
@@ -1102,6 +1217,11 @@ k_hotinj(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
         if (p0 + THREADS <= (long long)nc) bulk_prefetch_l2(inj + p0, THREADS * 4);
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    {   // rows this CTA sums: [first, last] of its slice of the injection list when that list is ascending (mono), else unknown
+        int ra = 0, rb = 0x7fffffff;
+        if (mono) { ra = __ldg(inj + min((int)blockIdx.x * THREADS, nc - 1)); rb = __ldg(inj + min((int)blockIdx.x * THREADS + THREADS - 1, nc - 1)) + 1; }
+        halo_wait(hf, ra, rb);
+    }
     const int code = ld_stream_u8(rcodes + r);
     double xv[HOTN];
 #pragma unroll
@@ -1148,8 +1268,8 @@ __device__ __forceinline__ int ld_stream_i32(const int32_t* p)
 template <int THREADS, int RPT, int JW, int MINB, class Epi>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ anchor, const int2* __restrict__ phead,
-          const DictEnt* __restrict__ pent, int ndict, int npent, const int4* __restrict__ desc, int ntiles, int rb, int re, int pf,
-          const double* x, Epi epi)
+          const DictEnt* __restrict__ pent, int ndict, int npent, const __grid_constant__ HaloFuse hf, const int4* __restrict__ desc,
+          int ntiles, int rb, int re, int pf, const double* x, Epi epi)
 {
     static_assert(Epi::CONTIG, "anchored-pattern kernel needs contiguous epilogue operands");
     static_assert(JW == 4 || JW == 8, "chunk width");
@@ -1161,7 +1281,8 @@ k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ 
     int* sdelta = reinterpret_cast<int*>(smem_anch + (size_t)npent * 8 + 256 * 8);   // [npent]
     const int tid = threadIdx.x;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    int row0 = rb + (int)blockIdx.x * T, rend = re;
+    const int tile = desc ? (int)blockIdx.x : halo_tile(hf, (int)blockIdx.x, ntiles);
+    int row0 = rb + tile * T, rend = re;
     if (desc) { const int4 d = __ldg(desc + blockIdx.x); row0 = d.x; rend = d.x + d.y; }
     int code[RPT], anc[RPT];
     const bool full = row0 + T <= rend;                      // CTA-uniform
@@ -1183,7 +1304,7 @@ k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ 
         for (int k = 0; k < NOPS; ++k) o[j][k] = ld_stream_f64(epi.operand(k) + r);
         if constexpr (NIOPS > 0) io[j] = epi.ioperand()[r];
     }
-    if (pf > 0 && tid < 32 && (int)blockIdx.x + pf < ntiles) {   // L2 prefetch for the tile pf tiles ahead
+    if (pf > 0 && tid < 32 && tile + pf < ntiles) {          // L2 prefetch for the tile pf tiles ahead
         long long p0 = (long long)row0 + (long long)pf * T;
         int pn = T;
         if (desc) { const int4 d = __ldg(desc + blockIdx.x + pf); p0 = d.x; pn = (d.y + 15) & ~15; }
@@ -1195,6 +1316,8 @@ k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ 
         }
     }
     __syncthreads();                                         // the table is in shared memory
+    halo_wait(hf, row0, min(row0 + T, rend));                // rows whose columns reach into the ghost section of x
+    const int sends = halo_sends(hf, row0, min(row0 + T, rend));
     int2 ph[RPT];
     double xv[RPT][JW];
 #pragma unroll
@@ -1221,10 +1344,13 @@ k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ 
                 if (e0 + e < ph[j].y) sum = __dadd_rn(sum, __dmul_rn(sval[ph[j].x + e0 + e], xw[e]));
         }
         if (full || r < rend) {
-            if constexpr (NIOPS > 0) epi.store_i(r, sum, o[j], io[j]);
-            else epi.store(r, sum, o[j]);
+            double t;
+            if constexpr (NIOPS > 0) t = epi.store_i(r, sum, o[j], io[j]);
+            else t = epi.store(r, sum, o[j]);
+            if (sends) halo_send(hf, r, t);
         }
     }
+    if (sends) halo_publish(hf, row0, min(row0 + T, rend));
 }
 
 // ---- sub-warp family --------------------------------------------------------------------------------
@@ -1277,15 +1403,18 @@ k_seqrow(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, c
 
 // ---- small kernels ----------------------------------------------------------------------------------
 // zero initial guess + one Jacobi sweep collapses to v = g = w*(dinv*f)   (multigrid.py:253 + :226)
+// (sharded: the rows the neighbours hold as ghosts go to them as well, see HaloFuse)
 __global__ void k_init_guess(int n, const double* __restrict__ dinv, const double* __restrict__ f, double om,
-                             double* __restrict__ g, double* __restrict__ v)
+                             double* __restrict__ g, double* __restrict__ v, const __grid_constant__ HaloFuse hf)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const double gi = __dmul_rn(om, __dmul_rn(dinv[i], f[i]));
         g[i] = gi;
         v[i] = gi;
+        if (hf.send_n) halo_send(hf, i, gi);
     }
+    if (hf.send_n) halo_publish(hf, (int)(blockIdx.x * blockDim.x), min((int)((blockIdx.x + 1) * blockDim.x), n));
 }
 
 // injection: out[i] = r[inj[i]]   (Restriction2D_direct, multigrid.py:128-131)

@@ -47,6 +47,7 @@ struct DevCsr {
     // row-sharded operators: stream tiles split into [boundary-low | interior | boundary-high]; interior rows reference
     // no ghost column, so they can run while the halo exchange is in flight
     bool split = false;
+    int64_t int_r0 = 0, int_r1 = 0;  // sharded: rows [int_r0, int_r1) reference no ghost column
     int t_int0 = 0, t_int1 = 0;      // interior tiles = sdesc[t_int0 .. t_int1)
     int4* sdesc_bnd = nullptr;       // boundary tiles, low block then high block
     int n_bnd = 0;
@@ -71,11 +72,17 @@ struct P2PPlan {                             // passed to the halo kernels by va
     unsigned long long* flags = nullptr;     // this rank's arrival flags (indexed by sender rank)
     double* stage = nullptr;                 // this rank's staging copies (2 x n_ghost)
     int n_ghost = 0;
+    // fused exchange (HaloFuse): the neighbours' iterate buffers and a second set of flags
+    double* rvec[P2P_MAX_PEERS][2] = {};     // neighbour's v / vtmp, already offset to this rank's slot of its ghost section
+    unsigned long long* rflag2[P2P_MAX_PEERS] = {};  // neighbour's fused-exchange flag for this rank
+    unsigned long long* flags2 = nullptr;    // this rank's fused-exchange flags (indexed by sender rank)
 };
 
 struct P2PBlob {                             // what a rank publishes per level (mgb_p2p_export)
     cudaIpcMemHandle_t handle;
     long long n_ghost;
+    long long n_owned;                       // the iterate buffers v / vtmp live in the arena too: byte offsets of their first entry
+    long long off_vec[2];
     int npeers;
     int peer_rank[P2P_MAX_PEERS];
     int recv_off[P2P_MAX_PEERS + 1];
@@ -106,7 +113,11 @@ struct Level {
     int64_t send_total = 0;
     // peer-memory halo exchange (CUDA IPC over NVLink): flags + two staging copies of the ghost section live in one
     // exported allocation; the neighbours write into it directly
-    void* p2p_arena = nullptr;       // [flags: 256 x u64][stage 0: n_ghost][stage 1: n_ghost]
+    void* p2p_arena = nullptr;       // [flags: 256 x u64][fused flags: 256 x u64][stage 0: n_ghost][stage 1: n_ghost][v][vtmp]
+    bool vec_in_arena = false;       // v and vtmp point into the arena (the neighbours store their boundary rows into them)
+    int send_a[2] = {-1, -1};        // first row of the send list of neighbour p when the list is one run of consecutive rows
+    bool fuse_ok = false;            // halo exchange fused into the kernels on this level (HaloFuse)
+    unsigned long long* fuse_counters = nullptr;   // device: [p] epochs, [8 + p] CTA arrival counters
     unsigned long long* p2p_counters = nullptr;   // device: [0..15] send epochs, [16..31] recv epochs, [32] block counter x2
     std::vector<void*> p2p_opened;   // peers' arenas mapped into this process
     bool p2p_ready = false;
@@ -116,6 +127,7 @@ struct Level {
     DevCsr A, RJ, P, R, G;           // G: Gauss-Seidel off-diagonal operator, rows in execution order
     double* dinv = nullptr;
     int32_t* inj = nullptr;
+    bool inj_mono = false;           // the injection list is strictly ascending
     int32_t* cmap = nullptr;         // fine dof -> coarse dof or -1 (fused residual + injection)
     int4* inj_desc = nullptr;        // the stream tiles of A that contain at least one injected row
     int inj_ntiles = 0;
@@ -164,6 +176,9 @@ struct mgb_handle {
                                    // 1 x staged in shared memory by bulk copies (k_rowwin); 0 bulk-copied codes / operands + x gathered
                                    // through L1 (k_rowstream)
     int reuse_g = 1;               // cycles after the first of one call reuse the top level's w*(dinv*f) instead of forming it again
+    int fuse_halo = 1;             // row-sharded levels: halo exchange fused into the kernels that write / read the iterate (HaloFuse)
+    HaloFuse hf_cur{};             // the fused-exchange plan of the launch being enqueued (all zero: none)
+    bool in_cycle = false;         // inside enqueue_cycle: ghost sections of fused levels are kept valid by the kernels themselves
     int hot_inj = 1;               // fused residual + injection: thread per coarse row on a pattern-coded level matrix (k_hotinj)
     int anch_cfg = 1;              // anchored-pattern kernel: 1 128 threads x 4 rows, 2 128 x 2, 3 64 x 4, 4 256 x 1 (rows of > 4 entries)
     int hot_cfg = 1;               // hot-row kernel configuration (hot_choice)

@@ -42,12 +42,12 @@ def _worker(rank, world, port, case, q):
         mg.load_rhs()
         hist = mg.cycles(4, history=True)
         v = mg.gather_solution()
-        q.put((rank, v if rank == 0 else None, hist, None))
+        q.put((rank, v if rank == 0 else None, hist, None, mg.eng.describe()))
         td.barrier()
         mg.close()
     except Exception:       # noqa: BLE001
         import traceback
-        q.put((rank, None, None, traceback.format_exc()))
+        q.put((rank, None, None, traceback.format_exc(), ""))
     finally:
         td.destroy_process_group()
 
@@ -65,7 +65,14 @@ CASES = [
     (3, 4, 4, "generated", "injection", 1, {"overlap_halo": 2}),   # push -> interior rows -> pull -> boundary rows
     (3, 2, 4, None, "transpose", 1, {"overlap_halo": 2}),
     (2, 16, 4, "generated", "injection", 0, {}),
+    (3, 4, 4, "generated", "injection", 1, {"fuse_halo": 0}),      # push / pull kernels instead of the exchange fused into the sweeps
+    (2, 8, 4, None, "injection", 1, {"fuse_halo": 0}),
+    (3, 4, 5, "generated", "injection", 1, {}),       # 129^3 over up to 4 GPUs, three sharded levels
+    (3, 4, 4, "generated", "injection", 1, {"use_graph": 0}),
 ]
+# cases whose sharded levels must run with the halo exchange fused into the kernels (lexicographic numbering, injection, peer
+# memory, default options): a silent fall-back to the push / pull kernels would otherwise go unnoticed
+EXPECT_FUSED = {0, 8, 11, 14, 15}
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs at least 2 GPUs")
@@ -87,8 +94,12 @@ def test_sharded_equals_single_gpu(case):
         p.join(timeout=30)
         if p.is_alive():
             p.terminate()
-    for rank, v, hist, err in res:
+    for rank, v, hist, err, desc in res:
         assert err is None, err
+        if CASES.index(case) in EXPECT_FUSED:
+            assert "halo exchange fused" in desc, desc
+        if case[6].get("fuse_halo", 1) == 0 or case[6].get("p2p", 1) == 0:
+            assert "halo exchange fused" not in desc, desc
     v = [r[1] for r in res if r[0] == 0][0]
     hist = [r[2] for r in res if r[0] == 0][0]
     dim, c, lf, seed, r_mode, glevel, opts = case

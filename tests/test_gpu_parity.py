@@ -456,6 +456,50 @@ def test_full_size_properties_config3():
     eng.close()
 
 
+def test_full_size_config4_p2_vs_oracle():
+    """BASELINE config 4 at FULL size: 3-D P2 on 64^3 cells, DOF grid 129^3 = 2,146,689, 60,859,905 stored entries, rows of
+    10..65 entries, 5 levels, V(2,2) Jacobi, injection -- three cycles against the C oracle on the same hierarchy."""
+    H = pr.build_hierarchy_p2(c=4, coarsest_level=0, finest_level=4)
+    assert H.n(4) == 129 ** 3 and H.A_sp_dict[4][0].nnz == 60859905
+    eng = MGEngine.from_hierarchy(H)
+    f = H.b_dict[4][:, 0]
+    v1, h1 = eng.vcycle(4, np.zeros_like(f), f, ncycles=3, history=True)
+    cm = co.from_hierarchy(H)
+    vo, ho = cm.vcycle(np.zeros_like(f), f, ncycles=3, history=True)
+    r = float(np.abs(h1 - ho).max() / ho.max()); s = relmax(v1, vo)
+    _report("config4_full", resnorm_rel=r, solution_rel=s, hist=[float(x) for x in h1])
+    assert r <= RTOL_RESNORM and s <= RTOL_SOLUTION
+    A = H.A_sp_dict[4][0]
+    x = np.random.default_rng(4).standard_normal(A.shape[0])
+    assert np.array_equal(eng.spmv(4, x), A.dot(x))                          # 65-entry rows summed in stored order: bit-exact
+    assert np.array_equal(eng.vcycle(4, np.zeros_like(f), f, ncycles=3), v1)  # deterministic
+    eng.close()
+
+
+@pytest.mark.parametrize("smoother", ["gs", "gs_color"])
+def test_gauss_seidel_full_size_config2(smoother):
+    """BASELINE config 2 names the Gauss-Seidel smoothers: 2049^2 (4.2 M DOFs, 7 levels), one V(2,2) cycle with the level-scheduled
+    natural-order sweep (4097 dependency levels on the finest grid) and with the multicolour sweep, against the C oracle's
+    sequential sweeps (1e-12 on the residual norm, 1e-10 on the iterate), plus one bit-exact fine-level sweep."""
+    H = pr.build_hierarchy(dim=2, c=32, coarsest_level=0, finest_level=6, with_dicts=False)
+    lf = 6
+    assert H.n(lf) == 2049 ** 2
+    eng = MGEngine.from_hierarchy(H, smoother=smoother)
+    cm = co.from_hierarchy(H, smoother=smoother)
+    b = H.b_dict[lf][:, 0]
+    vo, ho = cm.vcycle(np.zeros_like(b), b, ncycles=1, history=True)
+    vg, hg = eng.vcycle(lf, np.zeros_like(b), b, ncycles=1, history=True)
+    r = float(np.abs(hg - ho).max() / ho.max()); s = relmax(vg, vo)
+    _report("config2_gs_full", smoother=smoother, resnorm_rel=r, solution_rel=s)
+    assert r <= RTOL_RESNORM and s <= RTOL_SOLUTION
+    A = H.A_sp_dict[lf][0]
+    rng = np.random.default_rng(1)
+    x, f = rng.standard_normal(H.n(lf)), rng.standard_normal(H.n(lf))
+    order = co.greedy_colouring(A)[1] if smoother == "gs_color" else None
+    assert np.array_equal(eng.smooth(lf, x, f, 1), co.gs_forward(A, x.copy(), f, order))
+    eng.close()
+
+
 def test_full_size_properties_config5():
     """BASELINE config 5 (513^3, 135 M DOFs, 2.0e9 stored entries, generated on the device): the CPU oracle cannot hold it,
     so size-independent properties: V-cycles are linear in f (exact for a power-of-two scale), deterministic, identical with
