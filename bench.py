@@ -283,7 +283,8 @@ def run_single(args):
     lf = H.finest_level
     opts = {"fuse_restrict": args.fuse_restrict, "stream_cfg": args.stream_cfg, "compress": args.compress, "code_cfg": args.code_cfg}
     opts.update(args.options)
-    eng = MGEngine.from_hierarchy(H, r_mode=args.restriction, smoother=args.smoother, device=0, options=opts)
+    eng = MGEngine.from_hierarchy(H, r_mode=args.restriction, smoother=args.smoother, device=0, options=opts,
+                                  reorder=bool(args.reorder) and args.perm != "lex")
     n = H.n(lf)
     f_host = H.b_dict[lf][:, 0]
     t_setup = time.perf_counter() - t_setup
@@ -354,7 +355,7 @@ def run_single(args):
 
     line = {"metric": METRIC, "value": dofu / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "numbering": args.perm, "restriction": args.restriction, "smoother": args.smoother,
+            "config": {"workload": f"{args.workload}: {desc}", "numbering": args.perm, "lattice_numbering_handed_over": bool(args.reorder) and args.perm != "lex", "restriction": args.restriction, "smoother": args.smoother,
                        "fine_dofs": n, "levels": lf - H.coarsest_level + 1, "mu1": H.mu1, "mu2": H.mu2, "omega": H.omega,
                        "compress": args.compress, "options": args.options,
                        "l2": "fine-level working set of one sweep (codes + 3 vectors) vs the 126 MB L2: " +
@@ -388,6 +389,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--perm", default="lex", choices=["lex", "rcm", "random"], help="DOF numbering of the host-assembled workloads")
+    ap.add_argument("--reorder", type=int, default=1, help="hand the engine the lattice numbering of a permuted workload (mgb_set_numbering), as the "
+                    "drop-in module does from the reference's coordinate dicts; 0: run in the caller's numbering")
     ap.add_argument("--gather-threshold", type=int, default=300000)
     ap.add_argument("--use-graph", type=int, default=1)
     ap.add_argument("--overlap", type=int, default=0, help="overlap the halo exchange with interior rows (sharded runs)")

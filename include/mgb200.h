@@ -223,6 +223,16 @@ int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, i
 int mgb_set_exact_solution(mgb_handle* h, int level, const double* u_exact, int mem);
 int mgb_fmg_error_history(mgb_handle* h, double* errnorm_hist, int capacity, int* count);
 
+/* Caller numbering.  The reference hands over operators and vectors in dolfinx's DOF numbering (Multigrid_prototype.py:68-74
+ * records it as coordinate dicts), which is not lexicographic; the lossless row-pattern codings need a banded numbering.
+ * new_index[i] = position of dof i in the numbering the engine should work in (a permutation of 0..n-1; the drop-in module
+ * passes the lexicographic lattice index recovered from the coordinate dicts).  mgb_finalize renumbers every operator once --
+ * rows moved, columns relabelled, the ENTRY ORDER inside every row kept, so every row sum adds the same products in the same
+ * order and the iterates stay bit-identical -- and every vector crossing the ABI (v, f, right-hand sides, per-operator calls) is
+ * permuted on the device on the way in and out.  Artefacts (mgb_get_artifact) and mgb_level_buffer show the engine's numbering.
+ * Call after mgb_set_level of that level, before mgb_finalize; single-device hierarchies only. */
+int mgb_set_numbering(mgb_handle* h, int level, int64_t n, const int64_t* new_index);
+
 /* ---- per-operator entry points (parity tests, profiling) -------------------------------------- */
 int mgb_spmv(mgb_handle* h, int level, const double* x, double* y, int mem);                       /* A.dot(x), multigrid.py:244 */
 int mgb_residual(mgb_handle* h, int level, const double* v, const double* f, double* r, int mem); /* f - A v, multigrid.py:244  */

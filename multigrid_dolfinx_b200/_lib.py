@@ -63,6 +63,7 @@ SYMBOLS = {
     "mgb_set_mass_matrix": (_i, [_vp, _i, _i64, _i64, _vp, _i, _vp, _vp]),
     "mgb_fmg": (_i, [_vp, _i, _d, _i, _vp, _i, C.POINTER(_i), _vp, _i]),
     "mgb_set_exact_solution": (_i, [_vp, _i, _vp, _i]),
+    "mgb_set_numbering": (_i, [_vp, _i, _i64, _vp]),
     "mgb_fmg_error_history": (_i, [_vp, _vp, _i, C.POINTER(_i)]),
     "mgb_spmv": (_i, [_vp, _i, _vp, _vp, _i]),
     "mgb_residual": (_i, [_vp, _i, _vp, _vp, _vp, _i]),

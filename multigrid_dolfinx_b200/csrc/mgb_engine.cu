@@ -958,6 +958,68 @@ int norm2_device(mgb_handle* h, int64_t n, const double* x, double* out_dev, int
     return rc;
 }
 
+// ---- coarse tail (k_tail): all levels of at most tail_rows rows in one cooperative launch ------------------------------
+TailOp tail_op(const DevCsr& D)
+{
+    TailOp o{};
+    o.mode = (D.cd.mode == 3 || D.cd.mode == 4) ? D.cd.mode : 0;
+    o.rowptr = D.rowptr; o.cols = D.cols; o.vals = D.vals;
+    o.codes = D.cd.codes; o.anchor = D.cd.anchor; o.phead = D.cd.phead; o.pent = D.cd.dict;
+    return o;
+}
+// top level of the tail for a cycle whose top level is `top` (-1: no tail).  The tail covers the coarsest level and every
+// level above it up to the last one that is small, lives entirely on this device and uses the reference configuration
+// (weighted Jacobi in the reference form, injection fused with the residual).
+int tail_top_for(mgb_handle* h, int top, bool debug)
+{
+    if (h->tail_rows <= 0 || debug || h->smoother != MGB_SM_JACOBI_RJ || h->mu1 < 1 || h->coarse_refine || !h->fuse_restrict) return -1;
+    if (h->levels[h->coarsest].stub || !h->coarse_inv) return -1;
+    int t = -1;
+    for (int l = h->coarsest + 1; l < top && l - h->coarsest < TAIL_MAX_LEVELS; ++l) {
+        const Level& L = h->levels[l];
+        if (L.n > h->tail_rows || L.stub || L.n_ghost > 0 || !L.has_transfer || L.r_mode != MGB_R_INJECTION || !L.inj) break;
+        if (h->dist && l > h->gather_level) break;
+        if (!L.A.present() || !L.RJ.present() || !L.P.present() || !L.dinv) break;
+        t = l;
+    }
+    return t;
+}
+int launch_tail(mgb_handle* h, int tail_top)
+{
+    TailPlan T{};
+    T.nlev = tail_top - h->coarsest + 1; T.mu1 = h->mu1; T.mu2 = h->mu2; T.om = h->omega; T.om1 = 1 - h->omega;
+    T.coarse_inv = h->coarse_inv;
+    const bool swap = (((h->mu1 - 1) + h->mu2) & 1) != 0;    // the iterate must END in L.v
+    double bytes = 0.0;
+    for (int k = 0; k < T.nlev; ++k) {
+        Level& L = h->levels[h->coarsest + k];
+        TailLevel& t = T.lev[k];
+        t.n = (int)L.n; t.nc = k > 0 ? (int)h->levels[h->coarsest + k - 1].n : 0;
+        t.f = L.f; t.g = L.g; t.dinv = L.dinv; t.inj = L.inj;
+        if (k == 0) { t.a = L.v; t.b = L.vtmp; bytes += 8.0 * (double)L.n * (double)L.n; continue; }
+        t.a = swap ? L.vtmp : L.v; t.b = swap ? L.v : L.vtmp;
+        t.A = tail_op(L.A); t.RJ = tail_op(L.RJ); t.P = tail_op(L.P);
+        bytes += (double)(h->mu1 - 1 + h->mu2) * bytes_rowsum(L.RJ, 3.0 * (double)L.n) + 32.0 * (double)L.n + bytes_rowsum(L.P, 3.0 * (double)L.n);
+    }
+    return launch(h, MGB_K_COARSE, tail_top, bytes, [&] {
+        static std::mutex mu;
+        static std::map<int, int> grid_of;                  // device -> co-resident CTAs
+        int grid = 0;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto it = grid_of.find(h->device);
+            if (it == grid_of.end()) {
+                int o = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_tail, 512, 0);
+                it = grid_of.emplace(h->device, std::max(1, std::min(o, 1)) * h->sm_count).first;
+            }
+            grid = it->second;
+        }
+        void* args[] = {(void*)&T};
+        cudaLaunchCooperativeKernel((void*)k_tail, dim3(grid), dim3(512), args, 0, h->stream);
+    });
+}
+
 // ---- one V-cycle, enqueued on the stream (multigrid.py:231-268 unrolled into a down and an up sweep) ----
 // v and f of the top level live in levels[top].v / .f.  dbg: copy the test=True outputs into L.r (err_h);
 // f2h / v2h are left in the coarse level's f / v buffers.
@@ -978,9 +1040,15 @@ int enqueue_cycle(mgb_handle* h, int top, bool debug, double** v2h_ptr, bool top
     const bool jacobi = h->smoother == MGB_SM_JACOBI_RJ || h->smoother == MGB_SM_JACOBI_A;
     // ranks other than 0 stop at the gathered level: everything below it runs on rank 0 only
     const int bottom = h->coarsest;            // (on those ranks the gathered level IS the coarsest level they hold)
+    const int tail_top = tail_top_for(h, top, debug);      // levels <= tail_top run in one cooperative launch (-1: none)
     for (int l = top; l > bottom; --l) {
         Level& L = h->levels[l];
         Level& C = h->levels[l - 1];
+        if (l == tail_top) {                                // its right-hand side is in place: the whole sub-cycle, one launch
+            TRY(launch_tail(h, tail_top));
+            cur[l] = L.v;
+            break;
+        }
         double* v = L.v; double* o = L.vtmp;
         bool g_valid = l == top && top_g_valid && h->smoother == MGB_SM_JACOBI_RJ;
         int sweeps = h->mu1;
@@ -1009,11 +1077,11 @@ int enqueue_cycle(mgb_handle* h, int top, bool debug, double** v2h_ptr, bool top
         cur[l] = v; oth[l] = o; gv[l] = g_valid;
     }
     Level& C0 = h->levels[h->coarsest];
-    if (!C0.stub) {
+    if (!C0.stub && tail_top < 0) {
         TRY(coarse_apply(h, C0, C0.f, C0.v));                              // multigrid.py:238-241
         cur[h->coarsest] = C0.v;
     }
-    for (int l = bottom + 1; l <= top; ++l) {
+    for (int l = (tail_top < 0 ? bottom : tail_top) + 1; l <= top; ++l) {
         Level& L = h->levels[l];
         double* v = cur[l]; double* o = oth[l];
         bool g_valid = gv[l];
@@ -1080,15 +1148,54 @@ int ensure_hist(mgb_handle* h, int n)
     return MGB_OK;
 }
 
-int copy_in(mgb_handle* h, double* dst, const double* src, int64_t n, int mem)
+// perm (device, optional): the level's numbering map, new index of every dof as the caller numbers them (mgb_set_numbering).
+// The engine's buffers hold the lexicographic numbering; vectors are permuted on the way in and out.
+__global__ void k_perm_scatter(int64_t n, const int32_t* __restrict__ perm, const double* __restrict__ src, double* __restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[perm[i]] = src[i];
+}
+__global__ void k_perm_gather(int64_t n, const int32_t* __restrict__ perm, const double* __restrict__ src, double* __restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[perm[i]];
+}
+int perm_scratch(mgb_handle* h, int64_t n)
+{
+    if (n <= h->perm_tmp_cap) return MGB_OK;
+    cudaFree(h->perm_tmp); h->perm_tmp = nullptr; h->perm_tmp_cap = 0;
+    TRY(dev_alloc(h, &h->perm_tmp, (size_t)n));
+    h->perm_tmp_cap = n;
+    return MGB_OK;
+}
+int copy_in(mgb_handle* h, double* dst, const double* src, int64_t n, int mem, const int32_t* perm = nullptr)
 {
     if (dst == src || n == 0) return MGB_OK;
+    if (perm) {
+        const double* from = src;
+        if (mem == MGB_MEM_HOST) {
+            TRY(perm_scratch(h, n));
+            CU(cudaMemcpyAsync(h->perm_tmp, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+            from = h->perm_tmp;
+        }
+        k_perm_scatter<<<(int)((n + 255) / 256), 256, 0, h->stream>>>(n, perm, from, dst);
+        CU(cudaGetLastError());
+        return MGB_OK;
+    }
     CU(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, mem == MGB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
     return MGB_OK;
 }
-int copy_out(mgb_handle* h, double* dst, const double* src, int64_t n, int mem)
+int copy_out(mgb_handle* h, double* dst, const double* src, int64_t n, int mem, const int32_t* perm = nullptr)
 {
     if (dst == src || n == 0) return MGB_OK;
+    if (perm) {
+        double* to = dst;
+        if (mem == MGB_MEM_HOST) { TRY(perm_scratch(h, n)); to = h->perm_tmp; }
+        k_perm_gather<<<(int)((n + 255) / 256), 256, 0, h->stream>>>(n, perm, src, to);
+        CU(cudaGetLastError());
+        if (mem == MGB_MEM_HOST) CU(cudaMemcpyAsync(dst, to, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        return MGB_OK;
+    }
     CU(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, mem == MGB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
     return MGB_OK;
 }
@@ -1132,6 +1239,48 @@ int cycles_on_buffers(mgb_handle* h, int top, int ncycles, double* resnorm_hist)
     }
     return MGB_OK;
 }
+
+// ---- caller numbering (mgb_set_numbering) -------------------------------------------------------------------------------
+// rows of M renumbered by pr (new index of every old row), columns by pc; the ENTRY ORDER inside every row is kept, so each
+// row sum adds the same products in the same order as before: results are bit-identical per row (nullptr: identity).
+void permute_csr(HostCsr& M, const std::vector<int64_t>* pr, const std::vector<int64_t>* pc)
+{
+    if (M.empty() || (!pr && !pc)) return;
+    const int64_t n = M.nrows;
+    HostCsr N;
+    N.nrows = M.nrows; N.ncols = M.ncols;
+    N.ip.assign((size_t)n + 1, 0);
+    for (int64_t i = 0; i < n; ++i) N.ip[(size_t)(pr ? (*pr)[(size_t)i] : i) + 1] = M.ip[(size_t)i + 1] - M.ip[(size_t)i];
+    for (int64_t i = 0; i < n; ++i) N.ip[(size_t)i + 1] += N.ip[(size_t)i];
+    N.ix.resize(M.ix.size()); N.ax.resize(M.ax.size());
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t o = N.ip[(size_t)(pr ? (*pr)[(size_t)i] : i)];
+        for (int64_t k = M.ip[(size_t)i]; k < M.ip[(size_t)i + 1]; ++k, ++o) {
+            N.ix[(size_t)o] = pc ? (int32_t)(*pc)[(size_t)M.ix[(size_t)k]] : M.ix[(size_t)k];
+            N.ax[(size_t)o] = M.ax[(size_t)k];
+        }
+    }
+    M = std::move(N);
+}
+
+}  // namespace
+extern "C" int mgb_set_numbering(mgb_handle* h, int level, int64_t n, const int64_t* new_index)
+{
+    if (!h || !new_index) return MGB_ERR_INVALID;
+    if (h->finalized) return fail(h, MGB_ERR_STATE, "hierarchy already finalized");
+    if (h->dist) return fail(h, MGB_ERR_UNSUPPORTED, "a caller numbering is not supported on row-sharded hierarchies");
+    Level* L = find_level(h, level);
+    if (!L || L->n != n) return fail(h, MGB_ERR_STATE, "set level %d (with %lld rows) before its numbering", level, (long long)n);
+    std::vector<char> seen((size_t)n, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        if (new_index[i] < 0 || new_index[i] >= n || seen[(size_t)new_index[i]]) return fail(h, MGB_ERR_INVALID, "level %d: the numbering is not a permutation", level);
+        seen[(size_t)new_index[i]] = 1;
+    }
+    L->perm_host.assign(new_index, new_index + n);
+    h->numbered = true;
+    return MGB_OK;
+}
+namespace {
 
 }  // namespace
 
@@ -1179,13 +1328,13 @@ int mgb_destroy(mgb_handle* h)
     for (auto& kv : h->levels) {
         Level& L = kv.second;
         free_csr(L.A); free_csr(L.RJ); free_csr(L.P); free_csr(L.R); free_csr(L.G); free_csr(L.M); cudaFree(L.b); cudaFree(L.uex);
-        cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.cmap); cudaFree(L.inj_desc); cudaFree(L.send_idx); cudaFree(L.send_buf); cudaFree(L.p2p_counters);
+        cudaFree(L.dinv); cudaFree(L.inj); cudaFree(L.cmap); cudaFree(L.perm); cudaFree(L.inj_desc); cudaFree(L.send_idx); cudaFree(L.send_buf); cudaFree(L.p2p_counters);
         for (void* q : L.p2p_opened) cudaIpcCloseMemHandle(q);
         if (!L.vec_in_arena) { cudaFree(L.v); cudaFree(L.vtmp); }
         cudaFree(L.p2p_arena); cudaFree(L.fuse_counters); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
         cudaFree(L.gs_order); cudaFree(L.gs_off); cudaFree(L.gs_diag); cudaFree(L.gs_ecols); cudaFree(L.gs_evals);
     }
-    cudaFree(h->coarse_inv); cudaFree(h->d_partial); cudaFree(h->d_hist);
+    cudaFree(h->coarse_inv); cudaFree(h->d_partial); cudaFree(h->d_hist); cudaFree(h->perm_tmp);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     for (auto& pe : h->prof_events) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
@@ -1535,6 +1684,7 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "hot_cfg" && pre) h->hot_cfg = iv;
     else if (k == "anch_cfg" && pre) h->anch_cfg = iv;
     else if (k == "reuse_g") { h->reuse_g = iv; drop_graphs(h); }
+    else if (k == "tail_rows") { h->tail_rows = iv; drop_graphs(h); }
     else if (k == "hot_inj") { h->hot_inj = iv; drop_graphs(h); }
     else if (k == "fuse_halo" && pre) h->fuse_halo = iv;
     else if (k == "hot_pf") { h->hot_pf = iv; drop_graphs(h); }
@@ -1585,6 +1735,33 @@ int mgb_finalize(mgb_handle* h)
     if (!h) return MGB_ERR_INVALID;
     TRY(validate_hierarchy(h));
     CU(cudaSetDevice(h->device));
+    if (h->numbered) {                      // caller numbering: renumber every operator once, here (entry order inside rows kept)
+        // the coarsest level keeps the caller's numbering: its dense inverse is computed by elimination, whose rounding follows the
+        // row order -- renumbering it would change the coarse solve in the last bits (and there is nothing to gain on ~1000 rows)
+        h->levels[h->coarsest].perm_host.clear();
+        for (auto& kv : h->levels) {
+            Level& L = kv.second;
+            const std::vector<int64_t>* pf = L.perm_host.empty() ? nullptr : &L.perm_host;
+            Level* C = find_level(h, kv.first - 1);
+            const std::vector<int64_t>* pc = (C && !C->perm_host.empty()) ? &C->perm_host : nullptr;
+            if (L.device_born) return fail(h, MGB_ERR_UNSUPPORTED, "a caller numbering needs host-assembled levels");
+            permute_csr(L.A_host, pf, pf);
+            if (L.has_transfer) {
+                permute_csr(L.P_host, pf, pc);
+                permute_csr(L.R_host, pc, pf);
+                if (!L.inj_host.empty()) {
+                    std::vector<int32_t> inj(L.inj_host.size());
+                    for (size_t i = 0; i < inj.size(); ++i)
+                        inj[(size_t)(pc ? (*pc)[i] : (int64_t)i)] = (int32_t)(pf ? (*pf)[(size_t)L.inj_host[i]] : L.inj_host[i]);
+                    L.inj_host.swap(inj);
+                }
+            }
+            if (pf) {
+                std::vector<int32_t> p32(pf->begin(), pf->end());
+                TRY(dev_upload(h, &L.perm, p32.data(), p32.size()));
+            }
+        }
+    }
     for (auto& kv : h->levels) {
         Level& L = kv.second;
         const size_t n = (size_t)L.n;
@@ -1747,10 +1924,10 @@ int mgb_vcycle(mgb_handle* h, int top_level, double* v, const double* f, int mem
     Level* T = nullptr;
     TRY(check_ready(h, top_level, &T));
     if (!v || !f || ncycles < 0) return fail(h, MGB_ERR_INVALID, "null vector or negative cycle count");
-    TRY(copy_in(h, T->f, f, T->n, mem));
-    TRY(copy_in(h, T->v, v, T->n, mem));
+    TRY(copy_in(h, T->f, f, T->n, mem, T->perm));
+    TRY(copy_in(h, T->v, v, T->n, mem, T->perm));
     TRY(cycles_on_buffers(h, top_level, ncycles, resnorm_hist));
-    TRY(copy_out(h, v, T->v, T->n, mem));
+    TRY(copy_out(h, v, T->v, T->n, mem, T->perm));
     if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream));
     return MGB_OK;
 }
@@ -1761,7 +1938,7 @@ int mgb_set_rhs(mgb_handle* h, int level, const double* b, int mem)
     TRY(check_ready(h, level, &L));
     if (!b) return fail(h, MGB_ERR_INVALID, "null right-hand side");
     if (!L->b) TRY(dev_alloc(h, &L->b, (size_t)L->n + 16));
-    TRY(copy_in(h, L->b, b, L->n, mem));
+    TRY(copy_in(h, L->b, b, L->n, mem, L->perm));
     if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream));
     return MGB_OK;
 }
@@ -1775,6 +1952,7 @@ int mgb_set_mass_matrix(mgb_handle* h, int level, int64_t n, int64_t nnz, const 
     HostCsr M;
     std::string e = import_csr(M, n, n, nnz, indptr, indptr_bytes, indices, values);
     if (!e.empty()) return fail(h, MGB_ERR_INVALID, "mass matrix: %s", e.c_str());
+    if (!L->perm_host.empty()) permute_csr(M, &L->perm_host, &L->perm_host);
     free_csr(L->M);
     TRY(upload_csr(h, M, L->M));
     CU(cudaStreamSynchronize(h->stream));
@@ -1846,7 +2024,7 @@ int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, i
     }
     if (cycles_done) *cycles_done = done;
     if (v_out) {
-        TRY(copy_out(h, v_out, T->v, T->n, mem));
+        TRY(copy_out(h, v_out, T->v, T->n, mem, T->perm));
         if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream));
     }
     return MGB_OK;
@@ -1858,7 +2036,7 @@ int mgb_set_exact_solution(mgb_handle* h, int level, const double* u_exact, int 
     TRY(check_ready(h, level, &L));
     if (!u_exact) { cudaFree(L->uex); L->uex = nullptr; return MGB_OK; }      // (null: forget it)
     if (!L->uex) TRY(dev_alloc(h, &L->uex, (size_t)L->n + 16));
-    TRY(copy_in(h, L->uex, u_exact, L->n, mem));
+    TRY(copy_in(h, L->uex, u_exact, L->n, mem, L->perm));
     if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream));
     return MGB_OK;
 }
@@ -1886,15 +2064,15 @@ int mgb_vcycle_debug(mgb_handle* h, int top_level, double* v, const double* f, i
     if (top_level == h->coarsest) return fail(h, MGB_ERR_INVALID, "the debug outputs need a level above the coarsest");
     if (!v || !f) return fail(h, MGB_ERR_INVALID, "null vector");
     Level& C = h->levels[top_level - 1];
-    TRY(copy_in(h, T->f, f, T->n, mem));
-    TRY(copy_in(h, T->v, v, T->n, mem));
+    TRY(copy_in(h, T->f, f, T->n, mem, T->perm));
+    TRY(copy_in(h, T->v, v, T->n, mem, T->perm));
     double* v2 = nullptr;
     // f2h must be saved before the coarse recursion overwrites nothing -- C.f is only written by the restriction
     TRY(enqueue_cycle(h, top_level, true, &v2));
-    TRY(copy_out(h, v, T->v, T->n, mem));
-    if (f2h) TRY(copy_out(h, f2h, C.f, C.n, mem));
-    if (v2h) TRY(copy_out(h, v2h, v2, C.n, mem));
-    if (err_h) TRY(copy_out(h, err_h, T->r, T->n, mem));
+    TRY(copy_out(h, v, T->v, T->n, mem, T->perm));
+    if (f2h) TRY(copy_out(h, f2h, C.f, C.n, mem, C.perm));
+    if (v2h) TRY(copy_out(h, v2h, v2, C.n, mem, C.perm));
+    if (err_h) TRY(copy_out(h, err_h, T->r, T->n, mem, T->perm));
     if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream));
     return MGB_OK;
 }
@@ -1903,12 +2081,13 @@ int mgb_spmv(mgb_handle* h, int level, const double* x, double* y, int mem)
 {
     Level* L = nullptr;
     TRY(check_ready(h, level, &L));
-    BorrowGuard guard(h, mem);
+    const bool stage = mem == MGB_MEM_HOST || h->numbered;      // (a caller numbering: vectors pass through the level buffers)
+    BorrowGuard guard(h, stage ? MGB_MEM_HOST : mem);
     const double* xd = x; double* yd = y;
-    if (mem == MGB_MEM_HOST) { TRY(copy_in(h, L->v, x, L->n, mem)); xd = L->v; yd = L->r; }
+    if (stage) { TRY(copy_in(h, L->v, x, L->n, mem, L->perm)); xd = L->v; yd = L->r; }
     EpiStore epi{yd};
     TRY(row_sums(h, MGB_K_SPMV, level, bytes_rowsum(L->A, 2.0 * (double)L->n), L->A, xd, epi));
-    if (mem == MGB_MEM_HOST) { TRY(copy_out(h, y, yd, L->n, mem)); CU(cudaStreamSynchronize(h->stream)); }
+    if (stage) { TRY(copy_out(h, y, yd, L->n, mem, L->perm)); if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream)); }
     return MGB_OK;
 }
 
@@ -1916,11 +2095,12 @@ int mgb_residual(mgb_handle* h, int level, const double* v, const double* f, dou
 {
     Level* L = nullptr;
     TRY(check_ready(h, level, &L));
-    BorrowGuard guard(h, mem);
+    const bool stage = mem == MGB_MEM_HOST || h->numbered;      // (a caller numbering: vectors pass through the level buffers)
+    BorrowGuard guard(h, stage ? MGB_MEM_HOST : mem);
     const double *vd = v, *fd = f; double* rd = r;
-    if (mem == MGB_MEM_HOST) { TRY(copy_in(h, L->v, v, L->n, mem)); TRY(copy_in(h, L->f, f, L->n, mem)); vd = L->v; fd = L->f; rd = L->r; }
+    if (stage) { TRY(copy_in(h, L->v, v, L->n, mem, L->perm)); TRY(copy_in(h, L->f, f, L->n, mem, L->perm)); vd = L->v; fd = L->f; rd = L->r; }
     TRY(residual(h, *L, vd, fd, rd));
-    if (mem == MGB_MEM_HOST) { TRY(copy_out(h, r, rd, L->n, mem)); CU(cudaStreamSynchronize(h->stream)); }
+    if (stage) { TRY(copy_out(h, r, rd, L->n, mem, L->perm)); if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream)); }
     return MGB_OK;
 }
 
@@ -1928,15 +2108,16 @@ int mgb_smooth(mgb_handle* h, int level, double* v, const double* f, int nsweeps
 {
     Level* L = nullptr;
     TRY(check_ready(h, level, &L));
-    BorrowGuard guard(h, mem);
+    const bool stage = mem == MGB_MEM_HOST || h->numbered;      // (a caller numbering: vectors pass through the level buffers)
+    BorrowGuard guard(h, stage ? MGB_MEM_HOST : mem);
     if (level == h->coarsest && h->smoother >= MGB_SM_GS_LEVEL) return fail(h, MGB_ERR_STATE, "no Gauss-Seidel operator on the coarsest level");
     double* vd = v; const double* fd = f;
-    if (mem == MGB_MEM_HOST) { TRY(copy_in(h, L->v, v, L->n, mem)); TRY(copy_in(h, L->f, f, L->n, mem)); vd = L->v; fd = L->f; }
+    if (stage) { TRY(copy_in(h, L->v, v, L->n, mem, L->perm)); TRY(copy_in(h, L->f, f, L->n, mem, L->perm)); vd = L->v; fd = L->f; }
     double* cur = vd; double* oth = L->vtmp;
     bool g_valid = false;
     TRY(smooth(h, *L, cur, oth, fd, nsweeps, g_valid));
     if (cur != vd) CU(cudaMemcpyAsync(vd, cur, sizeof(double) * (size_t)L->n, cudaMemcpyDeviceToDevice, h->stream));
-    if (mem == MGB_MEM_HOST) { TRY(copy_out(h, v, vd, L->n, mem)); CU(cudaStreamSynchronize(h->stream)); }
+    if (stage) { TRY(copy_out(h, v, vd, L->n, mem, L->perm)); if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream)); }
     return MGB_OK;
 }
 
@@ -1944,13 +2125,14 @@ int mgb_restrict(mgb_handle* h, int fine_level, const double* r_fine, double* f_
 {
     Level* L = nullptr;
     TRY(check_ready(h, fine_level, &L));
-    BorrowGuard guard(h, mem);
+    const bool stage = mem == MGB_MEM_HOST || h->numbered;      // (a caller numbering: vectors pass through the level buffers)
+    BorrowGuard guard(h, stage ? MGB_MEM_HOST : mem);
     if (!L->has_transfer) return fail(h, MGB_ERR_INVALID, "level %d has no coarser neighbour", fine_level);
     Level& C = h->levels[fine_level - 1];
     const double* rd = r_fine; double* fd = f_coarse;
-    if (mem == MGB_MEM_HOST) { TRY(copy_in(h, L->r, r_fine, L->n, mem)); rd = L->r; fd = C.f; }
+    if (stage) { TRY(copy_in(h, L->r, r_fine, L->n, mem, L->perm)); rd = L->r; fd = C.f; }
     TRY(restrict_to(h, *L, rd, fd));
-    if (mem == MGB_MEM_HOST) { TRY(copy_out(h, f_coarse, fd, C.n, mem)); CU(cudaStreamSynchronize(h->stream)); }
+    if (stage) { TRY(copy_out(h, f_coarse, fd, C.n, mem, C.perm)); if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream)); }
     return MGB_OK;
 }
 
@@ -1958,13 +2140,14 @@ int mgb_prolong_add(mgb_handle* h, int fine_level, const double* e_coarse, doubl
 {
     Level* L = nullptr;
     TRY(check_ready(h, fine_level, &L));
-    BorrowGuard guard(h, mem);
+    const bool stage = mem == MGB_MEM_HOST || h->numbered;      // (a caller numbering: vectors pass through the level buffers)
+    BorrowGuard guard(h, stage ? MGB_MEM_HOST : mem);
     if (!L->has_transfer) return fail(h, MGB_ERR_INVALID, "level %d has no coarser neighbour", fine_level);
     Level& C = h->levels[fine_level - 1];
     const double* ed = e_coarse; double* vd = v_fine;
-    if (mem == MGB_MEM_HOST) { TRY(copy_in(h, C.v, e_coarse, C.n, mem)); TRY(copy_in(h, L->v, v_fine, L->n, mem)); ed = C.v; vd = L->v; }
+    if (stage) { TRY(copy_in(h, C.v, e_coarse, C.n, mem, C.perm)); TRY(copy_in(h, L->v, v_fine, L->n, mem, L->perm)); ed = C.v; vd = L->v; }
     TRY(prolong_add(h, *L, ed, vd, nullptr));
-    if (mem == MGB_MEM_HOST) { TRY(copy_out(h, v_fine, vd, L->n, mem)); CU(cudaStreamSynchronize(h->stream)); }
+    if (stage) { TRY(copy_out(h, v_fine, vd, L->n, mem, L->perm)); if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream)); }
     return MGB_OK;
 }
 
@@ -1973,11 +2156,12 @@ int mgb_coarse_solve(mgb_handle* h, const double* f, double* u, int mem)
     Level* C = nullptr;
     if (!h) return MGB_ERR_INVALID;
     TRY(check_ready(h, h->coarsest, &C));
-    BorrowGuard guard(h, mem);
+    const bool stage = mem == MGB_MEM_HOST || h->numbered;      // (a caller numbering: vectors pass through the level buffers)
+    BorrowGuard guard(h, stage ? MGB_MEM_HOST : mem);
     const double* fd = f; double* ud = u;
-    if (mem == MGB_MEM_HOST) { TRY(copy_in(h, C->f, f, C->n, mem)); fd = C->f; ud = C->v; }
+    if (stage) { TRY(copy_in(h, C->f, f, C->n, mem, C->perm)); fd = C->f; ud = C->v; }
     TRY(coarse_apply(h, *C, fd, ud));
-    if (mem == MGB_MEM_HOST) { TRY(copy_out(h, u, ud, C->n, mem)); CU(cudaStreamSynchronize(h->stream)); }
+    if (stage) { TRY(copy_out(h, u, ud, C->n, mem, C->perm)); if (mem == MGB_MEM_HOST) CU(cudaStreamSynchronize(h->stream)); }
     return MGB_OK;
 }
 

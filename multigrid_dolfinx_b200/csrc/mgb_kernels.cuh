@@ -1455,26 +1455,127 @@ k_residual_injected(int nc, const int32_t* __restrict__ inj, const int32_t* __re
 }
 
 // dense coarsest apply: y = M x (+ y0), warp per row, M row-major n x n     (replaces spsolve, multigrid.py:239)
+// (one definition of the row's dot product: the stand-alone kernel and the coarse-tail kernel must give the same bits)
+__device__ __forceinline__ double dense_row_dot(int n, const double* __restrict__ row, const double* x, int lane)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int j = lane;
+    for (; j + 96 < n; j += 128) {
+        s0 = fma(row[j], __ldcg(x + j), s0);
+        s1 = fma(row[j + 32], __ldcg(x + j + 32), s1);
+        s2 = fma(row[j + 64], __ldcg(x + j + 64), s2);
+        s3 = fma(row[j + 96], __ldcg(x + j + 96), s3);
+    }
+    for (; j < n; j += 32) s0 = fma(row[j], __ldcg(x + j), s0);
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
 __global__ void __launch_bounds__(256)
-k_dense_gemv(int n, const double* __restrict__ M, const double* __restrict__ x, const double* __restrict__ y0, double* __restrict__ y)
+k_dense_gemv(int n, const double* __restrict__ M, const double* x, const double* y0, double* y)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= n) return;
-    const double* row = M + (size_t)warp * n;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int j = lane;
-    for (; j + 96 < n; j += 128) {
-        s0 = fma(row[j], x[j], s0);
-        s1 = fma(row[j + 32], x[j + 32], s1);
-        s2 = fma(row[j + 64], x[j + 64], s2);
-        s3 = fma(row[j + 96], x[j + 96], s3);
-    }
-    for (; j < n; j += 32) s0 = fma(row[j], x[j], s0);
-    double s = (s0 + s1) + (s2 + s3);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const double s = dense_row_dot(n, M + (size_t)warp * n, x, lane);
     if (lane == 0) y[warp] = y0 ? y0[warp] + s : s;
+}
+
+// ---- coarse tail: every level below a size threshold in ONE cooperative launch ----------------------------------------
+// Below ~3e5 rows a kernel is all launch latency: the cfg2 cycle spent a third of its time in ~30 launches of 8-12 us on levels
+// whose data fit L2 many times over (profiles/r1_*), and on 8 GPUs those levels run on rank 0 alone while 7 GPUs wait.  This
+// kernel runs the whole sub-cycle of those levels -- zero-guess sweep, sweeps, residual + injection, ..., dense coarsest apply,
+// prolongation + correction, sweeps (multigrid.py:238-261, recursion unrolled) -- with a grid-wide barrier between phases
+// instead of a launch.  Arithmetic is the same as in the per-level kernels: one accumulator per row, stored entry order,
+// separately rounded multiply and add; the operators are read in whichever form the level holds (CSR, row patterns, anchored
+// row patterns).  Vectors are read with L2-only loads (ld.global.cg): a buffer is rewritten by other SMs two phases after it
+// was read, and a grid barrier does not drop L1 lines.
+struct TailOp {
+    int mode;                                // 0 CSR, 3 row patterns, 4 anchored row patterns
+    const int32_t* rowptr; const int32_t* cols; const double* vals;
+    const unsigned char* codes; const int32_t* anchor; const int2* phead; const DictEnt* pent;
+};
+struct TailLevel {
+    int n, nc;                               // rows; rows of the next coarser level (0 on the coarsest)
+    TailOp A, RJ, P;                         // level matrix, smoother matrix, prolongation from the next coarser level
+    const int32_t* inj;                      // fine row of every coarse row
+    const double* dinv;
+    double *f, *g, *a, *b;                   // right-hand side, w*(dinv*f), the iterate's two buffers (a holds the zero-guess sweep)
+};
+constexpr int TAIL_MAX_LEVELS = 6;
+struct TailPlan {
+    int nlev, mu1, mu2;                      // lev[0] = coarsest ... lev[nlev - 1] = top of the tail
+    double om, om1;
+    const double* coarse_inv;                // dense inverse of the coarsest matrix, row-major
+    TailLevel lev[TAIL_MAX_LEVELS];
+};
+
+__device__ __forceinline__ double tail_rowsum(const TailOp& D, int r, const double* x)
+{
+    double sum = 0.0;                        // one accumulator, stored order
+    if (D.mode == 3 || D.mode == 4) {
+        const int2 ph = __ldg(D.phead + D.codes[r]);
+        const int base = D.mode == 3 ? r : __ldg(D.anchor + r);
+        for (int e = 0; e < ph.y; ++e) {
+            const double val = __ldg(&D.pent[ph.x + e].val);
+            const int dl = __ldg(&D.pent[ph.x + e].delta);
+            sum = __dadd_rn(sum, __dmul_rn(val, __ldcg(x + base + dl)));
+        }
+    } else {
+        const int a = __ldg(D.rowptr + r), b = __ldg(D.rowptr + r + 1);
+        for (int k = a; k < b; ++k) sum = __dadd_rn(sum, __dmul_rn(__ldg(D.vals + k), __ldcg(x + __ldg(D.cols + k))));
+    }
+    return sum;
+}
+
+__global__ void __launch_bounds__(512)
+k_tail(const __grid_constant__ TailPlan T)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+    const double om = T.om, om1 = T.om1;
+    auto sweep = [&](const TailLevel& L, const double* cur, double* oth) {     // multigrid.py:226
+        for (int r = gt; r < L.n; r += gs) {
+            const double s = tail_rowsum(L.RJ, r, cur);
+            oth[r] = __dsub_rn(__dadd_rn(__dmul_rn(om1, __ldcg(cur + r)), __ldcg(L.g + r)), __dmul_rn(om, s));
+        }
+    };
+    for (int k = T.nlev - 1; k >= 1; --k) {                  // ---- down: multigrid.py:243-253
+        const TailLevel& L = T.lev[k];
+        double* cur = L.a; double* oth = L.b;
+        for (int r = gt; r < L.n; r += gs) {                 // zero guess + first sweep: v = g = w*(dinv*f)
+            const double gi = __dmul_rn(om, __dmul_rn(__ldg(L.dinv + r), __ldcg(L.f + r)));
+            L.g[r] = gi; cur[r] = gi;
+        }
+        grid.sync();
+        for (int s = 1; s < T.mu1; ++s) { sweep(L, cur, oth); grid.sync(); double* t = cur; cur = oth; oth = t; }
+        double* fc = T.lev[k - 1].f;
+        for (int i = gt; i < L.nc; i += gs) {                // residual at the injected rows only (multigrid.py:244 + :128-131)
+            const int r = __ldg(L.inj + i);
+            fc[i] = __dsub_rn(__ldcg(L.f + r), tail_rowsum(L.A, r, cur));
+        }
+        grid.sync();
+    }
+    {                                                        // ---- coarsest: u = A^-1 f (multigrid.py:238-241)
+        const TailLevel& C = T.lev[0];
+        const int lane = threadIdx.x & 31, nw = gs >> 5;
+        for (int row = gt >> 5; row < C.n; row += nw) {
+            const double s = dense_row_dot(C.n, T.coarse_inv + (size_t)row * C.n, C.f, lane);
+            if (lane == 0) C.a[row] = s;
+        }
+        grid.sync();
+    }
+    for (int k = 1; k < T.nlev; ++k) {                       // ---- up: multigrid.py:258-261
+        const TailLevel& L = T.lev[k];
+        const TailLevel& C = T.lev[k - 1];
+        const double* e = (k == 1 || (((T.mu1 - 1) + T.mu2) & 1) == 0) ? C.a : C.b;     // where the coarser level's iterate ended
+        double* cur = ((T.mu1 - 1) & 1) ? L.b : L.a;
+        double* oth = ((T.mu1 - 1) & 1) ? L.a : L.b;
+        for (int r = gt; r < L.n; r += gs) cur[r] = __dadd_rn(__ldcg(cur + r), tail_rowsum(L.P, r, e));
+        grid.sync();
+        for (int s = 0; s < T.mu2; ++s) { sweep(L, cur, oth); grid.sync(); double* t = cur; cur = oth; oth = t; }
+    }
 }
 
 // ||x||_2: fixed grid, fixed trees -> bitwise reproducible

@@ -127,6 +127,8 @@ struct Level {
     DevCsr A, RJ, P, R, G;           // G: Gauss-Seidel off-diagonal operator, rows in execution order
     double* dinv = nullptr;
     int32_t* inj = nullptr;
+    std::vector<int64_t> perm_host;  // caller numbering (mgb_set_numbering): new index of every dof; kept for late operators (mass matrix)
+    int32_t* perm = nullptr;         // ... on the device: vectors are permuted on the way in and out
     bool inj_mono = false;           // the injection list is strictly ascending
     int32_t* cmap = nullptr;         // fine dof -> coarse dof or -1 (fused residual + injection)
     int4* inj_desc = nullptr;        // the stream tiles of A that contain at least one injected row
@@ -175,7 +177,13 @@ struct mgb_handle {
     int stage_x = 3;               // row-pattern-coded operators: 3 speculative loads at the hot pattern's offsets (k_hotrow, the default);
                                    // 1 x staged in shared memory by bulk copies (k_rowwin); 0 bulk-copied codes / operands + x gathered
                                    // through L1 (k_rowstream)
+    int tail_rows = 0;             // > 0: levels of at most this many rows (and everything below them) run in one cooperative launch
+                                   // (k_tail).  OFF by default: measured slower (profiles/r2_variants_tail_*.jsonl) -- inside a replayed
+                                   // graph a small kernel costs ~2.2 us, a grid-wide barrier phase ~6 us (cfg2: 0.229 -> 0.307 ms)
     int reuse_g = 1;               // cycles after the first of one call reuse the top level's w*(dinv*f) instead of forming it again
+    bool numbered = false;         // some level carries a caller numbering
+    double* perm_tmp = nullptr;    // device scratch of the permuting copies
+    int64_t perm_tmp_cap = 0;
     int fuse_halo = 1;             // row-sharded levels: halo exchange fused into the kernels that write / read the iterate (HaloFuse)
     HaloFuse hf_cur{};             // the fused-exchange plan of the launch being enqueued (all zero: none)
     bool in_cycle = false;         // inside enqueue_cycle: ghost sections of fused levels are kept valid by the kernels themselves

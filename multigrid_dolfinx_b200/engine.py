@@ -82,6 +82,14 @@ class MGEngine:
                                          ix.ctypes.data, ax.ctypes.data))
         self.n[int(level)] = n
 
+    def set_numbering(self, level, new_index):
+        """Caller numbering (``mgb_set_numbering``): ``new_index[i]`` = position of dof ``i`` in the numbering the engine should
+        work in -- the lexicographic lattice index for the uniform meshes of the reference, which is what makes the lossless
+        row-pattern codings apply to dolfinx-ordered input.  Operators are renumbered once at ``finalize`` with the entry order of
+        every row kept (bit-identical row sums); vectors are permuted on the device on the way in and out."""
+        p = np.ascontiguousarray(new_index, dtype=np.int64).reshape(-1)
+        self._ck(self._lib.mgb_set_numbering(self._h, int(level), len(p), p.ctypes.data))
+
     # -- row-sharded hierarchies (one engine per rank; see dist.py) -----------------------------------------
     def dist_unique_id(self):
         buf = C.create_string_buffer(256)
@@ -162,14 +170,21 @@ class MGEngine:
         self.finalized = True
 
     @classmethod
-    def from_hierarchy(cls, H, r_mode="injection", smoother="jacobi", device=0, options=None, levels=None):
-        """Upload a ``problems.Hierarchy`` (or any object with A_sp_dict / P / inj / mu1 / mu2 / omega)."""
+    def from_hierarchy(cls, H, r_mode="injection", smoother="jacobi", device=0, options=None, levels=None, reorder=False):
+        """Upload a ``problems.Hierarchy`` (or any object with A_sp_dict / P / inj / mu1 / mu2 / omega).
+        ``reorder``: hand the engine the lattice numbering of every level (``H.perms[l][lexicographic node] = dof``, the
+        information the reference keeps as coordinate dicts) so that it works in lexicographic order internally."""
         eng = cls(device)
         lv = list(H.levels()) if levels is None else list(levels)
         for k, v in (options or {}).items():
             eng.set_option(k, v)
         for l in lv:
             eng.set_level(l, H.A_sp_dict[l][0])
+            if reorder:
+                perm = np.asarray(H.perms[l], dtype=np.int64)            # perm[lex] = dof
+                new_index = np.empty_like(perm)
+                new_index[perm] = np.arange(len(perm), dtype=np.int64)   # new_index[dof] = lex
+                eng.set_numbering(l, new_index)
         for l in lv[:-1]:
             eng.set_transfer(l, H.P[l], r_mode=r_mode, inj=H.inj[l] if r_mode == "injection" else None, dim=H.dim)
         eng.set_params(H.omega, H.mu1, H.mu2, smoother)

@@ -51,10 +51,13 @@ V_fine_dolfx = None
 restriction = "injection"      # what the reference cycle executes (multigrid.py:251-252)
 smoother = "jacobi"            # multigrid.py:223-228
 device = 0
+reorder = True                 # tell the engine the lattice numbering found in the coordinate dicts (mgb_set_numbering): it then
+                               # works in lexicographic order internally, results unchanged bit for bit
 max_fmg_cycles = 10000         # the reference's finest-level loop has no cap (multigrid.py:288)
 engine_options = {}
 
 _engine = None
+_numbering = {}                # level -> (new_index[dof] = lexicographic node, perm[lexicographic node] = dof) handed to the engine
 _dim = 2
 _index_maps = {}               # level -> (N, lex->dof array)
 
@@ -72,6 +75,8 @@ class _LazyJacobiPart:
             if _engine is None:
                 raise RuntimeError("initialize_problem() has not been called yet")
             RO, dinv = _engine.rj_matrix(self.level)
+            if self.level in _numbering:                  # artefacts come in the engine's (lexicographic) numbering: back to the caller's
+                RO, dinv = _to_caller_numbering(RO, dinv, *_numbering[self.level])
             self._m = RO if self.which == 0 else sp.diags(dinv, 0)
         return self._m
 
@@ -80,6 +85,18 @@ class _LazyJacobiPart:
 
     def __getattr__(self, name):
         return getattr(self._get(), name)
+
+
+def _to_caller_numbering(RO, dinv, new_index, perm):
+    """R_omega / D^-1 as the engine holds them (row new_index[i] = caller's row i) -> the caller's numbering; the stored entry
+    order of every row is kept (it is the reference's, multigrid.py:52-55)."""
+    import scipy.sparse as sp
+    ip, ix, ax = RO.indptr.astype(np.int64), RO.indices, RO.data
+    lens = (ip[1:] - ip[:-1])[new_index]
+    ipu = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=ipu[1:])
+    src = np.repeat(ip[:-1][new_index] - ipu[:-1], lens) + np.arange(ipu[-1], dtype=np.int64)
+    return sp.csr_matrix((ax[src], perm[ix[src]].astype(np.int32), ipu.astype(np.int32)), shape=RO.shape), dinv[new_index]
 
 
 def getJacobiMatrices(A):
@@ -108,7 +125,7 @@ def initialize_problem(obj):
     """multigrid.py:28-45, plus the upload of the whole hierarchy to the device."""
     global mesh_dof_list_dict, element_size, coarsest_level_elements_per_dim, coarsest_level, finest_level, A_sp_dict, \
         A_jacobi_sp_dict, b_dict, mu0, mu1, mu2, omega, residual_per_V_cycle_finest, error_per_V_cycle_finest, \
-        u_exact_fine, V_fine_dolfx, _engine, _dim, _index_maps
+        u_exact_fine, V_fine_dolfx, _engine, _dim, _index_maps, _numbering
     mesh_dof_list_dict = obj.mesh_dof_list_dict
     element_size = obj.element_size
     coarsest_level_elements_per_dim = obj.coarsest_level_elements_per_dim
@@ -137,6 +154,18 @@ def initialize_problem(obj):
     for l in levels:
         eng.set_level(l, A_sp_dict[l][0])
     _index_maps = {}
+    _numbering = {}
+    if reorder and mesh_dof_list_dict is not None and all(l in mesh_dof_list_dict for l in levels):
+        # dolfinx's DOF numbering is not lexicographic; the coordinate dicts (Multigrid_prototype.py:68-74) say where every DOF
+        # sits on the lattice, so the engine is told to work in lexicographic order internally (bit-identical row sums: the entry
+        # order of every row is kept) -- that is what lets the one-byte-per-row operator codings apply to the reference's input
+        for l in levels:
+            _index_maps[l] = _index_map_from_dict(mesh_dof_list_dict[l], A_sp_dict[l][0].shape[0], element_size[l], _dim)
+            perm = _index_maps[l][1]                                  # perm[lex] = dof
+            new_index = np.empty_like(perm)
+            new_index[perm] = np.arange(len(perm), dtype=np.int64)
+            eng.set_numbering(l, new_index)
+            _numbering[l] = (new_index, perm)
     have_matrix_form = hasattr(obj, "P") and hasattr(obj, "inj") and all(l in obj.P for l in levels[:-1])
     for l in levels[:-1]:
         if have_matrix_form:

@@ -95,3 +95,43 @@ def test_device_fmg_matches_restated_fmg(with_mass):
     assert np.abs(h_g[:k] - np.array(h_o[:k])).max() <= 1e-9 * h_o[0]
     assert np.abs(v_g - v_o[:, 0]).max() <= 1e-10 * np.abs(v_o).max()
     eng.close()
+
+
+@pytest.mark.parametrize("with_mass", [False, True])
+def test_fmg_records_error_and_residual_every_cycle(with_mass):
+    """multigrid.py:288-302: the finest-level loop appends the error norm (:292-293) AND the residual norm (:294-295) after EVERY
+    V-cycle, then writes [cells per dimension, cycle count] to the iteration CSV.  Here both norms are formed on the device in
+    the norm the reference uses (sqrt(x^T M x) with the mass matrix standing in for the dolfinx form, else l2)."""
+    import csv, os, tempfile
+    import scipy.sparse as sp
+    from multigrid_dolfinx_b200 import multigrid as mg
+    H = pr.build_hierarchy(dim=2, c=8, coarsest_level=0, finest_level=3, mu1=2, mu2=2, perm_seed=4, with_dicts=True)
+    n = H.n(3)
+    A = H.A_sp_dict[3][0]
+    import scipy.sparse.linalg as spla
+    H.u_exact_fine = spla.spsolve(A.tocsc(), H.b_dict[3][:, 0])                 # nodal values of the discrete solution
+    H.V_fine_dolfx = sp.diags(np.linspace(0.5, 1.5, n) / n, 0).tocsr() if with_mass else None
+    H.residual_per_V_cycle_finest, H.error_per_V_cycle_finest = [], []
+    mg.restriction = "transpose"
+    cwd = os.getcwd()
+    try:
+        H.A_jacobi_sp_dict = {k: mg.getJacobiMatrices(v) for k, v in H.A_sp_dict.items()}
+        mg.initialize_problem(H)
+        assert "hotrow(" in mg.engine().describe()                               # permuted numbering + coordinate dicts -> lattice numbering handed over
+        with tempfile.TemporaryDirectory() as td:
+            os.chdir(td)
+            u = mg.FullMultiGrid(H.A_jacobi_sp_dict[3], H.b_dict[3])
+            rows = list(csv.reader(open("iter_count_for_diff_num_elems_4_levels.csv")))
+            os.chdir(cwd)
+    finally:
+        os.chdir(cwd)
+        mg.restriction = "injection"
+    res, err = H.residual_per_V_cycle_finest, H.error_per_V_cycle_finest
+    assert len(res) == len(err) >= 3 and rows == [[str(8 * 2 ** 3), str(len(res))]]
+    assert res[-1] <= 1e-11 and all(res[k + 1] < res[k] for k in range(len(res) - 1))
+    assert all(err[k + 1] < err[k] for k in range(min(len(err), 6) - 1))
+    # the last entries are the norms of the returned iterate
+    M = H.V_fine_dolfx
+    nrm = (lambda x: float(np.sqrt(x @ M.dot(x)))) if with_mass else (lambda x: float(np.linalg.norm(x)))
+    assert abs(err[-1] - nrm(u[:, 0] - H.u_exact_fine)) <= 1e-9 * max(err[0], 1e-300) + 1e-14
+    assert abs(res[-1] - nrm(H.b_dict[3][:, 0] - A.dot(u[:, 0]))) <= 1e-9 * res[0]

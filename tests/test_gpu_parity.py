@@ -456,6 +456,42 @@ def test_full_size_properties_config3():
     eng.close()
 
 
+@pytest.mark.parametrize("dim,c,lf,seed,rcm", [(2, 8, 4, 3, False), (3, 2, 3, 5, False), (2, 8, 4, 3, True)])
+def test_caller_numbering_is_bit_identical_and_unlocks_the_row_codings(dim, c, lf, seed, rcm):
+    """dolfinx numbers DOFs its own way; the reference records where every DOF sits (coordinate dicts, Multigrid_prototype.py:68-74).
+    With that lattice numbering handed to the engine (mgb_set_numbering) it works in lexicographic order internally: the level
+    operators get the one-byte-per-row codings and the hot-row kernels, while every iterate stays BIT-IDENTICAL to the run in the
+    caller's numbering (rows are moved, the entry order inside a row is kept)."""
+    import torch
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=seed, with_dicts=False, rcm=rcm)
+    n, nc = H.n(lf), H.n(lf - 1)
+    plain = MGEngine.from_hierarchy(H)
+    eng = MGEngine.from_hierarchy(H, reorder=True)
+    dp, de = plain.describe(), eng.describe()
+    fine = lambda d, tag: [ln for ln in d.splitlines() if ln.strip().startswith(tag) and f"rows={n} " in ln][0]
+    assert "hotrow(" not in fine(dp, "A ")
+    if rcm:     # a banded numbering stores every row's entries in the same lattice order: whole rows repeat once renumbered
+        assert "hotrow(" in fine(de, "A ") and "hotrow(" in fine(de, "RJ ") and "coded mode=4" in fine(de, "P ")
+    else:       # a random numbering stores every row's entries in its own order (kept: it IS the summation order): no row patterns,
+        assert "coded mode=1" in fine(de, "A ")     # but the offsets are few again -> one byte per entry and coalesced gathers
+    rng = np.random.default_rng(2)
+    x, f, e = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(nc)
+    b = H.b_dict[lf][:, 0]
+    for fn in (lambda E: E.vcycle(lf, np.zeros_like(b), b, ncycles=3), lambda E: E.spmv(lf, x), lambda E: E.residual(lf, x, f),
+               lambda E: E.smooth(lf, x, f, 3), lambda E: E.prolong_add(lf, e, x), lambda E: E.restrict(lf, x),
+               lambda E: E.vcycle_debug(lf, np.zeros_like(b), b)[1]):
+        assert np.array_equal(fn(plain), fn(eng))
+    A = H.A_sp_dict[lf][0]
+    assert np.array_equal(eng.spmv(lf, x), A.dot(x))
+    xt, ft = torch.from_numpy(x).cuda(), torch.from_numpy(f).cuda()                 # device pointers take the same route
+    assert np.array_equal(eng.smooth(lf, xt, ft, 2).cpu().numpy(), plain.smooth(lf, x, f, 2))
+    assert np.array_equal(eng.vcycle(lf, torch.zeros_like(xt), torch.from_numpy(b).cuda(), ncycles=2).cpu().numpy(), plain.vcycle(lf, np.zeros_like(b), b, ncycles=2))
+    _, h1 = eng.vcycle(lf, np.zeros_like(b), b, ncycles=3, history=True)
+    _, h0 = plain.vcycle(lf, np.zeros_like(b), b, ncycles=3, history=True)
+    assert np.abs(h1 - h0).max() <= RTOL_RESNORM * h0.max()                           # (the norm's summation order follows the numbering)
+    plain.close(); eng.close()
+
+
 def test_full_size_config4_p2_vs_oracle():
     """BASELINE config 4 at FULL size: 3-D P2 on 64^3 cells, DOF grid 129^3 = 2,146,689, 60,859,905 stored entries, rows of
     10..65 entries, 5 levels, V(2,2) Jacobi, injection -- three cycles against the C oracle on the same hierarchy."""
@@ -544,7 +580,8 @@ def test_coded_operators_bit_identical_to_uncoded(dim, c, lf, seed, r_mode):
     # (the default is compress = 3, hot-row kernels (stage_x = 3), fused thread-per-coarse-row residual, g reused across cycles)
     for opts in [{"compress": 0}, {"stream_cfg": 0}, {"compress": 1}, {"compress": 2}, {"code_cfg": 3}, {"compress": 1, "code_cfg": 3},
                  {"compress": 3}, {"anch_cfg": 2}, {"stage_x": 0}, {"stage_x": 1}, {"hot_cfg": 2}, {"hot_cfg": 3}, {"hot_cfg": 4},
-                 {"hot_inj": 0}, {"hot_pf": 0}, {"reuse_g": 0}, {"compress": 2, "stage_x": 0, "hot_inj": 0, "reuse_g": 0}]:
+                 {"hot_inj": 0}, {"hot_pf": 0}, {"reuse_g": 0}, {"tail_rows": 300000}, {"tail_rows": 300},
+                 {"compress": 2, "stage_x": 0, "hot_inj": 0, "reuse_g": 0, "tail_rows": 0}]:
         eng = MGEngine.from_hierarchy(H, r_mode=r_mode, options=opts)
         desc = eng.describe()
         coded = "coded" in desc

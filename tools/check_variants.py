@@ -26,6 +26,8 @@ VARIANTS = {
     "hot1a2": {"stage_x": 3, "hot_cfg": 1, "anch_cfg": 2},
     "hot1a3": {"stage_x": 3, "hot_cfg": 1, "anch_cfg": 3},
     "hot1a4": {"stage_x": 3, "hot_cfg": 1, "anch_cfg": 4},
+    "tail300k": {"tail_rows": 300000},             # small levels in one cooperative launch (k_tail; off by default: measured slower)
+    "tail50k": {"tail_rows": 50000},
     "hot1noinj": {"stage_x": 3, "hot_cfg": 1, "hot_inj": 0, "reuse_g": 0},
     "hot1pf0": {"stage_x": 3, "hot_cfg": 1, "hot_pf": 0},
     "hot1pf128k": {"stage_x": 3, "hot_cfg": 1, "hot_pf": 131072},
