@@ -646,8 +646,8 @@ void launch_anchrow(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles
     if (D.max_row <= 4) {
         switch (h->anch_cfg) {
             case 2: return launch_anchrow_cfg<128, 2, 4, 8, Epi>(h, D, desc, ntiles, x, epi);
-            case 3: return launch_anchrow_cfg<64, 4, 4, 16, Epi>(h, D, desc, ntiles, x, epi);
-            default: return launch_anchrow_cfg<128, 4, 4, 8, Epi>(h, D, desc, ntiles, x, epi);
+            case 3: return launch_anchrow_cfg<64, 4, 4, 12, Epi>(h, D, desc, ntiles, x, epi);
+            default: return launch_anchrow_cfg<128, 4, 4, 6, Epi>(h, D, desc, ntiles, x, epi);
         }
     }
     switch (h->anch_cfg) {

@@ -1318,14 +1318,30 @@ k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ 
     __syncthreads();                                         // the table is in shared memory
     halo_wait(hf, row0, min(row0 + T, rend));                // rows whose columns reach into the ghost section of x
     const int sends = halo_sends(hf, row0, min(row0 + T, rend));
+    // Entries are fetched in two halves of JW / 2: the second half only by warps in which some row is longer than the first
+    // (warp-uniform test).  Rows of a prolongation alternate between short and long patterns along a mesh line, and whole lines
+    // are short: on the trilinear P three warps in four never need entries 4..7.
+    // (Measured and dropped: the pattern table as a kernel parameter instead of shared memory -- divergent constant-bank loads
+    // made the 513^3 prolongation 1.05 -> 1.31 ms, profiles/r2_variants_hot_513i.jsonl.)
+    constexpr int HW = JW / 2;
     int2 ph[RPT];
     double xv[RPT][JW];
+    bool more[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
         ph[j] = sphead[code[j]];
         const int* sd = sdelta + ph[j].x;
 #pragma unroll
-        for (int e = 0; e < JW; ++e) xv[j][e] = x[anc[j] + sd[e]];            // (coherent load: see ld_x; padded entries repeat the last one)
+        for (int e = 0; e < HW; ++e) xv[j][e] = x[anc[j] + sd[e]];            // (coherent load: see ld_x; padded entries repeat the last one)
+        more[j] = __any_sync(0xffffffffu, ph[j].y > HW);
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        if (more[j]) {
+            const int* sd = sdelta + ph[j].x;
+#pragma unroll
+            for (int e = HW; e < JW; ++e) xv[j][e] = x[anc[j] + sd[e]];
+        }
     }
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
@@ -1333,8 +1349,13 @@ k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ 
         double sum = 0.0;                                    // one accumulator, stored order
         const double* sv = sval + ph[j].x;
 #pragma unroll
-        for (int e = 0; e < JW; ++e)
+        for (int e = 0; e < HW; ++e)
             if (e < ph[j].y) sum = __dadd_rn(sum, __dmul_rn(sv[e], xv[j][e]));
+        if (more[j]) {
+#pragma unroll
+            for (int e = HW; e < JW; ++e)
+                if (e < ph[j].y) sum = __dadd_rn(sum, __dmul_rn(sv[e], xv[j][e]));
+        }
         for (int e0 = JW; e0 < ph[j].y; e0 += JW) {          // rows longer than JW entries
             double xw[JW];
 #pragma unroll

@@ -11,12 +11,15 @@ import sys
 
 def main(src, dst):
     rows = list(csv.reader(open(src)))
-    hdr, data = rows[0], rows[2:]
+    hdr, units, data = rows[0], rows[1], rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}
+    # ncu picks the unit per report (us / ms, Mbyte / Gbyte): normalise to microseconds and megabytes
+    SCALE = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6,
+             "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
 
     def f(r, key, scale=1.0):
         try:
-            return float(r[ix[key]]) * scale
+            return float(r[ix[key]]) * scale * SCALE.get(units[ix[key]], 1.0)
         except (KeyError, ValueError):
             return None
 
