@@ -565,22 +565,27 @@ void launch_hotrow_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nti
 {
     constexpr int MINB = hot_minb<HOTN, T, RPT, Epi::NOPS>();
     constexpr int ROWS = T * RPT;
-    auto kern = k_hotrow<HOTN, T, RPT, MINB, Epi>;
     const bool linear = desc == D.sdesc && ntiles == D.sntiles;              // all rows: tiles follow from blockIdx, no descriptor is read
     const int grid = linear ? (int)((D.nrows + ROWS - 1) / ROWS) : ntiles;
     if (grid <= 0) return;
-    // L2 prefetch distance in tiles; none while borrowed user pointers are in play (bulk prefetches need 16-byte aligned operands)
-    const int pf = h->allow_stream && h->hot_pf > 0 ? std::max(1, h->hot_pf / ROWS) : 0;
+    // L2 prefetch distance in tiles (linear tiling only); none while borrowed user pointers are in play (bulk prefetches need
+    // 16-byte aligned operands).  pf_last: last tile whose slices -- whole tile of codes / operands, x shifted by the largest hot
+    // offset -- lie inside their arrays.
+    int pf = linear && h->allow_stream && h->hot_pf > 0 && D.cd.hot.dmax >= 0 ? std::max(1, h->hot_pf / ROWS) : 0;
+    const int64_t pf_last = std::min<int64_t>(D.nrows / ROWS, (D.ncols - (D.cd.hot.dmax & ~1)) / ROWS) - 1;
+    if (pf_last < pf) pf = 0;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = h->pdl != 0 ? 1 : 0;
-    HaloFuse hf = linear ? h->hf_cur : no_hf();    // (tile subsets never run inside a fused exchange)
+    HaloFuse hf = linear ? h->hf_cur : no_hf();              // (tile subsets never run inside a fused exchange)
     finish_hf(hf, ROWS, D.nrows);
-    cudaLaunchKernelEx(&cfg, kern, (const unsigned char*)D.cd.codes, (const uint32_t*)D.cd.pmask, (const int2*)D.cd.phead, (const DictEnt*)D.cd.dict,
-                       D.cd.hot, hf, linear ? (const int4*)nullptr : desc, grid, 0, (int)D.nrows, (int)D.ncols, pf, x, epi);
+    const bool halo = hf.wait_n > 0 || hf.send_n > 0;       // single GPU: the instantiation without any exchange code
+    cudaLaunchKernelEx(&cfg, halo ? k_hotrow<HOTN, T, RPT, MINB, true, Epi> : k_hotrow<HOTN, T, RPT, MINB, false, Epi>,
+                       (const unsigned char*)D.cd.codes, (const uint32_t*)D.cd.pmask, (const int2*)D.cd.phead, (const DictEnt*)D.cd.dict,
+                       D.cd.hot, hf, linear ? (const int4*)nullptr : desc, grid, 0, (int)D.nrows, (int)D.ncols, pf, (int)pf_last, x, epi);
 }
 
 template <int HOTN, class Epi>

@@ -1103,11 +1103,13 @@ __device__ __forceinline__ double ld_stream_f64(const double* p)
 // read: the tile's rows follow from blockIdx); with a descriptor list, tile t holds the rows [desc[t].x, desc[t].x + desc[t].y),
 // desc[t].y <= T (tile subsets: the interior / boundary split of a sharded operator, the tiles holding injected rows).
 // Thread t owns rows t, t + THREADS, ... of its tile.
-template <int HOTN, int THREADS, int RPT, int MINB, class Epi>
+// HALO: compiled with the fused halo exchange (HaloFuse); the single-GPU instantiation carries none of its tests -- the kernel
+// issues at ~65 % of its slots (profiles/r2_ncu_full_k_hotrow_cfg5.json), so per-CTA bookkeeping is not free.
+template <int HOTN, int THREADS, int RPT, int MINB, bool HALO, class Epi>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ pmask, const int2* __restrict__ phead,
          const DictEnt* __restrict__ pent, const __grid_constant__ HotArgs H, const __grid_constant__ HaloFuse hf,
-         const int4* __restrict__ desc, int ntiles, int rb, int re, int xlen, int pf, const double* x, Epi epi)
+         const int4* __restrict__ desc, int ntiles, int rb, int re, int xlen, int pf, int pf_last, const double* x, Epi epi)
 {
     static_assert(Epi::CONTIG, "hot-row kernel needs contiguous epilogue operands");
     static_assert(HOTN >= 1 && HOTN <= WIN_HOT, "hot pattern length");
@@ -1117,12 +1119,16 @@ k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
     bool alias = false;                                      // the operand that is x itself (old iterate of a Jacobi sweep)
     if constexpr (XOP >= 0) alias = epi.operand(XOP) == x;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int tile = desc ? (int)blockIdx.x : halo_tile(hf, (int)blockIdx.x, ntiles);       // (sharded: boundary tiles first)
+    int tile = (int)blockIdx.x;
+    if constexpr (HALO) { if (!desc) tile = halo_tile(hf, (int)blockIdx.x, ntiles); }       // (sharded: boundary tiles first)
     int row0 = rb + tile * T, rend = re;                     // this tile: rows [row0, min(row0 + T, rend))
     if (desc) { const int4 d = __ldg(desc + blockIdx.x); row0 = d.x; rend = d.x + d.y; }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    halo_wait(hf, row0, min(row0 + T, rend));                // rows that read ghost entries: the neighbours' rows have arrived
-    const int sends = halo_sends(hf, row0, min(row0 + T, rend));
+    int sends = 0;
+    if constexpr (HALO) {
+        halo_wait(hf, row0, min(row0 + T, rend));            // rows that read ghost entries: the neighbours' rows have arrived
+        sends = halo_sends(hf, row0, min(row0 + T, rend));
+    }
     int code[RPT];
     double xv[RPT][HOTN];
     double o[RPT][NOPS > 0 ? NOPS : 1];
@@ -1152,16 +1158,17 @@ k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
             if constexpr (NIOPS > 0) io[j] = epi.ioperand()[r];
         }
     }
-    if (pf > 0 && tid < 32 && tile + pf < ntiles) {          // L2 prefetch for the tile pf tiles ahead (whole 16-byte groups, in bounds)
-        long long p0 = (long long)row0 + (long long)pf * T;
-        int pn = T;
-        if (desc) { const int4 d = __ldg(desc + blockIdx.x + pf); p0 = d.x; pn = (d.y + 15) & ~15; }
-        if (p0 + pn <= (long long)re) {
-            if (tid == 0) bulk_prefetch_l2(rcodes + (p0 & ~15LL), pn);
-            if (tid == 1) { const long long q = (p0 + H.dmax) & ~1LL; if (q >= 0 && q + pn <= (long long)xlen) bulk_prefetch_l2(x + q, pn * 8); }
-            if (tid >= 2 && tid < 2 + NOPS) { const int k = tid - 2; if (!(alias && k == XOP)) bulk_prefetch_l2(epi.operand(k) + (p0 & ~1LL), pn * 8); }
-            if constexpr (NIOPS > 0) if (tid == 2 + NOPS) bulk_prefetch_l2(epi.ioperand() + (p0 & ~3LL), pn * 4);
-        }
+    if (pf > 0 && tid < 3 + NOPS && tile + pf <= pf_last) {  // L2 prefetch for the tile pf tiles ahead (linear tiling only; the host
+        const long long p0 = (long long)row0 + (long long)pf * T;         // bounds pf_last so that every slice stays inside its array)
+        const void* ptr = rcodes + p0;
+        uint32_t bytes = T;
+        if (tid == 1) { ptr = x + p0 + (H.dmax & ~1); bytes = T * 8; }
+#pragma unroll
+        for (int k = 0; k < NOPS; ++k)
+            if (tid == 2 + k) { ptr = (alias && k == XOP) ? nullptr : (const void*)(epi.operand(k) + p0); bytes = T * 8; }
+        if constexpr (NIOPS > 0) { if (tid == 2 + NOPS) { ptr = epi.ioperand() + p0; bytes = T * 4; } }
+        else { if (tid == 2 + NOPS) ptr = nullptr; }
+        if (ptr) bulk_prefetch_l2(ptr, bytes);
     }
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
@@ -1189,10 +1196,10 @@ k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
             double t;
             if constexpr (NIOPS > 0) t = epi.store_i(r, sum, o[j], io[j]);
             else t = epi.store(r, sum, o[j]);
-            if (sends) halo_send(hf, r, t);
+            if constexpr (HALO) { if (sends) halo_send(hf, r, t); }
         }
     }
-    if (sends) halo_publish(hf, row0, min(row0 + T, rend));
+    if constexpr (HALO) { if (sends) halo_publish(hf, row0, min(row0 + T, rend)); }
 }
 
 // Fused residual + injection on a row-pattern-coded operator, one thread per COARSE row i: out[i] = f[g_i] - (A v)[g_i],

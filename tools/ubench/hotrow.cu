@@ -3,6 +3,8 @@
 // boundary carrying sub-patterns) -- the dominant kernel of BASELINE config 5 -- against a plain table-walk kernel.
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/ubench/hotrow tools/ubench/hotrow.cu
 //   tools/ubench/hotrow [N] > gpurun_out/r2_hotrow.jsonl
+// Persistent (grid-sized, tile-walking) variants were measured with an earlier version of the kernel and dropped: no better without
+// prefetch (680 us against 681) and far worse with a per-warp prefetch (990 us); results in profiles/r2_hotrow_ubench_513.jsonl.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -70,22 +72,21 @@ struct Problem {
     unsigned long long* bad;
 };
 
-template <int THREADS, int RPT, int MINB, bool PERSIST = false>
+template <int THREADS, int RPT, int MINB>
 void run_variant(Problem& P, int pf_rows, const char* name, int reps)
 {
     constexpr int T = THREADS * RPT;
     int pf = pf_rows / T;                              // prefetch distance in tiles
-    auto kern = k_hotrow<6, THREADS, RPT, MINB, PERSIST, EpiJacobiRJ>;
+    auto kern = k_hotrow<6, THREADS, RPT, MINB, false, EpiJacobiRJ>;
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0);
     const int ntiles = (int)((P.n + T - 1) / T);
-    const int grid = PERSIST ? std::min(ntiles, 148 * occ) : ntiles;
-    if (PERSIST) pf = pf_rows / T / grid * 1;               // persistent: distance in tiles = whole passes of the grid
-    if (PERSIST && pf_rows > 0) pf = std::max(1, (pf_rows + T * grid / 2) / (T * grid)) * grid;
+    const int grid = ntiles;
     cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
     auto launch = [&](const double* in, double* out) {
         EpiJacobiRJ epi{in, P.g, out, 1.0 - 2.0 / 3.0, 2.0 / 3.0};
-        kern<<<grid, THREADS>>>(P.codes, P.pmask, P.phead, P.pent, P.H, 0, (int)P.n, P.xlen, pf, in, epi);
+        kern<<<grid, THREADS>>>(P.codes, P.pmask, P.phead, P.pent, P.H, HaloFuse{}, nullptr, grid, 0, (int)P.n, P.xlen, pf,
+                                (int)(std::min<long long>(P.n / T, (P.xlen - (P.H.dmax & ~1)) / T) - 1), in, epi);
     };
     // correctness: one sweep x -> out against the reference
     CK(cudaMemset(P.out, 0xFF, sizeof(double) * P.n));
@@ -158,7 +159,8 @@ int main(int argc, char** argv)
     const int reps = N >= 400 ? 10 : 40;
     const int set = argc > 2 ? atoi(argv[2]) : 0;
     for (int pf : {0, 1 << 18, 1 << 19}) {
-        if (set == 0) {
+        (void)set;
+        {
             run_variant<64, 1, 16>(P, pf, "t64r1", reps);
             run_variant<64, 2, 16>(P, pf, "t64r2", reps);
             run_variant<64, 4, 8>(P, pf, "t64r4", reps);
@@ -166,14 +168,6 @@ int main(int argc, char** argv)
             run_variant<128, 2, 8>(P, pf, "t128r2", reps);
             run_variant<128, 3, 6>(P, pf, "t128r3", reps);
             run_variant<256, 1, 8>(P, pf, "t256r1", reps);
-        } else {
-            run_variant<256, 1, 8, true>(P, pf, "p256r1", reps);
-            run_variant<128, 1, 16, true>(P, pf, "p128r1", reps);
-            run_variant<128, 2, 8, true>(P, pf, "p128r2", reps);
-            run_variant<256, 2, 4, true>(P, pf, "p256r2", reps);
-            run_variant<64, 2, 16, true>(P, pf, "p64r2", reps);
-            run_variant<128, 3, 6, true>(P, pf, "p128r3", reps);
-            run_variant<1024, 1, 2, true>(P, pf, "p1024r1", reps);
         }
     }
     printf("{\"err\": \"%s\"}\n", cudaGetErrorString(cudaGetLastError()));
