@@ -846,6 +846,9 @@ int smooth(mgb_handle* h, Level& L, double*& v, double*& o, const double* f, int
             TRY(row_sums_halo(h, MGB_K_JACOBI, L.level, bytes_rowsum(L.A, 4 * n), L.A, L, v, epi));
             std::swap(v, o);
         } else {
+            // row-sharded level: Gauss-Seidel inside every row block, the neighbours' unknowns taken from before the sweep
+            // (block-Jacobi between GPUs) -- their current values are fetched once per sweep
+            TRY(exchange(h, L, v));
             TRY(gs_sweep(h, L, v, f));
         }
     }
@@ -1722,8 +1725,6 @@ static int validate_hierarchy(mgb_handle* h)
     }
     if (h->opt_iter && h->opt_iter != 1 && h->opt_iter != 2) return fail(h, MGB_ERR_INVALID, "tile_iter must be 1 or 2");
     if (h->opt_lpr && (h->opt_lpr & (h->opt_lpr - 1) || h->opt_lpr > 32)) return fail(h, MGB_ERR_INVALID, "lanes_per_row must be a power of two <= 32");
-    if (h->dist && h->smoother >= MGB_SM_GS_LEVEL)
-        return fail(h, MGB_ERR_UNSUPPORTED, "Gauss-Seidel smoothers are single-GPU only in this version (see DESIGN.md, multi-GPU)");
     if (h->dist && h->world > 1 && h->gather_level == INT_MIN)
         return fail(h, MGB_ERR_STATE, "row-sharded hierarchy without a gathered level (mgb_set_gather_level)");
     return MGB_OK;

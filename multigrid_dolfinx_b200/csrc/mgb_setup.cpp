@@ -122,8 +122,8 @@ static void lower_sym_graph(const HostCsr& A, std::vector<int64_t>& lp, std::vec
         for (int64_t i = 0; i < n; ++i)
             for (int64_t k = A.ip[i]; k < A.ip[i + 1]; ++k) {
                 int64_t j = A.ix[k];
-                if (j == i || A.ax[k] == 0.0) continue;
-                fn(std::max(i, j), std::min(i, j));
+                if (j == i || j >= n || A.ax[k] == 0.0) continue;      // (j >= n: a ghost column of a row block -- another block's
+                fn(std::max(i, j), std::min(i, j));                       //  unknown, coupled Jacobi-style, never a dependency)
             }
     };
     visit([&](int64_t hi, int64_t) { lp[hi + 1]++; });
