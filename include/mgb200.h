@@ -223,6 +223,14 @@ int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, i
 int mgb_set_exact_solution(mgb_handle* h, int level, const double* u_exact, int mem);
 int mgb_fmg_error_history(mgb_handle* h, double* errnorm_hist, int capacity, int* count);
 
+/* Fused halo exchange: whether the kernels of `level` exchange the ghost rows themselves.  Decided per rank at
+ * mgb_finalize from what that rank's shard looks like -- and it MUST be the same on every rank (a rank that sends without a
+ * neighbour that waits, or the reverse, dead-locks), so the caller agrees on it after mgb_finalize: query every rank, switch the
+ * level off everywhere unless all ranks qualified (multigrid_dolfinx_b200/dist.py does this with one all-gather).
+ * mgb_set_halo_fused can only switch a level OFF. */
+int mgb_halo_fused(mgb_handle* h, int level, int* fused);
+int mgb_set_halo_fused(mgb_handle* h, int level, int on);
+
 /* Caller numbering.  The reference hands over operators and vectors in dolfinx's DOF numbering (Multigrid_prototype.py:68-74
  * records it as coordinate dicts), which is not lexicographic; the lossless row-pattern codings need a banded numbering.
  * new_index[i] = position of dof i in the numbering the engine should work in (a permutation of 0..n-1; the drop-in module

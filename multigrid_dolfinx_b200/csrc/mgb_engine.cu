@@ -348,11 +348,19 @@ void launch_stream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nti
 {
     auto kern = k_stream<T, E, S, true, Epi>;
     constexpr int smem = StreamCfg<T, E, Epi::NOPS, EpiNI<Epi>::value>::smem_bytes(S);
-    static int occ = -1;                 // per instantiation (one device per process)
-    if (occ < 0) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T + 32, smem);
-        if (occ < 1) occ = 1;
+    int occ = 1;
+    {   // per instantiation and device; handles are independent, so first use is guarded
+        static std::mutex mu;
+        static std::map<int, int> occ_of;
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = occ_of.find(h->device);
+        if (it == occ_of.end()) {
+            int o = 0;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, T + 32, smem);
+            it = occ_of.emplace(h->device, std::max(o, 1)).first;
+        }
+        occ = it->second;
     }
     int grid = std::min(ntiles, h->sm_count * occ), tpc = 0;
     if (chunked) {                       // CTAs that retire after tpc tiles: `overlap_waves` waves of them (see k_stream)
@@ -375,17 +383,17 @@ void launch_rowstream_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int 
     const int npent = MODE == 3 ? D.cd.npent : 0;            // the pattern table's size decides the shared-memory footprint
     const int smem = RowCfg<T, RPT, EPR, Epi::NOPS, EpiNI<Epi>::value, MODE>::smem_bytes(S, npent * (int)sizeof(DictEnt));
     int occ = 1;
-    {   // per-instantiation cache (one device per process); handles are independent, so guard it against concurrent first use
+    {   // per-instantiation cache keyed by (device, bytes): the attribute is per device, and handles are independent, so first use is guarded
         static std::mutex mu;
-        static std::map<int, int> occ_by_smem;
-        static int smem_attr = 0;
+        static std::map<std::pair<int, int>, int> occ_by_smem;
+        static std::map<int, int> smem_attr;
         std::lock_guard<std::mutex> lock(mu);
-        if (smem > smem_attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_attr = smem; }
-        auto it = occ_by_smem.find(smem);
+        if (smem > smem_attr[h->device]) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_attr[h->device] = smem; }
+        auto it = occ_by_smem.find({h->device, smem});
         if (it == occ_by_smem.end()) {
             int o = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, T + 32, smem);
-            it = occ_by_smem.emplace(smem, std::max(o, 1)).first;
+            it = occ_by_smem.emplace(std::make_pair(h->device, smem), std::max(o, 1)).first;
         }
         occ = it->second;
     }
@@ -1597,6 +1605,25 @@ int mgb_p2p_import(mgb_handle* h, int level, int peer_rank, const void* blob, in
         pl.n_ghost = (int)L->n_ghost;
         L->p2p_ready = true;
     }
+    return MGB_OK;
+}
+
+int mgb_halo_fused(mgb_handle* h, int level, int* fused)
+{
+    if (!h || !fused) return MGB_ERR_INVALID;
+    Level* L = find_level(h, level);
+    if (!L) return fail(h, MGB_ERR_INVALID, "no level %d", level);
+    *fused = L->fuse_ok ? 1 : 0;
+    return MGB_OK;
+}
+
+int mgb_set_halo_fused(mgb_handle* h, int level, int on)
+{
+    if (!h) return MGB_ERR_INVALID;
+    Level* L = find_level(h, level);
+    if (!L) return fail(h, MGB_ERR_INVALID, "no level %d", level);
+    if (on && !L->fuse_ok) return fail(h, MGB_ERR_STATE, "level %d: the fused exchange can only be switched off (it did not qualify at mgb_finalize)", level);
+    if (!on && L->fuse_ok) { L->fuse_ok = false; drop_graphs(h); }
     return MGB_OK;
 }
 

@@ -82,6 +82,15 @@ class MGEngine:
                                          ix.ctypes.data, ax.ctypes.data))
         self.n[int(level)] = n
 
+    def halo_fused(self, level):
+        """Whether the kernels of a row-sharded ``level`` exchange the ghost rows themselves (``mgb_halo_fused``)."""
+        out = C.c_int()
+        self._ck(self._lib.mgb_halo_fused(self._h, int(level), C.byref(out)))
+        return bool(out.value)
+
+    def set_halo_fused(self, level, on):
+        self._ck(self._lib.mgb_set_halo_fused(self._h, int(level), int(bool(on))))
+
     def set_numbering(self, level, new_index):
         """Caller numbering (``mgb_set_numbering``): ``new_index[i]`` = position of dof ``i`` in the numbering the engine should
         work in -- the lexicographic lattice index for the uniform meshes of the reference, which is what makes the lossless

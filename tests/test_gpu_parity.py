@@ -252,6 +252,29 @@ def test_device_pointer_path_and_resident_mode():
     eng.close()
 
 
+def test_device_tensor_path_matches_host_path_at_large_n():
+    """The engine stream is non-blocking: the torch-side clone / contiguous copies of device tensors must be ordered before the
+    engine's first kernel (the event is recorded AFTER the marshalling).  A race shows up only when the copies take long enough,
+    hence 4.2 M unknowns (config 2's finest level) and fresh, non-contiguous inputs every call."""
+    import torch
+    H = pr.build_hierarchy(dim=2, c=32, coarsest_level=3, finest_level=6, with_dicts=False)
+    lf = 6
+    eng = MGEngine.from_hierarchy(H)
+    n = H.n(lf)
+    rng = np.random.default_rng(8)
+    for trial in range(3):
+        x, f = rng.standard_normal(n), rng.standard_normal(n)
+        xt = torch.from_numpy(np.stack([x, x], axis=1)).cuda()[:, 0]          # a strided view: .contiguous() has to copy
+        ft = torch.from_numpy(np.stack([f, f], axis=1)).cuda()[:, 1]
+        assert np.array_equal(eng.smooth(lf, xt, ft, 2).cpu().numpy(), eng.smooth(lf, x, f, 2))
+        assert np.array_equal(eng.residual(lf, xt, ft).cpu().numpy(), eng.residual(lf, x, f))
+        assert np.array_equal(eng.vcycle(lf, xt, ft).cpu().numpy(), eng.vcycle(lf, x, f))
+        e = rng.standard_normal(H.n(lf - 1))
+        et = torch.from_numpy(np.stack([e, e], axis=1)).cuda()[:, 0]
+        assert np.array_equal(eng.prolong_add(lf, et, xt).cpu().numpy(), eng.prolong_add(lf, e, x))
+    eng.close()
+
+
 def test_errors_are_reported_not_swallowed():
     H = pr.build_hierarchy(dim=2, c=4, coarsest_level=0, finest_level=1, with_dicts=False)
     eng = MGEngine(0)
