@@ -223,6 +223,13 @@ int mgb_fmg(mgb_handle* h, int mu0, double tol, int max_cycles, double* v_out, i
 int mgb_set_exact_solution(mgb_handle* h, int level, const double* u_exact, int mem);
 int mgb_fmg_error_history(mgb_handle* h, double* errnorm_hist, int capacity, int* count);
 
+/* Restriction of a transfer that is already set (mgb_set_transfer) or generated (mgb_synth_poisson_transfer), before
+ * mgb_finalize: MGB_R_INJECTION (Restriction2D_direct, multigrid.py:123-132; needs the injection list the transfer came with),
+ * MGB_R_FULL_WEIGHTING (2^-dim_for_fw P^T, Restriction2D, multigrid.py:135-198) or MGB_R_TRANSPOSE (P^T).  The transposed
+ * operator is formed at mgb_finalize: on the device (mgb_devsetup.cu) for generated levels and under the option
+ * "device_setup" = 1, else on the host; both give the same arrays bit for bit (MGB_ART_R_*). */
+int mgb_set_restriction(mgb_handle* h, int coarse_level, int r_mode, int dim_for_fw);
+
 /* Fused halo exchange: whether the kernels of `level` exchange the ghost rows themselves.  Decided per rank at
  * mgb_finalize from what that rank's shard looks like -- and it MUST be the same on every rank (a rank that sends without a
  * neighbour that waits, or the reverse, dead-locks), so the caller agrees on it after mgb_finalize: query every rank, switch the

@@ -64,6 +64,7 @@ SYMBOLS = {
     "mgb_fmg": (_i, [_vp, _i, _d, _i, _vp, _i, C.POINTER(_i), _vp, _i]),
     "mgb_set_exact_solution": (_i, [_vp, _i, _vp, _i]),
     "mgb_set_numbering": (_i, [_vp, _i, _i64, _vp]),
+    "mgb_set_restriction": (_i, [_vp, _i, _i, _i]),
     "mgb_halo_fused": (_i, [_vp, _i, C.POINTER(_i)]),
     "mgb_set_halo_fused": (_i, [_vp, _i, _i]),
     "mgb_fmg_error_history": (_i, [_vp, _vp, _i, C.POINTER(_i)]),

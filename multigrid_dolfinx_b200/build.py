@@ -13,9 +13,15 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgb200.so")
-SOURCES = ["mgb_engine.cu", "mgb_setup.cpp"]
-HEADERS = ["mgb_kernels.cuh", "mgb_internal.h", "mgb_types.cuh", "mgb_dist.cuh", "mgb_synth.cuh", "mgb_code.cuh",
+SOURCES = ["mgb_engine.cu", "mgb_devsetup.cu", "mgb_setup.cpp"]
+HEADERS = ["mgb_kernels.cuh", "mgb_internal.h", "mgb_types.cuh", "mgb_dist.cuh", "mgb_synth.cuh", "mgb_code.cuh", "mgb_devsetup.h",
            os.path.join("..", "..", "include", "mgb200.h")]
+# what each translation unit includes (a header that changes only recompiles the units that see it)
+DEPENDS = {"mgb_engine.cu": HEADERS,
+           "mgb_devsetup.cu": ["mgb_devsetup.h"],
+           "mgb_setup.cpp": ["mgb_internal.h", os.path.join("..", "..", "include", "mgb200.h")]}
+OBJDIR = os.path.join(HERE, "_build")
+FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp,-O3"]
 
 
 def nvcc_path():
@@ -25,21 +31,39 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
+def _newer(path, t):
+    return os.path.getmtime(path) > t
+
+
 def up_to_date():
     if not os.path.exists(LIB):
         return False
     t = os.path.getmtime(LIB)
-    return all(os.path.getmtime(os.path.join(CSRC, f)) <= t for f in SOURCES + HEADERS)
+    return not any(_newer(os.path.join(CSRC, f), t) for f in SOURCES + HEADERS)
 
 
 def build(force=False, verbose=False):
+    """One object per source under _build/ (git-ignored), compiled in parallel and only when the source or a header it
+    includes is newer; then one link.  Every object is sm_100a SASS + compute_100a PTX with -lineinfo."""
     if not force and up_to_date():
         return LIB
-    cmd = [nvcc_path(), "-O3", "-std=c++17", "--split-compile", "0", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC,-fopenmp,-O3", "-shared", "-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
-    subprocess.check_call(cmd)
+    os.makedirs(OBJDIR, exist_ok=True)
+    nvcc = nvcc_path()
+    jobs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        stale = force or not os.path.exists(obj) or any(
+            _newer(os.path.join(CSRC, f), os.path.getmtime(obj)) for f in [src] + DEPENDS[src])
+        if stale:
+            cmd = [nvcc] + FLAGS + (["--split-compile", "0"] if src.endswith(".cu") else []) + \
+                  (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+            jobs.append((src, subprocess.Popen(cmd)))
+    failed = [src for src, p in jobs if p.wait() != 0]
+    if failed:
+        raise RuntimeError(f"nvcc failed on {failed}")
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC,-fopenmp",
+                           "-o", LIB] + objs)
     return LIB
 
 

@@ -19,6 +19,7 @@
 
 #include "../../include/mgb200.h"
 #include "mgb_internal.h"
+#include "mgb_devsetup.h"
 #include "mgb_kernels.cuh"
 
 using namespace mgb;
@@ -1683,6 +1684,22 @@ int mgb_set_transfer(mgb_handle* h, int coarse_level, int64_t n_fine, int64_t n_
     return MGB_OK;
 }
 
+int mgb_set_restriction(mgb_handle* h, int coarse_level, int r_mode, int dim_for_fw)
+{
+    if (!h) return MGB_ERR_INVALID;
+    if (h->finalized) return fail(h, MGB_ERR_STATE, "hierarchy already finalized");
+    Level* F = find_level(h, coarse_level + 1);
+    if (!F || !F->has_transfer) return fail(h, MGB_ERR_STATE, "set or generate the transfer between levels %d and %d first", coarse_level, coarse_level + 1);
+    if (r_mode != MGB_R_INJECTION && r_mode != MGB_R_FULL_WEIGHTING && r_mode != MGB_R_TRANSPOSE)
+        return fail(h, MGB_ERR_INVALID, "r_mode must be injection, full weighting or transpose (explicit rows come with mgb_set_transfer)");
+    if (r_mode == MGB_R_INJECTION && F->inj_host.empty() && F->n_coarse > 0)
+        return fail(h, MGB_ERR_INVALID, "the transfer was set without an injection list");
+    if (r_mode == MGB_R_FULL_WEIGHTING && dim_for_fw != 2 && dim_for_fw != 3) return fail(h, MGB_ERR_INVALID, "dim_for_fw must be 2 or 3");
+    F->r_mode = r_mode;
+    if (r_mode == MGB_R_FULL_WEIGHTING) F->dim_fw = dim_for_fw;
+    return MGB_OK;
+}
+
 int mgb_set_params(mgb_handle* h, double omega, int mu1, int mu2, int smoother)
 {
     if (!h) return MGB_ERR_INVALID;
@@ -1722,6 +1739,7 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "tail_rows") { h->tail_rows = iv; drop_graphs(h); }
     else if (k == "hot_inj") { h->hot_inj = iv; drop_graphs(h); }
     else if (k == "fuse_halo" && pre) h->fuse_halo = iv;
+    else if (k == "device_setup" && pre) h->device_setup = iv;
     else if (k == "hot_pf") { h->hot_pf = iv; drop_graphs(h); }
     else if (k == "win_prefetch") { h->win_prefetch = iv; drop_graphs(h); }
     else if (k == "gs_cluster") h->gs_cluster = iv;
@@ -1732,6 +1750,77 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else return fail(h, pre ? MGB_ERR_INVALID : MGB_ERR_STATE, "option '%s' unknown or not settable %s finalize", key, pre ? "before" : "after");
     return MGB_OK;
 }
+
+// Gauss-Seidel set-up from the level matrix in HBM (mgb_devsetup.cu): symmetrised lower graph, level sets and / or first-fit
+// colouring, stable order, reordered off-diagonal operator, ELL copy -- the same artefacts, bit for bit, as the host path in
+// mgb_finalize (level_sets / greedy_colouring / split_offdiag / permute_rows of mgb_setup.cpp).  Above 32 M rows only the
+// ordering the chosen smoother runs in is built (the other one's artefact is then empty).
+extern "C++" {
+struct DevTemps {
+    std::vector<void*> p;
+    template <class T> T* keep(T* q) { p.push_back((void*)q); return q; }
+    void release(void* q) { p.erase(std::remove(p.begin(), p.end(), q), p.end()); }
+    ~DevTemps() { for (void* q : p) cudaFree(q); }
+};
+
+static int build_gs_device(mgb_handle* h, Level& L)
+{
+    const int n = (int)L.n;
+    const bool lvl = h->smoother == MGB_SM_GS_LEVEL, both = L.n <= ((int64_t)32 << 20);
+    cudaStream_t s = h->stream;
+    DevTemps tmp;
+    int32_t *lp = nullptr, *lx = nullptr, *lev = nullptr, *col = nullptr, *lev_order = nullptr, *col_order = nullptr;
+    CU(dev::lower_sym_graph(s, n, L.A.rowptr, L.A.cols, L.A.vals, &lp, &lx));
+    tmp.keep(lp); tmp.keep(lx);
+    auto download = [&](std::vector<int32_t>& dst, const int32_t* src) -> int {
+        dst.resize((size_t)n);
+        if (n) CU(cudaMemcpyAsync(dst.data(), src, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        return MGB_OK;
+    };
+    if (lvl || both) {
+        CU(dev::level_sets(s, n, lp, lx, &lev, &L.gs_setup_passes[0]));
+        tmp.keep(lev);
+        CU(dev::order_from_keys(s, n, lev, &lev_order, L.lev_off));
+        tmp.keep(lev_order);
+        TRY(download(L.lev_of_row, lev)); TRY(download(L.lev_order, lev_order));
+    }
+    if (!lvl || both) {
+        int overflow = 0;
+        CU(dev::colouring(s, n, lp, lx, &col, &L.gs_setup_passes[1], &overflow));
+        tmp.keep(col);
+        if (overflow) return fail(h, MGB_ERR_UNSUPPORTED, "level %d: more than 128 colours (the device colouring holds the used colours in two words)", L.level);
+        CU(dev::order_from_keys(s, n, col, &col_order, L.col_off));
+        tmp.keep(col_order);
+        TRY(download(L.col_of_row, col)); TRY(download(L.col_order, col_order));
+    }
+    int32_t* order = lvl ? lev_order : col_order;
+    const std::vector<int32_t>& off = lvl ? L.lev_off : L.col_off;
+    int64_t gnnz = 0; int bad = 0;
+    CU(dev::gs_operator(s, n, order, L.A.rowptr, L.A.cols, L.A.vals, &L.G.rowptr, &L.G.cols, &L.G.vals, &L.gs_diag, &gnnz, &bad));
+    if (bad) return fail(h, MGB_ERR_SINGULAR, "level %d: zero or missing diagonal entry", L.level);
+    L.G.nrows = n; L.G.ncols = L.A.ncols; L.G.nnz = gnnz;
+    std::vector<int64_t> ip;
+    TRY(fetch_rowptr(h, L.G, ip));
+    L.gs_groups = (int)off.size() - 1;
+    for (int g = 0; g < L.gs_groups; ++g) L.gs_max_width = std::max(L.gs_max_width, off[g + 1] - off[g]);
+    if (lvl) {
+        const int sf = h->opt_family; h->opt_family = 2;      // rows are read directly by k_gs_levels
+        int rc = finish_csr(h, L.G, ip); h->opt_family = sf; TRY(rc);
+    } else {
+        TRY(finish_csr(h, L.G, ip, off));
+    }
+    if (lvl && L.G.max_row <= 8 && n > 0) {                  // ELL copy for the pipelined kernel
+        const int W = L.G.max_row <= 4 ? 4 : (L.G.max_row <= 6 ? 6 : 8);
+        CU(dev::gs_ell(s, n, W, L.G.rowptr, L.G.cols, L.G.vals, &L.gs_ecols, &L.gs_evals));
+        L.gs_W = W;
+    }
+    tmp.release(order);
+    L.gs_order = order;
+    TRY(dev_upload(h, &L.gs_off, off.data(), off.size()));
+    return MGB_OK;
+}
+}  // extern "C++"
 
 // everything mgb_finalize can reject without touching the device or the network (also exported as mgb_precheck so
 // that a row-sharded setup can agree on success BEFORE entering the collective part of mgb_finalize)
@@ -1747,8 +1836,8 @@ static int validate_hierarchy(mgb_handle* h)
         if (l > h->coarsest && !L->has_transfer) return fail(h, MGB_ERR_STATE, "transfer between levels %d and %d missing", l - 1, l);
         if (h->dist && l > h->gather_level && L->has_transfer && (L->r_mode == MGB_R_FULL_WEIGHTING || L->r_mode == MGB_R_TRANSPOSE))
             return fail(h, MGB_ERR_UNSUPPORTED, "row-sharded levels need the restriction rows explicitly (MGB_R_EXPLICIT) or injection");
-        if (L->device_born && h->smoother >= MGB_SM_GS_LEVEL)
-            return fail(h, MGB_ERR_UNSUPPORTED, "Gauss-Seidel needs the host copy of the level matrix; generated levels have none");
+        if (L->device_born && L->has_transfer && L->r_mode == MGB_R_EXPLICIT)
+            return fail(h, MGB_ERR_UNSUPPORTED, "generated levels restrict by injection or by the transposed prolongation (mgb_set_restriction)");
     }
     if (h->opt_iter && h->opt_iter != 1 && h->opt_iter != 2) return fail(h, MGB_ERR_INVALID, "tile_iter must be 1 or 2");
     if (h->opt_lpr && (h->opt_lpr & (h->opt_lpr - 1) || h->opt_lpr > 32)) return fail(h, MGB_ERR_INVALID, "lanes_per_row must be a power of two <= 32");
@@ -1806,7 +1895,6 @@ int mgb_finalize(mgb_handle* h)
         }
         const int64_t xo_self = (h->dist && L.n_ghost > 0) ? L.n : -1;       // operators reading this level's vectors
         if (L.device_born) {
-            if (h->smoother >= MGB_SM_GS_LEVEL) return fail(h, MGB_ERR_UNSUPPORTED, "Gauss-Seidel needs the host copy of the level matrix; generated levels have none");
             std::vector<int64_t> ip;
             int64_t in[2];
             TRY(fetch_rowptr(h, L.A, ip));
@@ -1821,7 +1909,10 @@ int mgb_finalize(mgb_handle* h)
             TRY(upload_csr(h, RJ, L.RJ, {}, xo_self));
             TRY(dev_upload(h, &L.dinv, dinv.data(), n, 16));
         }
-        if (h->smoother >= MGB_SM_GS_LEVEL && kv.first > h->coarsest) {
+        const bool on_device = L.device_born || h->device_setup;       // set-up part 2 from the arrays in HBM (mgb_devsetup.cu)
+        if (h->smoother >= MGB_SM_GS_LEVEL && kv.first > h->coarsest && on_device) {
+            TRY(build_gs_device(h, L));
+        } else if (h->smoother >= MGB_SM_GS_LEVEL && kv.first > h->coarsest) {
             HostCsr G0, G; std::vector<double> diag, dperm(n);
             if (!split_offdiag(L.A_host, G0, diag)) return fail(h, MGB_ERR_SINGULAR, "level %d: zero or missing diagonal entry", kv.first);
             level_sets(L.A_host, L.lev_of_row, L.lev_order, L.lev_off);
@@ -1904,9 +1995,20 @@ int mgb_finalize(mgb_handle* h)
                     L.inj_fraction = L.A.nnz ? (double)ent / (double)L.A.nnz : 1.0;
                 }
             } else {
-                if (L.r_mode == MGB_R_FULL_WEIGHTING) transpose_scaled(L.P_host, std::ldexp(1.0, -L.dim_fw), L.R_host);
-                else if (L.r_mode == MGB_R_TRANSPOSE) transpose_scaled(L.P_host, 1.0, L.R_host);
-                TRY(upload_csr(h, L.R_host, L.R, {}, xo_self));
+                const double scale = L.r_mode == MGB_R_FULL_WEIGHTING ? std::ldexp(1.0, -L.dim_fw) : 1.0;   // multigrid.py:135-198: 2^-d P^T
+                if (on_device && L.r_mode != MGB_R_EXPLICIT) {
+                    CU(dev::transpose_scaled(h->stream, L.P.nrows, L.P.ncols, L.P.nnz, L.P.rowptr, L.P.cols, L.P.vals, scale,
+                                             &L.R.rowptr, &L.R.cols, &L.R.vals));
+                    L.R.nrows = L.P.ncols; L.R.ncols = L.P.nrows; L.R.nnz = L.P.nnz;
+                    std::vector<int64_t> ip;
+                    int64_t in[2];
+                    TRY(fetch_rowptr(h, L.R, ip));
+                    if (xo_self >= 0) TRY(interior_rows(h, L.R, xo_self, in));
+                    TRY(finish_csr(h, L.R, ip, {}, xo_self >= 0 ? in : nullptr));
+                } else {
+                    if (L.r_mode != MGB_R_EXPLICIT) transpose_scaled(L.P_host, scale, L.R_host);
+                    TRY(upload_csr(h, L.R_host, L.R, {}, xo_self));
+                }
             }
         }
         const size_t np = n + (size_t)L.n_ghost + 16;   // [owned | ghost | tail padding for 16-byte bulk copies]

@@ -149,6 +149,7 @@ struct Level {
     int32_t* gs_ecols = nullptr;     // GS_LEVEL, rows of <= 8 entries: the operator again in ELL form (W x n, level-major)
     double* gs_evals = nullptr;
     int gs_W = 0;
+    int gs_setup_passes[2] = {0, 0}; // device set-up: relaxation passes the level sets / the colouring took
 };
 
 struct ProfEvent { int kind, level; double bytes, moved; cudaEvent_t e0, e1; };
@@ -184,6 +185,8 @@ struct mgb_handle {
     bool numbered = false;         // some level carries a caller numbering
     double* perm_tmp = nullptr;    // device scratch of the permuting copies
     int64_t perm_tmp_cap = 0;
+    int device_setup = 0;          // 1: transposed restriction, level sets, colourings and Gauss-Seidel operators are built on the device for
+                                   //    host-assembled levels too (generated levels always are); bit-identical to the host build
     int fuse_halo = 1;             // row-sharded levels: halo exchange fused into the kernels that write / read the iterate (HaloFuse)
     HaloFuse hf_cur{};             // the fused-exchange plan of the launch being enqueued (all zero: none)
     bool in_cycle = false;         // inside enqueue_cycle: ghost sections of fused levels are kept valid by the kernels themselves

@@ -148,6 +148,12 @@ class MGEngine:
     def synth_transfer(self, coarse_level, inj_coarse_begin, inj_coarse_end):
         self._ck(self._lib.mgb_synth_poisson_transfer(self._h, int(coarse_level), int(inj_coarse_begin), int(inj_coarse_end)))
 
+    def set_restriction(self, coarse_level, r_mode, dim=2):
+        """Restriction of a transfer that is already set or generated (``mgb_set_restriction``): injection, full weighting
+        (2^-dim P^T, multigrid.py:135-198) or the plain transpose; the transposed operator is formed at ``finalize``."""
+        mode = L.R_MODES[r_mode] if isinstance(r_mode, str) else int(r_mode)
+        self._ck(self._lib.mgb_set_restriction(self._h, int(coarse_level), mode, int(dim)))
+
     def set_transfer(self, coarse_level, P, r_mode="injection", inj=None, R=None, dim=2, n_fine=None, n_coarse_rows=None):
         pip, pix, pax = _as_csr_arrays(P)
         mode = L.R_MODES[r_mode] if isinstance(r_mode, str) else int(r_mode)

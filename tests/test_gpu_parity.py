@@ -212,6 +212,65 @@ def test_gauss_seidel_multicolour(dim, c, lf, seed):
     eng.close()
 
 
+GS_ARTS = (L.ART_LEVEL_OF_ROW, L.ART_LEVEL_ORDER, L.ART_LEVEL_OFFSETS, L.ART_COLOUR_OF_ROW, L.ART_COLOUR_ORDER, L.ART_COLOUR_OFFSETS)
+R_ARTS = (L.ART_R_INDPTR, L.ART_R_INDICES, L.ART_R_VALUES)
+
+
+@pytest.mark.parametrize("dim,c,lf,seed,smoother,r_mode", [
+    (2, 8, 3, None, "gs", "full_weighting"), (2, 8, 3, 6, "gs_color", "transpose"), (3, 2, 3, None, "gs_color", "full_weighting"),
+    (3, 2, 2, 7, "gs", "full_weighting"), (2, 5, 3, 3, "gs", "transpose")])
+def test_device_setup_matches_host_setup(dim, c, lf, seed, smoother, r_mode):
+    """Set-up part 2 on the device (mgb_devsetup.cu, option device_setup = 1): the transposed restriction, the level sets, the
+    first-fit colouring, their stable orders and the reordered Gauss-Seidel operator are the SAME ARRAYS as the host build of
+    mgb_setup.cpp -- and as the C oracle's -- on lexicographic and on scrambled (ragged) numberings; so are sweeps and cycles."""
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=seed, with_dicts=False)
+    host = MGEngine.from_hierarchy(H, smoother=smoother, r_mode=r_mode, options={"device_setup": 0})
+    dev = MGEngine.from_hierarchy(H, smoother=smoother, r_mode=r_mode, options={"device_setup": 1})
+    for l in range(1, lf + 1):
+        for kind in GS_ARTS + R_ARTS:
+            a, b = host.artifact(l, kind), dev.artifact(l, kind)
+            assert a.size > 0 and np.array_equal(a, b), (l, kind)
+        A = H.A_sp_dict[l][0]
+        lev, order, off = co.level_sets(A)
+        assert np.array_equal(dev.artifact(l, L.ART_LEVEL_OF_ROW), lev) and np.array_equal(dev.artifact(l, L.ART_LEVEL_ORDER), order)
+        assert np.array_equal(dev.artifact(l, L.ART_LEVEL_OFFSETS), off)
+        col, order, off = co.greedy_colouring(A)
+        assert np.array_equal(dev.artifact(l, L.ART_COLOUR_OF_ROW), col) and np.array_equal(dev.artifact(l, L.ART_COLOUR_ORDER), order)
+        assert np.array_equal(dev.artifact(l, L.ART_COLOUR_OFFSETS), off)
+    rng = np.random.default_rng(2)
+    x, f = rng.standard_normal(H.n(lf)), rng.standard_normal(H.n(lf))
+    assert np.array_equal(host.smooth(lf, x, f, 3), dev.smooth(lf, x, f, 3))
+    assert np.array_equal(host.restrict(lf, x), dev.restrict(lf, x))
+    b = H.b_dict[lf][:, 0]
+    v0, h0 = host.vcycle(lf, np.zeros_like(b), b, ncycles=3, history=True)
+    v1, h1 = dev.vcycle(lf, np.zeros_like(b), b, ncycles=3, history=True)
+    assert np.array_equal(v0, v1) and np.array_equal(h0, h1)
+    host.close(); dev.close()
+
+
+@pytest.mark.parametrize("dim,c,lf,glevel,smoother,r_mode", [(2, 8, 4, 1, "gs", "full_weighting"), (3, 2, 4, 0, "gs_color", "full_weighting"),
+                                                             (3, 4, 3, 2, "gs", "injection"), (2, 16, 3, 0, "jacobi", "transpose")])
+def test_generated_levels_take_gauss_seidel_and_transposed_restrictions(dim, c, lf, glevel, smoother, r_mode):
+    """Levels generated on the device have no host copy: their Gauss-Seidel operators and 2^-d P^T are built from the arrays in
+    HBM and must equal what the host path builds from the host-assembled twin of the same hierarchy -- artefacts and cycles."""
+    from multigrid_dolfinx_b200 import dist as ds
+    src = ds.StructuredSource(dim, c, 0, lf)
+    mg = ds.DistMG(src, device=0, gather_level=glevel, device_gen=True, smoother=smoother, r_mode=r_mode)
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, with_dicts=False)
+    ref = MGEngine.from_hierarchy(H, smoother=smoother, r_mode=r_mode)
+    for l in range(glevel + 1, lf + 1):
+        for kind in (GS_ARTS if smoother != "jacobi" else ()) + (R_ARTS if r_mode != "injection" else ()):
+            a, b = ref.artifact(l, kind), mg.eng.artifact(l, kind)
+            assert a.size > 0 and np.array_equal(a, b), (l, kind)
+    f = src.rhs_rows(lf, 0, src.n(lf))
+    mg.load_rhs()
+    h1 = mg.cycles(3, history=True)
+    v0, h0 = ref.vcycle(lf, np.zeros_like(f), f, ncycles=3, history=True)
+    assert np.array_equal(mg.local_solution(), v0) and np.array_equal(h1, h0)
+    assert h0[2] < h0[0]
+    mg.close(); ref.close()
+
+
 def test_edge_cases():
     """nw = 0 returns v (multigrid.py:223-228); mu1 = 0 / mu2 = 0 / odd sweep totals; top level = any level
     (FullMultiGrid calls the cycle with every level as top, multigrid.py:305-306); coarsest as top = direct solve."""
