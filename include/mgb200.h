@@ -99,7 +99,8 @@ enum { MGB_BUF_V = 0, MGB_BUF_F = 1, MGB_BUF_R = 2 };
 enum {
     MGB_K_JACOBI = 0, MGB_K_RESIDUAL = 1, MGB_K_RESTRICT = 2, MGB_K_PROLONG_ADD = 3, MGB_K_COARSE = 4,
     MGB_K_INIT_GUESS = 5, MGB_K_GS = 6, MGB_K_NORM = 7, MGB_K_SPMV = 8, MGB_K_HALO = 9, MGB_K_COPY = 10,
-    MGB_K_COUNT = 11
+    MGB_K_JACOBI2 = 11,   /* two Jacobi sweeps in one launch (k_hotrow2) */
+    MGB_K_COUNT = 12
 };
 
 typedef struct {
@@ -173,16 +174,20 @@ int mgb_synth_poisson_transfer(mgb_handle* h, int coarse_level, int64_t inj_coar
 
 /* mu1, mu2, omega (multigrid.py:19-21), smoother = MGB_SM_* */
 int mgb_set_params(mgb_handle* h, double omega, int mu1, int mu2, int smoother);
-/* named numeric options, see DESIGN.md:  "rj_order" (0 = as stored in A, 1 = reversed = scipy's
- * DIA*CSR product order, default 1), "use_graph" (default 1), "kernel_family" (0 auto, 1 tile, 2 sub-warp),
- * "lanes_per_row" (0 auto), "coarse_refine" (0/1), "fuse_restrict" (0/1), "stream_cfg" (TMA stream kernel shape),
- * "compress" (0 off; 1: operators whose stored entries repeat -- few distinct values and column offsets, as on the
- * uniform meshes of the reference -- are additionally kept as one byte per entry + a dictionary; 2, the default: also
- * one byte per ROW + a table of row patterns where whole rows repeat.  Every coding is verified lossless on the device
- * before it is used and results are bit-identical either way), "code_cfg" (row-stream kernel shape),
- * "pdl" (programmatic dependent launch: -1, the default, for the row-stream kernels of coded operators; 1 also for the CSR
- * stream kernels; 0 never), "stage_x" (EXPERIMENTAL, default 0: x staged in shared memory for row-pattern-coded operators;
- * written at the end of round 1 and not yet measured) */
+/* named numeric options (defaults in brackets), see DESIGN.md.  Results are bit-identical under every one of them except
+ * "rj_order" and "kernel_family" = 2 (a different, still deterministic summation order).
+ *  before mgb_finalize:  "rj_order" [1] (0 = R_omega rows as stored in A, 1 = reversed = the order scipy's DIA*CSR product leaves),
+ *   "compress" [3] (lossless operator codings, each verified on the device before use: 0 off, 1 one byte per stored entry + a
+ *   dictionary, 2 + one byte per ROW where whole rows repeat, 3 + anchored row patterns for rectangular operators),
+ *   "stage_x" [3] (kernel for row-pattern-coded operators: 3 k_hotrow, 1 k_rowwin, 0 k_rowstream), "stream_cfg" [3] (0: register-
+ *   staged tile kernel only), "code_cfg", "hot_cfg", "anch_cfg", "win_cfg" (kernel shapes), "kernel_family" [0 auto],
+ *   "lanes_per_row", "tile_iter", "stream_auto", "fuse_halo" [1] (row-sharded levels: halo exchange inside the kernels),
+ *   "device_setup" [0] (1: P^T, level sets, colourings and Gauss-Seidel operators of host-assembled levels are built on the
+ *   device too -- generated levels always are), "s2_min_rows" [2^20] (smallest level that runs two Jacobi sweeps per launch);
+ *  any time:  "use_graph" [1], "pdl" [-1: programmatic dependent launch for the coded kernels; 1 also the CSR stream kernels; 0
+ *   never], "fuse_restrict" [1], "reuse_g" [1], "hot_inj" [1], "hot_pf" [262144 rows of L2 prefetch distance], "fuse_sweeps" [0]
+ *   (1: pairs of Jacobi sweeps in ONE launch on unsharded hot-row levels, k_hotrow2; measured no faster), "s2_slack", "s2_tiles", "coarse_refine" [0],
+ *   "tail_rows" [0], "gs_cluster" [2], "p2p_enable" [1], "overlap_halo" [0], "overlap_waves", "win_prefetch". */
 int mgb_set_option(mgb_handle* h, const char* key, double value);
 /* builds R_omega and D^-1 (getJacobiMatrices, multigrid.py:48-56), R from P, the dense inverse of the
  * coarsest matrix (replaces spsolve, multigrid.py:239), level sets / colours when a GS smoother is

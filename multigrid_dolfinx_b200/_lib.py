@@ -22,7 +22,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
  ART_COARSE_INVERSE, ART_A_INDPTR, ART_A_INDICES, ART_A_VALUES, ART_P_INDPTR, ART_P_INDICES, ART_P_VALUES,
  ART_INJECTION) = range(21)
 BUF_V, BUF_F, BUF_R = 0, 1, 2
-KERNEL_KINDS = ["jacobi", "residual", "restrict", "prolong_add", "coarse", "init_guess", "gs", "norm", "spmv", "halo", "copy"]
+KERNEL_KINDS = ["jacobi", "residual", "restrict", "prolong_add", "coarse", "init_guess", "gs", "norm", "spmv", "halo", "copy", "jacobi2"]
 
 R_MODES = {"injection": R_INJECTION, "full_weighting": R_FULL_WEIGHTING, "transpose": R_TRANSPOSE, "explicit": R_EXPLICIT}
 SMOOTHERS = {"jacobi": SM_JACOBI_RJ, "jacobi_rj": SM_JACOBI_RJ, "jacobi_a": SM_JACOBI_A, "gs": SM_GS_LEVEL,

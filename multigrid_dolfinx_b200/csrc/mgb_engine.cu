@@ -625,6 +625,61 @@ bool launch_hotrow(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles,
     return false;
 }
 
+// Two Jacobi sweeps in one launch (k_hotrow2): x -> y -> out on an unsharded hot-row operator, linear tiling.  reach: tiles a row's
+// hot offsets can lie away from its own tile.  false: shape not covered (the caller runs two launches).
+struct Sweep2Plan { int rows, ntiles, reach, groups, ngrid_groups_max; };
+bool sweep2_plan(const mgb_handle* h, const DevCsr& D, Sweep2Plan& p)
+{
+    if (D.cd.mode != 3 || D.hcfg <= 0 || !D.sdesc) return false;
+    const int hl = D.cd.hotplan.hotlen;
+    if (hl != 4 && hl != 6) return false;
+    const HotChoice hc = hot_choice(D.hcfg);
+    p.rows = hc.threads * hc.rpt;
+    p.ntiles = (int)((D.nrows + p.rows - 1) / p.rows);
+    const int64_t far = std::max<int64_t>(std::abs((int64_t)D.cd.hot.dmin), std::abs((int64_t)D.cd.hot.dmax));
+    p.reach = (int)((far + p.rows - 1) / p.rows) + 1;
+    p.groups = (p.ntiles + S2_GROUP - 1) / S2_GROUP;
+    return 2 * p.reach / S2_GROUP + 2 <= hc.threads && D.nrows == D.ncols;
+}
+
+template <int HOTN, int T, int RPT, class Epi1>
+void launch_hotrow2_cfg(mgb_handle* h, const DevCsr& D, const Sweep2Plan& p, unsigned long long* s2, const double* x, const Epi1& epi1,
+                        const double* y, const EpiJacobiRJ& epi2)
+{
+    constexpr int MINB = hot_minb<HOTN, T, RPT, Epi1::NOPS>();
+    constexpr int ROWS = T * RPT;
+    int pf = h->allow_stream && h->hot_pf > 0 && D.cd.hot.dmax >= 0 ? std::max(1, h->hot_pf / ROWS) : 0;
+    const int64_t pf_last = std::min<int64_t>(D.nrows / ROWS, (D.ncols - (D.cd.hot.dmax & ~1)) / ROWS) - 1;
+    if (pf_last < pf) pf = 0;
+    int kt = 1;
+    while (kt < S2_GROUP && kt < h->s2_tiles) kt *= 2;                          // tiles per CTA: a power of two <= S2_GROUP
+    const int nchunks = (p.ntiles + kt - 1) / kt;
+    const int lagc = (p.reach + S2_GROUP + h->s2_slack + kt - 1) / kt + 1;      // chunks the second sweep trails the first by
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (nchunks + lagc)); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->pdl != 0 ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k_hotrow2<HOTN, T, RPT, MINB, false, true, Epi1, EpiJacobiRJ>,
+                       (const unsigned char*)D.cd.codes, (const uint32_t*)D.cd.pmask, (const int2*)D.cd.phead, (const DictEnt*)D.cd.dict,
+                       D.cd.hot, p.ntiles, (int)D.nrows, (int)D.ncols, pf, (int)pf_last, x, epi1, y, epi2, s2, kt, lagc, p.reach);
+    k_s2_reset<<<(p.groups + 255) / 256, 256, 0, h->stream>>>(p.groups, s2);    // (stream-ordered after the whole pair)
+}
+
+template <class Epi1>
+void launch_hotrow2(mgb_handle* h, const DevCsr& D, const Sweep2Plan& p, unsigned long long* s2, const double* x, const Epi1& epi1,
+                    const double* y, const EpiJacobiRJ& epi2)
+{
+    const int hl = D.cd.hotplan.hotlen;
+    switch (D.hcfg) {                    // hot_choice()
+        case 2: if (hl == 4) launch_hotrow2_cfg<4, 256, 1>(h, D, p, s2, x, epi1, y, epi2); else launch_hotrow2_cfg<6, 256, 1>(h, D, p, s2, x, epi1, y, epi2); break;
+        case 3: if (hl == 4) launch_hotrow2_cfg<4, 128, 1>(h, D, p, s2, x, epi1, y, epi2); else launch_hotrow2_cfg<6, 128, 1>(h, D, p, s2, x, epi1, y, epi2); break;
+        case 4: if (hl == 4) launch_hotrow2_cfg<4, 256, 2>(h, D, p, s2, x, epi1, y, epi2); else launch_hotrow2_cfg<6, 256, 2>(h, D, p, s2, x, epi1, y, epi2); break;
+        default: if (hl == 4) launch_hotrow2_cfg<4, 128, 2>(h, D, p, s2, x, epi1, y, epi2); else launch_hotrow2_cfg<6, 128, 2>(h, D, p, s2, x, epi1, y, epi2); break;
+    }
+}
+
 // Anchored row patterns (k_anchrow).  Configurations (option "anch_cfg"): threads x rows per thread.
 template <int T, int RPT, int JW, int MINB, class Epi>
 void launch_anchrow_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi)
@@ -840,6 +895,25 @@ int smooth(mgb_handle* h, Level& L, double*& v, double*& o, const double* f, int
 {
     const double n = (double)L.n;
     for (int s = 0; s < nsweeps; ++s) {
+        if (h->smoother == MGB_SM_JACOBI_RJ && s + 2 <= nsweeps && L.s2 && h->fuse_sweeps && h->allow_stream && h->stream_cfg > 0) {
+            // two sweeps in one launch, the second trailing the first through L2 (k_hotrow2): v -> o -> v, no swap
+            Sweep2Plan p;
+            if (sweep2_plan(h, L.RJ, p) && p.groups == L.s2_groups) {
+                const EpiJacobiRJ epi2{o, L.g, v, 1 - h->omega, h->omega};
+                const double b1 = bytes_rowsum(L.RJ, g_valid ? 3 * n : 5 * n), b2 = bytes_rowsum(L.RJ, 3 * n);
+                const double moved = b1 + b2 - 2.0 * coded_saving(L.RJ) - 16.0 * n;        // the second sweep's y and g are L2 hits
+                if (!g_valid) {
+                    const EpiJacobiRJFirst epi1{v, L.dinv, f, L.g, o, 1 - h->omega, h->omega};
+                    TRY(launch(h, MGB_K_JACOBI2, L.level, b1 + b2, [&] { launch_hotrow2(h, L.RJ, p, L.s2, v, epi1, o, epi2); }, moved));
+                } else {
+                    const EpiJacobiRJ epi1{v, L.g, o, 1 - h->omega, h->omega};
+                    TRY(launch(h, MGB_K_JACOBI2, L.level, b1 + b2, [&] { launch_hotrow2(h, L.RJ, p, L.s2, v, epi1, o, epi2); }, moved));
+                }
+                g_valid = true;
+                ++s;
+                continue;
+            }
+        }
         if (h->smoother == MGB_SM_JACOBI_RJ) {     // (the ghost entries of the iterate are exchanged inside row_sums_halo)
             if (!g_valid) {
                 EpiJacobiRJFirst epi{v, L.dinv, f, L.g, o, 1 - h->omega, h->omega};
@@ -1349,7 +1423,7 @@ int mgb_destroy(mgb_handle* h)
         for (void* q : L.p2p_opened) cudaIpcCloseMemHandle(q);
         if (!L.vec_in_arena) { cudaFree(L.v); cudaFree(L.vtmp); }
         cudaFree(L.p2p_arena); cudaFree(L.fuse_counters); cudaFree(L.f); cudaFree(L.r); cudaFree(L.g);
-        cudaFree(L.gs_order); cudaFree(L.gs_off); cudaFree(L.gs_diag); cudaFree(L.gs_ecols); cudaFree(L.gs_evals);
+        cudaFree(L.gs_order); cudaFree(L.gs_off); cudaFree(L.gs_diag); cudaFree(L.gs_ecols); cudaFree(L.gs_evals); cudaFree(L.s2);
     }
     cudaFree(h->coarse_inv); cudaFree(h->d_partial); cudaFree(h->d_hist); cudaFree(h->perm_tmp);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -1741,6 +1815,10 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "fuse_halo" && pre) h->fuse_halo = iv;
     else if (k == "device_setup" && pre) h->device_setup = iv;
     else if (k == "hot_pf") { h->hot_pf = iv; drop_graphs(h); }
+    else if (k == "fuse_sweeps") { h->fuse_sweeps = iv; drop_graphs(h); }
+    else if (k == "s2_slack") { h->s2_slack = std::min(std::max(0, iv), 1 << 20); drop_graphs(h); }
+    else if (k == "s2_min_rows" && pre) h->s2_min_rows = iv;
+    else if (k == "s2_tiles") { h->s2_tiles = std::max(1, iv); drop_graphs(h); }
     else if (k == "win_prefetch") { h->win_prefetch = iv; drop_graphs(h); }
     else if (k == "gs_cluster") h->gs_cluster = iv;
     else if (k == "pdl") { h->pdl = iv; drop_graphs(h); }
@@ -1908,6 +1986,15 @@ int mgb_finalize(mgb_handle* h)
                 return fail(h, MGB_ERR_SINGULAR, "level %d: zero or missing diagonal entry", kv.first);
             TRY(upload_csr(h, RJ, L.RJ, {}, xo_self));
             TRY(dev_upload(h, &L.dinv, dinv.data(), n, 16));
+        }
+        {   // counters of the two-sweep kernel (k_hotrow2): unsharded hot-row smoother matrices of at least s2_min_rows rows
+            Sweep2Plan p;
+            if (L.n_ghost == 0 && !(h->dist && !L.peers.empty()) && L.n >= h->s2_min_rows && sweep2_plan(h, L.RJ, p)) {
+                const size_t cnt = (size_t)p.groups + 2;
+                TRY(dev_alloc(h, &L.s2, cnt));
+                CU(cudaMemsetAsync(L.s2, 0, cnt * sizeof(unsigned long long), h->stream));
+                L.s2_groups = p.groups;
+            }
         }
         const bool on_device = L.device_born || h->device_setup;       // set-up part 2 from the arrays in HBM (mgb_devsetup.cu)
         if (h->smoother >= MGB_SM_GS_LEVEL && kv.first > h->coarsest && on_device) {
@@ -2469,8 +2556,11 @@ static int vcycle_bytes_impl(mgb_handle* h, int top_level, double* bytes, bool m
         Level& L = h->levels[l];
         const double n = (double)L.n, nc = (double)L.n_coarse;
         const int sweeps = h->mu1 + h->mu2;
-        if (h->smoother == MGB_SM_JACOBI_RJ) b += sweeps * bytes_rowsum(L.RJ, 3 * n);
-        else if (h->smoother == MGB_SM_JACOBI_A) b += sweeps * bytes_rowsum(L.A, 4 * n);
+        if (h->smoother == MGB_SM_JACOBI_RJ) {
+            b += sweeps * bytes_rowsum(L.RJ, 3 * n);
+            if (moved && L.s2 && h->fuse_sweeps && h->stream_cfg > 0)      // k_hotrow2: the second sweep of a pair reads y and g from L2
+                b -= 16.0 * n * ((l == top_level ? h->mu1 / 2 : std::max(h->mu1 - 1, 0) / 2) + h->mu2 / 2);
+        } else if (h->smoother == MGB_SM_JACOBI_A) b += sweeps * bytes_rowsum(L.A, 4 * n);
         else b += sweeps * (12.0 * (double)L.G.nnz + 8.0 * n + 24.0 * n);
         b += bytes_rowsum(L.A, 3 * n);
         b += L.r_mode == MGB_R_INJECTION ? 20.0 * nc : bytes_rowsum(L.R, n + nc);

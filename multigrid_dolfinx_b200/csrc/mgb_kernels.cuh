@@ -52,6 +52,29 @@ struct EpiResidual {
     __host__ __device__ __forceinline__ const double* operand(int) const { return f; }
     __device__ __forceinline__ double store(int i, double s, const double* o) const { const double t = __dsub_rn(o[0], s); r[i] = t; return t; }
 };
+// L2 eviction priorities for the two-sweep kernel (k_hotrow2): 0 none, 1 keep (evict_last), 2 stream (evict_first)
+__device__ __forceinline__ unsigned long long l2_policy(int kind)
+{
+    unsigned long long p = 0;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+template <int KIND>
+__device__ __forceinline__ void st_l2(double* q, double v, unsigned long long pol)
+{
+    if constexpr (KIND == 0) *q = v;
+    else asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(q), "d"(v), "l"(pol) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ double ld_stream_l2(const double* q, unsigned long long pol)
+{
+    double v;
+    if constexpr (KIND == 0) asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(q));
+    else asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(q), "l"(pol));
+    return v;
+}
+
 // weighted Jacobi, reference form (multigrid.py:226): out = ((1-w)*v + g) - w*s, g = w*(dinv*f)
 struct EpiJacobiRJ {
     static constexpr int NOPS = 2; static constexpr bool CONTIG = true; static constexpr int XOP = 0;
@@ -62,6 +85,11 @@ struct EpiJacobiRJ {
         const double t = __dsub_rn(__dadd_rn(__dmul_rn(om1, o[0]), o[1]), __dmul_rn(om, s));
         out[i] = t;
         return t;
+    }
+    template <int KOUT>                                      // same, the result stored with an L2 eviction priority
+    __device__ __forceinline__ void store_p(int i, double s, const double* o, unsigned long long pout, unsigned long long) const
+    {
+        st_l2<KOUT>(out + i, __dsub_rn(__dadd_rn(__dmul_rn(om1, o[0]), o[1]), __dmul_rn(om, s)), pout);
     }
 };
 // same, first sweep of a relaxation call: also produces g (multigrid.py:226 recomputes w*(Dinv f) per sweep;
@@ -77,6 +105,13 @@ struct EpiJacobiRJFirst {
         const double t = __dsub_rn(__dadd_rn(__dmul_rn(om1, o[0]), gi), __dmul_rn(om, s));
         out[i] = t;
         return t;
+    }
+    template <int KOUT>                                      // (g is read again by the second sweep: always kept)
+    __device__ __forceinline__ void store_p(int i, double s, const double* o, unsigned long long pout, unsigned long long pkeep) const
+    {
+        const double gi = __dmul_rn(om, __dmul_rn(o[1], o[2]));
+        if constexpr (KOUT == 0) g[i] = gi; else st_l2<1>(g + i, gi, pkeep);
+        st_l2<KOUT>(out + i, __dsub_rn(__dadd_rn(__dmul_rn(om1, o[0]), gi), __dmul_rn(om, s)), pout);
     }
 };
 // single-matrix Jacobi: out = v + w*(dinv*(f - s)), s = (A v)_i
@@ -1200,6 +1235,164 @@ k_hotrow(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ 
         }
     }
     if constexpr (HALO) { if (sends) halo_publish(hf, row0, min(row0 + T, rend)); }
+}
+
+// ---- two Jacobi sweeps in one launch (k_hotrow2) -----------------------------------------------------------------------------
+// A sweep of the 513^3 level streams 25 B per row and every byte comes from / goes to DRAM: the iterate (1.08 GB) is far larger than
+// L2, so sweep s + 1 finds nothing of what sweep s wrote.  Rows are swept in storage order, however, and row i of sweep s + 1 only
+// needs the rows i + dmin .. i + dmax of sweep s: the second sweep can follow the first at a distance of `lag` tiles INSIDE ONE
+// KERNEL, while the intermediate iterate y (and g) of those tiles are still in L2.  CTA 2i sums tile i of the first sweep (x -> y),
+// CTA 2i + 1 tile i - lag of the second (y -> out, which may be x itself: every reader of that part of x is among the tiles waited
+// for).
+// Dependencies: a CTA that has stored a first-sweep tile fences and counts itself into the tile's GROUP counter (64 tiles per
+// group); before its second-sweep tile a CTA waits until the groups covering the tiles [t - reach, t + reach] are complete (one
+// polling thread per group, relaxed loads, __syncthreads).  The counters are zeroed by a one-block kernel after every launch
+// (k_s2_reset: a counter of CTAs that finished, to let the last one do it, would cost every CTA an atomic round trip), so the
+// pair replays inside a CUDA graph.  No deadlock: the second sweep trails by at least reach + 64 tiles, so a CTA only ever waits
+// for first-sweep tiles of CTAs with a SMALLER block index -- already dispatched, and first-sweep CTAs wait for nothing; a wait
+// that still does not end traps.
+// What it saves: y and g of the second sweep are L2 hits, i.e. 33 instead of 50 B per row from DRAM for the pair.  Arithmetic per
+// row is that of k_hotrow: results are bit-identical to two separate sweeps.
+constexpr int S2_GROUP = 64;
+
+// one tile of the hot-row body without the fused exchange: rows [tile * T, min(tile * T + T, rend))  (see k_hotrow)
+__device__ __forceinline__ double ld_l2_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// XL2: x is read past L1 (at L2, the point of coherence).  POL: L2 eviction priorities -- 0 none; 1 first-sweep role (the result
+// and g are needed again `lag` tiles later: evict_last); 2 second-sweep role (the result and g are not needed again: evict_first)
+template <int HOTN, int THREADS, int RPT, bool XL2, int POL, class Epi>
+__device__ __forceinline__ void hot_tile(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ pmask,
+                                         const int2* __restrict__ phead, const DictEnt* __restrict__ pent, const HotArgs& H, int tile,
+                                         int rend, int xlen, int pf, int pf_last, const double* x, const Epi& epi)
+{
+    constexpr int T = THREADS * RPT;
+    constexpr int NOPS = Epi::NOPS, XOP = EpiXop<Epi>::value;
+    const int tid = threadIdx.x;
+    bool alias = false;
+    if constexpr (XOP >= 0) alias = epi.operand(XOP) == x;
+    const int row0 = tile * T;
+    const unsigned long long pkeep = l2_policy(POL ? 1 : 0), pout = l2_policy(POL);   // (operands other than the old iterate: g / dinv / f)
+    int code[RPT];
+    double xv[RPT][HOTN];
+    double o[RPT][NOPS > 0 ? NOPS : 1];
+    const bool fast = row0 + H.dmin >= 0 && (long long)row0 + T + H.dmax <= (long long)xlen && row0 + T <= rend;   // CTA-uniform
+    if (fast) {
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int r = row0 + tid + j * THREADS;
+            code[j] = ld_stream_u8(rcodes + r);
+            const double* xr = x + r;
+#pragma unroll
+            for (int e = 0; e < HOTN; ++e) xv[j][e] = XL2 ? ld_l2_f64(xr + H.hd[e]) : xr[H.hd[e]];
+#pragma unroll
+            for (int k = 0; k < NOPS; ++k) o[j][k] = (alias && k == XOP) ? (XL2 ? ld_l2_f64(xr) : xr[0]) : ld_stream_l2<POL>(epi.operand(k) + r, pout);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int r = min(row0 + tid + j * THREADS, rend - 1);        // threads past the end redo the last row (and do not store)
+            code[j] = ld_stream_u8(rcodes + r);
+#pragma unroll
+            for (int e = 0; e < HOTN; ++e) { const double* q = x + min(max(r + H.hd[e], 0), xlen - 1); xv[j][e] = XL2 ? ld_l2_f64(q) : *q; }
+#pragma unroll
+            for (int k = 0; k < NOPS; ++k) o[j][k] = XL2 ? ld_l2_f64(epi.operand(k) + r) : epi.operand(k)[r];
+        }
+    }
+    if (pf > 0 && tid < 2 + NOPS && tile + pf <= pf_last) {  // L2 prefetch for the tile pf tiles ahead
+        const long long p0 = (long long)row0 + (long long)pf * T;
+        const void* ptr = rcodes + p0;
+        uint32_t bytes = T;
+        if (tid == 1) { ptr = x + p0 + (H.dmax & ~1); bytes = T * 8; }
+#pragma unroll
+        for (int k = 0; k < NOPS; ++k)
+            if (tid == 2 + k) { ptr = (alias && k == XOP) ? nullptr : (const void*)(epi.operand(k) + p0); bytes = T * 8; }
+        if (ptr) bulk_prefetch_l2(ptr, bytes);
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int r = row0 + tid + j * THREADS;
+        const uint32_t m = __ldg(pmask + code[j]);
+        double sum = 0.0;                                    // one accumulator, stored order
+        if (__all_sync(0xffffffffu, m == (1u << HOTN) - 1u)) {
+#pragma unroll
+            for (int e = 0; e < HOTN; ++e) sum = __dadd_rn(sum, __dmul_rn(H.hv[e], xv[j][e]));
+        } else if (!(m & HOT_SLOW)) {
+#pragma unroll
+            for (int e = 0; e < HOTN; ++e)
+                if ((m >> e) & 1u) sum = __dadd_rn(sum, __dmul_rn(H.hv[e], xv[j][e]));
+        } else if (r < rend) {                               // any other pattern: walk its entry list
+            const int2 ph = __ldg(phead + code[j]);
+            for (int e = 0; e < ph.y; ++e) {
+                const double val = __ldg(&pent[ph.x + e].val);
+                const int dl = __ldg(&pent[ph.x + e].delta);
+                sum = __dadd_rn(sum, __dmul_rn(val, XL2 ? ld_l2_f64(x + r + dl) : x[r + dl]));
+            }
+        }
+        if (fast || r < rend) {
+            if constexpr (POL == 0) epi.store(r, sum, o[j]);
+            else epi.template store_p<POL>(r, sum, o[j], pout, pkeep);
+        }
+    }
+}
+
+// cnt[g]: first-sweep tiles of group g finished in this launch (zeroed again by k_s2_reset after every launch).
+// kt: tiles per CTA, a power of two <= S2_GROUP -- a CTA lives ~1.4 us per tile, a release or a poll costs about as much, so both
+// are paid once per kt tiles (tiles of one CTA are consecutive, the other resident CTAs hide the latency as separate CTAs would).
+template <int HOTN, int THREADS, int RPT, int MINB, bool XL2, bool POL, class Epi1, class Epi2>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_hotrow2(const unsigned char* __restrict__ rcodes, const uint32_t* __restrict__ pmask, const int2* __restrict__ phead,
+          const DictEnt* __restrict__ pent, const __grid_constant__ HotArgs H, int ntiles, int rend, int xlen, int pf, int pf_last,
+          const double* x, Epi1 epi1, const double* y, Epi2 epi2, unsigned long long* cnt, int kt, int lagc, int reach)
+{
+    static_assert(Epi1::CONTIG && Epi2::CONTIG, "hot-row kernel needs contiguous epilogue operands");
+    const int tid = threadIdx.x, b = (int)blockIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // roles alternate with the block index: even blocks sum first-sweep tiles, odd blocks second-sweep tiles lagc chunks behind --
+    // a CTA that did both in turn would sit through two memory latencies, a fence and a poll with nothing in flight
+    if (!(b & 1)) {
+        const int t0 = (b >> 1) * kt, t1 = min(t0 + kt, ntiles);
+        if (t0 < ntiles) {
+#pragma unroll 1
+            for (int t = t0; t < t1; ++t)
+                hot_tile<HOTN, THREADS, RPT, false, POL ? 1 : 0, Epi1>(rcodes, pmask, phead, pent, H, t, rend, xlen, pf, pf_last, x, epi1);
+            __syncthreads();                                 // every thread's stores are ordered before thread 0's release (cumulativity)
+            // release without an acquire: MEMBAR + REDG (a fence would also invalidate this SM's L1 under every CTA resident on it)
+            if (tid == 0)
+                asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(cnt + t0 / S2_GROUP), "l"((unsigned long long)(t1 - t0)) : "memory");
+        }
+    } else {
+        const int t0 = ((b >> 1) - lagc) * kt, t1 = min(t0 + kt, ntiles);
+        if (t0 >= 0 && t0 < ntiles) {
+            const int g0 = max(t0 - reach, 0) / S2_GROUP, g1 = min(t1 - 1 + reach, ntiles - 1) / S2_GROUP;
+            if (tid <= g1 - g0) {
+                const int g = g0 + tid;
+                const unsigned long long want = (unsigned long long)min(S2_GROUP, ntiles - g * S2_GROUP);
+                const long long c0 = clock64();
+                while (ld_relaxed_gpu(cnt + g) < want)
+                    if (clock64() - c0 > 8000000000LL) __trap();     // ~4 s: a lost tile must fault, never hang the GPU
+            }
+            // No acquire fence: it would invalidate the SM's whole L1 (CCTL.IVALL) once per CTA, and no line of y can be stale in
+            // it -- y is only ever loaded by second-sweep CTAs, each after ITS wait, and every line a tile touches lies inside the
+            // tiles waited for, i.e. was complete at L2 (the writers' release) before any SM could have fetched it.  Ordering: the
+            // loads below are issued after the barrier, the barrier after the polls returned.  XL2 reads y past L1 altogether.
+            __syncthreads();
+#pragma unroll 1
+            for (int t = t0; t < t1; ++t)
+                hot_tile<HOTN, THREADS, RPT, XL2, POL ? 2 : 0, Epi2>(rcodes, pmask, phead, pent, H, t, rend, xlen, 0, 0, y, epi2);
+        }
+    }
+}
+
+__global__ void k_s2_reset(int n, unsigned long long* cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cnt[i] = 0ULL;
 }
 
 // Fused residual + injection on a row-pattern-coded operator, one thread per COARSE row i: out[i] = f[g_i] - (A v)[g_i],

@@ -149,6 +149,8 @@ struct Level {
     int32_t* gs_ecols = nullptr;     // GS_LEVEL, rows of <= 8 entries: the operator again in ELL form (W x n, level-major)
     double* gs_evals = nullptr;
     int gs_W = 0;
+    unsigned long long* s2 = nullptr;   // k_hotrow2 (two Jacobi sweeps per launch): first-sweep tiles finished per tile group
+    int s2_groups = 0;
     int gs_setup_passes[2] = {0, 0}; // device set-up: relaxation passes the level sets / the colouring took
 };
 
@@ -193,6 +195,12 @@ struct mgb_handle {
     int hot_inj = 1;               // fused residual + injection: thread per coarse row on a pattern-coded level matrix (k_hotinj)
     int anch_cfg = 1;              // anchored-pattern kernel: 1 128 threads x 4 rows, 2 128 x 2, 3 64 x 4, 4 256 x 1 (rows of > 4 entries)
     int hot_cfg = 1;               // hot-row kernel configuration (hot_choice)
+    int fuse_sweeps = 0;           // Jacobi: 1 = pairs of sweeps in one launch on unsharded hot-row levels of at least s2_min_rows rows (k_hotrow2).
+                                   //   OFF by default: bit-identical, DRAM traffic of a pair 6.7 -> 4.6 GB at 513^3, but no faster -- the sweep is
+                                   //   bound by rows in flight x latency, not by bytes (profiles/r2_hotrow2_*.jsonl)
+    int s2_slack = 3072;           //   tiles the second sweep trails the first by, beyond the reach of a row (+ one counter group)
+    int s2_min_rows = 1 << 20;
+    int s2_tiles = 4;              //   consecutive tiles per CTA (one release / one poll per CTA)
     int hot_pf = 262144;           // hot-row kernel: L2 prefetch distance in rows (0: none)
     int win_cfg = 1;               // row-window kernel configuration (win_choice)
     int win_prefetch = 0;          // row-window kernel: tiles (per CTA) whose DRAM streams are prefetched into L2 ahead of the copies

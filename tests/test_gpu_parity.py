@@ -150,6 +150,40 @@ def test_kernel_options_do_not_change_results(opts):
         base.close(); eng.close()
 
 
+@pytest.mark.parametrize("dim,c,lf,mu", [(2, 8, 6, (2, 2)), (3, 4, 4, (2, 2)), (2, 8, 6, (3, 5)), (3, 2, 5, (4, 1))])
+@pytest.mark.parametrize("slack,tiles", [(0, 1), (7, 4), (2048, 8), (300, 64)])
+def test_two_sweeps_per_launch_bit_identical(dim, c, lf, mu, slack, tiles):
+    """k_hotrow2 (pairs of Jacobi sweeps in one launch, the second trailing the first through L2) against one launch per sweep:
+    the same bits, for every trailing distance -- slack 0 makes almost every second-sweep tile wait for its neighbours' first-sweep
+    tiles, i.e. it is the dependency tracking that is under test -- for odd sweep counts, on graph replay and eagerly, through the
+    smoother entry point, and against the oracle's sweep."""
+    H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, with_dicts=False, mu1=mu[0], mu2=mu[1])
+    f = H.b_dict[lf][:, 0]
+    base = MGEngine.from_hierarchy(H, options={"fuse_sweeps": 0})
+    eng = MGEngine.from_hierarchy(H, options={"fuse_sweeps": 1, "s2_min_rows": 1000, "s2_slack": slack, "s2_tiles": tiles})
+    v0, h0 = base.vcycle(lf, np.zeros_like(f), f, ncycles=4, history=True)
+    v1, h1 = eng.vcycle(lf, np.zeros_like(f), f, ncycles=4, history=True)
+    assert np.array_equal(v1, v0) and np.array_equal(h1, h0)
+    kinds = {r["kind"] for r in _profile_of(eng, lf)}
+    assert "jacobi2" in kinds
+    eng.set_option("use_graph", 0)
+    assert np.array_equal(eng.vcycle(lf, np.zeros_like(f), f, ncycles=4), v0)
+    rng = np.random.default_rng(3)
+    x, g = rng.standard_normal(H.n(lf)), rng.standard_normal(H.n(lf))
+    for nsweeps in (2, 3, 4, 5):
+        assert np.array_equal(eng.smooth(lf, x, g, nsweeps), base.smooth(lf, x, g, nsweeps)), nsweeps
+    A = H.A_sp_dict[lf][0]
+    RO, dinv = rs.jacobi_matrices(A)
+    assert np.array_equal(eng.smooth(lf, x, g, 4), rs.jacobi_relaxation(RO, dinv, x, g, 4, H.omega))
+    base.close(); eng.close()
+
+
+def _profile_of(eng, lf):
+    eng.profile_begin()
+    eng.vcycle_resident(lf, 1)
+    return eng.profile_end()
+
+
 def test_jacobi_a_form_and_coarse_refine():
     H = pr.build_hierarchy(dim=2, c=8, coarsest_level=0, finest_level=3, perm_seed=4, with_dicts=False)
     f = H.b_dict[3][:, 0]
