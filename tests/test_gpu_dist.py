@@ -206,3 +206,57 @@ def test_sharded_gauss_seidel_is_block_jacobi_between_ranks(case):
     vo, ho = mg.solve_cycles(np.zeros_like(f), f, 3)
     assert np.abs(hist - np.array(ho)).max() <= 1e-12 * max(ho)
     assert np.abs(v - vo[:, 0]).max() <= 1e-10 * np.abs(vo).max()
+
+
+def _gs_generated_worker(rank, world, port, case, q):
+    import torch
+    import torch.distributed as td
+    from multigrid_dolfinx_b200 import dist as ds
+    from multigrid_dolfinx_b200 import problems as pr
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    td.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        dim, c, lf, smoother, glevel = case
+        out = []
+        for generated in (False, True):
+            src = ds.StructuredSource(dim, c, 0, lf)      # same hierarchy and right-hand side; row blocks assembled on the host or generated
+            mg = ds.DistMG(src, device=rank, r_mode="injection", smoother=smoother, gather_level=glevel, device_gen=generated)
+            mg.load_rhs()
+            hist = mg.cycles(3, history=True)
+            out.append((mg.gather_solution(), hist, mg.row_range))
+            td.barrier()
+            mg.close()
+        q.put((rank, out if rank == 0 else None, None))
+    except Exception:       # noqa: BLE001
+        import traceback
+        q.put((rank, None, traceback.format_exc()))
+    finally:
+        td.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("case", [(2, 8, 4, "gs", 1), (3, 4, 3, "gs_color", 1), (3, 4, 3, "gs", 0)])
+def test_sharded_gauss_seidel_on_generated_levels(case):
+    """Row blocks generated on the device have no host copy: their level sets / colourings and Gauss-Seidel operators are built
+    from the arrays in HBM (mgb_devsetup.cu; ghost columns are never dependencies).  Same partition, same iteration, hence the
+    same bits as the host-assembled blocks, which the test above ties to the numpy restatement."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gs_generated_worker, args=(r, world, port, case, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+        if p.is_alive():
+            p.terminate()
+    for rank, out, err in res:
+        assert err is None, err
+    (v_host, h_host, rr_host), (v_gen, h_gen, rr_gen) = [r[1] for r in res if r[0] == 0][0]
+    assert rr_host == rr_gen
+    assert np.array_equal(h_host, h_gen) and np.array_equal(v_host, v_gen)
+    assert h_gen[2] < h_gen[0]
