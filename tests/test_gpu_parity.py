@@ -350,7 +350,7 @@ def test_device_tensor_path_matches_host_path_at_large_n():
     engine's first kernel (the event is recorded AFTER the marshalling).  A race shows up only when the copies take long enough,
     hence 4.2 M unknowns (config 2's finest level) and fresh, non-contiguous inputs every call."""
     import torch
-    H = pr.build_hierarchy(dim=2, c=32, coarsest_level=3, finest_level=6, with_dicts=False)
+    H = pr.build_hierarchy(dim=2, c=32, coarsest_level=0, finest_level=6, with_dicts=False)
     lf = 6
     eng = MGEngine.from_hierarchy(H)
     n = H.n(lf)
