@@ -685,7 +685,8 @@ template <int T, int RPT, int JW, int MINB, class Epi>
 void launch_anchrow_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int ntiles, const double* x, const Epi& epi)
 {
     constexpr int ROWS = T * RPT;
-    auto kern = k_anchrow<T, RPT, JW, MINB, Epi>;
+    auto kern_halo = k_anchrow<T, RPT, JW, MINB, true, Epi>;
+    auto kern_plain = k_anchrow<T, RPT, JW, MINB, false, Epi>;       // single GPU: the instantiation without any exchange code
     const bool linear = desc == D.sdesc && ntiles == D.sntiles;
     const int grid = linear ? (int)((D.nrows + ROWS - 1) / ROWS) : ntiles;
     if (grid <= 0) return;
@@ -695,7 +696,11 @@ void launch_anchrow_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nt
         static std::mutex mu;
         static std::map<int, int> attr;
         std::lock_guard<std::mutex> lock(mu);
-        if (smem > attr[h->device]) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr[h->device] = smem; }
+        if (smem > attr[h->device]) {
+            cudaFuncSetAttribute(kern_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr[h->device] = smem;
+        }
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = h->stream;
@@ -705,7 +710,8 @@ void launch_anchrow_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nt
     cfg.attrs = at; cfg.numAttrs = h->pdl != 0 ? 1 : 0;
     HaloFuse hf = linear ? h->hf_cur : no_hf();
     finish_hf(hf, ROWS, D.nrows);
-    cudaLaunchKernelEx(&cfg, kern, (const unsigned char*)D.cd.codes, (const int32_t*)D.cd.anchor, (const int2*)D.cd.phead, (const DictEnt*)D.cd.dict,
+    const bool halo = hf.wait_n > 0 || hf.send_n > 0;
+    cudaLaunchKernelEx(&cfg, halo ? kern_halo : kern_plain, (const unsigned char*)D.cd.codes, (const int32_t*)D.cd.anchor, (const int2*)D.cd.phead, (const DictEnt*)D.cd.dict,
                        D.cd.ndict, D.cd.npent, hf, linear ? (const int4*)nullptr : desc, grid, 0, (int)D.nrows, pf, x, epi);
 }
 

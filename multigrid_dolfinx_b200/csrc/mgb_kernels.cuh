@@ -1465,7 +1465,8 @@ __device__ __forceinline__ int ld_stream_i32(const int32_t* p)
 // (2) the pattern table sits in shared memory (copied by the CTA while those requests are in flight), which turns two of the
 // three latencies into shared-memory look-ups; (3) a thread keeps RPT rows in flight, holding only their x values in registers
 // (the entry values are looked up again when the row is summed).
-template <int THREADS, int RPT, int JW, int MINB, class Epi>
+// HALO: compiled with the fused halo exchange; the single-GPU instantiation carries none of its tests (as k_hotrow).
+template <int THREADS, int RPT, int JW, int MINB, bool HALO, class Epi>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ anchor, const int2* __restrict__ phead,
           const DictEnt* __restrict__ pent, int ndict, int npent, const __grid_constant__ HaloFuse hf, const int4* __restrict__ desc,
@@ -1481,7 +1482,8 @@ k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ 
     int* sdelta = reinterpret_cast<int*>(smem_anch + (size_t)npent * 8 + 256 * 8);   // [npent]
     const int tid = threadIdx.x;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int tile = desc ? (int)blockIdx.x : halo_tile(hf, (int)blockIdx.x, ntiles);
+    int tile = (int)blockIdx.x;
+    if constexpr (HALO) { if (!desc) tile = halo_tile(hf, (int)blockIdx.x, ntiles); }
     int row0 = rb + tile * T, rend = re;
     if (desc) { const int4 d = __ldg(desc + blockIdx.x); row0 = d.x; rend = d.x + d.y; }
     int code[RPT], anc[RPT];
@@ -1516,8 +1518,11 @@ k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ 
         }
     }
     __syncthreads();                                         // the table is in shared memory
-    halo_wait(hf, row0, min(row0 + T, rend));                // rows whose columns reach into the ghost section of x
-    const int sends = halo_sends(hf, row0, min(row0 + T, rend));
+    int sends = 0;
+    if constexpr (HALO) {
+        halo_wait(hf, row0, min(row0 + T, rend));            // rows whose columns reach into the ghost section of x
+        sends = halo_sends(hf, row0, min(row0 + T, rend));
+    }
     // Entries are fetched in two halves of JW / 2: the second half only by warps in which some row is longer than the first
     // (warp-uniform test).  Rows of a prolongation alternate between short and long patterns along a mesh line, and whole lines
     // are short: on the trilinear P three warps in four never need entries 4..7.
@@ -1531,16 +1536,18 @@ k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ 
     for (int j = 0; j < RPT; ++j) {
         ph[j] = sphead[code[j]];
         const int* sd = sdelta + ph[j].x;
+        const double* xa = x + anc[j];                       // (one wide multiply-add per gather instead of an add and one)
 #pragma unroll
-        for (int e = 0; e < HW; ++e) xv[j][e] = x[anc[j] + sd[e]];            // (coherent load: see ld_x; padded entries repeat the last one)
+        for (int e = 0; e < HW; ++e) xv[j][e] = xa[sd[e]];                    // (coherent load: see ld_x; padded entries repeat the last one)
         more[j] = __any_sync(0xffffffffu, ph[j].y > HW);
     }
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
         if (more[j]) {
             const int* sd = sdelta + ph[j].x;
+            const double* xa = x + anc[j];
 #pragma unroll
-            for (int e = HW; e < JW; ++e) xv[j][e] = x[anc[j] + sd[e]];
+            for (int e = HW; e < JW; ++e) xv[j][e] = xa[sd[e]];
         }
     }
 #pragma unroll
@@ -1568,10 +1575,10 @@ k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ 
             double t;
             if constexpr (NIOPS > 0) t = epi.store_i(r, sum, o[j], io[j]);
             else t = epi.store(r, sum, o[j]);
-            if (sends) halo_send(hf, r, t);
+            if constexpr (HALO) { if (sends) halo_send(hf, r, t); }
         }
     }
-    if (sends) halo_publish(hf, row0, min(row0 + T, rend));
+    if constexpr (HALO) { if (sends) halo_publish(hf, row0, min(row0 + T, rend)); }
 }
 
 // ---- sub-warp family --------------------------------------------------------------------------------
