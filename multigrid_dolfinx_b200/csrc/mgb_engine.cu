@@ -711,6 +711,15 @@ void launch_anchrow_cfg(mgb_handle* h, const DevCsr& D, const int4* desc, int nt
     HaloFuse hf = linear ? h->hf_cur : no_hf();
     finish_hf(hf, ROWS, D.nrows);
     const bool halo = hf.wait_n > 0 || hf.send_n > 0;
+    const int kt = std::abs(h->anch_tiles);                  // (negative: also on grids too small to fill the GPU that way -- tests)
+    if (!halo && linear && kt > 1 && (h->anch_tiles < 0 || grid >= 4 * kt * h->sm_count)) {    // several tiles per CTA, next anchors in flight
+        auto kern_loop = k_anchloop<T, RPT, JW, (MINB > 1 ? MINB - 1 : 1), Epi>;       // (the next tile's anchors cost registers: one CTA fewer per SM instead of spills)
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cfg.gridDim = dim3((grid + kt - 1) / kt);
+        cudaLaunchKernelEx(&cfg, kern_loop, (const unsigned char*)D.cd.codes, (const int32_t*)D.cd.anchor, (const int2*)D.cd.phead,
+                           (const DictEnt*)D.cd.dict, D.cd.ndict, D.cd.npent, grid, (int)D.nrows, kt, pf, x, epi);
+        return;
+    }
     cudaLaunchKernelEx(&cfg, halo ? kern_halo : kern_plain, (const unsigned char*)D.cd.codes, (const int32_t*)D.cd.anchor, (const int2*)D.cd.phead, (const DictEnt*)D.cd.dict,
                        D.cd.ndict, D.cd.npent, hf, linear ? (const int4*)nullptr : desc, grid, 0, (int)D.nrows, pf, x, epi);
 }
@@ -1815,6 +1824,7 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "win_cfg" && pre) h->win_cfg = iv;
     else if (k == "hot_cfg" && pre) h->hot_cfg = iv;
     else if (k == "anch_cfg" && pre) h->anch_cfg = iv;
+    else if (k == "anch_tiles") { h->anch_tiles = iv == 0 ? 1 : iv; drop_graphs(h); }
     else if (k == "reuse_g") { h->reuse_g = iv; drop_graphs(h); }
     else if (k == "tail_rows") { h->tail_rows = iv; drop_graphs(h); }
     else if (k == "hot_inj") { h->hot_inj = iv; drop_graphs(h); }

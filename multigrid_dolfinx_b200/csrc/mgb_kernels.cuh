@@ -1581,6 +1581,120 @@ k_anchrow(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ 
     if constexpr (HALO) { if (sends) halo_publish(hf, row0, min(row0 + T, rend)); }
 }
 
+// Several consecutive tiles per CTA, the next tile's anchors and codes requested while the current tile is being summed.  The ncu
+// source view of k_anchrow (profiles/r2_ncu_k_anchrow_plain_cfg5_*.json) shows three exposed waits per tile -- (anchor, code) ->
+// shared-memory table -> gathered x values -- that account for 37 % of the stall samples at 20 resident warps per SM; here the
+// first of them is paid once per CTA instead of once per tile, and so are the table copy and its barrier.  Linear tiling of all
+// rows, no fused exchange (single GPU / unsharded levels); arithmetic per row as in k_anchrow, hence the same bits.
+template <int THREADS, int RPT, int JW, int MINB, class Epi>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_anchloop(const unsigned char* __restrict__ rcodes, const int32_t* __restrict__ anchor, const int2* __restrict__ phead,
+           const DictEnt* __restrict__ pent, int ndict, int npent, int ntiles, int re, int kt, int pf, const double* x, Epi epi)
+{
+    static_assert(Epi::CONTIG, "anchored-pattern kernel needs contiguous epilogue operands");
+    static_assert(JW == 4 || JW == 8, "chunk width");
+    constexpr int T = THREADS * RPT;
+    constexpr int NOPS = Epi::NOPS, NIOPS = EpiNI<Epi>::value;
+    constexpr int HW = JW / 2;
+    extern __shared__ __align__(16) unsigned char smem_anch[];
+    double* sval = reinterpret_cast<double*>(smem_anch);                       // [npent]
+    int2* sphead = reinterpret_cast<int2*>(smem_anch + (size_t)npent * 8);      // [256]
+    int* sdelta = reinterpret_cast<int*>(smem_anch + (size_t)npent * 8 + 256 * 8);   // [npent]
+    const int tid = threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int t0 = (int)blockIdx.x * kt, t1 = min(t0 + kt, ntiles);
+    int code[RPT], anc[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {                          // static data: requested before the predecessor has finished
+        const int r = min(t0 * T + tid + j * THREADS, re - 1);
+        code[j] = ld_stream_u8(rcodes + r);
+        anc[j] = ld_stream_i32(anchor + r);
+    }
+    for (int k = tid; k < npent; k += THREADS) { const DictEnt d = pent[k]; sval[k] = d.val; sdelta[k] = d.delta; }
+    for (int k = tid; k < ndict; k += THREADS) sphead[k] = phead[k];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __syncthreads();                                         // the table is in shared memory
+#pragma unroll 1
+    for (int t = t0; t < t1; ++t) {
+        const int row0 = t * T;
+        const bool full = row0 + T <= re;                    // CTA-uniform
+        double o[RPT][NOPS > 0 ? NOPS : 1];
+        int io[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int r = full ? row0 + tid + j * THREADS : min(row0 + tid + j * THREADS, re - 1);
+#pragma unroll
+            for (int k = 0; k < NOPS; ++k) o[j][k] = ld_stream_f64(epi.operand(k) + r);
+            if constexpr (NIOPS > 0) io[j] = epi.ioperand()[r];
+        }
+        int2 ph[RPT];
+        double xv[RPT][JW];
+        bool more[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            ph[j] = sphead[code[j]];
+            const int* sd = sdelta + ph[j].x;
+#pragma unroll
+            for (int e = 0; e < HW; ++e) xv[j][e] = x[anc[j] + sd[e]];        // (coherent load; padded entries repeat the last one)
+            more[j] = __any_sync(0xffffffffu, ph[j].y > HW);
+        }
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            if (more[j]) {
+                const int* sd = sdelta + ph[j].x;
+#pragma unroll
+                for (int e = HW; e < JW; ++e) xv[j][e] = x[anc[j] + sd[e]];
+            }
+        }
+        int canc[RPT];                                       // (rows longer than JW entries still need this tile's anchors)
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) canc[j] = anc[j];
+        if (t + 1 < t1) {                                    // the next tile's anchors and codes travel while this tile is summed
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                const int r = min(row0 + T + tid + j * THREADS, re - 1);
+                code[j] = ld_stream_u8(rcodes + r);
+                anc[j] = ld_stream_i32(anchor + r);
+            }
+        }
+        if (pf > 0 && tid < 2 + NOPS + (NIOPS > 0 ? 1 : 0) && t + pf < ntiles) {     // L2 prefetch for the tile pf tiles ahead
+            const long long p0 = (long long)row0 + (long long)pf * T;
+            if (p0 + T <= (long long)re) {
+                if (tid == 0) bulk_prefetch_l2(rcodes + p0, T);
+                if (tid == 1) bulk_prefetch_l2(anchor + p0, T * 4);
+                if (tid >= 2 && tid < 2 + NOPS) bulk_prefetch_l2(epi.operand(tid - 2) + p0, T * 8);
+                if constexpr (NIOPS > 0) if (tid == 2 + NOPS) bulk_prefetch_l2(epi.ioperand() + p0, T * 4);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int r = row0 + tid + j * THREADS;
+            double sum = 0.0;                                // one accumulator, stored order
+            const double* sv = sval + ph[j].x;
+#pragma unroll
+            for (int e = 0; e < HW; ++e)
+                if (e < ph[j].y) sum = __dadd_rn(sum, __dmul_rn(sv[e], xv[j][e]));
+            if (more[j]) {
+#pragma unroll
+                for (int e = HW; e < JW; ++e)
+                    if (e < ph[j].y) sum = __dadd_rn(sum, __dmul_rn(sv[e], xv[j][e]));
+            }
+            for (int e0 = JW; e0 < ph[j].y; e0 += JW) {      // rows longer than JW entries
+                double xw[JW];
+#pragma unroll
+                for (int e = 0; e < JW; ++e) xw[e] = x[canc[j] + sdelta[ph[j].x + e0 + e]];
+#pragma unroll
+                for (int e = 0; e < JW; ++e)
+                    if (e0 + e < ph[j].y) sum = __dadd_rn(sum, __dmul_rn(sval[ph[j].x + e0 + e], xw[e]));
+            }
+            if (full || r < re) {
+                if constexpr (NIOPS > 0) epi.store_i(r, sum, o[j], io[j]);
+                else epi.store(r, sum, o[j]);
+            }
+        }
+    }
+}
+
 // ---- sub-warp family --------------------------------------------------------------------------------
 // LPR lanes cooperate on one row (LPR = 32: warp per row), partial sums combined with a shuffle tree.
 template <int LPR, bool NCX, class Epi>

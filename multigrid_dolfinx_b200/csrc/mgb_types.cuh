@@ -194,6 +194,8 @@ struct mgb_handle {
     bool in_cycle = false;         // inside enqueue_cycle: ghost sections of fused levels are kept valid by the kernels themselves
     int hot_inj = 1;               // fused residual + injection: thread per coarse row on a pattern-coded level matrix (k_hotinj)
     int anch_cfg = 1;              // anchored-pattern kernel: 1 128 threads x 4 rows, 2 128 x 2, 3 64 x 4, 4 256 x 1 (rows of > 4 entries)
+    int anch_tiles = 8;            // > 1: consecutive tiles per CTA of the anchored-pattern kernel on one GPU, the next tile's anchors / codes in flight
+                                   //   (k_anchloop; 513^3 prolongation 0.91 -> 0.83 ms; 1: one tile per CTA, k_anchrow; negative: also on small grids)
     int hot_cfg = 1;               // hot-row kernel configuration (hot_choice)
     int fuse_sweeps = 0;           // Jacobi: 1 = pairs of sweeps in one launch on unsharded hot-row levels of at least s2_min_rows rows (k_hotrow2).
                                    //   OFF by default: bit-identical, DRAM traffic of a pair 6.7 -> 4.6 GB at 513^3, but no faster -- the sweep is

@@ -134,7 +134,8 @@ def test_subwarp_family_within_tolerance(family, lanes):
 
 @pytest.mark.parametrize("opts", [{"tile_iter": 1}, {"tile_iter": 2}, {"use_graph": 0}, {"fuse_restrict": 1}, {"rj_order": 0},
                                   {"stream_cfg": 1}, {"stream_cfg": 2}, {"stream_cfg": 3}, {"stream_cfg": 4}, {"stream_cfg": 5}, {"stream_cfg": 6},
-                                  {"stream_cfg": 1, "fuse_restrict": 0}, {"pdl": 1}, {"pdl": 0}, {"pdl": 1, "compress": 0}, {"stream_cfg": 7}, {"code_cfg": 3}])
+                                  {"stream_cfg": 1, "fuse_restrict": 0}, {"pdl": 1}, {"pdl": 0}, {"pdl": 1, "compress": 0}, {"stream_cfg": 7}, {"code_cfg": 3},
+                                  {"anch_tiles": -2}, {"anch_tiles": -5}, {"anch_tiles": -64}])
 def test_kernel_options_do_not_change_results(opts):
     for dim, c, lf, seed, r_mode in [(2, 8, 4, 1, "injection"), (3, 2, 3, None, "transpose"), (2, 5, 3, None, "full_weighting")]:
         H = pr.build_hierarchy(dim=dim, c=c, coarsest_level=0, finest_level=lf, perm_seed=seed, with_dicts=False)
@@ -697,6 +698,7 @@ def test_coded_operators_bit_identical_to_uncoded(dim, c, lf, seed, r_mode):
     for opts in [{"compress": 0}, {"stream_cfg": 0}, {"compress": 1}, {"compress": 2}, {"code_cfg": 3}, {"compress": 1, "code_cfg": 3},
                  {"compress": 3}, {"anch_cfg": 2}, {"stage_x": 0}, {"stage_x": 1}, {"hot_cfg": 2}, {"hot_cfg": 3}, {"hot_cfg": 4},
                  {"hot_inj": 0}, {"hot_pf": 0}, {"reuse_g": 0}, {"tail_rows": 300000}, {"tail_rows": 300},
+                 {"anch_tiles": -3}, {"anch_tiles": -16, "anch_cfg": 2},
                  {"compress": 2, "stage_x": 0, "hot_inj": 0, "reuse_g": 0, "tail_rows": 0}]:
         eng = MGEngine.from_hierarchy(H, r_mode=r_mode, options=opts)
         desc = eng.describe()
