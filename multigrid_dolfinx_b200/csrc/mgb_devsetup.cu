@@ -48,38 +48,23 @@ __global__ void k_tr_count(int64_t nnz, const int32_t* __restrict__ cols, int32_
     if (k < nnz) atomicAdd(&cnt[cols[k]], 1);
 }
 
-// every stored entry k of P drops its own index into the row of R it belongs to (arrival order is arbitrary)
-__global__ void k_tr_scatter(int nrows, const int32_t* __restrict__ rp, const int32_t* __restrict__ cols,
-                             const int32_t* __restrict__ t_rp, int32_t* __restrict__ pos, int32_t* __restrict__ t_src)
+// entry d of R comes from stored entry k = src[d] of P: (row of P that holds k, value * scale)
+__global__ void k_tr_gather(int64_t nnz, int nrows, const int32_t* __restrict__ rp, const double* __restrict__ vals, double scale,
+                            const int32_t* __restrict__ src, int32_t* __restrict__ t_cols, double* __restrict__ t_vals)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nrows) return;
-    for (int k = rp[i]; k < rp[i + 1]; ++k) {
-        const int c = cols[k];
-        t_src[t_rp[c] + atomicAdd(&pos[c], 1)] = k;
-    }
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= nnz) return;
+    const int k = src[d];
+    int lo = 0, hi = nrows;                                 // the row i of P with rp[i] <= k < rp[i + 1]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rp[mid] <= k) lo = mid; else hi = mid; }
+    t_cols[d] = lo;
+    t_vals[d] = __dmul_rn(vals[k], scale);
 }
 
-// per row of R: source indices ascending (= rows of P ascending, duplicates in storage order), then source index -> (row of P, value)
-__global__ void k_tr_finish(int ncols, int nrows, const int32_t* __restrict__ rp, const double* __restrict__ vals, double scale,
-                            const int32_t* __restrict__ t_rp, int32_t* __restrict__ t_cols, double* __restrict__ t_vals)
+__global__ void k_iota(int n, int32_t* a)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncols) return;
-    const int b = t_rp[c], e = t_rp[c + 1];
-    for (int a = b + 1; a < e; ++a) {                       // insertion sort: rows of a restriction are short
-        const int key = t_cols[a];
-        int q = a - 1;
-        while (q >= b && t_cols[q] > key) { t_cols[q + 1] = t_cols[q]; --q; }
-        t_cols[q + 1] = key;
-    }
-    for (int a = b; a < e; ++a) {
-        const int k = t_cols[a];
-        int lo = 0, hi = nrows;                             // the row i of P with rp[i] <= k < rp[i + 1]
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rp[mid] <= k) lo = mid; else hi = mid; }
-        t_cols[a] = lo;
-        t_vals[a] = __dmul_rn(vals[k], scale);
-    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
 }
 
 // ---- symmetrised lower graph ----------------------------------------------------------------------------------------------
@@ -158,12 +143,6 @@ cudaError_t relax_until_fixed(cudaStream_t s, int n, Launch&& pass, int* passes)
     return rc;
 }
 
-__global__ void k_iota(int n, int32_t* a)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] = i;
-}
-
 __global__ void k_hist(int n, const int32_t* __restrict__ keys, int32_t* __restrict__ cnt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -218,18 +197,31 @@ __global__ void k_gs_ell(int n, const int32_t* __restrict__ g_rp, const int32_t*
 cudaError_t transpose_scaled(cudaStream_t s, int64_t nrows, int64_t ncols, int64_t nnz, const int32_t* rp, const int32_t* cols,
                              const double* vals, double scale, int32_t** t_rp, int32_t** t_cols, double** t_vals)
 {
-    int32_t* pos = nullptr;
+    // Stable sort of the stored entries by column: entries of one column stay in storage order, i.e. rows of P ascending and
+    // duplicates in the order they are stored -- exactly the order the sequential transpose leaves (one pass over the rows of P
+    // appending to the rows of R).  Row lengths of R do not matter (a dense column of P costs no more than a sparse one).
     DCU(zalloc(s, t_rp, (size_t)ncols + 1 + 8));
     DCU(zalloc(s, t_cols, (size_t)nnz + 16));
     DCU(zalloc(s, t_vals, (size_t)nnz + 16));
-    DCU(zalloc(s, &pos, (size_t)ncols));
-    if (nnz > 0) k_tr_count<<<blocks_for(nnz), TPB, 0, s>>>(nnz, cols, *t_rp);
-    cudaError_t rc = exclusive_scan(s, *t_rp, ncols + 1);
-    if (rc == cudaSuccess && nrows > 0) k_tr_scatter<<<blocks_for(nrows), TPB, 0, s>>>((int)nrows, rp, cols, *t_rp, pos, *t_cols);
-    if (rc == cudaSuccess && ncols > 0) k_tr_finish<<<blocks_for(ncols), TPB, 0, s>>>((int)ncols, (int)nrows, rp, vals, scale, *t_rp, *t_cols, *t_vals);
-    if (rc == cudaSuccess) rc = cudaGetLastError();
-    if (rc == cudaSuccess) rc = cudaStreamSynchronize(s);
-    cudaFree(pos);
+    if (nnz == 0 || nrows == 0 || ncols == 0) return cudaStreamSynchronize(s);
+    int32_t *iota = nullptr, *keys = nullptr, *src = nullptr;
+    void* tmp = nullptr; size_t bytes = 0;
+    cudaError_t rc = cudaSuccess;
+    auto step = [&](cudaError_t e) { if (rc == cudaSuccess) rc = e; return rc == cudaSuccess; };
+    k_tr_count<<<blocks_for(nnz), TPB, 0, s>>>(nnz, cols, *t_rp);
+    step(exclusive_scan(s, *t_rp, ncols + 1));
+    int end_bit = 1;
+    while (end_bit < 31 && ((int64_t)1 << end_bit) < ncols) ++end_bit;
+    if (step(zalloc(s, &iota, (size_t)nnz)) && step(zalloc(s, &keys, (size_t)nnz)) && step(zalloc(s, &src, (size_t)nnz))) {
+        k_iota<<<blocks_for(nnz), TPB, 0, s>>>((int)nnz, iota);
+        if (step(cub::DeviceRadixSort::SortPairs(tmp, bytes, cols, keys, iota, src, (int)nnz, 0, end_bit, s)) &&
+            step(cudaMalloc(&tmp, std::max<size_t>(bytes, 1))) &&
+            step(cub::DeviceRadixSort::SortPairs(tmp, bytes, cols, keys, iota, src, (int)nnz, 0, end_bit, s)))
+            k_tr_gather<<<blocks_for(nnz), TPB, 0, s>>>(nnz, (int)nrows, rp, vals, scale, src, *t_cols, *t_vals);
+    }
+    step(cudaGetLastError());
+    step(cudaStreamSynchronize(s));
+    cudaFree(iota); cudaFree(keys); cudaFree(src); cudaFree(tmp);
     return rc;
 }
 

@@ -5,7 +5,8 @@ check the claims the kernels rest on, against the sequential definitions of the 
     and in-place (chaotic) updates reach the same answer;
   * the colouring is the UNIQUE solution of col[i] = mex{col[j] : j ~ i, j < i}; a row of dependency level k is final after pass
     k + 1 whatever the other rows hold in the meantime;
-  * the transposed restriction built by scatter + per-row sort by source entry equals the sequential transpose, duplicates included.
+  * the transposed restriction built by one stable sort of the stored entries by column equals the sequential transpose, duplicates
+    included.
 The GPU tests (tests/test_gpu_parity.py::test_device_setup_matches_host_setup) compare the kernels' output with the same oracle."""
 import numpy as np
 import pytest
@@ -89,7 +90,7 @@ def test_colouring_as_fixed_point():
         assert np.array_equal(col, col_ref)
 
 
-def test_transpose_by_scatter_and_sort():
+def test_transpose_by_stable_sort():
     rng = np.random.default_rng(3)
     H = pr.build_hierarchy(dim=2, c=4, coarsest_level=0, finest_level=2, perm_seed=8, with_dicts=False)
     P = H.P[1].tocsr()
@@ -108,15 +109,13 @@ def test_transpose_by_scatter_and_sort():
         for k in range(ip[i], ip[i + 1]):
             d = pos[ix[k]]; pos[ix[k]] += 1
             tix[d] = i; tax[d] = ax[k] * scale
-    # device form: entries arrive in ANY order, each row is then sorted by source entry index
-    src = [[] for _ in range(nc)]
-    for k in rng.permutation(len(ix)):
-        src[ix[k]].append(int(k))
-    dix, dax = [], []
-    for c in range(nc):
-        for k in sorted(src[c]):
-            dix.append(int(np.searchsorted(ip, k, side="right") - 1)); dax.append(ax[k] * scale)
-    assert np.array_equal(tix, np.array(dix)) and np.array_equal(tax, np.array(dax))
+    # device form: ONE stable sort of the stored entries by column (entries of a column keep their storage order), then every
+    # entry looks up the row of P it came from
+    src = np.argsort(ix, kind="stable")
+    dix = np.searchsorted(ip, src, side="right") - 1
+    dax = ax[src] * scale
+    assert np.array_equal(tix, dix) and np.array_equal(tax, dax)
+    assert np.array_equal(np.concatenate([[0], np.cumsum(np.bincount(ix, minlength=nc))]), tp)
     R = pr.full_weighting(H.P[1], 2).tocsr()                              # and the definition equals scipy's 2^-d P^T
     cntP = np.bincount(H.P[1].tocsr().indices, minlength=nc)
     assert np.array_equal(np.diff(R.indptr), cntP)
