@@ -187,7 +187,7 @@ int mgb_set_params(mgb_handle* h, double omega, int mu1, int mu2, int smoother);
  *  any time:  "use_graph" [1], "pdl" [-1: programmatic dependent launch for the coded kernels; 1 also the CSR stream kernels; 0
  *   never], "fuse_restrict" [1], "reuse_g" [1], "hot_inj" [1], "hot_pf" [262144 rows of L2 prefetch distance], "fuse_sweeps" [0]
  *   (1: pairs of Jacobi sweeps in ONE launch on unsharded hot-row levels, k_hotrow2; measured no faster), "s2_slack", "s2_tiles", "anch_tiles" [8: consecutive tiles per CTA of the anchored-pattern kernel, k_anchloop], "coarse_refine" [0],
- *   "tail_rows" [0], "gs_cluster" [2], "p2p_enable" [1], "overlap_halo" [0], "overlap_waves", "win_prefetch". */
+ *   "tail_rows" [0], "tail_cluster" [0], "gs_cluster" [2], "p2p_enable" [1], "overlap_halo" [0], "overlap_waves", "win_prefetch". */
 int mgb_set_option(mgb_handle* h, const char* key, double value);
 /* builds R_omega and D^-1 (getJacobiMatrices, multigrid.py:48-56), R from P, the dense inverse of the
  * coarsest matrix (replaces spsolve, multigrid.py:239), level sets / colours when a GS smoother is

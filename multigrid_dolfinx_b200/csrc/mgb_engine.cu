@@ -1107,6 +1107,17 @@ int launch_tail(mgb_handle* h, int tail_top)
         t.A = tail_op(L.A); t.RJ = tail_op(L.RJ); t.P = tail_op(L.P);
         bytes += (double)(h->mu1 - 1 + h->mu2) * bytes_rowsum(L.RJ, 3.0 * (double)L.n) + 32.0 * (double)L.n + bytes_rowsum(L.P, 3.0 * (double)L.n);
     }
+    if (h->tail_cluster) {                                   // one 8-CTA cluster, hardware cluster barrier between the phases
+        return launch(h, MGB_K_COARSE, tail_top, bytes, [&] {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(8); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, k_tail<true>, T);
+        });
+    }
     return launch(h, MGB_K_COARSE, tail_top, bytes, [&] {
         static std::mutex mu;
         static std::map<int, int> grid_of;                  // device -> co-resident CTAs
@@ -1116,13 +1127,13 @@ int launch_tail(mgb_handle* h, int tail_top)
             auto it = grid_of.find(h->device);
             if (it == grid_of.end()) {
                 int o = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_tail, 512, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_tail<false>, 512, 0);
                 it = grid_of.emplace(h->device, std::max(1, std::min(o, 1)) * h->sm_count).first;
             }
             grid = it->second;
         }
         void* args[] = {(void*)&T};
-        cudaLaunchCooperativeKernel((void*)k_tail, dim3(grid), dim3(512), args, 0, h->stream);
+        cudaLaunchCooperativeKernel((void*)k_tail<false>, dim3(grid), dim3(512), args, 0, h->stream);
     });
 }
 
@@ -1827,6 +1838,7 @@ int mgb_set_option(mgb_handle* h, const char* key, double value)
     else if (k == "anch_tiles") { h->anch_tiles = iv == 0 ? 1 : iv; drop_graphs(h); }
     else if (k == "reuse_g") { h->reuse_g = iv; drop_graphs(h); }
     else if (k == "tail_rows") { h->tail_rows = iv; drop_graphs(h); }
+    else if (k == "tail_cluster") { h->tail_cluster = iv; drop_graphs(h); }
     else if (k == "hot_inj") { h->hot_inj = iv; drop_graphs(h); }
     else if (k == "fuse_halo" && pre) h->fuse_halo = iv;
     else if (k == "device_setup" && pre) h->device_setup = iv;

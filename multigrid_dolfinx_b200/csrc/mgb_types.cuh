@@ -183,6 +183,8 @@ struct mgb_handle {
     int tail_rows = 0;             // > 0: levels of at most this many rows (and everything below them) run in one cooperative launch
                                    // (k_tail).  OFF by default: measured slower (profiles/r2_variants_tail_*.jsonl) -- inside a replayed
                                    // graph a small kernel costs ~2.2 us, a grid-wide barrier phase ~6 us (cfg2: 0.229 -> 0.307 ms)
+    int tail_cluster = 0;          // k_tail as ONE 8-CTA cluster with the hardware cluster barrier between phases instead of the cooperative grid
+                                   // (bit-identical, measured slower as well: cfg2 0.221 -> 0.278 ms)
     int reuse_g = 1;               // cycles after the first of one call reuse the top level's w*(dinv*f) instead of forming it again
     bool numbered = false;         // some level carries a caller numbering
     double* perm_tmp = nullptr;    // device scratch of the permuting copies

@@ -698,7 +698,7 @@ def test_coded_operators_bit_identical_to_uncoded(dim, c, lf, seed, r_mode):
     for opts in [{"compress": 0}, {"stream_cfg": 0}, {"compress": 1}, {"compress": 2}, {"code_cfg": 3}, {"compress": 1, "code_cfg": 3},
                  {"compress": 3}, {"anch_cfg": 2}, {"stage_x": 0}, {"stage_x": 1}, {"hot_cfg": 2}, {"hot_cfg": 3}, {"hot_cfg": 4},
                  {"hot_inj": 0}, {"hot_pf": 0}, {"reuse_g": 0}, {"tail_rows": 300000}, {"tail_rows": 300},
-                 {"anch_tiles": -3}, {"anch_tiles": -16, "anch_cfg": 2},
+                 {"anch_tiles": -3}, {"anch_tiles": -16, "anch_cfg": 2}, {"tail_rows": 300000, "tail_cluster": 1}, {"tail_rows": 300, "tail_cluster": 1},
                  {"compress": 2, "stage_x": 0, "hot_inj": 0, "reuse_g": 0, "tail_rows": 0}]:
         eng = MGEngine.from_hierarchy(H, r_mode=r_mode, options=opts)
         desc = eng.describe()
