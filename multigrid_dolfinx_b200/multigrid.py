@@ -221,8 +221,8 @@ def _level_pair_engine(mesh_dict_coarse, mesh_dict_fine, n_c, n_f, h_c=None, h_f
         P = _pr.prolongation(Nc, dim, pc, pf)
         eng.set_transfer(0, P, r_mode=restriction, inj=_pr.injection(Nc, dim, pc, pf) if restriction == "injection" else None, dim=dim)
         eng.finalize()
-        _standalone[key] = eng
-    return _standalone[key], 1
+        _standalone[key] = (eng, mesh_dict_coarse, mesh_dict_fine)     # the dicts are kept alive: the key holds their id()s
+    return _standalone[key][0], 1
 
 
 def Interpolation2D(vec_2h, mesh_dict_coarse, mesh_dict_fine, element_size_coarse, element_size_fine, vec_h_dim):
