@@ -26,6 +26,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -188,22 +189,37 @@ def expected_from_file(key):
         return None
 
 
-def ncu_traffic(workload, kernel_kind):
+def ncu_traffic(workload, kernel_kind, describe=None):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, from the committed `ncu --set full` capture of THIS
-    workload's fine-level sweep (profiles/r2_ncu_traffic.json names the kernel it was taken from); None when none matches."""
+    workload's fine-level sweep (profiles/r2_ncu_traffic.json names the kernel it was taken from); None when none matches.
+    The figure belongs to ONE kernel: the record carries the operator, kernel family and grid it was captured with ("expects"),
+    and when the engine's own description of what it will launch (mgb_describe) is at hand and disagrees, the figure is withheld
+    as stale instead of being attached to another kernel."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
         rec = t.get(f"{workload}:{kernel_kind}")
-        return (float(rec["dram_bytes"]), rec["kernel"], rec["file"]) if rec else (None, None, None)
+        if not rec:
+            return None, None, None
+        exp = rec.get("expects")
+        if exp and describe is not None:
+            want = f"{exp['family']}("
+            block = describe.split(f"level {exp['level']} ", 1)[1].split("\nlevel ", 1)[0] if f"level {exp['level']} " in describe else ""
+            line = next((l for l in block.splitlines() if l.strip().startswith(exp["operator"] + " ")), "")
+            tiles = re.search(r"tiles=(\d+)\s*$", line)
+            # (an operator line that cannot be found or read decides nothing: only a description that names another kernel family
+            # or another grid withholds the figure)
+            if line and (want not in line or (tiles is not None and int(tiles.group(1)) != int(exp["tiles"]))):
+                return None, "stale", f"{rec['file']} was captured on {exp['operator']}@{exp['level']} = {exp['family']}, tiles={exp['tiles']}; the engine now reports: {line.strip() or 'no such operator'}"
+        return float(rec["dram_bytes"]), rec["kernel"], rec["file"]
     except Exception:
         return None, None, None
 
 
-def roofline_block(dom, peak, peak_src, workload, prof, extra=None):
-    traffic, tk, tf = ncu_traffic(workload, dom["kind"])
+def roofline_block(dom, peak, peak_src, workload, prof, extra=None, describe=None):
+    traffic, tk, tf = ncu_traffic(workload, dom["kind"], describe)
     r = {"bound": "hbm", "kernel": f"{dom['kind']}@level{dom['level']}", "achieved": dom["moved_gbs"], "peak": peak, "unit": "GB/s",
          "frac": dom["moved_gbs"] / peak, "frac_of_8TBs": dom["moved_gbs"] / 8000.0, "traffic": traffic,
-         "traffic_source": f"{tf} ({tk})" if tf else None, "peak_source": peak_src,
+         "traffic_source": (f"withheld: {tf}" if tk == "stale" else f"{tf} ({tk})") if tf else None, "peak_source": peak_src,
          "bytes_per_launch": dom["moved_bytes"], "ms_per_launch": dom["ms_per_launch"],
          "algorithmic_bytes_per_launch": dom["bytes"], "algorithmic_gbs": dom["gbs"],
          "note": "achieved/frac: bytes the kernel streams per launch (one code byte per row + the vectors for pattern-coded operators) over the "
@@ -212,6 +228,13 @@ def roofline_block(dom, peak, peak_src, workload, prof, extra=None):
     if extra:
         r.update(extra)
     return r
+
+
+def _describe(eng):
+    try:
+        return eng.describe()
+    except Exception:
+        return None
 
 
 def run_reference(args):
@@ -324,7 +347,7 @@ def run_single(args):
     cyc_ms_prof = sum(r["total_ms"] for r in prof) / max(3, min(args.steps, 10))
     roofline = roofline_block(dom, peak, peak_src, args.workload if args.perm == "lex" else f"{args.workload}-{args.perm}", prof,
                               {"vcycle_bytes_moved": eng.vcycle_bytes_moved(lf), "vcycle_moved_gbs": eng.vcycle_bytes_moved(lf) / (ms * 1e-3) / 1e9,
-                               "vcycle_algorithmic_bytes": eng.vcycle_bytes(lf)})
+                               "vcycle_algorithmic_bytes": eng.vcycle_bytes(lf)}, describe=_describe(eng))
     kernels = sorted(prof, key=lambda r: -r["total_ms"])[:8]
 
     # ---- end to end through the C ABI with pinned host buffers -----------------------------------------

@@ -149,7 +149,7 @@ def run(args):
                            "setup_s": setup_s},
                 "fine_dof_cycles_per_s": n_glob / (ms * 1e-3), "parity": parity,
                 "roofline": B.roofline_block(dom, peak, peak_src, name if not multi else f"{name}-n{world}", prof,
-                                             {"kernel": f"{dom['kind']}@level{dom['level']}" + (" (rank 0 shard)" if multi else "")}),
+                                             {"kernel": f"{dom['kind']}@level{dom['level']}" + (" (rank 0 shard)" if multi else "")}, describe=B._describe(eng)),
                 "halo_ms_per_cycle_rank0": halo_ms, "profiled_cycle_ms_rank0": tot_ms,
                 "cpu_baseline": cpu,
                 "e2e": {"value": dofu / e2e_s, "unit": B.UNIT, "h2d_bytes_per_step": 16 * n_glob, "d2h_bytes_per_step": 8 * n_glob, "ms_per_step": e2e_s * 1e3,

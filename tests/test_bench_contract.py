@@ -119,3 +119,29 @@ def test_reference_arm_sets_the_thread_count_explicitly():
     r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
     import bench
     assert r["cpu_baseline"]["cores"] == bench.cpu_threads() and f"omp_set_num_threads({bench.cpu_threads()})" in r["cpu_baseline"]["sample"]
+
+
+def test_ncu_traffic_is_withheld_when_the_engine_describes_another_kernel():
+    """roofline.traffic comes from a committed ncu capture of ONE kernel; it must not be attached to a different one."""
+    sys.path.insert(0, ROOT)
+    import bench
+    good = ("level 5 n=16974593\n  A   rows=16974593 nnz=1 max_row=15 hotrow(coded mode=3: 9 row patterns; cfg=1, 128 x 2 rows) tiles=66308\n"
+            "level 6 n=135005697\n  A   rows=135005697 nnz=2018775553 max_row=15 hotrow(coded mode=3: 27 row patterns, 100 table entries, hot pattern 3 of 15 entries, "
+            "0 patterns take the table walk; cfg=1, 128 x 2 rows) tiles=527367\n"
+            "  RJ  rows=135005697 nnz=799000000 max_row=6 hotrow(coded mode=3: 27 row patterns, 90 table entries, hot pattern 1 of 6 entries, "
+            "0 patterns take the table walk; cfg=1, 128 x 2 rows) tiles=527367\n  P   rows=135005697 nnz=4 max_row=8 anchrow(coded mode=4) tiles=527367\n")
+    t, kern, src = bench.ncu_traffic("cfg5", "jacobi", good)
+    assert t and t > 3e9 and "k_hotrow" in kern and src.startswith("profiles/")
+    assert bench.ncu_traffic("cfg5", "jacobi", None)[0] == t                        # no description at hand: the record as committed
+    other_kernel = good.replace("max_row=6 hotrow(", "max_row=6 rowstream(")
+    other_grid = good.replace("0 patterns take the table walk; cfg=1, 128 x 2 rows) tiles=527367\n  P ", "0 patterns take the table walk; cfg=2, 256 x 1 rows) tiles=263684\n  P ")
+    assert bench.ncu_traffic("cfg5", "jacobi", "level 6 n=1\n")[0] == t            # no RJ line to compare with: nothing is decided
+    for d in (other_kernel, other_grid):
+        t2, tag, why = bench.ncu_traffic("cfg5", "jacobi", d)
+        assert t2 is None and tag == "stale" and "captured on RJ@6" in why
+    dom = {"kind": "jacobi", "level": 6, "moved_gbs": 5000.0, "moved_bytes": 3.4e9, "ms_per_launch": 0.6, "bytes": 1.3e10, "gbs": 2e4, "total_ms": 1.0}
+    r = bench.roofline_block(dom, 6538.6, "measured", "cfg5", [dom], describe=other_kernel)
+    assert r["traffic"] is None and r["traffic_source"].startswith("withheld: ")
+    r = bench.roofline_block(dom, 6538.6, "measured", "cfg5", [dom], describe=good)
+    assert r["traffic"] == t and "k_hotrow" in r["traffic_source"]
+    assert bench.ncu_traffic("cfg2", "jacobi", good) == (None, None, None)          # no capture for that workload
