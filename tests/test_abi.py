@@ -87,3 +87,29 @@ def test_singular_diagonal_is_reported(lib_built):
     import scipy.sparse as sp
     with pytest.raises(_lib.MGBError):
         en.host_build_rj(sp.csr_matrix(np.array([[0.0, 1.0], [1.0, 2.0]])))
+
+
+def test_every_entry_point_refuses_null_arguments_without_crashing(lib_built):
+    """Error behaviour of the boundary (every call returns MGB_OK or a negative code, nothing throws or crashes):
+    all 50+ entry points called with a null handle / null pointers, in a child process so that a crash is a test failure."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from multigrid_dolfinx_b200 import _lib as L
+lib = L.load()
+n = 0
+for name, (res, args) in L.SYMBOLS.items():
+    if name in ("mgb_version", "mgb_last_error"):
+        continue
+    vals = [None if (a is C.c_void_p or a is C.c_char_p or hasattr(a, "contents")) else 0.0 if a is C.c_double else 5 for a in args]
+    rc = getattr(lib, name)(*vals)
+    assert rc < 0 or name == "mgb_destroy", (name, rc)          # destroying nothing is not an error
+    n += 1
+assert lib.mgb_last_error(None)                                 # the text of the last refusal
+print("refused", n)
+''' % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert int(out.stdout.split()[-1]) >= 50
