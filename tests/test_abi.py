@@ -113,3 +113,31 @@ print("refused", n)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr[-2000:]
     assert int(out.stdout.split()[-1]) >= 50
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(lib_built, tmp_path):
+    """include/mgb200.h is the boundary a maintainer binds: it must be valid C (not only C++), and a C caller must get the
+    documented error code -- not a crash, not a silent CPU path -- when there is no device."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "mgb200.h")
+    chk = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert chk.returncode == 0, chk.stderr
+    src = tmp_path / "caller.c"
+    src.write_text('#include <stdio.h>\n#include "mgb200.h"\n'
+                   'int main(void) {\n    mgb_handle* h = NULL;\n    int rc = mgb_create(&h, 0);\n'
+                   '    printf("version %d rc %d: %s\\n", mgb_version(), rc, rc == MGB_OK ? "created" : mgb_last_error(NULL));\n'
+                   '    if (rc == MGB_OK) rc = mgb_destroy(h);\n    return rc == MGB_OK ? 0 : 2;\n}\n')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(lib_built)
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                         "-L" + libdir, "-l:libmgb200.so", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert "version 100" in run.stdout
+    if have_gpu():
+        assert run.returncode == 0 and "rc 0: created" in run.stdout, run.stdout
+    else:
+        assert run.returncode == 2 and f"rc {_lib.ERR_CUDA}:" in run.stdout and "no CPU fallback" in run.stdout, run.stdout
