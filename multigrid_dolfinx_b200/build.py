@@ -21,6 +21,7 @@ DEPENDS = {"mgb_engine.cu": HEADERS,
            "mgb_devsetup.cu": ["mgb_devsetup.h"],
            "mgb_setup.cpp": ["mgb_internal.h", os.path.join("..", "..", "include", "mgb200.h")]}
 OBJDIR = os.path.join(HERE, "_build")
+SPLIT_COMPILE = 4
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp,-O3"]
 
 
@@ -56,7 +57,11 @@ def build(force=False, verbose=False):
         stale = force or not os.path.exists(obj) or any(
             _newer(os.path.join(CSRC, f), os.path.getmtime(obj)) for f in [src] + DEPENDS[src])
         if stale:
-            cmd = [nvcc] + FLAGS + (["--split-compile", "0"] if src.endswith(".cu") else []) + \
+            # --split-compile with a FIXED count: the number of pieces the optimiser works on changes the machine code ptxas ends up
+            # with (register allocation, instruction counts: observed on mgb_engine.cu, 0 = "one per core" gave different SASS on a
+            # 4-core and an 8-core build box), so the count is pinned to the one every measured and GPU-tested build of this
+            # library was made with -- a fresh build anywhere reproduces that SASS instruction for instruction
+            cmd = [nvcc] + FLAGS + (["--split-compile", str(SPLIT_COMPILE)] if src.endswith(".cu") else []) + \
                   (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
             jobs.append((src, subprocess.Popen(cmd)))
     failed = [src for src, p in jobs if p.wait() != 0]
