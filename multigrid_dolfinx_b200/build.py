@@ -57,12 +57,13 @@ def build(force=False, verbose=False):
         stale = force or not os.path.exists(obj) or any(
             _newer(os.path.join(CSRC, f), os.path.getmtime(obj)) for f in [src] + DEPENDS[src])
         if stale:
-            # --split-compile with a FIXED count: the PTX the front end emits depends on the number of pieces (checked on
-            # mgb_engine.cu: byte-identical PTX for equal counts, 33.5 MB with 4 pieces against 41.6 MB with 8), so "0 = one piece
-            # per core" made the library depend on the build box's core count.  4 is the count the measured and GPU-tested builds of
-            # round 2 were made with.  (ptxas itself was still seen to produce two variants of SASS from identical PTX depending on
-            # the launching environment -- same instruction mix, different register allocation, +-3 % instructions; what matters for
-            # parity, no fused multiply-add in any row-sum kernel, is checked on the built library by tests/test_sass.py.)
+            # --split-compile: the optimiser works on the translation unit in pieces, and the PTX (hence ptxas's register allocation
+            # and instruction counts, +-3 %) depends on how many.  With "0 = one piece per core" the library followed the build box's
+            # core count, so the count is fixed at 4, the value the shipped, GPU-tested library of round 2 was built with.  Even so,
+            # repeated builds of mgb_engine.cu on one 8-core box gave EITHER the 4-piece PTX (33.5 MB) or exactly the PTX that 8 pieces
+            # give (41.6 MB), not tied to anything in the launching environment; ptxas is deterministic for a given PTX.  Both
+            # variants have run on B200s in this round.  What parity depends on -- no fused multiply-add in any row-sum kernel -- holds
+            # in both and is checked on whatever library is present by tests/test_sass.py.
             cmd = [nvcc] + FLAGS + (["--split-compile", str(SPLIT_COMPILE)] if src.endswith(".cu") else []) + \
                   (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
             jobs.append((src, subprocess.Popen(cmd)))
