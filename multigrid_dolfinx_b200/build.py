@@ -61,8 +61,8 @@ def build(force=False, verbose=False):
             # and instruction counts, +-3 %) depends on how many.  With "0 = one piece per core" the library followed the build box's
             # core count, so the count is fixed at 4, the value the shipped, GPU-tested library of round 2 was built with.  Even so,
             # repeated builds of mgb_engine.cu on one 8-core box gave EITHER the 4-piece PTX (33.5 MB) or exactly the PTX that 8 pieces
-            # give (41.6 MB), not tied to anything in the launching environment; ptxas is deterministic for a given PTX.  Both
-            # variants have run on B200s in this round.  What parity depends on -- no fused multiply-add in any row-sum kernel -- holds
+            # give (41.6 MB), not tied to anything in the launching environment; ptxas is deterministic for a given PTX.  The
+            # library shipped at the end of round 2 (final GPU test run, smoke) is the 4-piece variant.  What parity depends on -- no fused multiply-add in any row-sum kernel -- holds
             # in both and is checked on whatever library is present by tests/test_sass.py.
             cmd = [nvcc] + FLAGS + (["--split-compile", str(SPLIT_COMPILE)] if src.endswith(".cu") else []) + \
                   (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
